@@ -1,0 +1,82 @@
+"""Regenerates the simulated data sets of the reference's vignettes, whose
+rendered outputs (docs/articles/*.html) are the only known-answer values the
+reference publishes for the hot path.
+TEST INFRASTRUCTURE ONLY.
+
+  binary_data()         vignettes/GLMMadaptive.Rmd:82-107 == vignettes/Methods.Rmd:27-52
+  hurdle_lognormal_data()  vignettes/ZeroInflated_and_TwoPart_Models.Rmd:143-178
+  hurdle_count_data()   vignettes/ZeroInflated_and_TwoPart_Models.Rmd:313-351
+"""
+import numpy as np
+from scipy import stats
+from scipy.special import expit
+from .r_rng import RRng
+
+
+def _design(rng, n, K, t_max):
+    # time = c(replicate(n, c(0, sort(runif(K - 1, 0, t_max)))))
+    time = np.empty(n * K)
+    for i in range(n):
+        time[i * K] = 0.0
+        time[i * K + 1:(i + 1) * K] = np.sort(rng.runif(K - 1, 0.0, t_max))
+    ids = np.repeat(np.arange(n), K)
+    sex = np.repeat((np.arange(n) >= n // 2).astype(float), K)   # gl(2, n/2): first half "male"
+    X = np.column_stack([np.ones(n * K), sex, time, sex * time])  # ~ sex * time
+    Z = np.column_stack([np.ones(n * K), time])                   # ~ time
+    return ids, time, sex, X, Z
+
+
+def binary_data():
+    rng = RRng(1234)
+    n, K, t_max = 100, 8, 15
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    betas = np.array([-2.13, -0.25, 0.24, -0.05])
+    D11, D22 = 0.48, 0.1
+    b = np.column_stack([rng.rnorm(n, sd=np.sqrt(D11)), rng.rnorm(n, sd=np.sqrt(D22))])
+    eta_y = X @ betas + np.sum(Z * b[ids], axis=1)
+    y = rng.rbinom1(n * K, expit(eta_y))
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z, y=y)
+
+
+def hurdle_lognormal_data():
+    rng = RRng(1234)
+    n, K, t_max = 100, 8, 5
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    X_zi = np.column_stack([np.ones(n * K), sex])
+    Z_zi = np.ones((n * K, 1))
+    betas = np.array([-2.13, -0.25, 0.24, -0.05])
+    sigma = 0.5
+    gammas = np.array([-1.5, 0.5])
+    D11, D22, D33 = 0.5, 0.1, 0.4
+    b = np.column_stack([rng.rnorm(n, sd=np.sqrt(D11)), rng.rnorm(n, sd=np.sqrt(D22)),
+                         rng.rnorm(n, sd=np.sqrt(D33))])
+    eta_y = X @ betas + np.sum(Z * b[ids, :2], axis=1)
+    eta_zi = X_zi @ gammas + Z_zi[:, 0] * b[ids, 2]
+    y = np.exp(rng.rnorm(n * K, mean=eta_y, sd=sigma))
+    zero = rng.rbinom1(n * K, expit(eta_zi)).astype(bool)
+    y[zero] = 0.0
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z, X_zi=X_zi, Z_zi=Z_zi, y=y)
+
+
+def hurdle_count_data():
+    rng = RRng(123)
+    n, K, t_max = 100, 8, 5
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    X_zi = np.column_stack([np.ones(n * K), sex])
+    Z_zi = np.ones((n * K, 1))
+    betas = np.array([1.5, 0.05, 0.05, -0.03])
+    shape = 2.0
+    gammas = np.array([-1.5, 0.5])
+    D11, D22, D33 = 0.5, 0.1, 0.4
+    b = np.column_stack([rng.rnorm(n, sd=np.sqrt(D11)), rng.rnorm(n, sd=np.sqrt(D22)),
+                         rng.rnorm(n, sd=np.sqrt(D33))])
+    eta_y = X @ betas + np.sum(Z * b[ids, :2], axis=1)
+    eta_zi = X_zi @ gammas + Z_zi[:, 0] * b[ids, 2]
+    mu = np.exp(eta_y)
+    prob = shape / (shape + mu)                     # pnbinom(., mu =, size =)
+    lower = stats.nbinom.cdf(0, shape, prob)
+    u = rng.runif(n * K, lower, 1.0)
+    y = stats.nbinom.ppf(u, shape, prob).astype(float)
+    zero = rng.rbinom1(n * K, expit(eta_zi)).astype(bool)
+    y[zero] = 0.0
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z, X_zi=X_zi, Z_zi=Z_zi, y=y)
