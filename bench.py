@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the AGQ hot path: fused log-likelihood + score evaluations per second.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one fused evaluation (logLik_mixed value + full score_mixed vector,
+reference R/Fit_Funs.R:1-293) of the BASELINE.json config-3 workload -- negative
+binomial, random intercepts + slopes (q = 2), nAGQ = 11 (K = 121 nodes), 1e6 clusters x 8
+observations -- on a fixed quadrature grid, clusters sharded over the N GPUs ("strong"
+scaling: the metric is quoted at 1M clusters for every N).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "loglik+score evals/s (1M clusters, nAGQ=11)"
+UNIT = "evals/s"
+
+# SURVEY.md section 8(d), flop convention v1 (dense grid): per-point family cost incl. score
+F_PT = {"negative.binomial": 95, "poisson": 36, "binomial": 78, "zi.poisson": 137,
+        "censored.normal": 57, "beta.fam": 460}
+F_OBS_SPECIALS = {"negative.binomial": 400, "poisson": 100, "binomial": 0, "zi.poisson": 100,
+                  "censored.normal": 0, "beta.fam": 200}
+
+
+def algorithmic_flops(family, n, N, K, p, q_y, q_zi, p_zi):
+    q = q_y + q_zi
+    f_node = 2 * q * q + 3 * q + 2 * q * q + 30 + 6
+    f_obs = 2 * (p + p_zi) + F_OBS_SPECIALS[family]
+    return N * K * (F_PT[family] + 2 * q_y + 2 * q_zi) + n * K * f_node + N * f_obs
+
+
+def algorithmic_bytes(n, N, p, q_y, q_zi, p_zi, n_phis, c_y=1):
+    q = q_y + q_zi
+    return 8 * N * (c_y + p + q_y + p_zi + q_zi) + n * (4 + 8 * q + 8 * q * (q + 1) // 2) + \
+        8 * (2 + p + n_phis + p_zi + q * q)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_eval_time(d, th, n_sample, reps=1):
+    """Times the CPU oracle (numpy restatement of the reference's N x K vectorised R code):
+    logLik_mixed + score_mixed, each recomputing everything as optim's fn/gr do
+    (R/Fit_Funs.R:1-42 and :44-293).  Returns seconds per evaluation on n_sample clusters."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import agq
+    from helpers import oracle_family, thetas_vec
+    rp = np.concatenate(([0], np.flatnonzero(np.diff(d["id"])) + 1, [len(d["id"])]))
+    r1 = int(rp[n_sample])
+    od = agq.Data(y=d["y"][:r1], X=d["X"][:r1], Z=d["Z"][:r1], id=d["id"][:r1])
+    fam = oracle_family(d["family"])
+    q = od.nRE
+    # grid at the data-generating theta: identity-ish Hessians are enough for timing, but use
+    # a real grid so that the arithmetic is representative
+    invD = np.linalg.inv(th["D"])
+    modes, hess, _ = agq.find_modes_newton(np.zeros((min(od.n, 200), q)), _head(od, 200), fam, th["betas"], invD,
+                                           th["phis"], th["gammas"])
+    H = np.mean(np.array(hess), axis=0)
+    gh = agq.GHfun_from_modes(od, np.zeros((od.n, q)), [H] * od.n, th["nAGQ"], q)
+    tv = thetas_vec(th)
+    best = np.inf
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        agq.logLik_mixed(tv, od, fam, gh)
+        agq.score_mixed(tv, od, fam, gh)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def _head(od, k):
+    from oracle import agq
+    k = min(k, od.n)
+    r1 = int(od.row_ptr[k])
+    return agq.Data(y=od.y[:r1], X=od.X[:r1], Z=od.Z[:r1], id=od.id[:r1])
+
+
+def _oracle_worker(args):
+    d, th, n_sample = args
+    return oracle_eval_time(d, th, n_sample)
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path.  R is not installed in this image
+    (and the reference is pure R), so this times the oracle port of the R code, on all host
+    cores: the sample's clusters are split over a process pool."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from glmmadaptive_b200 import synth
+    from concurrent.futures import ProcessPoolExecutor
+    cores = max(1, min(os.cpu_count() or 1, 16))
+    per_worker = 4000
+    d, th = synth.make("C3", n=per_worker, ni=8, seed=3)
+    n_total = 1_000_000
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        for it in range(args.warmup + args.steps):
+            # each process times its own logLik_mixed + score_mixed pass (grid set-up excluded);
+            # the step takes as long as the slowest process
+            dt = max(ex.map(_oracle_worker, [(d, th, per_worker)] * cores))
+            if it >= args.warmup:
+                times.append(dt)
+    t_step = float(np.mean(times))
+    n_sample = per_worker * cores
+    value = 1.0 / (t_step * n_total / n_sample)
+    sample = (f"{n_sample} clusters x 8 obs per step ({per_worker} per process x {cores} processes), "
+              f"logLik_mixed + score_mixed of the numpy port; evals/s extrapolated linearly to 1e6 clusters")
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": "C3: negative.binomial, q=2, nAGQ=11 (K=121), 1e6 clusters x 8 obs"},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "R is not installed in the image; the reference (pure R) cannot run, its numpy port is timed"}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import glmmadaptive_b200 as gb
+    from glmmadaptive_b200 import synth, sharded
+    from glmmadaptive_b200.engine import measure_fp64_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    n_total = args.clusters
+    d, th = synth.make(args.workload, n=n_total, seed=None)
+    fam_name = d.pop("family")
+    cfg = synth.CONFIGS[args.workload]
+    ni = cfg["ni"]
+    arrays = {k: d.get(k) for k in ("y", "X", "Z", "X_zi", "Z_zi")}
+    loc, (c0, c1), (r0, r1) = sharded.shard_arrays(arrays, d["id"], rank, world)
+    stream = torch.cuda.current_stream()
+
+    t0 = time.perf_counter()
+    eng = gb.Engine(loc["y"], loc["X"], loc["Z"], loc["id"], fam_name, nAGQ=th["nAGQ"],
+                    X_zi=loc.get("X_zi"), Z_zi=loc.get("Z_zi"), device=local_rank)
+    eng.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+    t_create = time.perf_counter() - t0
+    sh = sharded.ShardedEngine(eng, dist if world > 1 else None)
+    invD = np.linalg.inv(th["D"])
+    betas, D, phis, gammas = th["betas"], th["D"], th["phis"], th["gammas"]
+
+    # grid: the engine's own Newton search at the data-generating theta (timed separately)
+    t0 = time.perf_counter()
+    st = eng.find_modes(betas, invD, phis, gammas, warm=False)
+    torch.cuda.synchronize()
+    t_modes_cold = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.find_modes(betas, invD, phis, gammas, warm=True)
+    torch.cuda.synchronize()
+    t_modes_warm = time.perf_counter() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sh.eval_enqueue(betas, D, phis, gammas, True)
+    barrier()
+
+    # ---- device-resident throughput: K fused evaluations, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        buf = sh.eval_enqueue(betas, D, phis, gammas, True)
+    e1.record(stream)
+    barrier()
+    launches = eng.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    res = eng.unpack(buf.cpu().numpy())
+
+    # ---- end to end through the C ABI with host buffers: theta in, result vector out, sync per step
+    barrier()
+    tv = np.concatenate([betas, gb.chol_transf(D), phis if phis is not None else [], gammas if gammas is not None else []])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        r = sh.eval(betas, D, phis, gammas, True)
+    barrier()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = args.steps / float(t_e2e.item())
+    h2d = 8 * (len(betas) + D.size + (0 if phis is None else len(phis)) + (0 if gammas is None else len(gammas)))
+    d2h = 8 * eng.result_len
+
+    # ---- kernel-level timing of the dominant kernel (rank-local) and the roofline
+    ms_eval, ms_kernel = eng.time_eval(betas, D, phis, gammas, True, iters=max(3, min(args.steps, 10)))
+    barrier()
+    out = None
+    if rank == 0:
+        peak = measure_fp64_peak(local_rank)
+        N_loc, n_loc = eng.N, eng.n
+        flops = algorithmic_flops(fam_name, n_loc, N_loc, eng.K, eng.p, eng.q_y, eng.q_zi, eng.p_zi)
+        byts = algorithmic_bytes(n_loc, N_loc, eng.p, eng.q_y, eng.q_zi, eng.p_zi, eng.n_phis)
+        achieved = flops / (ms_kernel * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None,
+                    "kernel": "eval_kernel<FamNegBin,2,0,true>", "kernel_ms": ms_kernel,
+                    "flops_per_launch": flops, "flop_convention": "SURVEY.md 8(d) v1, dense grid",
+                    "peak_source": "DFMA microbenchmark measured in this run (glmma_measure_fp64_peak); "
+                                   "MEASURED_PEAKS.json has no FP64 entry",
+                    "hbm": {"achieved": byts / (ms_kernel * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": byts / (ms_kernel * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": byts,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_s = 20000
+            dd = dict(d); dd["family"] = fam_name
+            t_s = oracle_eval_time(dd, th, n_s, reps=2)
+            cpu = {"value": 1.0 / (t_s * n_total / n_s), "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {n_s} clusters of the same workload, logLik_mixed + score_mixed of the numpy port "
+                             f"of the R code ({t_s:.2f} s), extrapolated linearly to {n_total} clusters; "
+                             f"host has {os.cpu_count()} cores, the R path is single-threaded"}
+        out = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"{args.workload}: {fam_name}, q={eng.q}, nAGQ={eng.nAGQ} (K={eng.K}), "
+                                      f"{n_total} clusters x {ni} obs, clusters sharded over {world} GPU(s)",
+                          "l2": "inputs larger than L2 (0.43 GB data + work arrays per evaluation)",
+                          "cluster_evals_per_s": n_total * 1e3 / ms_step,
+                          "point_evals_per_s": n_total * ni * eng.K * 1e3 / ms_step},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "what": "glmma_eval through the C ABI: host theta in (kernel parameters), result vector "
+                               "copied back and synchronised every step; the data set is uploaded once by "
+                               "glmma_create, as the R glue does",
+                       "create_s": t_create, "upload_bytes": eng.input_bytes},
+               "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+               "find_modes": {"cold_clusters_per_s": n_total / t_modes_cold, "warm_clusters_per_s": n_total / t_modes_warm,
+                              "mean_iterations_cold": st["mean_iterations"], "not_converged": st["n_not_converged"]},
+               "ms_per_eval_local": ms_eval,
+               "check": {"loglik": res["loglik"], "n_nonfinite": res["n_nonfinite"]}}
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--clusters", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,8 @@
+"""glmmadaptive_b200 -- B200-native engine for GLMMadaptive's adaptive
+Gauss-Hermite marginal log-likelihood / score hot path.
+
+Host-side mirror of the reference closures (GHfun, logLik_mixed, score_mixed)
+over the C ABI in include/glmma.h.  See DESIGN.md.
+"""
+from .engine import Engine, GH, GHfun, logLik_mixed, score_mixed, chol_transf, family_spec  # noqa: F401
+from .sharded import ShardedEngine, shard_bounds  # noqa: F401

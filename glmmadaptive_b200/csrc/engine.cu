@@ -1,0 +1,760 @@
+// C ABI of the AGQ engine (include/glmma.h): handle lifetime, host-side theta
+// algebra, kernel sequencing.  No CPU fallback: every compute entry point needs
+// a CUDA device and fails with GLMMA_ERR_CUDA otherwise.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/glmma.h"
+#include "kernels.cuh"
+#include "engine.h"
+
+#define SCORE_THREADS 256
+#define FINAL_THREADS 256
+
+static thread_local std::string g_create_error;
+
+struct glmma_handle {
+    DevData d;                 // device pointers + sizes
+    int family, link, device, nagq, q, K, y_cols;
+    const FamOps* ops;
+    cudaStream_t stream;
+    GridPar* d_grid;
+    // launch shape of the eval kernel, [0] = loglik only, [1] = with score
+    int jt;
+    int eval_grid[2];
+    size_t eval_smem[2];
+    int score_grid;
+    double* d_partials;        // eval block partials
+    double* d_score_partials;  // score_grid * (p + p_zi)
+    double* d_result;          // result vector
+    unsigned long long* d_stats;
+    bool have_modes;
+    int64_t launches;
+    std::vector<void*> allocs;
+    std::string error;
+    int sticky;                // sticky CUDA error status
+    cudaEvent_t ev[4];
+};
+
+// ------------------------------------------------------------------------------
+// small host math
+// ------------------------------------------------------------------------------
+// gauher(n): Gauss-Hermite nodes (descending) and weights by Newton iteration on the
+// orthonormal Hermite recurrence, same start values and tolerance as the
+// reference's gauher() (R/Functions.R:306-341) so that the tables agree to rounding.
+static void gauher_table(int n, double* x, double* w) {
+    const int m = (n + 1) / 2;
+    double z = 0.0, pp = 0.0;
+    for (int i = 1; i <= m; ++i) {
+        if (i == 1) z = std::sqrt(2.0 * n + 1.0) - 1.85575 * std::pow(2.0 * n + 1.0, -0.16667);
+        else if (i == 2) z = z - 1.14 * std::pow((double)n, 0.426) / z;
+        else if (i == 3) z = 1.86 * z - 0.86 * x[0];
+        else if (i == 4) z = 1.91 * z - 0.91 * x[1];
+        else z = 2.0 * z - x[i - 3];
+        for (int its = 0; its < 10; ++its) {
+            double p1 = 0.751125544464943, p2 = 0.0;
+            for (int j = 1; j <= n; ++j) {
+                const double p3 = p2;
+                p2 = p1;
+                p1 = z * std::sqrt(2.0 / j) * p2 - std::sqrt((j - 1.0) / j) * p3;
+            }
+            pp = std::sqrt(2.0 * n) * p2;
+            const double z1 = z;
+            z = z1 - p1 / pp;
+            if (std::fabs(z - z1) <= 3e-14) break;
+        }
+        x[i - 1] = z;
+        x[n - i] = -z;
+        w[i - 1] = 2.0 / (pp * pp);
+        w[n - i] = w[i - 1];
+    }
+}
+
+// inverse and log-determinant of a symmetric positive definite q x q matrix
+static bool spd_inverse(const double* A, int q, double* Ainv, double* logdet) {
+    double L[GLMMA_QMAX * GLMMA_QMAX] = {0};
+    double ld = 0.0;
+    for (int c = 0; c < q; ++c) {
+        double s = A[c * q + c];
+        for (int t = 0; t < c; ++t) s -= L[c * q + t] * L[c * q + t];
+        if (!(s > 0.0) || !std::isfinite(s)) return false;
+        L[c * q + c] = std::sqrt(s);
+        ld += std::log(s);
+        for (int r = c + 1; r < q; ++r) {
+            double v = 0.5 * (A[r * q + c] + A[c * q + r]);
+            for (int t = 0; t < c; ++t) v -= L[r * q + t] * L[c * q + t];
+            L[r * q + c] = v / L[c * q + c];
+        }
+    }
+    double Li[GLMMA_QMAX * GLMMA_QMAX] = {0};
+    for (int c = 0; c < q; ++c)
+        for (int r = c; r < q; ++r) {
+            double s = (r == c) ? 1.0 : 0.0;
+            for (int t = c; t < r; ++t) s -= L[r * q + t] * Li[t * q + c];
+            Li[r * q + c] = s / L[r * q + r];
+        }
+    for (int r = 0; r < q; ++r)
+        for (int c = 0; c < q; ++c) {
+            double s = 0.0;
+            for (int t = 0; t < q; ++t) s += Li[t * q + r] * Li[t * q + c];
+            Ainv[r * q + c] = s;
+        }
+    if (logdet) *logdet = ld;
+    return true;
+}
+
+static bool fill_fampar(int family, int n_phis, const double* phis, FamPar* fp, std::string& err) {
+    std::memset(fp, 0, sizeof(*fp));
+    const bool needs = family == GLMMA_NEGBIN || family == GLMMA_ZI_NEGBIN || family == GLMMA_HURDLE_NEGBIN ||
+                       family == GLMMA_HURDLE_LOGNORMAL || family == GLMMA_BETA || family == GLMMA_HURDLE_BETA ||
+                       family == GLMMA_GAMMA || family == GLMMA_CENSORED_NORMAL;
+    if (!needs) return true;
+    if (n_phis != 1 || !phis) { err = "this family needs exactly one phis value"; return false; }
+    const double ph = std::exp(phis[0]);
+    switch (family) {
+        case GLMMA_NEGBIN: case GLMMA_ZI_NEGBIN: case GLMMA_HURDLE_NEGBIN: case GLMMA_GAMMA:
+            fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = std::lgamma(ph); fp->a[3] = glmma_digamma(ph); break;
+        case GLMMA_HURDLE_LOGNORMAL:
+            fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = 1.0 / (ph * ph); break;
+        case GLMMA_BETA: case GLMMA_HURDLE_BETA:
+            fp->a[0] = ph; fp->a[1] = std::lgamma(ph); fp->a[2] = glmma_digamma(ph); break;
+        case GLMMA_CENSORED_NORMAL:
+            fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = 1.0 / ph; break;
+    }
+    return true;
+}
+
+static const FamOps* lookup_ops(int family, int link, int qy, int qz) {
+    switch (family) {
+        case GLMMA_BINOMIAL: return glmma_ops_binomial(link, qy, qz);
+        case GLMMA_POISSON: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_LOG) ? glmma_ops_poisson(qy, qz) : nullptr;
+        case GLMMA_NEGBIN: return glmma_ops_negbin(qy, qz);
+        case GLMMA_ZI_POISSON: return glmma_ops_zi_poisson(qy, qz);
+        case GLMMA_ZI_NEGBIN: return glmma_ops_zi_negbin(qy, qz);
+        case GLMMA_ZI_BINOMIAL: return glmma_ops_zi_binomial(qy, qz);
+        case GLMMA_HURDLE_POISSON: return glmma_ops_hurdle_poisson(qy, qz);
+        case GLMMA_HURDLE_NEGBIN: return glmma_ops_hurdle_negbin(qy, qz);
+        case GLMMA_HURDLE_LOGNORMAL: return glmma_ops_hurdle_lognormal(qy, qz);
+        case GLMMA_BETA: return glmma_ops_beta(qy, qz);
+        case GLMMA_HURDLE_BETA: return glmma_ops_hurdle_beta(qy, qz);
+        case GLMMA_GAMMA: return glmma_ops_gamma(qy, qz);
+        case GLMMA_CENSORED_NORMAL: return glmma_ops_censored_normal(qy, qz);
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------
+// small kernels owned by this file
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    // fixed-order block reduction (deterministic)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+    return t;   // valid on thread 0
+}
+
+// g_beta[l] = sum_j X[j,l] zbar[j],  g_gamma[l] = sum_j X_zi[j,l] zbar_zi[j]   (block partials)
+__global__ void __launch_bounds__(SCORE_THREADS) score_reduce_kernel(DevData d, double* partials) {
+    __shared__ double sh[SCORE_THREADS / 32];
+    const int64_t chunk = (d.N + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = min(lo + chunk, d.N);
+    const int ncol = d.p + d.p_zi;
+    for (int l = 0; l < ncol; ++l) {
+        const double* col = (l < d.p) ? d.X + (int64_t)l * d.N : d.X_zi + (int64_t)(l - d.p) * d.N;
+        const double* z = (l < d.p) ? d.zbar : d.zbar_zi;
+        double s = 0.0;
+        for (int64_t r = lo + threadIdx.x; r < hi; r += SCORE_THREADS) s = fma(col[r], z[r], s);
+        const double t = block_sum(s, sh);
+        if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * ncol + l] = t;
+    }
+}
+
+// result vector (include/glmma.h, glmma_eval) from the block partials, one block
+__global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* eval_partials, int n_eval_blocks,
+                                                                  const double* score_partials, int n_score_blocks,
+                                                                  int p, int n_phis, int p_zi, int q, int want_score,
+                                                                  double* result) {
+    __shared__ double sh[FINAL_THREADS / 32];
+    const int np = q * (q + 1) / 2;
+    double acc[GLMMA_NACC];
+    for (int a = 0; a < 4 + np; ++a) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < n_eval_blocks; b += FINAL_THREADS) s += eval_partials[(int64_t)b * GLMMA_NACC + a];
+        acc[a] = block_sum(s, sh);
+    }
+    const int ncol = p + p_zi;
+    if (threadIdx.x == 0) {
+        result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
+    }
+    if (!want_score) return;
+    for (int l = 0; l < ncol; ++l) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < n_score_blocks; b += FINAL_THREADS) s += score_partials[(int64_t)b * ncol + l];
+        const double t = block_sum(s, sh);
+        if (threadIdx.x == 0) {
+            if (l < p) result[4 + l] = t;
+            else result[4 + p + n_phis + (l - p)] = t;
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3];
+        double* S = result + 4 + p + n_phis + p_zi;
+        int t = 0;
+        for (int dd = 0; dd < q; ++dd)
+            for (int e = dd; e < q; ++e) {
+                S[dd + e * q] = acc[4 + t];
+                S[e + dd * q] = acc[4 + t];
+                ++t;
+            }
+    }
+}
+
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    // 8 independent DFMA chains per thread
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------
+static int fail(glmma_handle* h, int code, const std::string& msg) {
+    if (h) h->error = msg; else g_create_error = msg;
+    return code;
+}
+static int cuda_fail(glmma_handle* h, cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    if (h) { h->error = msg; h->sticky = GLMMA_ERR_CUDA; } else g_create_error = msg;
+    return GLMMA_ERR_CUDA;
+}
+#define CU(h, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail((h), e_, #call); } while (0)
+
+template <class T>
+static int dev_alloc(glmma_handle* h, T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc");
+    h->allocs.push_back(p);
+    *out = (T*)p;
+    return GLMMA_OK;
+}
+template <class T>
+static int dev_upload(glmma_handle* h, const T** out, const T* src, size_t count) {
+    T* p = nullptr;
+    int rc = dev_alloc(h, &p, count);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *out = p;
+    return GLMMA_OK;
+}
+
+extern "C" {
+
+int glmma_version(void) { return GLMMA_VERSION; }
+
+int glmma_family_id(const char* name) {
+    if (!name) return -1;
+    static const struct { const char* n; int id; } tab[] = {
+        {"binomial", GLMMA_BINOMIAL}, {"poisson", GLMMA_POISSON}, {"negative binomial", GLMMA_NEGBIN},
+        {"zero-inflated poisson", GLMMA_ZI_POISSON}, {"zero-inflated negative binomial", GLMMA_ZI_NEGBIN},
+        {"zero-inflated binomial", GLMMA_ZI_BINOMIAL}, {"hurdle poisson", GLMMA_HURDLE_POISSON},
+        {"hurdle negative binomial", GLMMA_HURDLE_NEGBIN}, {"hurdle log-normal", GLMMA_HURDLE_LOGNORMAL},
+        {"beta", GLMMA_BETA}, {"hurdle beta", GLMMA_HURDLE_BETA}, {"Gamma", GLMMA_GAMMA},
+        {"censored normal", GLMMA_CENSORED_NORMAL}};
+    for (auto& t : tab) if (std::strcmp(t.n, name) == 0) return t.id;
+    return -1;
+}
+
+const char* glmma_last_error(const glmma_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+void glmma_destroy(glmma_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    delete h;
+}
+
+int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
+    if (!data || !out) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int64_t N = data->n_obs;
+    const int q = data->q_y + data->q_zi;
+    if (N <= 0 || data->p <= 0 || data->q_y <= 0 || !data->y || !data->X || !data->Z)
+        return fail(nullptr, GLMMA_ERR_ARG, "y, X, Z and positive sizes are required");
+    if (N >= (int64_t)1 << 31) return fail(nullptr, GLMMA_ERR_ARG, "n_obs must be below 2^31");
+    if (data->p > GLMMA_PMAX || data->p_zi > GLMMA_PZIMAX) return fail(nullptr, GLMMA_ERR_ARG, "too many fixed-effect columns");
+    if (data->nAGQ < 1 || data->nAGQ > GLMMA_NAGQ_MAX) return fail(nullptr, GLMMA_ERR_ARG, "nAGQ out of range");
+    if (data->family < 0 || data->family >= GLMMA_N_FAMILIES) return fail(nullptr, GLMMA_ERR_ARG, "unknown family");
+    if (data->y_cols != 1 && data->y_cols != 2) return fail(nullptr, GLMMA_ERR_ARG, "y_cols must be 1 or 2");
+    if (data->family == GLMMA_CENSORED_NORMAL && data->y_cols != 2)
+        return fail(nullptr, GLMMA_ERR_ARG, "censored normal needs a two-column response");
+    if ((data->q_zi > 0 && !data->Z_zi) || (data->p_zi > 0 && !data->X_zi))
+        return fail(nullptr, GLMMA_ERR_ARG, "X_zi / Z_zi missing");
+    const FamOps* ops = lookup_ops(data->family, data->link, data->q_y, data->q_zi);
+    if (!ops) return fail(nullptr, GLMMA_ERR_ARG, "family / link / random-effects dimensions not supported by the engine");
+    if (ops->has_zi && data->p_zi <= 0) return fail(nullptr, GLMMA_ERR_ARG, "this family needs X_zi (zi_fixed)");
+    if (!ops->has_zi && (data->p_zi > 0 || data->q_zi > 0)) return fail(nullptr, GLMMA_ERR_ARG, "family has no zero part");
+    double Kd = 1.0;
+    for (int i = 0; i < q; ++i) Kd *= data->nAGQ;
+    if (Kd > 1 << 20) return fail(nullptr, GLMMA_ERR_ARG, "nAGQ^q too large");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+        return fail(nullptr, GLMMA_ERR_CUDA, std::string("no usable CUDA device (the engine has no CPU fallback): ") +
+                                                 (ce != cudaSuccess ? cudaGetErrorString(ce) : "bad device index"));
+    ce = cudaSetDevice(device);
+    if (ce != cudaSuccess) return cuda_fail(nullptr, ce, "cudaSetDevice");
+
+    // CSR cluster index
+    std::vector<int32_t> row_ptr;
+    if (data->row_ptr) {
+        if (data->n_clusters <= 0) return fail(nullptr, GLMMA_ERR_ARG, "n_clusters must be positive");
+        row_ptr.resize(data->n_clusters + 1);
+        for (int64_t i = 0; i <= data->n_clusters; ++i) row_ptr[i] = (int32_t)data->row_ptr[i];
+        if (data->row_ptr[0] != 0 || data->row_ptr[data->n_clusters] != N)
+            return fail(nullptr, GLMMA_ERR_ARG, "row_ptr must start at 0 and end at n_obs");
+        for (int64_t i = 0; i < data->n_clusters; ++i)
+            if (row_ptr[i + 1] <= row_ptr[i]) return fail(nullptr, GLMMA_ERR_ARG, "row_ptr must be strictly increasing");
+    } else if (data->id) {
+        row_ptr.push_back(0);
+        for (int64_t r = 1; r < N; ++r)
+            if (data->id[r] != data->id[r - 1]) row_ptr.push_back((int32_t)r);
+        row_ptr.push_back((int32_t)N);
+        if (data->n_clusters > 0 && (int64_t)row_ptr.size() - 1 != data->n_clusters)
+            return fail(nullptr, GLMMA_ERR_ARG, "id is not contiguous per cluster (n_clusters mismatch)");
+    } else {
+        return fail(nullptr, GLMMA_ERR_ARG, "id or row_ptr is required");
+    }
+    const int64_t n = (int64_t)row_ptr.size() - 1;
+
+    glmma_handle* h = new glmma_handle();
+    h->family = data->family; h->link = data->link; h->device = device; h->nagq = data->nAGQ;
+    h->q = q; h->K = (int)Kd; h->y_cols = data->y_cols; h->ops = ops; h->stream = nullptr;
+    h->have_modes = false; h->launches = 0; h->sticky = 0;
+    for (auto& e : h->ev) e = nullptr;
+    std::memset(&h->d, 0, sizeof(h->d));
+    DevData& d = h->d;
+    d.N = N; d.n = n; d.p = data->p; d.q_y = data->q_y; d.p_zi = data->p_zi; d.q_zi = data->q_zi; d.n_phis = data->n_phis;
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_) { g_create_error = h->error; glmma_destroy(h); return rc_; } } while (0)
+
+    // response transform (see families.cuh header)
+    std::vector<double> y1(N), y2;
+    const double* ya = data->y;
+    const double* yb = data->y_cols == 2 ? data->y + N : nullptr;
+    switch (data->family) {
+        case GLMMA_BINOMIAL: case GLMMA_ZI_BINOMIAL:
+            y2.resize(N);
+            for (int64_t r = 0; r < N; ++r) { y1[r] = ya[r]; y2[r] = yb ? ya[r] + yb[r] : 1.0; }
+            break;
+        case GLMMA_GAMMA: case GLMMA_HURDLE_LOGNORMAL:
+            y2.resize(N);
+            for (int64_t r = 0; r < N; ++r) { y1[r] = ya[r]; y2[r] = ya[r] > 0.0 ? std::log(ya[r]) : -INFINITY; }
+            break;
+        case GLMMA_BETA: case GLMMA_HURDLE_BETA:
+            y2.resize(N);
+            for (int64_t r = 0; r < N; ++r) { y1[r] = ya[r] > 0.0 ? std::log(ya[r]) : -INFINITY; y2[r] = std::log1p(-ya[r]); }
+            break;
+        case GLMMA_CENSORED_NORMAL:
+            y2.resize(N);
+            for (int64_t r = 0; r < N; ++r) { y1[r] = ya[r]; y2[r] = yb[r]; }
+            break;
+        default:
+            for (int64_t r = 0; r < N; ++r) y1[r] = ya[r];
+    }
+    TRY(dev_upload(h, &d.y1, y1.data(), N));
+    if (!y2.empty()) TRY(dev_upload(h, &d.y2, y2.data(), N));
+    TRY(dev_upload(h, &d.X, data->X, (size_t)N * d.p));
+    TRY(dev_upload(h, &d.Z, data->Z, (size_t)N * d.q_y));
+    if (d.p_zi) TRY(dev_upload(h, &d.X_zi, data->X_zi, (size_t)N * d.p_zi));
+    if (d.q_zi) TRY(dev_upload(h, &d.Z_zi, data->Z_zi, (size_t)N * d.q_zi));
+    if (data->offset) TRY(dev_upload(h, &d.offset, data->offset, N));
+    if (data->offset_zi && ops->has_zi) TRY(dev_upload(h, &d.offset_zi, data->offset_zi, N));
+    if (data->weights) TRY(dev_upload(h, &d.weights, data->weights, n));
+    TRY(dev_upload(h, &d.row_ptr, row_ptr.data(), n + 1));
+
+    const int np = q * (q + 1) / 2;
+    TRY(dev_alloc(h, &d.xb, N));
+    if (ops->has_zi) TRY(dev_alloc(h, &d.xg, N));
+    TRY(dev_alloc(h, &d.cll, N));
+    if (ops->has_phi) TRY(dev_alloc(h, &d.cphi, N));
+    TRY(dev_alloc(h, &d.zbar, N));
+    if (ops->has_zi) TRY(dev_alloc(h, &d.zbar_zi, N));
+    TRY(dev_alloc(h, &d.modes, (size_t)n * q));
+    TRY(dev_alloc(h, &d.rinv, (size_t)n * np));
+    TRY(dev_alloc(h, &d.chol, (size_t)n * np));
+    TRY(dev_alloc(h, &d.logdet, n));
+    cudaMemsetAsync(d.modes, 0, sizeof(double) * n * q, h->stream);
+
+    // Gauss-Hermite table
+    GridPar g;
+    std::memset(&g, 0, sizeof(g));
+    double gw[GLMMA_NAGQ_MAX];
+    gauher_table(h->nagq, g.x, gw);
+    for (int a = 0; a < h->nagq; ++a) g.lw[a] = std::log(gw[a]) + g.x[a] * g.x[a];
+    g.lw_const = 0.5 * q * std::log(2.0);
+    g.nagq = h->nagq;
+    g.K = h->K;
+    TRY(dev_alloc(h, &h->d_grid, 1));
+    cudaMemcpyAsync(h->d_grid, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream);
+
+    // launch shape: the observation tile covers (nearly) all clusters; larger ones stream
+    int max_ni = 0;
+    std::vector<int> cnt(GLMMA_JT_CAP + 2, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int ni = row_ptr[i + 1] - row_ptr[i];
+        max_ni = std::max(max_ni, ni);
+        cnt[std::min(ni, GLMMA_JT_CAP + 1)]++;
+    }
+    d.max_ni = max_ni;
+    int jt = 1;
+    {
+        int64_t cum = 0;
+        for (int v = 1; v <= GLMMA_JT_CAP; ++v) {
+            cum += cnt[v];
+            jt = v;
+            if (cum >= (int64_t)std::ceil(0.995 * (double)n)) break;
+        }
+    }
+    h->jt = jt;
+    cudaDeviceProp prop;
+    ce = cudaGetDeviceProperties(&prop, device);
+    if (ce != cudaSuccess) { cuda_fail(h, ce, "cudaGetDeviceProperties"); g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA; }
+    const int wpb = GLMMA_EVAL_THREADS / 32;
+    int max_grid = 1;
+    for (int s = 0; s < 2; ++s) {
+        int bps = 0;
+        ce = ops->eval_config(s, jt, &bps, &h->eval_smem[s]);
+        if (ce != cudaSuccess || bps < 1) {
+            cuda_fail(h, ce, "eval kernel configuration");
+            g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
+        }
+        const int64_t want = (n + wpb - 1) / wpb;
+        h->eval_grid[s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
+        max_grid = std::max(max_grid, h->eval_grid[s]);
+    }
+    h->score_grid = (int)std::min<int64_t>((N + SCORE_THREADS * 8 - 1) / (SCORE_THREADS * 8), (int64_t)prop.multiProcessorCount * 4);
+    TRY(dev_alloc(h, &h->d_partials, (size_t)max_grid * GLMMA_NACC));
+    TRY(dev_alloc(h, &h->d_score_partials, (size_t)h->score_grid * (d.p + d.p_zi)));
+    TRY(dev_alloc(h, &h->d_result, (size_t)glmma_result_len(h)));
+    TRY(dev_alloc(h, &h->d_stats, 4));
+    for (auto& e : h->ev) {
+        ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) { cuda_fail(h, ce, "cudaEventCreate"); g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA; }
+    }
+    ce = cudaStreamSynchronize(h->stream);
+    if (ce != cudaSuccess) { cuda_fail(h, ce, "upload"); g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA; }
+#undef TRY
+    *out = h;
+    return GLMMA_OK;
+}
+
+int glmma_set_stream(glmma_handle* h, void* cuda_stream) {
+    if (!h) return GLMMA_ERR_ARG;
+    h->stream = (cudaStream_t)cuda_stream;
+    return GLMMA_OK;
+}
+
+int64_t glmma_n_clusters(const glmma_handle* h) { return h ? h->d.n : 0; }
+int64_t glmma_n_obs(const glmma_handle* h) { return h ? h->d.N : 0; }
+int glmma_nre(const glmma_handle* h) { return h ? h->q : 0; }
+int glmma_n_nodes(const glmma_handle* h) { return h ? h->K : 0; }
+int glmma_result_len(const glmma_handle* h) { return h ? 4 + h->d.p + h->d.n_phis + h->d.p_zi + h->q * h->q : 0; }
+int64_t glmma_launch_count(const glmma_handle* h) { return h ? h->launches : 0; }
+
+static int enter(glmma_handle* h) {
+    if (!h) return GLMMA_ERR_ARG;
+    if (h->sticky) return h->sticky;
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaSetDevice");
+    return GLMMA_OK;
+}
+
+static int fill_prior(glmma_handle* h, const double* M, bool is_inverse, PriorPar* pr) {
+    // M is D (eval) or invD (find_modes), q x q
+    const int q = h->q;
+    std::memset(pr, 0, sizeof(*pr));
+    if (is_inverse) {
+        for (int r = 0; r < q; ++r)
+            for (int c = 0; c < q; ++c) pr->Dinv[r * q + c] = 0.5 * (M[r + c * q] + M[c + r * q]);
+        pr->logprior_const = 0.0;
+        return GLMMA_OK;
+    }
+    double A[GLMMA_QMAX * GLMMA_QMAX], Ai[GLMMA_QMAX * GLMMA_QMAX], ld = 0.0;
+    for (int r = 0; r < q; ++r)
+        for (int c = 0; c < q; ++c) A[r * q + c] = M[r + c * q];
+    if (!spd_inverse(A, q, Ai, &ld)) return fail(h, GLMMA_ERR_NUMERIC, "D is not positive definite");
+    for (int i = 0; i < q * q; ++i) pr->Dinv[i] = Ai[i];
+    pr->logprior_const = -0.5 * (q * GLMMA_LOG_2PI + ld);
+    return GLMMA_OK;
+}
+
+static int fill_coef(glmma_handle* h, const double* betas, const double* gammas, CoefPar* c) {
+    std::memset(c, 0, sizeof(*c));
+    if (!betas) return fail(h, GLMMA_ERR_ARG, "betas is null");
+    for (int l = 0; l < h->d.p; ++l) c->betas[l] = betas[l];
+    if (h->d.p_zi) {
+        if (!gammas) return fail(h, GLMMA_ERR_ARG, "gammas is null");
+        for (int l = 0; l < h->d.p_zi; ++l) c->gammas[l] = gammas[l];
+    }
+    return GLMMA_OK;
+}
+
+static int run_prep(glmma_handle* h, const double* betas, const double* phis, const double* gammas, FamPar* fp) {
+    CoefPar c;
+    int rc = fill_coef(h, betas, gammas, &c);
+    if (rc) return rc;
+    if (!fill_fampar(h->family, h->d.n_phis, phis, fp, h->error)) return GLMMA_ERR_ARG;
+    PrepArgs pa;
+    pa.d = h->d; pa.fam = *fp; pa.want_score = 1;
+    h->ops->prep(pa, c, h->stream);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return GLMMA_OK;
+}
+
+int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
+                     const double* gammas, int warm, glmma_mode_stats* stats) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!invD) return fail(h, GLMMA_ERR_ARG, "invD is null");
+    FamPar fp;
+    rc = run_prep(h, betas, phis, gammas, &fp);
+    if (rc) return rc;
+    ModeArgs ma;
+    ma.d = h->d; ma.fam = fp; ma.warm = warm && h->have_modes; ma.maxit = 100; ma.tol = 1e-10; ma.stats = h->d_stats;
+    fill_prior(h, invD, true, &ma.prior);
+    CU(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
+    const double mean_ni = (double)h->d.N / (double)h->d.n;
+    const int G = mean_ni <= 12.0 ? 1 : (mean_ni <= 96.0 ? 8 : 32);
+    h->ops->modes(ma, G, h->stream);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    unsigned long long st[4];
+    CU(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_modes = true;
+    if (stats) {
+        stats->n_not_converged = (int64_t)st[0];
+        stats->n_chol_failed = (int64_t)st[1];
+        stats->max_iterations = (int32_t)st[3];
+        stats->reserved = 0;
+        stats->mean_iterations = (double)st[2] / (double)h->d.n;
+    }
+    return GLMMA_OK;
+}
+
+int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
+    const int64_t n = h->d.n;
+    const int q = h->q, np = q * (q + 1) / 2;
+    if (post_modes) {
+        // device layout is cluster-major (n rows of q); R wants an n x q column-major matrix
+        std::vector<double> tmp((size_t)n * q);
+        CU(h, cudaMemcpyAsync(tmp.data(), h->d.modes, sizeof(double) * n * q, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        for (int64_t i = 0; i < n; ++i)
+            for (int dd = 0; dd < q; ++dd) post_modes[i + dd * n] = tmp[i * q + dd];
+    }
+    if (chol_upper) CU(h, cudaMemcpyAsync(chol_upper, h->d.chol, sizeof(double) * n * np, cudaMemcpyDeviceToHost, h->stream));
+    if (log_dets) CU(h, cudaMemcpyAsync(log_dets, h->d.logdet, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return GLMMA_OK;
+}
+
+int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!post_modes || !chol_upper) return fail(h, GLMMA_ERR_ARG, "null argument");
+    const int64_t n = h->d.n;
+    const int q = h->q, np = q * (q + 1) / 2;
+    std::vector<double> tmp((size_t)n * q);
+    for (int64_t i = 0; i < n; ++i)
+        for (int dd = 0; dd < q; ++dd) tmp[i * q + dd] = post_modes[i + dd * n];
+    CU(h, cudaMemcpyAsync(h->d.modes, tmp.data(), sizeof(double) * n * q, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d.chol, chol_upper, sizeof(double) * n * np, cudaMemcpyHostToDevice, h->stream));
+    h->ops->rinv(h->d, h->stream);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_modes = true;
+    return GLMMA_OK;
+}
+
+// enqueue one evaluation on the stream; the result vector ends up at d_out
+static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                        const double* gammas, int want_score, double* d_out, const DevData* dd_override,
+                        cudaEvent_t k0, cudaEvent_t k1) {
+    if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
+    if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
+    const int s = want_score ? 1 : 0;
+    FamPar fp;
+    int rc = run_prep(h, betas, phis, gammas, &fp);
+    if (rc) return rc;
+    EvalArgs ea;
+    ea.d = dd_override ? *dd_override : h->d;
+    ea.fam = fp; ea.grid = h->d_grid; ea.partials = h->d_partials; ea.jt = h->jt;
+    rc = fill_prior(h, D, false, &ea.prior);
+    if (rc) return rc;
+    if (k0) CU(h, cudaEventRecord(k0, h->stream));
+    h->ops->eval(ea, s, h->eval_grid[s], h->eval_smem[s], h->stream);
+    if (k1) CU(h, cudaEventRecord(k1, h->stream));
+    h->launches++;
+    CU(h, cudaGetLastError());
+    if (s) {
+        score_reduce_kernel<<<h->score_grid, SCORE_THREADS, 0, h->stream>>>(ea.d, h->d_score_partials);
+        h->launches++;
+    }
+    finalize_kernel<<<1, FINAL_THREADS, 0, h->stream>>>(h->d_partials, h->eval_grid[s], h->d_score_partials, h->score_grid,
+                                                         h->d.p, h->d.n_phis, h->d.p_zi, h->q, s, d_out);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return GLMMA_OK;
+}
+
+int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                      const double* gammas, int want_score, double* d_result) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!d_result) return fail(h, GLMMA_ERR_ARG, "d_result is null");
+    return enqueue_eval(h, betas, D, phis, gammas, want_score, d_result, nullptr, nullptr, nullptr);
+}
+
+int glmma_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
+               const double* gammas, int want_score, double* result) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
+    rc = enqueue_eval(h, betas, D, phis, gammas, want_score, h->d_result, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    const int len = want_score ? glmma_result_len(h) : 4;
+    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * len, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return GLMMA_OK;
+}
+
+int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                       const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
+                       double* sphi_obs, double* S_i) {
+    int rc = enter(h);
+    if (rc) return rc;
+    const int64_t n = h->d.n, N = h->d.N;
+    const int q = h->q;
+    DevData dd = h->d;
+    double *d_ll = nullptr, *d_S = nullptr, *d_sphi = nullptr;
+    cudaError_t e = cudaMalloc(&d_ll, sizeof(double) * n);
+    if (e == cudaSuccess && S_i) e = cudaMalloc(&d_S, sizeof(double) * n * q * q);
+    if (e == cudaSuccess && sphi_obs && h->ops->has_phi) e = cudaMalloc(&d_sphi, sizeof(double) * N);
+    if (e != cudaSuccess) { cudaFree(d_ll); cudaFree(d_S); cudaFree(d_sphi); return cuda_fail(h, e, "cudaMalloc (contrib)"); }
+    dd.ll_i = d_ll; dd.S_i = d_S; dd.sphi_obs = d_sphi;
+    rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, &dd, nullptr, nullptr);
+    if (rc == GLMMA_OK && d_sphi) {
+        EvalArgs ea;
+        ea.d = dd; ea.grid = h->d_grid; ea.partials = h->d_partials; ea.jt = h->jt;
+        fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error);
+        fill_prior(h, D, false, &ea.prior);
+        h->ops->sphi(ea, h->eval_grid[1], h->eval_smem[1], h->stream);
+        h->launches++;
+    }
+    if (rc == GLMMA_OK) {
+        if (ll_i) cudaMemcpyAsync(ll_i, d_ll, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+        if (S_i) cudaMemcpyAsync(S_i, d_S, sizeof(double) * n * q * q, cudaMemcpyDeviceToHost, h->stream);
+        if (zbar) cudaMemcpyAsync(zbar, h->d.zbar, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream);
+        if (zbar_zi && h->d.zbar_zi) cudaMemcpyAsync(zbar_zi, h->d.zbar_zi, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream);
+        if (sphi_obs && d_sphi) cudaMemcpyAsync(sphi_obs, d_sphi, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream);
+        e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "eval_contrib");
+    }
+    cudaFree(d_ll); cudaFree(d_S); cudaFree(d_sphi);
+    return rc;
+}
+
+int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                    const double* gammas, int want_score, int iters, float* ms_per_eval, float* ms_main_kernel) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (iters < 1) return fail(h, GLMMA_ERR_ARG, "iters must be positive");
+    std::vector<cudaEvent_t> k0(iters), k1(iters);
+    for (int i = 0; i < iters; ++i) { cudaEventCreate(&k0[i]); cudaEventCreate(&k1[i]); }
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    for (int i = 0; i < iters && rc == GLMMA_OK; ++i)
+        rc = enqueue_eval(h, betas, D, phis, gammas, want_score, h->d_result, nullptr, k0[i], k1[i]);
+    if (rc == GLMMA_OK) {
+        cudaEventRecord(h->ev[1], h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = cuda_fail(h, e, "time_eval");
+    }
+    if (rc == GLMMA_OK) {
+        float tot = 0.f, ker = 0.f;
+        cudaEventElapsedTime(&tot, h->ev[0], h->ev[1]);
+        for (int i = 0; i < iters; ++i) { float t = 0.f; cudaEventElapsedTime(&t, k0[i], k1[i]); ker += t; }
+        if (ms_per_eval) *ms_per_eval = tot / iters;
+        if (ms_main_kernel) *ms_main_kernel = ker / iters;
+    }
+    for (int i = 0; i < iters; ++i) { cudaEventDestroy(k0[i]); cudaEventDestroy(k1[i]); }
+    return rc;
+}
+
+int glmma_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return GLMMA_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = "no usable CUDA device";
+        return GLMMA_ERR_CUDA;
+    }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double* out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return GLMMA_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_peak_kernel<<<blocks, threads>>>(out, 64);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return GLMMA_ERR_CUDA;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return GLMMA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,33 @@
+// Internal host-side interface between engine.cu (the C ABI) and the per-family
+// translation units.
+#pragma once
+#include "common.cuh"
+
+struct PrepArgs;
+struct EvalArgs;
+struct ModeArgs;
+
+struct FamOps {
+    void (*prep)(const PrepArgs&, const CoefPar&, cudaStream_t);
+    cudaError_t (*eval_config)(int score, int jt, int* blocks_per_sm, size_t* smem_bytes);
+    void (*eval)(const EvalArgs&, int score, int grid, size_t smem, cudaStream_t);
+    void (*sphi)(const EvalArgs&, int grid, size_t smem, cudaStream_t);
+    void (*modes)(const ModeArgs&, int G, cudaStream_t);
+    void (*rinv)(const DevData&, cudaStream_t);
+    bool has_zi, has_phi, uses_y2;
+};
+
+// one lookup per family translation unit (nullptr: dimensions not compiled in)
+const FamOps* glmma_ops_binomial(int link, int qy, int qz);
+const FamOps* glmma_ops_poisson(int qy, int qz);
+const FamOps* glmma_ops_negbin(int qy, int qz);
+const FamOps* glmma_ops_zi_poisson(int qy, int qz);
+const FamOps* glmma_ops_zi_negbin(int qy, int qz);
+const FamOps* glmma_ops_zi_binomial(int qy, int qz);
+const FamOps* glmma_ops_hurdle_poisson(int qy, int qz);
+const FamOps* glmma_ops_hurdle_negbin(int qy, int qz);
+const FamOps* glmma_ops_hurdle_lognormal(int qy, int qz);
+const FamOps* glmma_ops_beta(int qy, int qz);
+const FamOps* glmma_ops_hurdle_beta(int qy, int qz);
+const FamOps* glmma_ops_gamma(int qy, int qz);
+const FamOps* glmma_ops_censored_normal(int qy, int qz);

@@ -1,0 +1,3 @@
+// Instantiations of the AGQ kernels for one family functor (see families.cuh).
+#include "ops.cuh"
+const FamOps* glmma_ops_negbin(int qy, int qz) { return dispatch_ops<FamNegBin>(qy, qz); }

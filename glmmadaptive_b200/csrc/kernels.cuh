@@ -1,0 +1,767 @@
+// Kernels of the AGQ hot path (sm_100a, fp64).  One warp owns one cluster; the
+// 32 lanes own 32 quadrature nodes at a time ("a round") and walk the cluster's
+// observations together, so every observation record is a shared-memory
+// broadcast and the log-sum-exp over nodes / score accumulation are warp
+// reductions.  Nothing of size N x K is ever materialised (the reference builds
+// Ztb, eta_y, log_Lik, p_by ... as N x K matrices, R/Functions.R:128-134,
+// R/Fit_Funs.R:21-33,63-90).
+#pragma once
+#include "families.cuh"
+
+#define GLMMA_EVAL_THREADS 128
+#define GLMMA_JT_CAP 32
+
+struct EvalArgs {
+    DevData d;
+    PriorPar prior;
+    FamPar fam;
+    const GridPar* grid;     // device copy of the Gauss-Hermite table
+    double* partials;        // gridDim.x * GLMMA_NACC block partial sums
+    int jt;                  // observation tile held in shared memory per warp (<= GLMMA_JT_CAP)
+};
+
+struct PrepArgs {
+    DevData d;
+    FamPar fam;
+    int want_score;
+};
+
+struct ModeArgs {
+    DevData d;
+    PriorPar prior;          // Dinv = invD as handed to find_modes
+    FamPar fam;
+    int warm;
+    int maxit;
+    double tol;
+    unsigned long long* stats;   // [0] not converged, [1] chol failed, [2] sum iterations, [3] max iterations
+};
+
+template <int Q> struct Tri {
+    __host__ __device__ static constexpr int rm(int d, int e) { return d * Q - d * (d - 1) / 2 + (e - d); }   // row-major d<=e
+    __host__ __device__ static constexpr int cm(int r, int c) { return c * (c + 1) / 2 + r; }               // R upper.tri order r<=c
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------
+// prep: per-observation theta-dependent quantities (X beta, X_zi gamma and the
+// node-independent parts of log f and d log f / d phis).
+// ------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) prep_kernel(PrepArgs A, CoefPar C) {
+    const DevData& d = A.d;
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= d.N) return;
+    double xb = d.offset ? d.offset[row] : 0.0;
+    for (int l = 0; l < d.p; ++l) xb = fma(d.X[row + (int64_t)l * d.N], C.betas[l], xb);
+    d.xb[row] = xb;
+    if (F::HAS_ZI) {
+        double xg = d.offset_zi ? d.offset_zi[row] : 0.0;
+        for (int l = 0; l < d.p_zi; ++l) xg = fma(d.X_zi[row + (int64_t)l * d.N], C.gammas[l], xg);
+        d.xg[row] = xg;
+    }
+    double cll, cphi;
+    F::obs_const(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, A.fam, cll, cphi);
+    d.cll[row] = cll;
+    if (F::HAS_PHI) d.cphi[row] = cphi;
+}
+
+// ------------------------------------------------------------------------------
+// eval: fused logLik_mixed + score_mixed sufficient statistics
+// ------------------------------------------------------------------------------
+template <class F, int QY, int QZ>
+struct EvalLayout {
+    static constexpr int Q = QY + QZ;
+    static constexpr int NP = Q * (Q + 1) / 2;
+    static constexpr int OFF_XG = 3;
+    static constexpr int OFF_Z = F::HAS_ZI ? 4 : 3;
+    static constexpr int W0 = OFF_Z + QY + QZ;
+    static constexpr int W = (W0 + 1) & ~1;                      // even: records stay 16-byte aligned
+    static constexpr int NSCR = F::HAS_ZI ? 4 : 2;               // scr_eta, acc_eta [, scr_zi, acc_zi]
+    __host__ __device__ static size_t warp_doubles(int jt, bool score) {
+        return (size_t)jt * W + (score ? (size_t)NSCR * jt * 32 : 0);
+    }
+    __host__ static size_t smem_bytes(int jt, bool score, int warps) {
+        return sizeof(double) * (2 * GLMMA_NAGQ_MAX + warps * warp_doubles(jt, score));
+    }
+};
+
+// decode node k -> b_k = mode + sqrt(2) R^-1 z_k, returns log prior + log wGH
+template <int Q>
+__device__ __forceinline__ double node_setup(int k, int nagq, const double* gx, const double* glw, double lw_const,
+                                             const double* m, const double* ri, const PriorPar& pr, double* b) {
+    double z[Q];
+    double lw = lw_const;
+    int kk = k;
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) {
+        const int a = kk % nagq;
+        kk /= nagq;
+        z[dd] = gx[a];
+        lw += glw[a];
+    }
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) {
+        double s = 0.0;
+#pragma unroll
+        for (int e = dd; e < Q; ++e) s = fma(ri[Tri<Q>::rm(dd, e)], z[e], s);
+        b[dd] = fma(GLMMA_SQRT2, s, m[dd]);
+    }
+    double quad = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) {
+        double s = 0.0;
+#pragma unroll
+        for (int e = 0; e < Q; ++e) s = fma(pr.Dinv[dd * Q + e], b[e], s);
+        quad = fma(b[dd], s, quad);
+    }
+    return pr.logprior_const - 0.5 * quad + lw;
+}
+
+template <class F, int QY, int QZ>
+__device__ __forceinline__ void stage_tile(const DevData& d, int64_t r0, int cnt, int lane, double* rec) {
+    using L = EvalLayout<F, QY, QZ>;
+    for (int j = lane; j < cnt; j += 32) {
+        const int64_t row = r0 + j;
+        double* r = rec + j * L::W;
+        r[0] = d.y1[row];
+        r[1] = F::USES_Y2 ? d.y2[row] : 0.0;
+        r[2] = d.xb[row];
+        if (F::HAS_ZI) r[L::OFF_XG] = d.xg[row];
+#pragma unroll
+        for (int dd = 0; dd < QY; ++dd) r[L::OFF_Z + dd] = d.Z[row + (int64_t)dd * d.N];
+#pragma unroll
+        for (int dd = 0; dd < QZ; ++dd) r[L::OFF_Z + QY + dd] = d.Z_zi[row + (int64_t)dd * d.N];
+    }
+}
+
+template <class F, int QY, int QZ>
+__device__ __forceinline__ void lin_pred(const double* r, const double* b, double& eta, double& ez) {
+    using L = EvalLayout<F, QY, QZ>;
+    eta = r[2];
+#pragma unroll
+    for (int dd = 0; dd < QY; ++dd) eta = fma(r[L::OFF_Z + dd], b[dd], eta);
+    ez = 0.0;
+    if (F::HAS_ZI) {
+        ez = r[L::OFF_XG];
+#pragma unroll
+        for (int dd = 0; dd < QZ; ++dd) ez = fma(r[L::OFF_Z + QY + dd], b[QY + dd], ez);
+    }
+}
+
+template <class F, int QY, int QZ, bool SCORE>
+__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
+    using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
+    constexpr int NP = L::NP;
+    const DevData& d = A.d;
+    extern __shared__ double smem[];
+    double* gx = smem;
+    double* glw = smem + GLMMA_NAGQ_MAX;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int jt = A.jt;
+    double* wbase = smem + 2 * GLMMA_NAGQ_MAX + wib * L::warp_doubles(jt, SCORE);
+    double* rec = wbase;
+    double* scr_eta = rec + jt * L::W;
+    double* acc_eta = scr_eta + jt * 32;
+    double* scr_zi = acc_eta + jt * 32;
+    double* acc_zi = scr_zi + jt * 32;
+
+    if (threadIdx.x < GLMMA_NAGQ_MAX) {
+        gx[threadIdx.x] = A.grid->x[threadIdx.x];
+        glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    }
+    __syncthreads();
+    const int nagq = A.grid->nagq;
+    const int K = A.grid->K;
+    const double lw_const = A.grid->lw_const;
+    const int nrounds = (K + 31) >> 5;
+    const int rc = ((K - 1) >> 1) >> 5;         // the round holding the central node
+
+    double tot[GLMMA_NACC];
+#pragma unroll
+    for (int a = 0; a < GLMMA_NACC; ++a) tot[a] = 0.0;
+
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
+        const int64_t r0 = d.row_ptr[i];
+        const int ni = (int)(d.row_ptr[i + 1] - r0);
+        const double w = d.weights ? d.weights[i] : 1.0;
+        double m[Q], ri[NP];
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) m[dd] = d.modes[i * Q + dd];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) ri[t] = d.rinv[i * NP + t];
+
+        // node-independent parts of the cluster's log-likelihood / phi score
+        double c_ll = 0.0, c_phi = 0.0;
+        for (int j = lane; j < ni; j += 32) {
+            c_ll += d.cll[r0 + j];
+            if (SCORE && F::HAS_PHI) c_phi += d.cphi[r0 + j];
+        }
+        c_ll = warp_sum(c_ll);
+        if (SCORE && F::HAS_PHI) c_phi = warp_sum(c_phi);
+
+        const bool fast = ni <= jt;
+        __syncwarp();
+        if (fast) stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
+
+        double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
+        double S[NP];
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            sum_e = 0.0; gphi = 0.0;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) S[t] = 0.0;
+            if (SCORE) {
+                if (fast) {
+                    for (int t = lane; t < ni * 32; t += 32) {
+                        acc_eta[t] = 0.0;
+                        if (F::HAS_ZI) acc_zi[t] = 0.0;
+                    }
+                } else {
+                    for (int j = lane; j < ni; j += 32) {
+                        d.zbar[r0 + j] = 0.0;
+                        if (F::HAS_ZI) d.zbar_zi[r0 + j] = 0.0;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int rr = 0; rr < nrounds; ++rr) {
+                const int r = (rr == 0) ? rc : (rr <= rc ? rr - 1 : rr);
+                const int k = (r << 5) + lane;
+                const bool valid = k < K;
+                double b[Q];
+                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b);
+                double vphi = 0.0;
+                if (fast) {
+                    for (int j = 0; j < ni; ++j) {
+                        const double* rj = rec + j * L::W;
+                        double eta, ez, ld, se, sz, sp;
+                        lin_pred<F, QY, QZ>(rj, b, eta, ez);
+                        F::template point<SCORE>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                        a += ld;
+                        if (SCORE) {
+                            scr_eta[j * 32 + lane] = se;
+                            if (F::HAS_ZI) scr_zi[j * 32 + lane] = sz;
+                            if (F::HAS_PHI) vphi += sp;
+                        }
+                    }
+                } else {
+                    // large cluster: stream tiles, log-density only (scores are recomputed below)
+                    for (int j0 = 0; j0 < ni; j0 += jt) {
+                        const int cnt = min(jt, ni - j0);
+                        __syncwarp();
+                        stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                        __syncwarp();
+                        for (int j = 0; j < cnt; ++j) {
+                            const double* rj = rec + j * L::W;
+                            double eta, ez, ld, se, sz, sp;
+                            lin_pred<F, QY, QZ>(rj, b, eta, ez);
+                            F::template point<false>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                            a += ld;
+                        }
+                    }
+                }
+                if (valid) amax = fmax(amax, a);
+                if (rr == 0 && attempt == 0) {
+                    shift = warp_max(valid ? a : -INFINITY);
+                    if (!(fabs(shift) < INFINITY)) shift = 0.0;
+                }
+                const double e = valid ? exp(a - shift) : 0.0;
+                sum_e += e;
+                if (SCORE) {
+                    int t = 0;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                        for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
+                    if (fast) {
+                        if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+                        for (int j = 0; j < ni; ++j) {
+                            acc_eta[j * 32 + lane] = fma(e, scr_eta[j * 32 + lane], acc_eta[j * 32 + lane]);
+                            if (F::HAS_ZI) acc_zi[j * 32 + lane] = fma(e, scr_zi[j * 32 + lane], acc_zi[j * 32 + lane]);
+                        }
+                    } else {
+                        for (int j0 = 0; j0 < ni; j0 += jt) {
+                            const int cnt = min(jt, ni - j0);
+                            __syncwarp();
+                            stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                            __syncwarp();
+                            for (int j = 0; j < cnt; ++j) {
+                                const double* rj = rec + j * L::W;
+                                double eta, ez, ld, se, sz, sp;
+                                lin_pred<F, QY, QZ>(rj, b, eta, ez);
+                                F::template point<true>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                                if (F::HAS_PHI) vphi += sp;
+                                scr_eta[j * 32 + lane] = e * se;
+                                if (F::HAS_ZI) scr_zi[j * 32 + lane] = e * sz;
+                            }
+                            __syncwarp();
+                            // un-normalised partial sums over this round's nodes, flushed per tile
+                            for (int j = lane; j < cnt; j += 32) {
+                                double s1 = 0.0, s2 = 0.0;
+                                for (int c = 0; c < 32; ++c) {
+                                    const int cc = (c + lane) & 31;
+                                    s1 += scr_eta[j * 32 + cc];
+                                    if (F::HAS_ZI) s2 += scr_zi[j * 32 + cc];
+                                }
+                                d.zbar[r0 + j0 + j] += s1;
+                                if (F::HAS_ZI) d.zbar_zi[r0 + j0 + j] += s2;
+                            }
+                        }
+                        if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+                    }
+                }
+            }
+            sum_e = warp_sum(sum_e);
+            // the shift came from the central round; if that was not enough to keep the sum
+            // in range, repeat once with the true maximum over all nodes
+            if (sum_e > 0.0 && sum_e < INFINITY) break;
+            const double mx = warp_max(amax);
+            if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
+            shift = mx;
+        }
+        const double ll = shift + log(sum_e) + d.logdet[i] + c_ll;
+        const bool ok = fabs(ll) < INFINITY;       // false for NaN and +-Inf
+        if (lane == 0) {
+            if (ok) { tot[0] += w * ll; tot[1] += w; } else tot[2] += 1.0;
+            if (d.ll_i) d.ll_i[i] = w * ll;
+        }
+        if (SCORE) {
+            const double inv = ok ? w / sum_e : 0.0;
+            if (F::HAS_PHI) {
+                tot[3] = fma(inv, gphi, tot[3]);
+                if (lane == 0 && ok) tot[3] = fma(w, c_phi, tot[3]);
+            }
+#pragma unroll
+            for (int t = 0; t < NP; ++t) tot[4 + t] = fma(inv, S[t], tot[4 + t]);
+            if (d.S_i) {
+                double Sr[NP];
+#pragma unroll
+                for (int t = 0; t < NP; ++t) Sr[t] = inv * warp_sum(S[t]);
+                if (lane == 0) {
+                    int t = 0;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                        for (int ee = dd; ee < Q; ++ee) {
+                            d.S_i[i * Q * Q + dd * Q + ee] = Sr[t];
+                            d.S_i[i * Q * Q + ee * Q + dd] = Sr[t];
+                            ++t;
+                        }
+                }
+            }
+            __syncwarp();
+            if (fast) {
+                for (int j = lane; j < ni; j += 32) {
+                    double s1 = 0.0, s2 = 0.0;
+                    for (int c = 0; c < 32; ++c) {
+                        const int cc = (c + lane) & 31;
+                        s1 += acc_eta[j * 32 + cc];
+                        if (F::HAS_ZI) s2 += acc_zi[j * 32 + cc];
+                    }
+                    d.zbar[r0 + j] = inv * s1;
+                    if (F::HAS_ZI) d.zbar_zi[r0 + j] = inv * s2;
+                }
+            } else {
+                for (int j = lane; j < ni; j += 32) {
+                    d.zbar[r0 + j] *= inv;
+                    if (F::HAS_ZI) d.zbar_zi[r0 + j] *= inv;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // block partials, fixed order (deterministic for a fixed launch shape)
+    __syncthreads();
+    double* red = smem;    // reuse: wpb * NACC doubles
+#pragma unroll
+    for (int a = 0; a < GLMMA_NACC; ++a) {
+        const double v = warp_sum(tot[a]);
+        if (lane == 0) red[wib * GLMMA_NACC + a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GLMMA_NACC) {
+        double v = 0.0;
+        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
+        A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------
+// per-observation phi-score contributions (i_contributions = TRUE path of
+// score_mixed, R/Fit_Funs.R:186-187): sphi_obs[j] = w_i (sum_k pi_ik s_phi(ijk)).
+// Rarely called (once per fit, for the sandwich estimator), so it simply
+// recomputes the node weights from ll_i of a preceding eval.
+// ------------------------------------------------------------------------------
+template <class F, int QY, int QZ>
+__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A) {
+    using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
+    constexpr int NP = L::NP;
+    const DevData& d = A.d;
+    extern __shared__ double smem[];
+    double* gx = smem;
+    double* glw = smem + GLMMA_NAGQ_MAX;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int jt = A.jt;
+    double* rec = smem + 2 * GLMMA_NAGQ_MAX + wib * L::warp_doubles(jt, true);
+    double* scr = rec + jt * L::W;
+    if (threadIdx.x < GLMMA_NAGQ_MAX) {
+        gx[threadIdx.x] = A.grid->x[threadIdx.x];
+        glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    }
+    __syncthreads();
+    const int nagq = A.grid->nagq, K = A.grid->K;
+    const int nrounds = (K + 31) >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
+        const int64_t r0 = d.row_ptr[i];
+        const int ni = (int)(d.row_ptr[i + 1] - r0);
+        const double w = d.weights ? d.weights[i] : 1.0;
+        double m[Q], ri[NP];
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) m[dd] = d.modes[i * Q + dd];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) ri[t] = d.rinv[i * NP + t];
+        double c_ll = 0.0;
+        for (int j = lane; j < ni; j += 32) c_ll += d.cll[r0 + j];
+        c_ll = warp_sum(c_ll);
+        // log normaliser of the node weights: ll_i / w_i - logdet - c_ll
+        const double lse = d.ll_i[i] / w - d.logdet[i] - c_ll;
+        for (int j = lane; j < ni; j += 32) d.sphi_obs[r0 + j] = 0.0;
+        __syncwarp();
+        for (int r = 0; r < nrounds; ++r) {
+            const int k = (r << 5) + lane;
+            const bool valid = k < K;
+            double b[Q];
+            double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, A.grid->lw_const, m, ri, A.prior, b);
+            for (int j0 = 0; j0 < ni; j0 += jt) {
+                const int cnt = min(jt, ni - j0);
+                __syncwarp();
+                stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                __syncwarp();
+                for (int j = 0; j < cnt; ++j) {
+                    const double* rj = rec + j * L::W;
+                    double eta, ez, ld, se, sz, sp;
+                    lin_pred<F, QY, QZ>(rj, b, eta, ez);
+                    F::template point<false>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                    a += ld;
+                }
+            }
+            const double e = valid ? exp(a - lse) : 0.0;
+            for (int j0 = 0; j0 < ni; j0 += jt) {
+                const int cnt = min(jt, ni - j0);
+                __syncwarp();
+                stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                __syncwarp();
+                for (int j = 0; j < cnt; ++j) {
+                    const double* rj = rec + j * L::W;
+                    double eta, ez, ld, se, sz, sp;
+                    lin_pred<F, QY, QZ>(rj, b, eta, ez);
+                    F::template point<true>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                    scr[j * 32 + lane] = e * sp;
+                }
+                __syncwarp();
+                for (int j = lane; j < cnt; j += 32) {
+                    double s1 = 0.0;
+                    for (int c = 0; c < 32; ++c) s1 += scr[j * 32 + ((c + lane) & 31)];
+                    d.sphi_obs[r0 + j0 + j] += s1;
+                }
+            }
+        }
+        __syncwarp();
+        for (int j = lane; j < ni; j += 32)
+            d.sphi_obs[r0 + j] = w * (d.sphi_obs[r0 + j] + d.cphi[r0 + j]);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------
+// find_modes: per-cluster damped Newton on the reference's objective
+//   g(b) = -sum_j log f(y_ij | b) + b' invD b / 2          (R/Functions.R:5-20)
+// with its analytic gradient (R/Functions.R:21-65); the Newton matrix and the
+// final Hessian are the reference's cd_vec of that gradient (R/Functions.R:90,
+// 249-262).  G lanes share one cluster (G = 1: a thread per cluster).
+// Control flow is warp-uniform: finished groups idle until the warp is done.
+// ------------------------------------------------------------------------------
+template <class F, int QY, int QZ, int G, bool SCORE>
+__device__ __noinline__ void mode_objective(const DevData& d, const PriorPar& pr, const FamPar& fam,
+                                               int64_t r0, int ni, int lg, unsigned gmask,
+                                               const double* b, double& f, double* g) {
+    constexpr int Q = QY + QZ;
+    double fl = 0.0, gl[Q];
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) gl[dd] = 0.0;
+    for (int j = lg; j < ni; j += G) {
+        const int64_t row = r0 + j;
+        double z[Q];
+        double eta = d.xb[row];
+#pragma unroll
+        for (int dd = 0; dd < QY; ++dd) { z[dd] = d.Z[row + (int64_t)dd * d.N]; eta = fma(z[dd], b[dd], eta); }
+        double ez = 0.0;
+        if (F::HAS_ZI) {
+            ez = d.xg[row];
+#pragma unroll
+            for (int dd = 0; dd < QZ; ++dd) {
+                z[QY + dd] = d.Z_zi[row + (int64_t)dd * d.N];
+                ez = fma(z[QY + dd], b[QY + dd], ez);
+            }
+        }
+        double ld, se, sz, sp;
+        F::template point<SCORE>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, eta, ez, fam, ld, se, sz, sp);
+        if (ld == ld) fl -= ld;            // sum(log_dens, na.rm = TRUE), R/Functions.R:19
+        if (SCORE) {
+#pragma unroll
+            for (int dd = 0; dd < QY; ++dd) gl[dd] = fma(-se, z[dd], gl[dd]);
+#pragma unroll
+            for (int dd = 0; dd < QZ; ++dd) gl[QY + dd] = fma(-sz, z[QY + dd], gl[QY + dd]);
+        }
+    }
+    if (G > 1) {
+        fl = group_sum<G>(fl, gmask);
+        if (SCORE) {
+#pragma unroll
+            for (int dd = 0; dd < Q; ++dd) gl[dd] = group_sum<G>(gl[dd], gmask);
+        }
+    }
+    double quad = 0.0;
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) {
+        double s = 0.0;
+#pragma unroll
+        for (int e = 0; e < Q; ++e) s = fma(pr.Dinv[dd * Q + e], b[e], s);
+        quad = fma(b[dd], s, quad);
+        if (SCORE) g[dd] = gl[dd] + s;
+    }
+    f = fl + 0.5 * quad;
+}
+
+// cd_vec(x, score_log_post_b): R/Functions.R:249-262, symmetrised
+template <class F, int QY, int QZ, int G>
+__device__ __forceinline__ void mode_hessian(const DevData& d, const PriorPar& pr, const FamPar& fam,
+                                             int64_t r0, int ni, int lg, unsigned gmask,
+                                             const double* x, double* H /* Q*Q */) {
+    constexpr int Q = QY + QZ;
+#pragma unroll
+    for (int c = 0; c < Q; ++c) {
+        double x1[Q], x2[Q], g1[Q], g2[Q], f;
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) { x1[dd] = x[dd]; x2[dd] = x[dd]; }
+        const double ex = 0.001 * fmax(fabs(x[c]), 1.0);
+        x1[c] = x[c] + ex;
+        x2[c] = x[c] - ex;
+        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, x1, f, g1);
+        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, x2, f, g2);
+        const double dx = x1[c] - x2[c];
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) H[dd * Q + c] = (g1[dd] - g2[dd]) / dx;
+    }
+#pragma unroll
+    for (int a = 0; a < Q; ++a)
+#pragma unroll
+        for (int c = a + 1; c < Q; ++c) {
+            const double v = 0.5 * (H[a * Q + c] + H[c * Q + a]);
+            H[a * Q + c] = v;
+            H[c * Q + a] = v;
+        }
+}
+
+// lower Cholesky factor of H + lam I; returns false if not positive definite
+template <int Q>
+__device__ __forceinline__ bool chol_lower(const double* H, double lam, double* Lc) {
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < Q; ++c) {
+        double s = H[c * Q + c] + lam;
+#pragma unroll
+        for (int t = 0; t < c; ++t) s -= Lc[c * Q + t] * Lc[c * Q + t];
+        if (!(s > 0.0)) ok = false;
+        const double dgl = sqrt(s);
+        Lc[c * Q + c] = dgl;
+#pragma unroll
+        for (int r = c + 1; r < Q; ++r) {
+            double v = H[r * Q + c];
+#pragma unroll
+            for (int t = 0; t < c; ++t) v -= Lc[r * Q + t] * Lc[c * Q + t];
+            Lc[r * Q + c] = v / dgl;
+        }
+    }
+    return ok;
+}
+
+template <class F, int QY, int QZ, int G>
+__global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
+    constexpr int Q = QY + QZ;
+    constexpr int NP = Q * (Q + 1) / 2;
+    const DevData& d = A.d;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = gtid / G;
+    const int lg = (int)(gtid % G);
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const bool live = i < d.n;
+    const int64_t r0 = live ? d.row_ptr[i] : 0;
+    const int ni = live ? (int)(d.row_ptr[i + 1] - r0) : 0;
+
+    double x[Q], g[Q], fx;
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) x[dd] = (live && A.warm) ? d.modes[i * Q + dd] : 0.0;
+    mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, x, fx, g);
+    bool done = !live;
+    bool conv = false;
+    int iters = 0;
+    for (int it = 0; it < A.maxit; ++it) {
+        if (__all_sync(0xffffffffu, done)) break;
+        double H[Q * Q], Lc[Q * Q], dir[Q];
+        mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, x, H);
+        // Levenberg shift until positive definite
+        double lam = 0.0, hmax = 1.0;
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) hmax = fmax(hmax, fabs(H[dd * Q + dd]));
+        bool pd = chol_lower<Q>(H, lam, Lc);
+        for (int t = 0; t < 60 && !pd; ++t) {
+            lam = fmax(10.0 * lam, 1e-3 * hmax);
+            pd = chol_lower<Q>(H, lam, Lc);
+        }
+        // dir = -(L L')^-1 g
+        double yv[Q];
+#pragma unroll
+        for (int r = 0; r < Q; ++r) {
+            double s = g[r];
+#pragma unroll
+            for (int t = 0; t < r; ++t) s -= Lc[r * Q + t] * yv[t];
+            yv[r] = s / Lc[r * Q + r];
+        }
+#pragma unroll
+        for (int r = Q - 1; r >= 0; --r) {
+            double s = yv[r];
+#pragma unroll
+            for (int t = r + 1; t < Q; ++t) s -= Lc[t * Q + r] * dir[t];
+            dir[r] = -s / Lc[r * Q + r];
+        }
+        double gd = 0.0, dmax = 0.0;
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) { gd = fma(g[dd], dir[dd], gd); dmax = fmax(dmax, fabs(dir[dd])); }
+        // Armijo backtracking (c = 1e-4, halving) with a rounding slack so that full steps
+        // inside the quadratic region are not rejected by noise in f
+        double step = 1.0;
+        bool accepted = done || !pd || !(dmax == dmax);
+        bool moved = false;
+        double xn[Q], gn[Q], fn = fx;
+        for (int h = 0; h < 60; ++h) {
+            if (__all_sync(0xffffffffu, accepted)) break;
+            double xt[Q], gt[Q], ft;
+#pragma unroll
+            for (int dd = 0; dd < Q; ++dd) xt[dd] = fma(step, dir[dd], x[dd]);
+            mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, xt, ft, gt);
+            if (!accepted) {
+                const bool acc = (fabs(ft) < INFINITY) &&
+                                 (ft <= fx + 1e-4 * step * gd + 1e-14 * (fabs(fx) + 1.0));
+                if (acc) {
+                    accepted = true; moved = true; fn = ft;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd) { xn[dd] = xt[dd]; gn[dd] = gt[dd]; }
+                } else {
+                    step *= 0.5;
+                }
+            }
+        }
+        if (!done) {
+            ++iters;
+            if (!moved) {
+                done = true;          // no acceptable step: leave the cluster flagged as not converged
+            } else {
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) { x[dd] = xn[dd]; g[dd] = gn[dd]; }
+                fx = fn;
+                if (step == 1.0 && dmax <= A.tol) { conv = true; done = true; }
+            }
+        }
+    }
+    // Hessian at the mode, its Cholesky factor, R^-1 and log_dets (R/Functions.R:90,115-122)
+    double H[Q * Q], Lc[Q * Q];
+    mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, x, H);
+    const bool pd = chol_lower<Q>(H, 0.0, Lc);
+    if (live && lg == 0) {
+        // R = Lc' (upper); R^-1 by back substitution, column by column
+        double Ri[Q * Q];
+#pragma unroll
+        for (int c = 0; c < Q; ++c) {
+#pragma unroll
+            for (int r = Q - 1; r >= 0; --r) {
+                if (r > c) { Ri[r * Q + c] = 0.0; continue; }
+                double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int t = r + 1; t <= c; ++t) s -= Lc[t * Q + r] * Ri[t * Q + c];   // R[r][t] = Lc[t][r]
+                Ri[r * Q + c] = s / Lc[r * Q + r];
+            }
+        }
+        double ldet = 0.0;
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) {
+            d.modes[i * Q + dd] = x[dd];
+            ldet -= log(Lc[dd * Q + dd]);
+        }
+        const double bad = pd ? 0.0 : NAN;
+        d.logdet[i] = ldet + bad;
+#pragma unroll
+        for (int r = 0; r < Q; ++r)
+#pragma unroll
+            for (int c = r; c < Q; ++c) {
+                d.chol[i * NP + Tri<Q>::cm(r, c)] = Lc[c * Q + r] + bad;
+                d.rinv[i * NP + Tri<Q>::rm(r, c)] = Ri[r * Q + c] + bad;
+            }
+        if (!conv) atomicAdd(&A.stats[0], 1ull);
+        if (!pd) atomicAdd(&A.stats[1], 1ull);
+        atomicAdd(&A.stats[2], (unsigned long long)iters);
+        atomicMax(&A.stats[3], (unsigned long long)iters);
+    }
+}
+
+// ------------------------------------------------------------------------------
+// set_modes: R^-1 and log_dets from injected Cholesky factors
+// ------------------------------------------------------------------------------
+template <int Q>
+__global__ void rinv_kernel(DevData d) {
+    constexpr int NP = Q * (Q + 1) / 2;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    double R[Q * Q], Ri[Q * Q];
+#pragma unroll
+    for (int r = 0; r < Q; ++r)
+#pragma unroll
+        for (int c = 0; c < Q; ++c) R[r * Q + c] = (r <= c) ? d.chol[i * NP + Tri<Q>::cm(r, c)] : 0.0;
+    double ldet = 0.0;
+#pragma unroll
+    for (int c = 0; c < Q; ++c) {
+        ldet -= log(fabs(R[c * Q + c]));
+#pragma unroll
+        for (int r = Q - 1; r >= 0; --r) {
+            if (r > c) { Ri[r * Q + c] = 0.0; continue; }
+            double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int t = r + 1; t <= c; ++t) s -= R[r * Q + t] * Ri[t * Q + c];
+            Ri[r * Q + c] = s / R[r * Q + r];
+        }
+    }
+    d.logdet[i] = ldet;
+#pragma unroll
+    for (int r = 0; r < Q; ++r)
+#pragma unroll
+        for (int c = r; c < Q; ++c) d.rinv[i * NP + Tri<Q>::rm(r, c)] = Ri[r * Q + c];
+}

@@ -1,0 +1,72 @@
+// Host-side launchers for one (family functor, q_y, q_zi) combination and the
+// dispatch from runtime dimensions to the compiled instantiation.  Each
+// fam_*.cu translation unit includes this file and exports one lookup function.
+#pragma once
+#include "kernels.cuh"
+#include "engine.h"
+
+template <class F, int QY, int QZ>
+struct OpsImpl {
+    using L = EvalLayout<F, QY, QZ>;
+
+    static void prep(const PrepArgs& a, const CoefPar& c, cudaStream_t s) {
+        const int64_t blocks = (a.d.N + 255) / 256;
+        prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
+    }
+    static cudaError_t eval_config(int score, int jt, int* blocks_per_sm, size_t* smem_bytes) {
+        const size_t smem = L::smem_bytes(jt, score != 0, GLMMA_EVAL_THREADS / 32);
+        *smem_bytes = smem;
+        cudaError_t e;
+        if (score) {
+            e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, true>,
+                                                                 GLMMA_EVAL_THREADS, smem);
+        }
+        e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, false>,
+                                                             GLMMA_EVAL_THREADS, smem);
+    }
+    static void eval(const EvalArgs& a, int score, int grid, size_t smem, cudaStream_t s) {
+        if (score) eval_kernel<F, QY, QZ, true><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        else eval_kernel<F, QY, QZ, false><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+    }
+    static void sphi(const EvalArgs& a, int grid, size_t smem, cudaStream_t s) {
+        sphi_obs_kernel<F, QY, QZ><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+    }
+    static void modes(const ModeArgs& a, int G, cudaStream_t s) {
+        const int64_t threads = a.d.n * G;
+        const unsigned blocks = (unsigned)((threads + 127) / 128);
+        if (G == 1) modes_kernel<F, QY, QZ, 1><<<blocks, 128, 0, s>>>(a);
+        else if (G == 8) modes_kernel<F, QY, QZ, 8><<<blocks, 128, 0, s>>>(a);
+        else modes_kernel<F, QY, QZ, 32><<<blocks, 128, 0, s>>>(a);
+    }
+    static void rinv(const DevData& d, cudaStream_t s) {
+        const unsigned blocks = (unsigned)((d.n + 127) / 128);
+        rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
+    }
+    static const FamOps* get() {
+        static const FamOps ops = {prep, eval_config, eval, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2};
+        return &ops;
+    }
+};
+
+template <class F>
+static const FamOps* dispatch_ops(int qy, int qz) {
+    if (!F::HAS_ZI && qz != 0) return nullptr;
+    if (qz == 0) {
+        if (qy == 1) return OpsImpl<F, 1, 0>::get();
+        if (qy == 2) return OpsImpl<F, 2, 0>::get();
+        if (qy == 3) return OpsImpl<F, 3, 0>::get();
+        return nullptr;
+    }
+    if (F::HAS_ZI) {
+        if (qy == 1 && qz == 1) return OpsImpl<F, 1, F::HAS_ZI ? 1 : 0>::get();
+        if (qy == 2 && qz == 1) return OpsImpl<F, 2, F::HAS_ZI ? 1 : 0>::get();
+        if (qy == 1 && qz == 2) return OpsImpl<F, 1, F::HAS_ZI ? 2 : 0>::get();
+    }
+    return nullptr;
+}

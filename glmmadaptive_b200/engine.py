@@ -1,0 +1,431 @@
+"""Host-side mirror of the reference's hot-path closures over the CUDA engine.
+
+Reference seam (paths relative to the reference tree):
+
+  GHfun()        R/Functions.R:105-138   -> :func:`GHfun`
+  logLik_mixed() R/Fit_Funs.R:1-42       -> :func:`logLik_mixed`
+  score_mixed()  R/Fit_Funs.R:44-293     -> :func:`score_mixed`
+
+The argument meaning and the returned shapes follow the reference; the lists of
+per-cluster data and the family closures that the R functions receive are
+replaced by one :class:`Engine` (the device-resident data set + family id).
+All arithmetic on N- or n-sized data happens on the GPU through libglmma.so;
+this module only does the theta <-> (betas, D, phis, gammas) bookkeeping and the
+q x q chain rule for the D parameters (R/Fit_Funs.R:237-286).
+There is no CPU fallback.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import GlmmaData, GlmmaError, GlmmaModeStats, FAMILY_IDS, LINK_IDS
+
+# reference constructor / family$family  ->  (family$family, default link, n_phis, zero part, y columns)
+_SPECS = {
+    "binomial": ("binomial", "logit", 0, False, None),
+    "poisson": ("poisson", "log", 0, False, 1),
+    "negative.binomial": ("negative binomial", "log", 1, False, 1),
+    "zi.poisson": ("zero-inflated poisson", "log", 0, True, 1),
+    "zi.negative.binomial": ("zero-inflated negative binomial", "log", 1, True, 1),
+    "zi.binomial": ("zero-inflated binomial", "logit", 0, True, None),
+    "hurdle.poisson": ("hurdle poisson", "log", 0, True, 1),
+    "hurdle.negative.binomial": ("hurdle negative binomial", "log", 1, True, 1),
+    "hurdle.lognormal": ("hurdle log-normal", "identity", 1, True, 1),
+    "beta.fam": ("beta", "logit", 1, False, 1),
+    "hurdle.beta.fam": ("hurdle beta", "logit", 1, True, 1),
+    "Gamma.fam": ("Gamma", "log", 1, False, 1),
+    "censored.normal": ("censored normal", "identity", 1, False, 2),
+}
+_BY_FAMILY_STRING = {v[0]: v for v in _SPECS.values()}
+
+
+@dataclass(frozen=True)
+class FamilySpec:
+    family: str          # family$family of the reference
+    link: str
+    n_phis: int
+    has_zi: bool
+
+
+def family_spec(name, link=None):
+    """Accepts the reference's constructor name (``"negative.binomial"``) or its
+    ``family$family`` string (``"negative binomial"``)."""
+    rec = _SPECS.get(name) or _BY_FAMILY_STRING.get(name)
+    if rec is None:
+        raise ValueError(f"family {name!r} is not accelerated by the engine (it stays on the reference path)")
+    fam, dlink, n_phis, zi, _ = rec
+    link = dlink if link is None else link
+    if fam == "binomial":
+        if link not in ("logit", "probit", "cloglog"):
+            raise ValueError(f"binomial link {link!r} is not accelerated")
+    elif link != dlink:
+        raise ValueError(f"{fam}: only the {dlink} link is accelerated")
+    return FamilySpec(fam, link, n_phis, zi)
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_lib.c_double_p)
+
+
+def _f(a, order="F"):
+    return None if a is None else np.require(np.asarray(a, dtype=np.float64), requirements=["A", "O"] + [order])
+
+
+class Engine:
+    """Device-resident data set + family: what ``mixed_fit()`` receives
+    (R/mixed_fit.R:1-25), uploaded once.  Wraps one ``glmma_handle``."""
+
+    def __init__(self, y, X, Z, id, family, link=None, nAGQ=None, X_zi=None, Z_zi=None, offset=None,
+                 offset_zi=None, weights=None, device=0):
+        self.lib = _lib.load()
+        self.spec = family_spec(family, link) if not isinstance(family, FamilySpec) else family
+        y = _f(y)
+        X = _f(X)
+        Z = _f(np.asarray(Z, float).reshape(len(X), -1))
+        X_zi = None if X_zi is None else _f(np.asarray(X_zi, float).reshape(len(X), -1))
+        Z_zi = None if Z_zi is None else _f(np.asarray(Z_zi, float).reshape(len(X), -1))
+        offset, offset_zi, weights = _f(offset), _f(offset_zi), _f(weights)
+        ids = np.ascontiguousarray(np.asarray(id).astype(np.int32))
+        N = X.shape[0]
+        self.N, self.p, self.q_y = N, X.shape[1], Z.shape[1]
+        self.p_zi = 0 if X_zi is None else X_zi.shape[1]
+        self.q_zi = 0 if Z_zi is None else Z_zi.shape[1]
+        self.q = self.q_y + self.q_zi
+        # control$nAGQ default, R/mixed_model.R:154
+        self.nAGQ = int(nAGQ) if nAGQ is not None else (11 if self.q < 3 else 7)
+        self.n_phis = self.spec.n_phis
+        d = GlmmaData()
+        d.family = FAMILY_IDS[self.spec.family]
+        d.link = LINK_IDS[self.spec.link]
+        d.n_obs, d.n_clusters = N, 0
+        d.p, d.q_y, d.p_zi, d.q_zi = self.p, self.q_y, self.p_zi, self.q_zi
+        d.n_phis, d.y_cols, d.nAGQ = self.n_phis, (2 if y.ndim == 2 and y.shape[1] == 2 else 1), self.nAGQ
+        d.y, d.X, d.Z, d.X_zi, d.Z_zi = _dp(y), _dp(X), _dp(Z), _dp(X_zi), _dp(Z_zi)
+        d.offset, d.offset_zi, d.weights = _dp(offset), _dp(offset_zi), _dp(weights)
+        d.id = ids.ctypes.data_as(C.POINTER(C.c_int32))
+        d.row_ptr = None
+        h = C.c_void_p()
+        rc = self.lib.glmma_create(C.byref(d), int(device), C.byref(h))
+        if rc != 0:
+            raise GlmmaError(rc, self.lib.glmma_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self.n = int(self.lib.glmma_n_clusters(h))
+        self.K = int(self.lib.glmma_n_nodes(h))
+        self.result_len = int(self.lib.glmma_result_len(h))
+        self.npack = self.q * (self.q + 1) // 2
+        self._modes_version = None
+        self._cache_key, self._cache_val = None, None
+        self._X_host, self._X_zi_host = X, X_zi
+        self.input_bytes = sum(a.nbytes for a in (y, X, Z, X_zi, Z_zi, offset, offset_zi, weights, ids) if a is not None)
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.glmma_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise GlmmaError(rc, self.lib.glmma_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.glmma_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.glmma_launch_count(self._h))
+
+    # -- GHfun pieces ---------------------------------------------------------
+    def _theta_ptrs(self, betas, M, phis, gammas):
+        b = _f(np.atleast_1d(betas), "C")
+        if b.shape != (self.p,):
+            raise ValueError("betas has the wrong length")
+        M = _f(np.asarray(M, float).reshape(self.q, self.q))
+        ph = None
+        if self.n_phis:
+            ph = _f(np.atleast_1d(phis), "C")
+            if ph.shape != (self.n_phis,):
+                raise ValueError("phis has the wrong length")
+        g = None
+        if self.p_zi:
+            g = _f(np.atleast_1d(gammas), "C")
+            if g.shape != (self.p_zi,):
+                raise ValueError("gammas has the wrong length")
+        return (b, M, ph, g), (_dp(b), _dp(M), _dp(ph), _dp(g))
+
+    def find_modes(self, betas, invD, phis=None, gammas=None, warm=True):
+        keep, ptrs = self._theta_ptrs(betas, invD, phis, gammas)
+        st = GlmmaModeStats()
+        self._check(self.lib.glmma_find_modes(self._h, *ptrs, int(bool(warm)), C.byref(st)))
+        self._modes_version = object()
+        self._cache_key = None
+        return dict(n_not_converged=st.n_not_converged, n_chol_failed=st.n_chol_failed,
+                    max_iterations=st.max_iterations, mean_iterations=st.mean_iterations)
+
+    def get_modes(self):
+        modes = np.empty((self.n, self.q), order="F")
+        chol = np.empty((self.n, self.npack))
+        logdet = np.empty(self.n)
+        self._check(self.lib.glmma_get_modes(self._h, _dp(modes), _dp(chol), _dp(logdet)))
+        return modes, chol, logdet
+
+    def set_modes(self, post_modes, chol_upper):
+        m = _f(np.asarray(post_modes, float).reshape(self.n, self.q))
+        c = _f(np.asarray(chol_upper, float).reshape(self.n, self.npack), "C")
+        self._check(self.lib.glmma_set_modes(self._h, _dp(m), _dp(c)))
+        self._modes_version = object()
+        self._cache_key = None
+
+    # -- evaluation -----------------------------------------------------------
+    def unpack(self, r, want_score=True):
+        out = dict(loglik=float(r[0]), sum_w=float(r[1]), n_nonfinite=int(r[2]))
+        if want_score:
+            o = 4
+            out["g_beta"] = np.array(r[o:o + self.p]); o += self.p
+            out["g_phi"] = np.array(r[o:o + self.n_phis]); o += self.n_phis
+            out["g_gamma"] = np.array(r[o:o + self.p_zi]); o += self.p_zi
+            out["S"] = np.array(r[o:o + self.q * self.q]).reshape(self.q, self.q)
+        return out
+
+    def eval_raw(self, betas, D, phis=None, gammas=None, want_score=True):
+        """The raw result vector of glmma_eval (layout in include/glmma.h)."""
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        res = np.zeros(self.result_len)
+        self._check(self.lib.glmma_eval(self._h, *ptrs, int(bool(want_score)), _dp(res)))
+        return res
+
+    def eval(self, betas, D, phis=None, gammas=None, want_score=True):
+        return self.unpack(self.eval_raw(betas, D, phis, gammas, want_score), want_score)
+
+    def eval_device(self, betas, D, phis, gammas, want_score, device_ptr):
+        """Enqueues one evaluation; the result vector is left at ``device_ptr`` (no sync)."""
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        self._check(self.lib.glmma_eval_device(self._h, *ptrs, int(bool(want_score)), C.c_void_p(device_ptr)))
+
+    def eval_contrib(self, betas, D, phis=None, gammas=None):
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        ll_i = np.empty(self.n)
+        zbar = np.empty(self.N)
+        zbar_zi = np.empty(self.N) if self.p_zi else None
+        sphi = np.empty(self.N) if self.n_phis else None
+        S_i = np.empty((self.n, self.q, self.q))
+        self._check(self.lib.glmma_eval_contrib(self._h, *ptrs, _dp(ll_i), _dp(zbar), _dp(zbar_zi), _dp(sphi), _dp(S_i)))
+        return dict(ll_i=ll_i, zbar=zbar, zbar_zi=zbar_zi, sphi_obs=sphi, S_i=S_i)
+
+    def time_eval(self, betas, D, phis=None, gammas=None, want_score=True, iters=10):
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.glmma_time_eval(self._h, *ptrs, int(bool(want_score)), int(iters), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def measure_fp64_peak(device=0):
+    lib = _lib.load()
+    v = C.c_double()
+    rc = lib.glmma_measure_fp64_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise GlmmaError(rc, lib.glmma_last_error(None).decode())
+    return v.value
+
+
+# ----------------------------------------------------------------------------
+# theta bookkeeping (R/mixed_fit.R:240-247; R/Functions.R:140-158)
+# ----------------------------------------------------------------------------
+def _upper_tri_colmajor(k):
+    return [(r, c) for c in range(k) for r in range(c + 1)]
+
+
+def chol_transf(x):
+    """D <-> its unconstrained parameters: the upper Cholesky factor U (U'U = D),
+    column-major over the upper triangle, diagonal on the log scale
+    (what the reference's chol_transf() computes, R/Functions.R:140-158).
+    Matrix in -> vector out; vector in -> (D, U)."""
+    x = np.asarray(x, float)
+    if x.ndim == 2:
+        k = x.shape[0]
+        U = np.linalg.cholesky(x).T.copy()
+        U[np.diag_indices(k)] = np.log(np.diag(U))
+        return np.array([U[r, c] for r, c in _upper_tri_colmajor(k)])
+    k = int(round((-1 + np.sqrt(1 + 8 * len(x))) / 2))
+    U = np.zeros((k, k))
+    for v, (r, c) in zip(x, _upper_tri_colmajor(k)):
+        U[r, c] = v
+    U[np.diag_indices(k)] = np.exp(np.diag(U))
+    return U.T @ U, U
+
+
+def split_thetas(thetas, eng, diag_D):
+    """c(betas, D-params, phis, gammas), R/mixed_fit.R:240-247."""
+    thetas = np.asarray(thetas, float)
+    nD = eng.q if diag_D else eng.npack
+    o = 0
+    betas = thetas[o:o + eng.p]; o += eng.p
+    Dp = thetas[o:o + nD]; o += nD
+    phis = thetas[o:o + eng.n_phis] if eng.n_phis else None; o += eng.n_phis
+    gammas = thetas[o:o + eng.p_zi] if eng.p_zi else None; o += eng.p_zi
+    if o != len(thetas):
+        raise ValueError("thetas has the wrong length")
+    if diag_D:
+        return betas, np.diag(np.exp(Dp)), None, phis, gammas
+    D, U = chol_transf(Dp)
+    return betas, D, U, phis, gammas
+
+
+def score_D(S, sum_w, n, D, U, diag_D):
+    """d(-loglik)/d(D-params) from S = sum_i w_i E[b b' | y_i] (R/Fit_Funs.R:237-286).
+
+    With M = (c D^-1 - D^-1 S D^-1) / 2 the derivative with respect to a symmetric
+    perturbation dD is <M, dD>; the reference assembles the same number through
+    deriv_D() and jacobian2().  c is n for the diagonal parameterisation
+    (Fit_Funs.R:246) and sum(weights) for the full one (Fit_Funs.R:283)."""
+    q = D.shape[0]
+    Dinv = np.linalg.inv(D)
+    if diag_D:
+        dd = np.diag(D)
+        return 0.5 * (n - np.diag(S) / dd)
+    M = 0.5 * (sum_w * Dinv - Dinv @ S @ Dinv)
+    out = []
+    for r, c in _upper_tri_colmajor(q):
+        dU = np.zeros((q, q))
+        dU[r, c] = U[r, c] if r == c else 1.0      # diagonal is exp(theta)
+        dD = dU.T @ U + U.T @ dU
+        out.append(np.sum(M * dD))
+    return np.array(out)
+
+
+# ----------------------------------------------------------------------------
+# GHfun / logLik_mixed / score_mixed
+# ----------------------------------------------------------------------------
+@dataclass
+class GH:
+    """What GHfun() returns that the rest of mixed_fit() reads (R/Functions.R:135-137).
+    The N x K / nK x q matrices b, b2, Ztb, Z_zitb are never built: the grid lives on
+    the device as (post_modes, chol)."""
+    engine: Engine
+    post_modes: np.ndarray       # n x q
+    chol: np.ndarray             # n x q(q+1)/2, chol(post_hessians)[upper.tri(., TRUE)]
+    log_dets: np.ndarray         # n
+    wGH: np.ndarray              # K
+    stats: dict
+    version: object = None
+
+    @property
+    def post_vars(self):
+        """lapply(post_hessians, solve): (R'R)^-1 per cluster."""
+        q = self.engine.q
+        out = np.empty((self.engine.n, q, q))
+        for i in range(self.engine.n):
+            R = np.zeros((q, q))
+            for v, (r, c) in zip(self.chol[i], _upper_tri_colmajor(q)):
+                R[r, c] = v
+            Ri = np.linalg.inv(R)
+            out[i] = Ri @ Ri.T
+        return out
+
+
+def gauss_hermite_wGH(k, q):
+    """wGH of R/Functions.R:124-125: 2^(q/2) prod(w) exp(sum z^2), first dimension fastest."""
+    x, w = np.polynomial.hermite.hermgauss(k)
+    x, w = x[::-1], w[::-1]
+    f = w * np.exp(x * x)
+    out = np.ones(1)
+    for _ in range(q):
+        out = (out[:, None] * f[None, :]).reshape(-1)
+    return 2 ** (q / 2) * out
+
+
+def GHfun(engine, b, betas, inv_D, phis=None, gammas=None):
+    """R/Functions.R:105-138.  ``b`` is the warm start (n x q) or None to reuse the modes
+    the engine already holds (mixed_fit carries post_modes between calls,
+    R/mixed_fit.R:100,117,287); zeros give the reference's cold start."""
+    warm = True
+    if b is not None:
+        b = np.asarray(b, float).reshape(engine.n, engine.q)
+        if np.any(b != 0.0):
+            eye = np.zeros((engine.n, engine.npack))
+            for t, (r, c) in enumerate(_upper_tri_colmajor(engine.q)):
+                eye[:, t] = 1.0 if r == c else 0.0
+            engine.set_modes(b, eye)
+        else:
+            warm = False
+    stats = engine.find_modes(betas, inv_D, phis, gammas, warm=warm)
+    modes, chol, logdet = engine.get_modes()
+    return GH(engine, modes, chol, logdet, gauss_hermite_wGH(engine.nAGQ, engine.q), stats,
+              version=engine._modes_version)
+
+
+def engine_X(engine, zi=False):
+    """host copy of X / X_zi kept for the per-observation score contributions"""
+    return engine._X_zi_host if zi else engine._X_host
+
+
+def _ensure_grid(engine, gh):
+    if gh is not None and gh.version is not engine._modes_version:
+        engine.set_modes(gh.post_modes, gh.chol)
+        gh.version = engine._modes_version
+
+
+def _fused_eval(thetas, engine, gh, diag_D):
+    _ensure_grid(engine, gh)
+    key = (np.asarray(thetas, float).tobytes(), bool(diag_D), id(engine._modes_version))
+    if engine._cache_key == key:
+        return engine._cache_val
+    betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
+    val = (engine.eval(betas, D, phis, gammas, want_score=True), D, U)
+    engine._cache_key, engine._cache_val = key, val
+    return val
+
+
+def logLik_mixed(thetas, engine, gh, diag_D=False, i_contributions=False, fused=True):
+    """R/Fit_Funs.R:1-42 (penalized = FALSE): the NEGATIVE marginal log-likelihood on the
+    fixed grid ``gh``; with ``i_contributions`` the per-cluster vector -w_i log p(y_i).
+    ``fused`` evaluates the score in the same pass and keeps it for a following
+    score_mixed() at the same thetas (optim calls fn then gr)."""
+    if i_contributions:
+        _ensure_grid(engine, gh)
+        betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
+        return -engine.eval_contrib(betas, D, phis, gammas)["ll_i"]
+    if fused:
+        res, _, _ = _fused_eval(thetas, engine, gh, diag_D)
+        return -res["loglik"]
+    _ensure_grid(engine, gh)
+    betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
+    return -engine.eval(betas, D, phis, gammas, want_score=False)["loglik"]
+
+
+def score_mixed(thetas, engine, gh, diag_D=False, i_contributions=False):
+    """R/Fit_Funs.R:44-293 (penalized = FALSE): gradient of the NEGATIVE log-likelihood,
+    c(score.betas, score.D, score.phis, score.gammas).  With ``i_contributions`` the
+    per-observation / per-cluster pieces (R/Fit_Funs.R:288-290)."""
+    if i_contributions:
+        _ensure_grid(engine, gh)
+        betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
+        c = engine.eval_contrib(betas, D, phis, gammas)
+        out = dict(score_betas=-engine_X(engine) * c["zbar"][:, None])
+        if diag_D:
+            dd = np.diag(D)
+            out["score_D"] = 0.5 * (1.0 - np.einsum("idd->id", c["S_i"]) / dd[None, :])
+        else:
+            out["score_D"] = np.array([score_D(Si, 1.0, 1, D, U, False) for Si in c["S_i"]])
+        if engine.n_phis:
+            out["score_phis"] = -c["sphi_obs"]
+        if engine.p_zi:
+            out["score_gammas"] = -engine_X(engine, zi=True) * c["zbar_zi"][:, None]
+        return out
+    res, D, U = _fused_eval(thetas, engine, gh, diag_D)
+    parts = [-res["g_beta"], score_D(res["S"], res["sum_w"], engine.n, D, U, diag_D)]
+    if engine.n_phis:
+        parts.append(-res["g_phi"])
+    if engine.p_zi:
+        parts.append(-res["g_gamma"])
+    return np.concatenate(parts)

@@ -1,0 +1,213 @@
+/*
+ * glmma.h -- C ABI of the B200-native engine for GLMMadaptive's AGQ hot path.
+ *
+ * The reference (drizopoulos/GLMMadaptive v0.9-7) is pure R and has no native
+ * boundary; the seam this library sits behind is the set of R closures
+ * mixed_fit() calls (paths relative to the reference tree):
+ *
+ *   GHfun() / find_modes()        R/Functions.R:1-138   (call sites R/mixed_fit.R:89,105,267,315)
+ *   logLik_mixed()                R/Fit_Funs.R:1-42     (optim fn,  R/mixed_fit.R:271,319-328)
+ *   score_mixed()                 R/Fit_Funs.R:44-293   (optim gr,  R/mixed_fit.R:271,329-342)
+ *   family log_dens / score_*     R/Fit_Funs.R:429-1435
+ *
+ * Every entry point below is what an R .Call shim or any
+ * other FFI (ctypes, cgo, JNI) binds: plain pointers and sizes, no C++ or torch
+ * types, int status codes (0 = ok), no exceptions across the boundary.
+ * All matrices are COLUMN-MAJOR doubles, exactly as R stores them, so the shim
+ * passes REAL(x) pointers through unchanged.  Inputs are borrowed for the
+ * duration of a call only.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * GLMMA_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef GLMMA_H
+#define GLMMA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLMMA_VERSION 100
+
+#if defined(__GNUC__)
+#define GLMMA_API __attribute__((visibility("default")))
+#else
+#define GLMMA_API
+#endif
+
+/* status codes */
+#define GLMMA_OK            0
+#define GLMMA_ERR_ARG       1   /* bad argument / unsupported configuration   */
+#define GLMMA_ERR_CUDA      2   /* CUDA runtime error (sticky on the handle)  */
+#define GLMMA_ERR_STATE     3   /* call order (e.g. eval before modes exist)  */
+#define GLMMA_ERR_NUMERIC   4   /* non-PD matrix on the host side (D, invD)   */
+
+/* family$family strings of the reference -> ids (R/Fit_Funs.R, see glmma_family_id) */
+enum glmma_family {
+    GLMMA_BINOMIAL = 0,          /* stats::binomial()            R/Fit_Funs.R:429-438   */
+    GLMMA_POISSON = 1,           /* stats::poisson()             R/Fit_Funs.R:440-445   */
+    GLMMA_NEGBIN = 2,            /* negative.binomial()          R/Fit_Funs.R:467-513   */
+    GLMMA_ZI_POISSON = 3,        /* zi.poisson()                 R/Fit_Funs.R:515-563   */
+    GLMMA_ZI_NEGBIN = 4,         /* zi.negative.binomial()       R/Fit_Funs.R:565-640   */
+    GLMMA_ZI_BINOMIAL = 5,       /* zi.binomial()                R/Fit_Funs.R:766-827   */
+    GLMMA_HURDLE_POISSON = 6,    /* hurdle.poisson()             R/Fit_Funs.R:642-688   */
+    GLMMA_HURDLE_NEGBIN = 7,     /* hurdle.negative.binomial()   R/Fit_Funs.R:690-764   */
+    GLMMA_HURDLE_LOGNORMAL = 8,  /* hurdle.lognormal()           R/Fit_Funs.R:829-885   */
+    GLMMA_BETA = 9,              /* beta.fam()                   R/Fit_Funs.R:887-930   */
+    GLMMA_HURDLE_BETA = 10,      /* hurdle.beta.fam()            R/Fit_Funs.R:932-1004  */
+    GLMMA_GAMMA = 11,            /* Gamma.fam()                  R/Fit_Funs.R:1323-1358 */
+    GLMMA_CENSORED_NORMAL = 12,  /* censored.normal()            R/Fit_Funs.R:1360-1435 */
+    GLMMA_N_FAMILIES = 13
+};
+
+/* family$link; only the link each family object is built with is accelerated
+ * (binomial: logit, probit, cloglog).  Anything else stays on the R path. */
+enum glmma_link {
+    GLMMA_LINK_DEFAULT = 0,
+    GLMMA_LINK_LOGIT = 1,
+    GLMMA_LINK_LOG = 2,
+    GLMMA_LINK_IDENTITY = 3,
+    GLMMA_LINK_PROBIT = 4,
+    GLMMA_LINK_CLOGLOG = 5
+};
+
+/* What mixed_fit() receives (R/mixed_fit.R:1-25), before it splits it into
+ * per-cluster lists.  Rows must be ordered so that each cluster is contiguous
+ * (mixed_model() sorts by the grouping factor, R/mixed_model.R:50,104). */
+typedef struct glmma_data {
+    int32_t family;         /* enum glmma_family                                         */
+    int32_t link;           /* enum glmma_link                                           */
+    int64_t n_obs;          /* N  = nrow(X)                                              */
+    int64_t n_clusters;     /* n  = length(unique(id))                                   */
+    int32_t p;              /* ncol(X)                                                   */
+    int32_t q_y;            /* ncol(Z)                                                   */
+    int32_t p_zi;           /* ncol(X_zi), 0 if zi_fixed absent                          */
+    int32_t q_zi;           /* ncol(Z_zi), 0 if zi_random absent                         */
+    int32_t n_phis;         /* length(phis)                                              */
+    int32_t y_cols;         /* NCOL(y): 1, or 2 (binomial successes/failures;
+                               censored.normal value/indicator)                          */
+    int32_t nAGQ;           /* control$nAGQ                                              */
+    int32_t reserved;
+    const double* y;        /* N x y_cols                                                */
+    const double* X;        /* N x p                                                     */
+    const double* Z;        /* N x q_y                                                   */
+    const double* X_zi;     /* N x p_zi or NULL                                          */
+    const double* Z_zi;     /* N x q_zi or NULL                                          */
+    const double* offset;   /* N or NULL                                                 */
+    const double* offset_zi;/* N or NULL                                                 */
+    const double* weights;  /* n (one per cluster, as mixed_model(weights=)) or NULL     */
+    const int32_t* id;      /* N cluster labels, equal values contiguous (R's `id`);
+                               used when row_ptr is NULL                                 */
+    const int64_t* row_ptr; /* n+1 CSR offsets into the rows, or NULL                    */
+} glmma_data;
+
+/* Per-call statistics of the mode search (replaces the silent behaviour of
+ * optim() inside find_modes, R/Functions.R:80-89). */
+typedef struct glmma_mode_stats {
+    int64_t n_not_converged;   /* clusters that hit the iteration cap                  */
+    int64_t n_chol_failed;     /* clusters whose Hessian at the mode is not PD
+                                  (the reference's chol() would stop(), Functions.R:115) */
+    int32_t max_iterations;    /* largest Newton iteration count over clusters          */
+    int32_t reserved;
+    double  mean_iterations;
+} glmma_mode_stats;
+
+typedef struct glmma_handle glmma_handle;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Copies the data to `device`, builds the CSR cluster index and the
+ * Gauss-Hermite table (gauher(nAGQ), R/Functions.R:306-341).  Modes start at
+ * 0 (post_modes <- matrix(0, n, nRE), R/mixed_fit.R:63). */
+GLMMA_API int glmma_create(const glmma_data* data, int device, glmma_handle** out);
+GLMMA_API void glmma_destroy(glmma_handle* h);
+GLMMA_API const char* glmma_last_error(const glmma_handle* h);   /* h may be NULL: last create() error */
+GLMMA_API int glmma_version(void);
+/* family$family (e.g. "zero-inflated poisson") -> enum glmma_family, -1 if not accelerated */
+GLMMA_API int glmma_family_id(const char* family_name);
+/* All kernels of this handle are launched on `cuda_stream` (a cudaStream_t;
+ * NULL = the legacy default stream). */
+GLMMA_API int glmma_set_stream(glmma_handle* h, void* cuda_stream);
+
+/* ---- sizes ------------------------------------------------------------- */
+GLMMA_API int64_t glmma_n_clusters(const glmma_handle* h);
+GLMMA_API int64_t glmma_n_obs(const glmma_handle* h);
+GLMMA_API int     glmma_nre(const glmma_handle* h);          /* q = q_y + q_zi              */
+GLMMA_API int     glmma_n_nodes(const glmma_handle* h);      /* K = nAGQ^q                  */
+/* length of the result vector of glmma_eval: 4 + p + n_phis + p_zi + q*q */
+GLMMA_API int     glmma_result_len(const glmma_handle* h);
+
+/* ---- GHfun / find_modes (R/Functions.R:1-138) -------------------------- */
+
+/* Per-cluster mode of  -sum_j log f(y_ij | b) + b' invD b / 2  (Functions.R:5-20)
+ * by damped Newton from the current modes (warm = 1, as mixed_fit carries
+ * post_modes between GHfun calls, R/mixed_fit.R:100,117,287) or from 0
+ * (warm = 0), then the reference's cd_vec Hessian of the analytic gradient at
+ * the mode (Functions.R:90,249-262), its upper Cholesky factor, R^-1 and
+ * log_dets = -sum log diag R (Functions.R:115-122).  invD is q x q. */
+GLMMA_API int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD,
+                     const double* phis, const double* gammas, int warm,
+                     glmma_mode_stats* stats /* may be NULL */);
+
+/* GH$post_modes (n x q), chol(post_hessians) as packed upper triangles
+ * (n x q(q+1)/2, entry order (0,0),(0,1),(1,1),(0,2),... = R's
+ * U[upper.tri(U, TRUE)] per cluster, cluster-major) and GH$log_dets (n).
+ * Any output pointer may be NULL. */
+GLMMA_API int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets);
+/* Injects modes and Cholesky factors computed elsewhere (tests use the oracle's
+ * so that eval parity is independent of the mode search). Same layouts. */
+GLMMA_API int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper);
+
+/* ---- logLik_mixed + score_mixed (R/Fit_Funs.R:1-293) -------------------- */
+
+/* One fused evaluation on the current grid.  D is the q x q covariance matrix
+ * (already back-transformed from thetas by the caller: diag(exp(.)) or
+ * chol_transf(.), Fit_Funs.R:10).  Result layout (doubles):
+ *   [0] loglik      =  sum_i w_i log p(y_i)        (logLik_mixed returns its negative)
+ *   [1] sum_w       =  sum of w_i over the clusters that entered the sums
+ *   [2] n_nonfinite =  clusters whose log p(y_i) is NaN/Inf (dropped, as na.rm = TRUE does)
+ *   [3] reserved
+ *   [4 .. 4+p)                 g_beta  = sum_i w_i sum_k pi_ik sum_j x_ij  s_eta(ijk)
+ *   [.. +n_phis)               g_phi   = sum_i w_i sum_k pi_ik sum_j s_phi(ijk)
+ *   [.. +p_zi)                 g_gamma = sum_i w_i sum_k pi_ik sum_j xzi_ij s_etazi(ijk)
+ *   [.. +q*q)                  S       = sum_i w_i E[b b' | y_i]   (column-major)
+ * score_mixed's vector is  c(-g_beta, score.D(S, sum_w, D), -g_phi, -g_gamma)
+ * (SURVEY.md section 8a row a12).  With want_score = 0 only [0..3] are computed. */
+GLMMA_API int glmma_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
+               const double* gammas, int want_score, double* result);
+
+/* Same, but the result vector is left in DEVICE memory at d_result (on the
+ * handle's stream, no synchronisation) so the caller can all-reduce it across
+ * ranks (NCCL) before reading it back. */
+GLMMA_API int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                      const double* gammas, int want_score, double* d_result);
+
+/* i_contributions = TRUE pieces (Fit_Funs.R:34-35, 102-103, 186-187, 228-229, 255-269):
+ *   ll_i     (n)      w_i log p(y_i)
+ *   zbar     (N)      w_i sum_k pi_ik s_eta(ijk)       -> score.betas[j, l]  = -X[j, l]   * zbar[j]
+ *   zbar_zi  (N)      w_i sum_k pi_ik s_etazi(ijk)     -> score.gammas[j, l] = -Xzi[j, l] * zbar_zi[j]
+ *   sphi_obs (N)      w_i sum_k pi_ik s_phi(ijk)       -> score.phis[j]      = -sphi_obs[j]
+ *   S_i      (n*q*q)  w_i E[b b' | y_i], cluster-major, each q x q column-major
+ * Any pointer may be NULL. Host pointers. */
+GLMMA_API int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                       const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
+                       double* sphi_obs, double* S_i);
+
+/* ---- measurement helpers (bench.py; not part of the reference seam) ----- */
+
+/* Runs `iters` evaluations back to back on the handle's stream and returns the
+ * average device time of one evaluation and of its dominant kernel (CUDA events). */
+GLMMA_API int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                    const double* gammas, int want_score, int iters, float* ms_per_eval,
+                    float* ms_main_kernel);
+/* Dependent-free DFMA microbenchmark on `device`: measured FP64 FMA peak in TFLOP/s. */
+GLMMA_API int glmma_measure_fp64_peak(int device, double* tflops);
+/* number of kernel launches issued by this handle so far */
+GLMMA_API int64_t glmma_launch_count(const glmma_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLMMA_H */

@@ -436,7 +436,8 @@ def find_modes_newton(b, data, family, betas, invD, phis, gammas, tol=1e-10, max
     reference's objective (R/Functions.R:5-20) with its analytic gradient
     (:21-65); the Newton matrix is the reference's own cd_vec Hessian of that
     gradient (:90, :249-262), Levenberg-shifted if not PD, Armijo backtracking
-    (c = 1e-4, halving).  Stops when the max-norm of an accepted full step is
+    (c = 1e-4, halving, plus a rounding slack of 1e-14 (|f| + 1) so that full steps
+    inside the quadratic region are not rejected by noise in f).  Stops when the max-norm of an accepted full step is
     <= tol.  Returns modes, Hessians (cd_vec at the mode) and a convergence flag."""
     n = data.n
     post_modes = np.array(b, float, copy=True)
@@ -463,7 +464,7 @@ def find_modes_newton(b, data, family, betas, invD, phis, gammas, tol=1e-10, max
             for _h in range(60):
                 xn = x + step * d
                 fnew = fn(xn)
-                if np.isfinite(fnew) and fnew <= fx + 1e-4 * step * gd:
+                if np.isfinite(fnew) and fnew <= fx + 1e-4 * step * gd + 1e-14 * (abs(fx) + 1.0):
                     ok = True
                     break
                 step *= 0.5
