@@ -11,6 +11,7 @@
 #include "../../include/glmma.h"
 #include "kernels.cuh"
 #include "engine.h"
+#include "fastmath_tables.h"
 
 #define SCORE_THREADS 256
 #define FINAL_THREADS 256
@@ -23,10 +24,14 @@ struct glmma_handle {
     const FamOps* ops;
     cudaStream_t stream;
     GridPar* d_grid;
+    double* d_fmtab;
     // launch shape of the eval kernel, [0] = loglik only, [1] = with score
     int jt;
     int eval_grid[2];
     size_t eval_smem[2];
+    int nj;                    // register-variant tile (8 / 16), 0 = generic kernel only
+    int fast_grid[2];
+    size_t fast_smem[2];
     int score_grid;
     double* d_partials;        // eval block partials
     double* d_score_partials;  // score_grid * (p + p_zi)
@@ -421,6 +426,14 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     TRY(dev_alloc(h, &h->d_grid, 1));
     cudaMemcpyAsync(h->d_grid, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream);
 
+    {
+        std::vector<double> fm(GLMMA_FM_DOUBLES);
+        for (int t = 0; t < 256; ++t) fm[t] = GLMMA_LOGTAB_HOST[t];
+        for (int t = 0; t < 64; ++t) fm[256 + t] = GLMMA_EXPTAB_HOST[t];
+        TRY(dev_alloc(h, &h->d_fmtab, GLMMA_FM_DOUBLES));
+        cudaMemcpy(h->d_fmtab, fm.data(), sizeof(double) * GLMMA_FM_DOUBLES, cudaMemcpyHostToDevice);
+    }
+
     // launch shape: the observation tile covers (nearly) all clusters; larger ones stream
     int max_ni = 0;
     std::vector<int> cnt(GLMMA_JT_CAP + 2, 0);
@@ -447,7 +460,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     int max_grid = 1;
     for (int s = 0; s < 2; ++s) {
         int bps = 0;
-        ce = ops->eval_config(s, jt, &bps, &h->eval_smem[s]);
+        ce = ops->eval_config(s, jt, h->nagq, &bps, &h->eval_smem[s]);
         if (ce != cudaSuccess || bps < 1) {
             cuda_fail(h, ce, "eval kernel configuration");
             g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
@@ -456,6 +469,25 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         h->eval_grid[s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
         max_grid = std::max(max_grid, h->eval_grid[s]);
     }
+    // register variant for small clusters (eval_fast_kernel)
+    h->nj = 0;
+    if (h->nagq <= GLMMA_NAGQ_FAST && jt <= 16 && !std::getenv("GLMMA_NO_FAST")) h->nj = jt <= 8 ? 8 : 16;
+    int max_fast = 0;
+    if (h->nj) {
+        for (int s = 0; s < 2; ++s) {
+            int bps = 0;
+            ce = ops->fast_config(s, h->nj, &bps, &h->fast_smem[s]);
+            if (ce != cudaSuccess || bps < 1) {
+                cuda_fail(h, ce, "fast eval kernel configuration");
+                g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
+            }
+            const int64_t want = (n + wpb - 1) / wpb;
+            h->fast_grid[s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
+            max_fast = std::max(max_fast, h->fast_grid[s]);
+        }
+        TRY(dev_alloc(h, &d.defer, n));
+    }
+    max_grid += max_fast;
     h->score_grid = (int)std::min<int64_t>((N + SCORE_THREADS * 8 - 1) / (SCORE_THREADS * 8), (int64_t)prop.multiProcessorCount * 4);
     TRY(dev_alloc(h, &h->d_partials, (size_t)max_grid * GLMMA_NACC));
     TRY(dev_alloc(h, &h->d_score_partials, (size_t)h->score_grid * (d.p + d.p_zi)));
@@ -545,7 +577,7 @@ int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, c
     rc = run_prep(h, betas, phis, gammas, &fp);
     if (rc) return rc;
     ModeArgs ma;
-    ma.d = h->d; ma.fam = fp; ma.warm = warm && h->have_modes; ma.maxit = 100; ma.tol = 1e-10; ma.stats = h->d_stats;
+    ma.d = h->d; ma.fam = fp; ma.fmtab = h->d_fmtab; ma.warm = warm && h->have_modes; ma.maxit = 100; ma.tol = 1e-10; ma.stats = h->d_stats;
     fill_prior(h, invD, true, &ma.prior);
     CU(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     const double mean_ni = (double)h->d.N / (double)h->d.n;
@@ -618,11 +650,22 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (rc) return rc;
     EvalArgs ea;
     ea.d = dd_override ? *dd_override : h->d;
-    ea.fam = fp; ea.grid = h->d_grid; ea.partials = h->d_partials; ea.jt = h->jt;
+    ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; ea.partials = h->d_partials; ea.jt = h->jt;
     rc = fill_prior(h, D, false, &ea.prior);
     if (rc) return rc;
     if (k0) CU(h, cudaEventRecord(k0, h->stream));
+    int n_blocks = 0;
+    ea.only_deferred = 0;
+    if (h->nj) {
+        // small clusters: register variant; it flags what it leaves to the generic kernel
+        h->ops->eval_fast(ea, s, h->nj, h->fast_grid[s], h->fast_smem[s], h->stream);
+        h->launches++;
+        n_blocks = h->fast_grid[s];
+        ea.only_deferred = 1;
+        ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
+    }
     h->ops->eval(ea, s, h->eval_grid[s], h->eval_smem[s], h->stream);
+    n_blocks += h->eval_grid[s];
     if (k1) CU(h, cudaEventRecord(k1, h->stream));
     h->launches++;
     CU(h, cudaGetLastError());
@@ -630,7 +673,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         score_reduce_kernel<<<h->score_grid, SCORE_THREADS, 0, h->stream>>>(ea.d, h->d_score_partials);
         h->launches++;
     }
-    finalize_kernel<<<1, FINAL_THREADS, 0, h->stream>>>(h->d_partials, h->eval_grid[s], h->d_score_partials, h->score_grid,
+    finalize_kernel<<<1, FINAL_THREADS, 0, h->stream>>>(h->d_partials, n_blocks, h->d_score_partials, h->score_grid,
                                                          h->d.p, h->d.n_phis, h->d.p_zi, h->q, s, d_out);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -675,7 +718,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
     rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, &dd, nullptr, nullptr);
     if (rc == GLMMA_OK && d_sphi) {
         EvalArgs ea;
-        ea.d = dd; ea.grid = h->d_grid; ea.partials = h->d_partials; ea.jt = h->jt;
+        ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
         fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error);
         fill_prior(h, D, false, &ea.prior);
         h->ops->sphi(ea, h->eval_grid[1], h->eval_smem[1], h->stream);

@@ -21,32 +21,52 @@
 //   censored.normal       : y1 = value, y2 = indicator (0 none, 1 left, 2 right)
 #pragma once
 #include "common.cuh"
+#include "fastmath.cuh"
 
 // ----- link pieces with R's clamps (stats::make.link) ------
+// The kernels hand every functor emu = exp(eta) and elam = exp(eta_zi) (from the
+// per-cluster separable tables, or fast_exp): the functors never call exp(eta).
 // log link: mu = pmax(exp(eta), eps); log mu follows the clamp
-__device__ __forceinline__ void link_log(double eta, double& mu, double& lmu) {
-    const bool lo = eta < GLMMA_LOG_DBL_EPS;
-    mu = lo ? GLMMA_DBL_EPS : exp(eta);
-    lmu = lo ? GLMMA_LOG_DBL_EPS : eta;
+// CAREFUL = false: the kernel has checked that no clamp is active anywhere on the cluster's grid
+// and that every argument of fast_log_rcp / fast_l1p_sigmoid is inside its fast range.
+template <bool CAREFUL>
+__device__ __forceinline__ void link_log(double eta, double emu, double& mu, double& lmu) {
+    mu = emu; lmu = eta;
+    if (CAREFUL && eta < GLMMA_LOG_DBL_EPS) { mu = GLMMA_DBL_EPS; lmu = GLMMA_LOG_DBL_EPS; }
 }
 // logit link: t = exp(eta) clamped to [eps, 1/eps] outside +-30; mu = t / (1 + t).
-// Returns mu, log(mu) and log(1 - mu) evaluated without cancellation.
-__device__ __forceinline__ void link_logit(double eta, double& mu, double& lp, double& lq) {
-    double t, lt;
-    if (eta < -30.0) { t = GLMMA_DBL_EPS; lt = GLMMA_LOG_DBL_EPS; }
-    else if (eta > 30.0) { t = GLMMA_INV_DBL_EPS; lt = -GLMMA_LOG_DBL_EPS; }
-    else { t = exp(eta); lt = eta; }
-    const double u = 1.0 + t;
-    mu = t / u;
-    const double L = (t < 0.5) ? log1p(t) : log(u);
-    lq = -L;
-    lp = lt - L;
+// Returns mu, log t and log(1 + t); log mu = lt - L, log(1 - mu) = -L.
+template <bool CAREFUL>
+__device__ __forceinline__ void link_logit(double eta, double emu, const MathCtx& cx, double& mu, double& lt, double& L) {
+    double t = emu;
+    lt = eta;
+    if (CAREFUL && fabs(eta) > 30.0) {
+        t = eta < 0.0 ? GLMMA_DBL_EPS : GLMMA_INV_DBL_EPS;
+        lt = eta < 0.0 ? GLMMA_LOG_DBL_EPS : -GLMMA_LOG_DBL_EPS;
+    }
+    double r;
+    fast_log_rcp<CAREFUL>(1.0 + t, cx, L, r);
+    mu = t * r;
 }
+
+// log(1 + lambda) and plogis(eta_zi) from elam = exp(eta_zi)
+template <bool CAREFUL>
+__device__ __forceinline__ void zero_part(double ez, double elam, const MathCtx& cx, double& l1p, double& pi) {
+    fast_l1p_sigmoid<CAREFUL>(elam, cx, l1p, pi);
+}
+
+#define GLMMA_POINT_ARGS double eta, double ez, double emu, double elam, const FamPar& fp, const MathCtx& cx, \
+                         double& ld, double& se, double& sz, double& sp
 
 struct FamBase {
     static constexpr bool HAS_ZI = false;    // family has a zero part (eta_zi)
     static constexpr bool HAS_PHI = false;   // family has a dispersion parameter
     static constexpr bool USES_Y2 = false;
+    static constexpr bool NEED_EMU = true;   // point() reads emu = exp(eta)
+    // range of exp(eta) over a cluster's grid inside which point<., CAREFUL = false> is exact:
+    // no link clamp is active and every fast_log_rcp argument is in its fast range
+    static constexpr double EMU_LO = 2.3e-16;     // log link: eta >= log(.Machine$double.eps)
+    static constexpr double EMU_HI = 1e290;
     __device__ static __forceinline__ void obs_const(double, double, const FamPar&, double& cll, double& cphi) {
         cll = 0.0; cphi = 0.0;
     }
@@ -54,19 +74,20 @@ struct FamBase {
 
 // ----- stats::binomial(), logit (canonical) -- R/Fit_Funs.R:429-438, :130-149 --
 struct FamBinomialLogit : FamBase {
+    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
+    static constexpr double EMU_HI = 1e13;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar&, double& cll, double& cphi) {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double N, double eta, double, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
-        double mu, lp, lq;
-        link_logit(eta, mu, lp, lq);
-        // y log p + (N - y) log q; 0 * (-inf) cannot occur (lp, lq are finite)
-        ld = y * lp + (N - y) * lq;
-        if (SCORE) se = y - N * mu;
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
+        double mu, lt, L;
+        link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
+        // y log p + (N - y) log q with log p = lt - L, log q = -L
+        ld = fma(y, lt, -N * L);
+        if (SCORE) se = fma(-N, mu, y);
         sz = 0.0; sp = 0.0;
     }
 };
@@ -76,12 +97,12 @@ struct FamBinomialLogit : FamBase {
 template <int LINK>   // 4 probit, 5 cloglog (enum glmma_link)
 struct FamBinomialOther : FamBase {
     static constexpr bool USES_Y2 = true;
+    static constexpr bool NEED_EMU = false;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
         FamBinomialLogit::obs_const(y, N, fp, cll, cphi);
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double N, double eta, double, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, dmu;
         if (LINK == 4) {
             const double thresh = 8.125890664701906;   // -qnorm(.Machine$double.eps)
@@ -107,12 +128,11 @@ struct FamPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = -lgamma(y + 1.0); cphi = 0.0;
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu;
-        link_log(eta, mu, lmu);
-        ld = y * lmu - mu;
+        link_log<CAREFUL>(eta, emu, mu, lmu);
+        ld = fma(y, lmu, -mu);
         if (SCORE) se = y - mu;
         sz = 0.0; sp = 0.0;
     }
@@ -132,20 +152,17 @@ struct FamNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         nb_const(y, fp, cll, cphi);
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
-        double mu, lmu;
-        link_log(eta, mu, lmu);
-        const double t = mu + phi;
-        const double L = log(t);
+        double mu, lmu, L, r;
+        link_log<CAREFUL>(eta, emu, mu, lmu);
+        fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
         const double yp = y + phi;
-        ld = y * lmu - yp * L;
+        ld = fma(y, lmu, -yp * L);
         if (SCORE) {
-            const double r = 1.0 / t;
-            se = y - yp * (mu * r);
-            sp = -phi * (L + yp * r);
+            se = fma(-yp, mu * r, y);
+            sp = -phi * fma(yp, r, L);
         }
         sz = 0.0;
     }
@@ -157,26 +174,23 @@ struct FamZiPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double ez, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
-        double mu, lmu;
-        link_log(eta, mu, lmu);
-        double pi, l1p;                    // plogis(eta_zi), log(1 + lambda)
-        glmma_sigmoid_l1pe(ez, pi, l1p);
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
+        double mu, lmu, pi, l1p;
+        link_log<CAREFUL>(eta, emu, mu, lmu);
+        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);          // plogis(eta_zi), log(1 + lambda)
         if (y > 0.0) {
-            ld = y * lmu - mu - l1p;
+            ld = fma(y, lmu, -mu) - l1p;
             if (SCORE) { se = y - mu; sz = -pi; }
         } else {
-            // log(lambda + exp(-mu)) - log(1 + lambda); lambda capped where it would overflow
-            const double lam = exp(fmin(ez, 700.0));
-            const double E = exp(-mu);
-            const double u = lam + E;
-            ld = log(u) - l1p;
+            // log(lambda + exp(-mu)) - log(1 + lambda)
+            const double E = fast_exp(-mu, cx);
+            double lu, ru;
+            fast_log_rcp<CAREFUL>(elam + E, cx, lu, ru);
+            ld = lu - l1p;
             if (SCORE) {
-                const double ru = 1.0 / u;
                 se = -mu * E * ru;
-                sz = lam * ru - pi;
+                sz = fma(elam, ru, -pi);
             }
         }
         sp = 0.0;
@@ -190,37 +204,32 @@ struct FamZiNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double ez, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
-        double mu, lmu;
-        link_log(eta, mu, lmu);
-        const double t = mu + phi;
-        const double L = log(t);
-        double pi, l1p;
-        glmma_sigmoid_l1pe(ez, pi, l1p);
+        double mu, lmu, L, r, pi, l1p;
+        link_log<CAREFUL>(eta, emu, mu, lmu);
+        fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
+        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
             const double yp = y + phi;
-            ld = y * lmu - yp * L - l1p;
+            ld = fma(y, lmu, -yp * L) - l1p;
             if (SCORE) {
-                const double r = 1.0 / t;
-                se = y - yp * (mu * r);
-                sp = -phi * (L + yp * r);
+                se = fma(-yp, mu * r, y);
+                sp = -phi * fma(yp, r, L);
                 sz = -pi;
             }
         } else {
-            const double lt = fp.a[1] - L;            // log(phi / (phi + mu))
-            const double tphi = exp(phi * lt);        // NB mass at zero
-            const double lam = exp(fmin(ez, 700.0));
-            const double u = lam + tphi;
-            ld = log(u) - l1p;
+            const double lt = fp.a[1] - L;                 // log(phi / (phi + mu))
+            const double tphi = fast_exp(phi * lt, cx);    // NB mass at zero
+            double lu, ru;
+            fast_log_rcp<CAREFUL>(elam + tphi, cx, lu, ru);
+            ld = lu - l1p;
             if (SCORE) {
-                const double ru = 1.0 / u;
-                const double m = mu / t;
+                const double m = mu * r;
                 se = -phi * m * tphi * ru;
-                sz = lam * ru - pi;
-                sp = tphi * (lt + m) * phi * ru;      // 1 - t = mu / (mu + phi)
+                sz = fma(elam, ru, -pi);
+                sp = tphi * (lt + m) * phi * ru;           // 1 - t = mu / (mu + phi)
             }
         }
     }
@@ -228,29 +237,28 @@ struct FamZiNegBin : FamBase {
 
 // ----- zi.binomial() -- R/Fit_Funs.R:766-827 -----------------------------------
 struct FamZiBinomial : FamBase {
+    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
+    static constexpr double EMU_HI = 1e13;
     static constexpr bool HAS_ZI = true;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar&, double& cll, double& cphi) {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double N, double eta, double ez, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
-        double mu, lp, lq;
-        link_logit(eta, mu, lp, lq);
-        double pi, l1p;
-        glmma_sigmoid_l1pe(ez, pi, l1p);
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
+        double mu, lt, L, pi, l1p;
+        link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
+        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
-            ld = y * lp + (N - y) * lq - l1p;
-            if (SCORE) { se = y - N * mu; sz = -pi; }
+            ld = fma(y, lt, -N * L) - l1p;
+            if (SCORE) { se = fma(-N, mu, y); sz = -pi; }
         } else {
-            const double F = exp(N * lq);             // (1 - mu)^N
-            const double lam = exp(fmin(ez, 700.0));
-            const double u = lam + F;
-            ld = log(u) - l1p;
+            const double F = fast_exp(-N * L, cx);         // (1 - mu)^N
+            double lu, ru;
+            fast_log_rcp<CAREFUL>(elam + F, cx, lu, ru);
+            ld = lu - l1p;
             if (SCORE) {
-                const double ru = 1.0 / u;
                 se = -N * mu * F * ru;
                 sz = pi * (1.0 - F) * ru;
             }
@@ -260,9 +268,10 @@ struct FamZiBinomial : FamBase {
 };
 
 // zero part shared by the hurdle families (e.g. R/Fit_Funs.R:652-655, 670-676)
-__device__ __forceinline__ void hurdle_zero(double ez, bool pos, double& lz, double& sz) {
+template <bool CAREFUL>
+__device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCtx& cx, bool pos, double& lz, double& sz) {
     double pi, l1p;
-    glmma_sigmoid_l1pe(ez, pi, l1p);
+    zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
     // positive: log(1 - pi) = -log(1 + e^ez); zero: log pi = ez - log(1 + e^ez)
     lz = pos ? -l1p : ez - l1p;
     sz = pos ? -pi : 1.0 - pi;
@@ -274,16 +283,15 @@ struct FamHurdlePoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double ez, const FamPar&,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero(ez, pos, lz, sz);
+        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double mu, lmu;
-            link_log(eta, mu, lmu);
+            link_log<CAREFUL>(eta, emu, mu, lmu);
             const double em1 = expm1(-mu);            // -(1 - e^-mu)
             ld += -mu + y * eta - log(-em1);
             if (SCORE) se = -mu + y + (em1 + 1.0) * mu / em1;
@@ -296,34 +304,27 @@ struct FamHurdleNegBin : FamBase {
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
-        if (y > 0.0) {
-            nb_const(y, fp, cll, cphi);
-            // the reference's hurdle NB score has digamma(y+phi) - digamma(phi) + log phi + 1
-            // in common with nb_const: nothing to adjust
-        } else { cll = 0.0; cphi = 0.0; }
+        if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double ez, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero(ez, pos, lz, sz);
+        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double phi = fp.a[0];
-            double mu, lmu;
-            link_log(eta, mu, lmu);
-            const double t = mu + phi;
-            const double L = log(t);
+            double mu, lmu, L, r;
+            link_log<CAREFUL>(eta, emu, mu, lmu);
+            fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
             const double yp = y + phi;
             const double lt = fp.a[1] - L;            // log(phi / (phi + mu)) = -log(1 + mu/phi)
-            const double tphi = exp(phi * lt);        // (1 + mu/phi)^-phi
-            const double om = -expm1(phi * lt);       // 1 - (1 + mu/phi)^-phi
-            ld += y * lmu - yp * L - log(om);
+            const double em1 = expm1(phi * lt);       // (1 + mu/phi)^-phi - 1
+            const double tphi = em1 + 1.0;
+            ld += y * lmu - yp * L - log(-em1);
             if (SCORE) {
-                const double r = 1.0 / t;
                 const double m = mu * r;
-                const double ratio = tphi / om;
+                const double ratio = -tphi / em1;
                 se = y - yp * m - mu * (phi * r) * ratio;
                 sp = phi * (-L - yp * r + ratio * (m + lt));
             }
@@ -337,16 +338,16 @@ struct FamHurdleLogNormal : FamBase {
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
+    static constexpr bool NEED_EMU = false;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double ly, double eta, double ez, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double ly, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero(ez, pos, lz, sz);
+        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double d = ly - eta;
@@ -358,12 +359,12 @@ struct FamHurdleLogNormal : FamBase {
 };
 
 // beta pieces; a[0] = phi, a[1] = lgamma(phi), a[2] = digamma(phi)
-template <bool SCORE>
-__device__ __forceinline__ void beta_point(double ly, double l1y, double eta, const FamPar& fp,
-                                           double& ld, double& se, double& sp) {
+template <bool SCORE, bool CAREFUL>
+__device__ __forceinline__ void beta_point(double ly, double l1y, double eta, double emu, const FamPar& fp,
+                                           const MathCtx& cx, double& ld, double& se, double& sp) {
     const double phi = fp.a[0];
-    double mu, lp, lq;
-    link_logit(eta, mu, lp, lq);
+    double mu, lt, L;
+    link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
     const double a = mu * phi;
     const double b = phi - a;
     const double dl = ly - l1y;
@@ -378,16 +379,17 @@ __device__ __forceinline__ void beta_point(double ly, double l1y, double eta, co
 
 // ----- beta.fam() -- R/Fit_Funs.R:887-930 ---------------------------------------
 struct FamBeta : FamBase {
+    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
+    static constexpr double EMU_HI = 1e13;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double ly, double l1y, const FamPar& fp, double& cll, double& cphi) {
         cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y;
         cphi = fp.a[0] * fp.a[2];
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double ly, double l1y, double eta, double, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
-        beta_point<SCORE>(ly, l1y, eta, fp, ld, se, sp);
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
+        beta_point<SCORE, CAREFUL>(ly, l1y, eta, emu, fp, cx, ld, se, sp);
         sz = 0.0;
     }
 };
@@ -395,6 +397,8 @@ struct FamBeta : FamBase {
 // ----- hurdle.beta.fam() -- R/Fit_Funs.R:932-1004 (scores evaluated at the true mu;
 // the reference's attr(mu_y) <- eta slip, SURVEY appendix G, is not replicated) ---
 struct FamHurdleBeta : FamBase {
+    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
+    static constexpr double EMU_HI = 1e13;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
@@ -402,16 +406,15 @@ struct FamHurdleBeta : FamBase {
         if (ly > -INFINITY) { cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y; cphi = fp.a[0] * fp.a[2]; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double ly, double l1y, double eta, double ez, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
         const bool pos = ly > -INFINITY;
         double lz;
-        hurdle_zero(ez, pos, lz, sz);
+        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double l2;
-            beta_point<SCORE>(ly, l1y, eta, fp, l2, se, sp);
+            beta_point<SCORE, CAREFUL>(ly, l1y, eta, emu, fp, cx, l2, se, sp);
             ld += l2;
         }
     }
@@ -427,13 +430,12 @@ struct FamGamma : FamBase {
         cll = (phi - 1.0) * ly - fp.a[2] + phi * fp.a[1];
         cphi = phi * (ly + fp.a[1] + 1.0 - fp.a[3]);
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double, double eta, double, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
-        const bool lo = eta < GLMMA_LOG_DBL_EPS;           // mu = pmax(exp(eta), eps)
-        const double lmu = lo ? GLMMA_LOG_DBL_EPS : eta;
-        const double ymu = y * (lo ? GLMMA_INV_DBL_EPS : exp(-eta));
+        double mu, lmu;
+        link_log<CAREFUL>(eta, emu, mu, lmu);                   // mu = pmax(exp(eta), eps)
+        const double ymu = y / mu;
         ld = -phi * (ymu + lmu);
         if (SCORE) { se = phi * (ymu - 1.0); sp = ld; }
         sz = 0.0;
@@ -445,13 +447,13 @@ struct FamGamma : FamBase {
 struct FamCensoredNormal : FamBase {
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
+    static constexpr bool NEED_EMU = false;
     __device__ static __forceinline__ void obs_const(double, double ind, const FamPar& fp, double& cll, double& cphi) {
         if (ind == 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE>
-    __device__ static __forceinline__ void point(double y, double ind, double eta, double, const FamPar& fp,
-                                                 double& ld, double& se, double& sz, double& sp) {
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double ind, GLMMA_POINT_ARGS) {
         const double sigma = fp.a[0], isig = fp.a[2];
         const double t = (y - eta) * isig;
         sz = 0.0; se = 0.0; sp = 0.0;

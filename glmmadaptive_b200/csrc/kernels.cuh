@@ -16,8 +16,10 @@ struct EvalArgs {
     PriorPar prior;
     FamPar fam;
     const GridPar* grid;     // device copy of the Gauss-Hermite table
+    const double* fmtab;     // device copy of the fastmath tables (log table, then exp table)
     double* partials;        // gridDim.x * GLMMA_NACC block partial sums
     int jt;                  // observation tile held in shared memory per warp (<= GLMMA_JT_CAP)
+    int only_deferred;       // eval_kernel: process only clusters flagged in d.defer
 };
 
 struct PrepArgs {
@@ -30,6 +32,7 @@ struct ModeArgs {
     DevData d;
     PriorPar prior;          // Dinv = invD as handed to find_modes
     FamPar fam;
+    const double* fmtab;
     int warm;
     int maxit;
     double tol;
@@ -77,7 +80,18 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs A, CoefPar C) {
 
 // ------------------------------------------------------------------------------
 // eval: fused logLik_mixed + score_mixed sufficient statistics
+//
+// Shared memory per block: [fastmath tables | GH nodes, log weights | per-warp areas].
+// Per warp: rec  (jt x W)            observation records y1, y2, xb, (xg), z.., zzi..
+//           tabF (jt x Q x nagq)     separable factors of exp(eta):   exp(eta_jk)    = prod_e tabF[j][e][a_e(k)]
+//           tabL (jt x QZ x nagq)    separable factors of exp(eta_zi) (zero-part families)
+//           scr_eta, acc_eta (jt x 32) [, scr_zi, acc_zi]   per-lane score scratch / accumulators
+// The separable tables use that R^-1 is triangular: eta_jk = base_j + sum_e c_je x_{a_e},
+// so exp(eta) over the K = nagq^Q nodes needs only Q * nagq exponentials per observation
+// ("optional algorithmic shortcut").
 // ------------------------------------------------------------------------------
+#define GLMMA_FM_DOUBLES (256 + 64)
+
 template <class F, int QY, int QZ>
 struct EvalLayout {
     static constexpr int Q = QY + QZ;
@@ -87,18 +101,20 @@ struct EvalLayout {
     static constexpr int W0 = OFF_Z + QY + QZ;
     static constexpr int W = (W0 + 1) & ~1;                      // even: records stay 16-byte aligned
     static constexpr int NSCR = F::HAS_ZI ? 4 : 2;               // scr_eta, acc_eta [, scr_zi, acc_zi]
-    __host__ __device__ static size_t warp_doubles(int jt, bool score) {
-        return (size_t)jt * W + (score ? (size_t)NSCR * jt * 32 : 0);
+    static constexpr int NTABL = F::HAS_ZI ? (QZ > 0 ? QZ : 1) : 0;
+    __host__ __device__ static size_t warp_doubles(int jt, int nagq, bool score) {
+        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * 32 : 0);
     }
-    __host__ static size_t smem_bytes(int jt, bool score, int warps) {
-        return sizeof(double) * (2 * GLMMA_NAGQ_MAX + warps * warp_doubles(jt, score));
+    __host__ __device__ static size_t head_doubles() { return GLMMA_FM_DOUBLES + 2 * GLMMA_NAGQ_MAX; }
+    __host__ static size_t smem_bytes(int jt, int nagq, bool score, int warps) {
+        return sizeof(double) * (head_doubles() + warps * warp_doubles(jt, nagq, score));
     }
 };
 
-// decode node k -> b_k = mode + sqrt(2) R^-1 z_k, returns log prior + log wGH
+// decode node k -> b_k = mode + sqrt(2) R^-1 z_k, returns log prior + log wGH; idx[e] = a_e(k)
 template <int Q>
 __device__ __forceinline__ double node_setup(int k, int nagq, const double* gx, const double* glw, double lw_const,
-                                             const double* m, const double* ri, const PriorPar& pr, double* b) {
+                                             const double* m, const double* ri, const PriorPar& pr, double* b, int* idx) {
     double z[Q];
     double lw = lw_const;
     int kk = k;
@@ -106,6 +122,7 @@ __device__ __forceinline__ double node_setup(int k, int nagq, const double* gx, 
     for (int dd = 0; dd < Q; ++dd) {
         const int a = kk % nagq;
         kk /= nagq;
+        idx[dd] = a;
         z[dd] = gx[a];
         lw += glw[a];
     }
@@ -144,17 +161,95 @@ __device__ __forceinline__ void stage_tile(const DevData& d, int64_t r0, int cnt
     }
 }
 
+// separable exp tables of one staged tile (lanes over (observation, dimension, node index))
 template <class F, int QY, int QZ>
-__device__ __forceinline__ void lin_pred(const double* r, const double* b, double& eta, double& ez) {
+__device__ __forceinline__ void build_tables(const double* rec, int cnt, int lane, int nagq, const double* gx,
+                                             const double* m, const double* ri, const MathCtx& cx,
+                                             double* tabF, double* tabL) {
     using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
+    if (F::NEED_EMU) {
+        const int items = cnt * Q * nagq;
+        for (int t = lane; t < items; t += 32) {
+            const int a = t % nagq;
+            const int je = t / nagq;
+            const int e = je % Q;
+            const int j = je / Q;
+            const double* r = rec + j * L::W;
+            // c_je = sqrt(2) sum_{d <= min(e, QY-1)} z_jd R^-1[d][e];  base_j = xb_j + z_j . mode
+            double c = 0.0, base = r[2];
+#pragma unroll
+            for (int dd = 0; dd < QY; ++dd) {
+                base = fma(r[L::OFF_Z + dd], m[dd], base);
+#pragma unroll
+                for (int ee = dd; ee < Q; ++ee)
+                    if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
+            }
+            const double arg = fma(GLMMA_SQRT2 * c, gx[a], e == 0 ? base : 0.0);
+            tabF[t] = fast_exp(arg, cx);
+        }
+    }
+    if (F::HAS_ZI) {
+        constexpr int NT = L::NTABL > 0 ? L::NTABL : 1;
+        const int items = cnt * NT * nagq;
+        for (int t = lane; t < items; t += 32) {
+            const int a = t % nagq;
+            const int je = t / nagq;
+            const int e = je % NT;            // table e <-> random-effect dimension QY + e
+            const int j = je / NT;
+            const double* r = rec + j * L::W;
+            double c = 0.0, base = r[L::OFF_XG];
+#pragma unroll
+            for (int dd = 0; dd < QZ; ++dd) {
+                base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
+#pragma unroll
+                for (int ee = dd; ee < QZ; ++ee)
+                    if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
+            }
+            const double arg = fma(GLMMA_SQRT2 * c, QZ > 0 ? gx[a] : 0.0, e == 0 ? base : 0.0);
+            tabL[t] = fast_exp(arg, cx);
+        }
+    }
+}
+
+// eta, eta_zi and (SEP: from the tables; else by fast_exp) exp(eta), exp(eta_zi) of one point
+template <class F, int QY, int QZ, bool SEP>
+__device__ __forceinline__ void lin_pred(const double* r, const double* b, const int* idx, int j, int nagq,
+                                         const double* tabF, const double* tabL, const MathCtx& cx,
+                                         double& eta, double& ez, double& emu, double& elam) {
+    using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
     eta = r[2];
 #pragma unroll
     for (int dd = 0; dd < QY; ++dd) eta = fma(r[L::OFF_Z + dd], b[dd], eta);
-    ez = 0.0;
+    ez = 0.0; emu = 0.0; elam = 0.0;
     if (F::HAS_ZI) {
         ez = r[L::OFF_XG];
 #pragma unroll
         for (int dd = 0; dd < QZ; ++dd) ez = fma(r[L::OFF_Z + QY + dd], b[QY + dd], ez);
+    }
+    if (F::NEED_EMU) {
+        if (SEP) {
+            const double* tf = tabF + j * Q * nagq;
+            emu = tf[idx[0]];
+#pragma unroll
+            for (int e = 1; e < Q; ++e) emu *= tf[e * nagq + idx[e]];
+            if (!(emu > 1e-300 && emu < 1e300)) emu = exp(eta);       // a factor under/overflowed
+        } else {
+            emu = fast_exp(eta, cx);
+        }
+    }
+    if (F::HAS_ZI) {
+        if (SEP) {
+            constexpr int NT = L::NTABL > 0 ? L::NTABL : 1;
+            const double* tl = tabL + j * NT * nagq;
+            elam = tl[QZ > 0 ? idx[QY] : 0];
+#pragma unroll
+            for (int e = 1; e < QZ; ++e) elam *= tl[e * nagq + idx[QY + e]];
+            if (!(elam > 1e-300 && elam < 1e300)) elam = exp(fmin(fmax(ez, -690.0), 690.0));
+        } else {
+            elam = fast_exp(fmin(fmax(ez, -690.0), 690.0), cx);
+        }
     }
 }
 
@@ -165,26 +260,31 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
     constexpr int NP = L::NP;
     const DevData& d = A.d;
     extern __shared__ double smem[];
-    double* gx = smem;
-    double* glw = smem + GLMMA_NAGQ_MAX;
+    double* fmtab = smem;
+    double* gx = smem + GLMMA_FM_DOUBLES;
+    double* glw = gx + GLMMA_NAGQ_MAX;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int jt = A.jt;
-    double* wbase = smem + 2 * GLMMA_NAGQ_MAX + wib * L::warp_doubles(jt, SCORE);
+    const int nagq = A.grid->nagq;
+    const int K = A.grid->K;
+    double* wbase = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, SCORE);
     double* rec = wbase;
-    double* scr_eta = rec + jt * L::W;
+    double* tabF = rec + jt * L::W;
+    double* tabL = tabF + jt * Q * nagq;
+    double* scr_eta = tabL + jt * L::NTABL * nagq;
     double* acc_eta = scr_eta + jt * 32;
     double* scr_zi = acc_eta + jt * 32;
     double* acc_zi = scr_zi + jt * 32;
 
+    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const int nagq = A.grid->nagq;
-    const int K = A.grid->K;
+    const MathCtx cx{fmtab, fmtab + 256};
     const double lw_const = A.grid->lw_const;
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;         // the round holding the central node
@@ -195,6 +295,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
+        if (A.only_deferred && d.defer[i] == 0) continue;      // done by eval_fast_kernel
         const int64_t r0 = d.row_ptr[i];
         const int ni = (int)(d.row_ptr[i + 1] - r0);
         const double w = d.weights ? d.weights[i] : 1.0;
@@ -215,7 +316,11 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 
         const bool fast = ni <= jt;
         __syncwarp();
-        if (fast) stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
+        if (fast) {
+            stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
+            __syncwarp();
+            build_tables<F, QY, QZ>(rec, ni, lane, nagq, gx, m, ri, cx, tabF, tabL);
+        }
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
@@ -242,14 +347,16 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                 const int k = (r << 5) + lane;
                 const bool valid = k < K;
                 double b[Q];
-                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b);
+                int idx[Q];
+                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
                 double vphi = 0.0;
                 if (fast) {
+#pragma unroll 2
                     for (int j = 0; j < ni; ++j) {
                         const double* rj = rec + j * L::W;
-                        double eta, ez, ld, se, sz, sp;
-                        lin_pred<F, QY, QZ>(rj, b, eta, ez);
-                        F::template point<SCORE>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                        double eta, ez, emu, elam, ld, se, sz, sp;
+                        lin_pred<F, QY, QZ, true>(rj, b, idx, j, nagq, tabF, tabL, cx, eta, ez, emu, elam);
+                        F::template point<SCORE, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                         a += ld;
                         if (SCORE) {
                             scr_eta[j * 32 + lane] = se;
@@ -266,9 +373,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                         __syncwarp();
                         for (int j = 0; j < cnt; ++j) {
                             const double* rj = rec + j * L::W;
-                            double eta, ez, ld, se, sz, sp;
-                            lin_pred<F, QY, QZ>(rj, b, eta, ez);
-                            F::template point<false>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                            double eta, ez, emu, elam, ld, se, sz, sp;
+                            lin_pred<F, QY, QZ, false>(rj, b, idx, j, nagq, tabF, tabL, cx, eta, ez, emu, elam);
+                            F::template point<false, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                             a += ld;
                         }
                     }
@@ -278,7 +385,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                     shift = warp_max(valid ? a : -INFINITY);
                     if (!(fabs(shift) < INFINITY)) shift = 0.0;
                 }
-                const double e = valid ? exp(a - shift) : 0.0;
+                const double e = valid ? fast_exp(a - shift, cx) : 0.0;
                 sum_e += e;
                 if (SCORE) {
                     int t = 0;
@@ -288,6 +395,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                         for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
                     if (fast) {
                         if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+#pragma unroll 2
                         for (int j = 0; j < ni; ++j) {
                             acc_eta[j * 32 + lane] = fma(e, scr_eta[j * 32 + lane], acc_eta[j * 32 + lane]);
                             if (F::HAS_ZI) acc_zi[j * 32 + lane] = fma(e, scr_zi[j * 32 + lane], acc_zi[j * 32 + lane]);
@@ -300,9 +408,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                             __syncwarp();
                             for (int j = 0; j < cnt; ++j) {
                                 const double* rj = rec + j * L::W;
-                                double eta, ez, ld, se, sz, sp;
-                                lin_pred<F, QY, QZ>(rj, b, eta, ez);
-                                F::template point<true>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                                double eta, ez, emu, elam, ld, se, sz, sp;
+                                lin_pred<F, QY, QZ, false>(rj, b, idx, j, nagq, tabF, tabL, cx, eta, ez, emu, elam);
+                                F::template point<true, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                                 if (F::HAS_PHI) vphi += sp;
                                 scr_eta[j * 32 + lane] = e * se;
                                 if (F::HAS_ZI) scr_zi[j * 32 + lane] = e * sz;
@@ -401,6 +509,327 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 }
 
 // ------------------------------------------------------------------------------
+// eval, register variant: clusters of at most NJ observations, nagq <= GLMMA_NAGQ_FAST.
+// The observation loop is fully unrolled: per-observation score terms and their
+// posterior-weighted sums live in registers, every shared-memory operand has an
+// immediate offset, and the NJ independent point evaluations give the FP64 pipe
+// instruction-level parallelism.  The functors run with CAREFUL = false, which is
+// exact when no link clamp is active on the cluster's grid and all separable factors
+// are in range; clusters that fail that test (or are larger than NJ) are flagged in
+// d.defer and handled by eval_kernel.
+// ------------------------------------------------------------------------------
+#define GLMMA_NAGQ_FAST 16
+
+template <class F, int QY, int QZ, int NJ>
+struct FastLayout {
+    using L = EvalLayout<F, QY, QZ>;
+    static constexpr int Q = QY + QZ;
+    static constexpr int W = L::W;
+    static constexpr int NT = L::NTABL;
+    static constexpr int TF = Q * GLMMA_NAGQ_FAST;          // doubles of tabF per observation
+    static constexpr int TL = NT * GLMMA_NAGQ_FAST;
+    static constexpr int NACCS = F::HAS_ZI ? 2 : 1;
+    static constexpr int WARP_DOUBLES = NJ * (W + TF + TL) + NACCS * NJ * 32;
+    __host__ static size_t smem_bytes(int warps) {
+        return sizeof(double) * (L::head_doubles() + (size_t)warps * WARP_DOUBLES);
+    }
+};
+
+template <class F, int QY, int QZ, bool SCORE, int NJ>
+__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs A) {
+    using FL = FastLayout<F, QY, QZ, NJ>;
+    using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
+    constexpr int NP = L::NP;
+    constexpr int W = L::W;
+    constexpr int NG = GLMMA_NAGQ_FAST;
+    const DevData& d = A.d;
+    extern __shared__ double smem[];
+    double* fmtab = smem;
+    double* gx = smem + GLMMA_FM_DOUBLES;
+    double* glw = gx + GLMMA_NAGQ_MAX;
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int nagq = A.grid->nagq;
+    const int K = A.grid->K;
+    double* rec = smem + L::head_doubles() + wib * FL::WARP_DOUBLES;
+    double* tabF = rec + NJ * W;
+    double* tabL = tabF + NJ * FL::TF;
+    double* acc_eta = tabL + NJ * FL::TL;
+    double* acc_zi = acc_eta + NJ * 32;
+
+    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    if (threadIdx.x < GLMMA_NAGQ_MAX) {
+        gx[threadIdx.x] = A.grid->x[threadIdx.x];
+        glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    }
+    __syncthreads();
+    const MathCtx cx{fmtab, fmtab + 256};
+    const double lw_const = A.grid->lw_const;
+    const int nrounds = (K + 31) >> 5;
+    const int rc = ((K - 1) >> 1) >> 5;
+
+    double tot[GLMMA_NACC];
+#pragma unroll
+    for (int a = 0; a < GLMMA_NACC; ++a) tot[a] = 0.0;
+
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
+        const int64_t r0 = d.row_ptr[i];
+        const int ni = (int)(d.row_ptr[i + 1] - r0);
+        if (ni > NJ) {
+            if (lane == 0) d.defer[i] = 1;
+            continue;
+        }
+        const double w = d.weights ? d.weights[i] : 1.0;
+        double m[Q], ri[NP];
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) m[dd] = d.modes[i * Q + dd];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) ri[t] = d.rinv[i * NP + t];
+
+        __syncwarp();
+        stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
+        double c_ll = 0.0, c_phi = 0.0;
+        if (lane < ni) {
+            c_ll = d.cll[r0 + lane];
+            if (SCORE && F::HAS_PHI) c_phi = d.cphi[r0 + lane];
+        }
+        __syncwarp();
+        // separable factor tables, stride NG per (observation, dimension)
+        if (F::NEED_EMU) {
+            const int items = ni * Q * nagq;
+            for (int t = lane; t < items; t += 32) {
+                const int a = t % nagq;
+                const int je = t / nagq;
+                const int e = je % Q;
+                const int j = je / Q;
+                const double* r = rec + j * W;
+                double c = 0.0, base = r[2];
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) {
+                    base = fma(r[L::OFF_Z + dd], m[dd], base);
+#pragma unroll
+                    for (int ee = dd; ee < Q; ++ee)
+                        if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
+                }
+                tabF[(j * Q + e) * NG + a] = fast_exp(fma(GLMMA_SQRT2 * c, gx[a], e == 0 ? base : 0.0), cx);
+            }
+        }
+        if (F::HAS_ZI) {
+            constexpr int NT = FL::NT > 0 ? FL::NT : 1;
+            const int items = ni * NT * nagq;
+            for (int t = lane; t < items; t += 32) {
+                const int a = t % nagq;
+                const int je = t / nagq;
+                const int e = je % NT;
+                const int j = je / NT;
+                const double* r = rec + j * W;
+                double c = 0.0, base = r[L::OFF_XG];
+#pragma unroll
+                for (int dd = 0; dd < QZ; ++dd) {
+                    base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
+#pragma unroll
+                    for (int ee = dd; ee < QZ; ++ee)
+                        if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
+                }
+                tabL[(j * NT + e) * NG + a] = fast_exp(fma(GLMMA_SQRT2 * c, QZ > 0 ? gx[a] : 0.0, e == 0 ? base : 0.0), cx);
+            }
+        }
+        __syncwarp();
+        // range test: extremes of exp(eta) / exp(eta_zi) over the grid are products of the
+        // per-dimension extremes of the (positive) factors
+        bool bad = false;
+        if (lane < ni) {
+            if (F::NEED_EMU) {
+                double lo = 1.0, hi = 1.0;
+#pragma unroll
+                for (int e = 0; e < Q; ++e) {
+                    double mn = INFINITY, mx = 0.0;
+                    for (int a = 0; a < nagq; ++a) {
+                        const double v = tabF[(lane * Q + e) * NG + a];
+                        mn = fmin(mn, v); mx = fmax(mx, v);
+                    }
+                    if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
+                    lo *= mn; hi *= mx;
+                }
+                if (!(lo >= F::EMU_LO && hi <= F::EMU_HI)) bad = true;
+            }
+            if (F::HAS_ZI) {
+                constexpr int NT = FL::NT > 0 ? FL::NT : 1;
+                double lo = 1.0, hi = 1.0;
+#pragma unroll
+                for (int e = 0; e < NT; ++e) {
+                    double mn = INFINITY, mx = 0.0;
+                    for (int a = 0; a < (QZ > 0 ? nagq : 1); ++a) {
+                        const double v = tabL[(lane * NT + e) * NG + a];
+                        mn = fmin(mn, v); mx = fmax(mx, v);
+                    }
+                    if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
+                    lo *= mn; hi *= mx;
+                }
+                if (!(lo >= 1e-290 && hi <= 1e290)) bad = true;
+            }
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) d.defer[i] = bad ? 1 : 0;
+        if (bad) continue;
+        c_ll = warp_sum(c_ll);
+        if (SCORE && F::HAS_PHI) c_phi = warp_sum(c_phi);
+
+        double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
+        double S[NP];
+        double acc_e[NJ], acc_z[F::HAS_ZI ? NJ : 1];
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            sum_e = 0.0; gphi = 0.0;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) S[t] = 0.0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { acc_e[j] = 0.0; if (F::HAS_ZI) acc_z[j] = 0.0; }
+            for (int rr = 0; rr < nrounds; ++rr) {
+                const int r = (rr == 0) ? rc : (rr <= rc ? rr - 1 : rr);
+                const int k = (r << 5) + lane;
+                const bool valid = k < K;
+                double b[Q];
+                int idx[Q];
+                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+                const double* pf[Q];
+#pragma unroll
+                for (int e = 0; e < Q; ++e) pf[e] = tabF + e * NG + idx[e];
+                const double* pl[QZ > 0 ? QZ : 1];
+#pragma unroll
+                for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e) pl[e] = tabL + e * NG + (QZ > 0 ? idx[QY + (QZ > 0 ? e : 0)] : 0);
+                double vphi = 0.0;
+                double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    se_[j] = 0.0;
+                    if (F::HAS_ZI) sz_[j] = 0.0;
+                    if (j < ni) {
+                        const double* rj = rec + j * W;
+                        double eta = rj[2];
+#pragma unroll
+                        for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
+                        double ez = 0.0, emu = 0.0, elam = 0.0;
+                        if (F::NEED_EMU) {
+                            emu = pf[0][j * FL::TF];
+#pragma unroll
+                            for (int e = 1; e < Q; ++e) emu *= pf[e][j * FL::TF];
+                        }
+                        if (F::HAS_ZI) {
+                            ez = rj[L::OFF_XG];
+#pragma unroll
+                            for (int dd = 0; dd < QZ; ++dd) ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);
+                            elam = pl[0][j * FL::TL];
+#pragma unroll
+                            for (int e = 1; e < QZ; ++e) elam *= pl[e][j * FL::TL];
+                        }
+                        double ld, se, sz, sp;
+                        F::template point<SCORE, false>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
+                        a += ld;
+                        if (SCORE) {
+                            se_[j] = se;
+                            if (F::HAS_ZI) sz_[j] = sz;
+                            if (F::HAS_PHI) vphi += sp;
+                        }
+                    }
+                }
+                if (valid) amax = fmax(amax, a);
+                if (rr == 0 && attempt == 0) {
+                    shift = warp_max(valid ? a : -INFINITY);
+                    if (!(fabs(shift) < INFINITY)) shift = 0.0;
+                }
+                const double e = valid ? fast_exp(a - shift, cx) : 0.0;
+                sum_e += e;
+                if (SCORE) {
+                    int t = 0;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                        for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
+                    if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) {
+                        acc_e[j] = fma(e, se_[j], acc_e[j]);
+                        if (F::HAS_ZI) acc_z[j] = fma(e, sz_[j], acc_z[j]);
+                    }
+                }
+            }
+            sum_e = warp_sum(sum_e);
+            if (sum_e > 0.0 && sum_e < INFINITY) break;
+            const double mx = warp_max(amax);
+            if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
+            shift = mx;
+        }
+        const double ll = shift + log(sum_e) + d.logdet[i] + c_ll;
+        const bool ok = fabs(ll) < INFINITY;
+        if (lane == 0) {
+            if (ok) { tot[0] += w * ll; tot[1] += w; } else tot[2] += 1.0;
+            if (d.ll_i) d.ll_i[i] = w * ll;
+        }
+        if (SCORE) {
+            const double inv = ok ? w / sum_e : 0.0;
+            if (F::HAS_PHI) {
+                tot[3] = fma(inv, gphi, tot[3]);
+                if (lane == 0 && ok) tot[3] = fma(w, c_phi, tot[3]);
+            }
+#pragma unroll
+            for (int t = 0; t < NP; ++t) tot[4 + t] = fma(inv, S[t], tot[4 + t]);
+            if (d.S_i) {
+                double Sr[NP];
+#pragma unroll
+                for (int t = 0; t < NP; ++t) Sr[t] = inv * warp_sum(S[t]);
+                if (lane == 0) {
+                    int t = 0;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                        for (int ee = dd; ee < Q; ++ee) {
+                            d.S_i[i * Q * Q + dd * Q + ee] = Sr[t];
+                            d.S_i[i * Q * Q + ee * Q + dd] = Sr[t];
+                            ++t;
+                        }
+                }
+            }
+            // per-observation sums over the 32 lanes: through shared memory, skewed columns
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                acc_eta[j * 32 + lane] = acc_e[j];
+                if (F::HAS_ZI) acc_zi[j * 32 + lane] = acc_z[j];
+            }
+            __syncwarp();
+            if (lane < ni) {
+                double s1 = 0.0, s2 = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < 32; ++c) {
+                    const int cc = (c + lane) & 31;
+                    s1 += acc_eta[lane * 32 + cc];
+                    if (F::HAS_ZI) s2 += acc_zi[lane * 32 + cc];
+                }
+                d.zbar[r0 + lane] = inv * s1;
+                if (F::HAS_ZI) d.zbar_zi[r0 + lane] = inv * s2;
+            }
+        }
+        __syncwarp();
+    }
+
+    __syncthreads();
+    double* red = smem;
+#pragma unroll
+    for (int a = 0; a < GLMMA_NACC; ++a) {
+        const double v = warp_sum(tot[a]);
+        if (lane == 0) red[wib * GLMMA_NACC + a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GLMMA_NACC) {
+        double v = 0.0;
+        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
+        A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------
 // per-observation phi-score contributions (i_contributions = TRUE path of
 // score_mixed, R/Fit_Funs.R:186-187): sphi_obs[j] = w_i (sum_k pi_ik s_phi(ijk)).
 // Rarely called (once per fit, for the sandwich estimator), so it simply
@@ -413,20 +842,23 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
     constexpr int NP = L::NP;
     const DevData& d = A.d;
     extern __shared__ double smem[];
-    double* gx = smem;
-    double* glw = smem + GLMMA_NAGQ_MAX;
+    double* fmtab = smem;
+    double* gx = smem + GLMMA_FM_DOUBLES;
+    double* glw = gx + GLMMA_NAGQ_MAX;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int jt = A.jt;
-    double* rec = smem + 2 * GLMMA_NAGQ_MAX + wib * L::warp_doubles(jt, true);
-    double* scr = rec + jt * L::W;
+    const int nagq = A.grid->nagq, K = A.grid->K;
+    double* rec = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, true);
+    double* scr = rec + jt * L::W + jt * (Q + L::NTABL) * nagq;
+    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const int nagq = A.grid->nagq, K = A.grid->K;
+    const MathCtx cx{fmtab, fmtab + 256};
     const int nrounds = (K + 31) >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
@@ -449,7 +881,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
             const int k = (r << 5) + lane;
             const bool valid = k < K;
             double b[Q];
-            double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, A.grid->lw_const, m, ri, A.prior, b);
+            int idx[Q];
+            double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, A.grid->lw_const, m, ri, A.prior, b, idx);
             for (int j0 = 0; j0 < ni; j0 += jt) {
                 const int cnt = min(jt, ni - j0);
                 __syncwarp();
@@ -457,9 +890,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
                 __syncwarp();
                 for (int j = 0; j < cnt; ++j) {
                     const double* rj = rec + j * L::W;
-                    double eta, ez, ld, se, sz, sp;
-                    lin_pred<F, QY, QZ>(rj, b, eta, ez);
-                    F::template point<false>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                    double eta, ez, emu, elam, ld, se, sz, sp;
+                    lin_pred<F, QY, QZ, false>(rj, b, idx, j, nagq, nullptr, nullptr, cx, eta, ez, emu, elam);
+                    F::template point<false, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                     a += ld;
                 }
             }
@@ -471,9 +904,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
                 __syncwarp();
                 for (int j = 0; j < cnt; ++j) {
                     const double* rj = rec + j * L::W;
-                    double eta, ez, ld, se, sz, sp;
-                    lin_pred<F, QY, QZ>(rj, b, eta, ez);
-                    F::template point<true>(rj[0], rj[1], eta, ez, A.fam, ld, se, sz, sp);
+                    double eta, ez, emu, elam, ld, se, sz, sp;
+                    lin_pred<F, QY, QZ, false>(rj, b, idx, j, nagq, nullptr, nullptr, cx, eta, ez, emu, elam);
+                    F::template point<true, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                     scr[j * 32 + lane] = e * sp;
                 }
                 __syncwarp();
@@ -501,7 +934,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
 // ------------------------------------------------------------------------------
 template <class F, int QY, int QZ, int G, bool SCORE>
 __device__ __noinline__ void mode_objective(const DevData& d, const PriorPar& pr, const FamPar& fam,
-                                               int64_t r0, int ni, int lg, unsigned gmask,
+                                               int64_t r0, int ni, int lg, unsigned gmask, const MathCtx& cx,
                                                const double* b, double& f, double* g) {
     constexpr int Q = QY + QZ;
     double fl = 0.0, gl[Q];
@@ -523,7 +956,9 @@ __device__ __noinline__ void mode_objective(const DevData& d, const PriorPar& pr
             }
         }
         double ld, se, sz, sp;
-        F::template point<SCORE>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, eta, ez, fam, ld, se, sz, sp);
+        const double emu = F::NEED_EMU ? fast_exp(eta, cx) : 0.0;
+        const double elam = F::HAS_ZI ? fast_exp(fmin(fmax(ez, -690.0), 690.0), cx) : 0.0;
+        F::template point<SCORE, true>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, eta, ez, emu, elam, fam, cx, ld, se, sz, sp);
         if (ld == ld) fl -= ld;            // sum(log_dens, na.rm = TRUE), R/Functions.R:19
         if (SCORE) {
 #pragma unroll
@@ -554,7 +989,7 @@ __device__ __noinline__ void mode_objective(const DevData& d, const PriorPar& pr
 // cd_vec(x, score_log_post_b): R/Functions.R:249-262, symmetrised
 template <class F, int QY, int QZ, int G>
 __device__ __forceinline__ void mode_hessian(const DevData& d, const PriorPar& pr, const FamPar& fam,
-                                             int64_t r0, int ni, int lg, unsigned gmask,
+                                             int64_t r0, int ni, int lg, unsigned gmask, const MathCtx& cx,
                                              const double* x, double* H /* Q*Q */) {
     constexpr int Q = QY + QZ;
 #pragma unroll
@@ -565,8 +1000,8 @@ __device__ __forceinline__ void mode_hessian(const DevData& d, const PriorPar& p
         const double ex = 0.001 * fmax(fabs(x[c]), 1.0);
         x1[c] = x[c] + ex;
         x2[c] = x[c] - ex;
-        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, x1, f, g1);
-        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, x2, f, g2);
+        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, cx, x1, f, g1);
+        mode_objective<F, QY, QZ, G, true>(d, pr, fam, r0, ni, lg, gmask, cx, x2, f, g2);
         const double dx = x1[c] - x2[c];
 #pragma unroll
         for (int dd = 0; dd < Q; ++dd) H[dd * Q + c] = (g1[dd] - g2[dd]) / dx;
@@ -614,6 +1049,10 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
     const int lg = (int)(gtid % G);
     const int lane = threadIdx.x & 31;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    __shared__ double fmtab[GLMMA_FM_DOUBLES];
+    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    __syncthreads();
+    const MathCtx cx{fmtab, fmtab + 256};
     const bool live = i < d.n;
     const int64_t r0 = live ? d.row_ptr[i] : 0;
     const int ni = live ? (int)(d.row_ptr[i + 1] - r0) : 0;
@@ -621,14 +1060,14 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
     double x[Q], g[Q], fx;
 #pragma unroll
     for (int dd = 0; dd < Q; ++dd) x[dd] = (live && A.warm) ? d.modes[i * Q + dd] : 0.0;
-    mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, x, fx, g);
+    mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, cx, x, fx, g);
     bool done = !live;
     bool conv = false;
     int iters = 0;
     for (int it = 0; it < A.maxit; ++it) {
         if (__all_sync(0xffffffffu, done)) break;
         double H[Q * Q], Lc[Q * Q], dir[Q];
-        mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, x, H);
+        mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, cx, x, H);
         // Levenberg shift until positive definite
         double lam = 0.0, hmax = 1.0;
 #pragma unroll
@@ -651,8 +1090,8 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
         for (int r = Q - 1; r >= 0; --r) {
             double s = yv[r];
 #pragma unroll
-            for (int t = r + 1; t < Q; ++t) s -= Lc[t * Q + r] * dir[t];
-            dir[r] = -s / Lc[r * Q + r];
+            for (int t = r + 1; t < Q; ++t) s += Lc[t * Q + r] * dir[t];   // dir[t] already holds -x[t]
+            dir[r] = -(s / Lc[r * Q + r]);
         }
         double gd = 0.0, dmax = 0.0;
 #pragma unroll
@@ -668,7 +1107,7 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
             double xt[Q], gt[Q], ft;
 #pragma unroll
             for (int dd = 0; dd < Q; ++dd) xt[dd] = fma(step, dir[dd], x[dd]);
-            mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, xt, ft, gt);
+            mode_objective<F, QY, QZ, G, true>(d, A.prior, A.fam, r0, ni, lg, gmask, cx, xt, ft, gt);
             if (!accepted) {
                 const bool acc = (fabs(ft) < INFINITY) &&
                                  (ft <= fx + 1e-4 * step * gd + 1e-14 * (fabs(fx) + 1.0));
@@ -695,7 +1134,7 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
     }
     // Hessian at the mode, its Cholesky factor, R^-1 and log_dets (R/Functions.R:90,115-122)
     double H[Q * Q], Lc[Q * Q];
-    mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, x, H);
+    mode_hessian<F, QY, QZ, G>(d, A.prior, A.fam, r0, ni, lg, gmask, cx, x, H);
     const bool pd = chol_lower<Q>(H, 0.0, Lc);
     if (live && lg == 0) {
         // R = Lc' (upper); R^-1 by back substitution, column by column

@@ -13,8 +13,8 @@ struct OpsImpl {
         const int64_t blocks = (a.d.N + 255) / 256;
         prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
     }
-    static cudaError_t eval_config(int score, int jt, int* blocks_per_sm, size_t* smem_bytes) {
-        const size_t smem = L::smem_bytes(jt, score != 0, GLMMA_EVAL_THREADS / 32);
+    static cudaError_t eval_config(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes) {
+        const size_t smem = L::smem_bytes(jt, nagq, score != 0, GLMMA_EVAL_THREADS / 32);
         *smem_bytes = smem;
         cudaError_t e;
         if (score) {
@@ -34,6 +34,35 @@ struct OpsImpl {
         if (score) eval_kernel<F, QY, QZ, true><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
         else eval_kernel<F, QY, QZ, false><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
     }
+    // register variant (eval_fast_kernel): nj = 8 or 16 observations per cluster
+    template <int NJ>
+    static cudaError_t fast_config_nj(int score, int* blocks_per_sm, size_t* smem_bytes) {
+        const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32);
+        *smem_bytes = smem;
+        cudaError_t e;
+        if (score) {
+            e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, true, NJ>,
+                                                                 GLMMA_EVAL_THREADS, smem);
+        }
+        e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, false, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, false, NJ>,
+                                                             GLMMA_EVAL_THREADS, smem);
+    }
+    static cudaError_t fast_config(int score, int nj, int* blocks_per_sm, size_t* smem_bytes) {
+        return nj == 8 ? fast_config_nj<8>(score, blocks_per_sm, smem_bytes) : fast_config_nj<16>(score, blocks_per_sm, smem_bytes);
+    }
+    static void eval_fast(const EvalArgs& a, int score, int nj, int grid, size_t smem, cudaStream_t s) {
+        if (nj == 8) {
+            if (score) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+            else eval_fast_kernel<F, QY, QZ, false, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        } else {
+            if (score) eval_fast_kernel<F, QY, QZ, true, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+            else eval_fast_kernel<F, QY, QZ, false, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        }
+    }
     static void sphi(const EvalArgs& a, int grid, size_t smem, cudaStream_t s) {
         sphi_obs_kernel<F, QY, QZ><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
     }
@@ -49,7 +78,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {prep, eval_config, eval, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2};
+        static const FamOps ops = {prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2};
         return &ops;
     }
 };

@@ -1,0 +1,86 @@
+"""Accuracy of the engine's fp64 special functions (glmmadaptive_b200/csrc/fastmath.cuh),
+compiled for the host with g++ and compared with mpmath at 40 digits.  The same source
+is what the kernels inline; fma() is correctly rounded on both sides."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+from mpmath import mp, mpf, log as mplog, exp as mpexp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    out = os.path.join(tempfile.mkdtemp(prefix="glmma_fm_"), "libfm.so")
+    subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-shared", "-fPIC",
+                    os.path.join(HERE, "fastmath_host.cpp"), "-o", out], check=True)
+    lib = C.CDLL(out)
+    dp = C.POINTER(C.c_double)
+    lib.hm_log_rcp.argtypes = [dp, C.c_int, dp, dp]
+    lib.hm_exp.argtypes = [dp, C.c_int, dp]
+    lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def ulp(x):
+    return np.spacing(np.abs(x))
+
+
+def test_log_rcp(hm):
+    mp.dps = 40
+    rng = np.random.default_rng(0)
+    t = np.concatenate([np.exp(rng.uniform(-690, 690, 20000)), rng.uniform(0.5, 2.0, 20000),
+                        1.0 + rng.uniform(-1e-3, 1e-3, 5000), [1.0, 2.0, 0.5, 1e-300, 1e300, 0.6875, 1.375],
+                        np.exp(rng.uniform(-5, 8, 20000))])
+    L = np.empty_like(t); r = np.empty_like(t)
+    hm.hm_log_rcp(_p(t), len(t), _p(L), _p(r))
+    Lref = np.array([float(mplog(mpf(float(v)))) for v in t])
+    rref = np.array([float(1 / mpf(float(v))) for v in t])
+    eL = np.abs(L - Lref)
+    assert np.all((eL <= 2 * ulp(Lref)) | (eL <= 2.3e-16)), (np.max(eL / ulp(Lref)), np.max(eL))
+    assert np.max(np.abs(r - rref) / ulp(rref)) <= 2.0
+    # out-of-range arguments take the library path
+    bad = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310])
+    L = np.empty_like(bad); r = np.empty_like(bad)
+    hm.hm_log_rcp(_p(bad), len(bad), _p(L), _p(r))
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(L, np.log(bad))
+        np.testing.assert_array_equal(r, 1.0 / bad)
+
+
+def test_exp(hm):
+    mp.dps = 40
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-700, 700, 30000), rng.uniform(-40, 40, 30000),
+                        rng.uniform(-1e-3, 1e-3, 3000), [0.0, -700.0, 700.0, 1e-320, -0.0]])
+    out = np.empty_like(x)
+    hm.hm_exp(_p(x), len(x), _p(out))
+    ref = np.array([float(mpexp(mpf(float(v)))) for v in x])
+    assert np.max(np.abs(out - ref) / ulp(ref)) <= 2.0
+    far = np.array([-800.0, 720.0, np.nan, -np.inf, np.inf, -745.0])
+    out = np.empty_like(far)
+    hm.hm_exp(_p(far), len(far), _p(out))
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(out, np.exp(far))
+
+
+def test_l1p_sigmoid(hm):
+    mp.dps = 40
+    rng = np.random.default_rng(2)
+    ez = rng.uniform(-60, 60, 20000)
+    ex = np.exp(ez)
+    l1p = np.empty_like(ex); sig = np.empty_like(ex)
+    hm.hm_l1p_sigmoid(_p(ex), len(ex), _p(l1p), _p(sig))
+    ref_l = np.array([float(mplog(1 + mpf(float(v)))) for v in ex])
+    ref_s = np.array([float(mpf(float(v)) / (1 + mpf(float(v)))) for v in ex])
+    assert np.max(np.abs(l1p - ref_l)) <= 4e-16 + 2 * np.max(ulp(ref_l))
+    assert np.all(np.abs(l1p - ref_l) <= np.maximum(3 * ulp(ref_l), 2.3e-16))
+    assert np.all(np.abs(sig - ref_s) <= np.maximum(3 * ulp(ref_s), 1e-300))
