@@ -135,9 +135,10 @@ static bool fill_fampar(int family, int n_phis, const double* phis, FamPar* fp, 
 
 static const FamOps* lookup_ops(int family, int link, int qy, int qz) {
     switch (family) {
+        case GLMMA_NEGBIN: return glmma_ops_negbin(qy, qz);
+#ifndef GLMMA_DEV_ONLY      // development builds (make DEV=1) link the negative binomial kernels only
         case GLMMA_BINOMIAL: return glmma_ops_binomial(link, qy, qz);
         case GLMMA_POISSON: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_LOG) ? glmma_ops_poisson(qy, qz) : nullptr;
-        case GLMMA_NEGBIN: return glmma_ops_negbin(qy, qz);
         case GLMMA_ZI_POISSON: return glmma_ops_zi_poisson(qy, qz);
         case GLMMA_ZI_NEGBIN: return glmma_ops_zi_negbin(qy, qz);
         case GLMMA_ZI_BINOMIAL: return glmma_ops_zi_binomial(qy, qz);
@@ -148,6 +149,7 @@ static const FamOps* lookup_ops(int family, int link, int qy, int qz) {
         case GLMMA_HURDLE_BETA: return glmma_ops_hurdle_beta(qy, qz);
         case GLMMA_GAMMA: return glmma_ops_gamma(qy, qz);
         case GLMMA_CENSORED_NORMAL: return glmma_ops_censored_normal(qy, qz);
+#endif
     }
     return nullptr;
 }
@@ -430,6 +432,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         std::vector<double> fm(GLMMA_FM_DOUBLES);
         for (int t = 0; t < 256; ++t) fm[t] = GLMMA_LOGTAB_HOST[t];
         for (int t = 0; t < 64; ++t) fm[256 + t] = GLMMA_EXPTAB_HOST[t];
+        fastmath_constants(fm.data() + 320);
         TRY(dev_alloc(h, &h->d_fmtab, GLMMA_FM_DOUBLES));
         cudaMemcpy(h->d_fmtab, fm.data(), sizeof(double) * GLMMA_FM_DOUBLES, cudaMemcpyHostToDevice);
     }

@@ -67,6 +67,18 @@ struct FamBase {
     // no link clamp is active and every fast_log_rcp argument is in its fast range
     static constexpr double EMU_LO = 2.3e-16;     // log link: eta >= log(.Machine$double.eps)
     static constexpr double EMU_HI = 1e290;
+    // Register-variant (CAREFUL = false) contract:
+    //  LIN_ETA: log f contains the term y1 * eta; the kernel adds sum_j y1_j eta_jk once per
+    //           node (from sum_j y1_j xb_j and Z'y1) and point<., false> leaves it out.
+    //  stage(): per-observation transform of (y1, y2) applied when the record is staged.
+    //  finish_se(): point<., false> may return a cheaper carrier c of the eta-score whose
+    //           posterior mean maps to the score mean by an affine per-observation map
+    //           (e.g. mu instead of y - mu); finish_se(mean(c), y1, y2) undoes it.
+    //  sp_scale(): factor applied once per cluster to the accumulated point<., false>().sp
+    static constexpr bool LIN_ETA = false;
+    __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
+    __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar&) { return c; }
+    __device__ static __forceinline__ double sp_scale(const FamPar&) { return 1.0; }
     __device__ static __forceinline__ void obs_const(double, double, const FamPar&, double& cll, double& cphi) {
         cll = 0.0; cphi = 0.0;
     }
@@ -86,10 +98,17 @@ struct FamBinomialLogit : FamBase {
         double mu, lt, L;
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
         // y log p + (N - y) log q with log p = lt - L, log q = -L
-        ld = fma(y, lt, -N * L);
-        if (SCORE) se = fma(-N, mu, y);
+        if (CAREFUL) {
+            ld = fma(y, lt, -N * L);
+            if (SCORE) se = fma(-N, mu, y);
+        } else {
+            ld = -N * L;                 // + y eta at node level
+            if (SCORE) se = mu;          // carrier: score = y - N mean(mu)
+        }
         sz = 0.0; sp = 0.0;
     }
+    static constexpr bool LIN_ETA = true;
+    __device__ static __forceinline__ double finish_se(double c, double y, double N, const FamPar&) { return fma(-N, c, y); }
 };
 
 // ----- stats::binomial(), probit / cloglog -- score via (y - N mu) mu'(eta) / V(mu),
@@ -132,10 +151,17 @@ struct FamPoisson : FamBase {
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu;
         link_log<CAREFUL>(eta, emu, mu, lmu);
-        ld = fma(y, lmu, -mu);
-        if (SCORE) se = y - mu;
+        if (CAREFUL) {
+            ld = fma(y, lmu, -mu);
+            if (SCORE) se = y - mu;
+        } else {
+            ld = -mu;                    // + y eta at node level
+            if (SCORE) se = mu;          // carrier: score = y - mean(mu)
+        }
         sz = 0.0; sp = 0.0;
     }
+    static constexpr bool LIN_ETA = true;
+    __device__ static __forceinline__ double finish_se(double c, double y, double, const FamPar&) { return y - c; }
 };
 
 // FamPar layout shared by the negative-binomial type families:
@@ -153,23 +179,39 @@ struct FamNegBin : FamBase {
         nb_const(y, fp, cll, cphi);
     }
     template <bool SCORE, bool CAREFUL>
-    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
+    __device__ static __forceinline__ void point(double y, double yp_, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu, L, r;
         link_log<CAREFUL>(eta, emu, mu, lmu);
         fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
-        const double yp = y + phi;
-        ld = fma(y, lmu, -yp * L);
-        if (SCORE) {
-            se = fma(-yp, mu * r, y);
-            sp = -phi * fma(yp, r, L);
+        if (CAREFUL) {
+            const double yp = y + phi;
+            ld = fma(y, lmu, -yp * L);
+            if (SCORE) {
+                se = fma(-yp, mu * r, y);
+                sp = -phi * fma(yp, r, L);
+            }
+        } else {
+            // staged record: yp_ = y + phi.  log f = y eta (node level) - yp log(mu + phi);
+            // with q = yp / (mu + phi): score_eta = phi (q - 1), score_phi = -phi (L + q)
+            ld = -yp_ * L;
+            if (SCORE) {
+                const double q = yp_ * r;
+                se = q;                  // carrier, see finish_se
+                sp = L + q;              // times sp_scale = -phi at cluster level
+            }
         }
         sz = 0.0;
     }
+    static constexpr bool LIN_ETA = true;
+    __device__ static __forceinline__ void stage(double& y1, double& y2, const FamPar& fp) { y2 = y1 + fp.a[0]; }
+    __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar& fp) { return fp.a[0] * (c - 1.0); }
+    __device__ static __forceinline__ double sp_scale(const FamPar& fp) { return -fp.a[0]; }
 };
 
 // ----- zi.poisson() -- R/Fit_Funs.R:515-563 ------------------------------------
 struct FamZiPoisson : FamBase {
+    static constexpr bool LIN_ETA = true;
     static constexpr bool HAS_ZI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
@@ -180,7 +222,7 @@ struct FamZiPoisson : FamBase {
         link_log<CAREFUL>(eta, emu, mu, lmu);
         zero_part<CAREFUL>(ez, elam, cx, l1p, pi);          // plogis(eta_zi), log(1 + lambda)
         if (y > 0.0) {
-            ld = fma(y, lmu, -mu) - l1p;
+            ld = (CAREFUL ? fma(y, lmu, -mu) : -mu) - l1p;     // fast variant: + y eta at node level
             if (SCORE) { se = y - mu; sz = -pi; }
         } else {
             // log(lambda + exp(-mu)) - log(1 + lambda)
@@ -199,6 +241,7 @@ struct FamZiPoisson : FamBase {
 
 // ----- zi.negative.binomial() -- R/Fit_Funs.R:565-640 --------------------------
 struct FamZiNegBin : FamBase {
+    static constexpr bool LIN_ETA = true;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
@@ -213,7 +256,7 @@ struct FamZiNegBin : FamBase {
         zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
             const double yp = y + phi;
-            ld = fma(y, lmu, -yp * L) - l1p;
+            ld = (CAREFUL ? fma(y, lmu, -yp * L) : -yp * L) - l1p;     // fast variant: + y eta at node level
             if (SCORE) {
                 se = fma(-yp, mu * r, y);
                 sp = -phi * fma(yp, r, L);
@@ -237,6 +280,7 @@ struct FamZiNegBin : FamBase {
 
 // ----- zi.binomial() -- R/Fit_Funs.R:766-827 -----------------------------------
 struct FamZiBinomial : FamBase {
+    static constexpr bool LIN_ETA = true;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
     static constexpr bool HAS_ZI = true;
@@ -251,7 +295,7 @@ struct FamZiBinomial : FamBase {
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
         zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
-            ld = fma(y, lt, -N * L) - l1p;
+            ld = (CAREFUL ? fma(y, lt, -N * L) : -N * L) - l1p;        // fast variant: + y eta at node level
             if (SCORE) { se = fma(-N, mu, y); sz = -pi; }
         } else {
             const double F = fast_exp(-N * L, cx);         // (1 - mu)^N

@@ -33,10 +33,25 @@ static GLMMA_NOINLINE double fm_slow_exp(double x) { return exp(x); }
 static GLMMA_NOINLINE double fm_slow_log(double x) { return log(x); }
 static GLMMA_NOINLINE double fm_slow_rcp(double x) { return 1.0 / x; }
 
+// Tables + the polynomial / range-reduction constants that are not encodable as
+// instruction immediates.  The kernels load the constants from shared memory once, so
+// they live in registers; as literals ptxas re-materialises each of them with two
+// moves at every use (ncu: 24 of 134 instructions per 32 points were such moves).
 struct MathCtx {
     const double* logtab;   // 128 x (invc, logc)
     const double* exptab;   // 64 x 2^(j/64)
+    double l6, l5, l3, ln2hi, ln2lo;                          // -1/6, 1/5, 1/3, ln2 split
+    double e64ln2, emagic, ehi, elo, e120, e24, e6;           // exp: 64/ln2, 1.5*2^52, -ln2/64 split, 1/5!, 1/4!, 1/3!
 };
+#define GLMMA_FM_NCONST 12
+// c must hold the GLMMA_FM_NCONST constants in this order (fastmath_constants())
+GLMMA_HD MathCtx make_mathctx(const double* logtab, const double* exptab, const double* c) {
+    MathCtx m;
+    m.logtab = logtab; m.exptab = exptab;
+    m.l6 = c[0]; m.l5 = c[1]; m.l3 = c[2]; m.ln2hi = c[3]; m.ln2lo = c[4];
+    m.e64ln2 = c[5]; m.emagic = c[6]; m.ehi = c[7]; m.elo = c[8]; m.e120 = c[9]; m.e24 = c[10]; m.e6 = c[11];
+    return m;
+}
 
 GLMMA_HD int fm_hi(double x) {
 #ifdef __CUDA_ARCH__
@@ -62,12 +77,21 @@ GLMMA_HD double fm_make(int hi, int lo) {
 
 #define FM_LN2_HI 0x1.62e42fefa3800p-1     // ln 2 with 11 trailing zero bits: k * LN2_HI is exact
 #define FM_LN2_LO 0x1.ef35793c76730p-45
+#define FM_64_LN2 0x1.71547652b82fep+6     // 64 / ln 2
+#define FM_LN2_64_HI 0x1.62e42fefa0000p-7  // ln2/64, trailing zeros: n * hi exact for |n| < 2^17
+#define FM_LN2_64_LO 0x1.cf79abc9e3b3ap-46
+#define FM_MAGIC 0x1.8p52
+inline void fastmath_constants(double* c) {
+    c[0] = -1.0 / 6.0; c[1] = 0.2; c[2] = 1.0 / 3.0; c[3] = FM_LN2_HI; c[4] = FM_LN2_LO;
+    c[5] = FM_64_LN2; c[6] = FM_MAGIC; c[7] = -FM_LN2_64_HI; c[8] = -FM_LN2_64_LO;
+    c[9] = 1.0 / 120.0; c[10] = 1.0 / 24.0; c[11] = 1.0 / 6.0;
+}
 
 // log t and 1/t for t > 0.
 //   t = 2^k z, z in [0.6875, 1.375); table entry (invc, logc) of z's sub-interval;
 //   r = z invc - 1 (one fma, exact to rounding), |r| < 0.0039
 //   log t = k ln2 + logc + r - r^2/2 + r^3/3 - r^4/4 + r^5/5 - r^6/6
-//   1/z   = two Newton steps from invc (1 - r)
+//   1/z   = invc (1 - r)(1 + r^2 + r^4 + r^6)
 // CHECK = false: the caller guarantees 1e-300 <= t <= 1e300 (no branch, no library fallback)
 template <bool CHECK = true>
 GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) {
@@ -91,37 +115,32 @@ GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) 
     const double kd = (double)k;
     const double r = fma(z, invc, -1.0);
     const double r2 = r * r;
-    double q = fma(r, -1.0 / 6.0, 0.2);
+    double q = fma(r, cx.l6, cx.l5);
     q = fma(r, q, -0.25);
-    q = fma(r, q, 1.0 / 3.0);
+    q = fma(r, q, cx.l3);
     q = fma(r, q, -0.5);
-    const double w = fma(kd, FM_LN2_HI, logc);
-    const double s = fma(kd, FM_LN2_LO, r);
+    const double w = fma(kd, cx.ln2hi, logc);
+    const double s = fma(kd, cx.ln2lo, r);
     L = w + fma(r2, q, s);
-    double y = fma(-invc, r, invc);
-    double e = fma(-z, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-z, y, 1.0);
-    y = fma(y, e, y);
+    // 1/z = invc / (1 + r) = invc (1 - r) (1 + r^2 + r^4 + r^6), |r|^8 < 6e-20
+    double u = fma(r2, r2, r2);                   // r^2 + r^4
+    u = fma(u, r2, r2);                           // r^2 + r^4 + r^6
+    const double y0 = fma(-invc, r, invc);
+    const double y = fma(y0, u, y0);
     rcp = fm_make(fm_hi(y) - ke, fm_lo(y));       // y * 2^-k
 }
-
-#define FM_64_LN2 0x1.71547652b82fep+6     // 64 / ln 2
-#define FM_LN2_64_HI 0x1.62e42fefa0000p-7  // ln2/64, trailing zeros: n * hi exact for |n| < 2^17
-#define FM_LN2_64_LO 0x1.cf79abc9e3b3ap-46
-#define FM_MAGIC 0x1.8p52
 
 // exp x = 2^(n/64) exp(r), n = rint(64 x / ln2), |r| <= ln2/128
 GLMMA_HD double fast_exp(double x, const MathCtx& cx) {
     if (!(fabs(x) <= 700.0)) return fm_slow_exp(x);
-    const double kf = fma(x, FM_64_LN2, FM_MAGIC);
+    const double kf = fma(x, cx.e64ln2, cx.emagic);
     const int n = fm_lo(kf);
-    const double nd = kf - FM_MAGIC;
-    double r = fma(nd, -FM_LN2_64_HI, x);
-    r = fma(nd, -FM_LN2_64_LO, r);
+    const double nd = kf - cx.emagic;
+    double r = fma(nd, cx.ehi, x);
+    r = fma(nd, cx.elo, r);
     const double r2 = r * r;
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(r, p, 1.0 / 6.0);
+    double p = fma(r, cx.e120, cx.e24);
+    p = fma(r, p, cx.e6);
     p = fma(r, p, 0.5);
     p = fma(r2, p, r);
     const double tj = cx.exptab[n & 63];

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs A, CoefPar C) {
 // so exp(eta) over the K = nagq^Q nodes needs only Q * nagq exponentials per observation
 // ("optional algorithmic shortcut").
 // ------------------------------------------------------------------------------
-#define GLMMA_FM_DOUBLES (256 + 64)
+#define GLMMA_FM_DOUBLES (256 + 64 + GLMMA_FM_NCONST)
 
 template <class F, int QY, int QZ>
 struct EvalLayout {
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx{fmtab, fmtab + 256};
+    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
     const double lw_const = A.grid->lw_const;
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;         // the round holding the central node
@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 // d.defer and handled by eval_kernel.
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
+#ifndef GLMMA_FAST_MINBLOCKS
+#define GLMMA_FAST_MINBLOCKS 4
+#endif
 
 template <class F, int QY, int QZ, int NJ>
 struct FastLayout {
@@ -536,7 +539,7 @@ struct FastLayout {
 };
 
 template <class F, int QY, int QZ, bool SCORE, int NJ>
-__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs A) {
+__global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval_fast_kernel(EvalArgs A) {
     using FL = FastLayout<F, QY, QZ, NJ>;
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx{fmtab, fmtab + 256};
+    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
     const double lw_const = A.grid->lw_const;
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;
@@ -592,49 +595,63 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
         __syncwarp();
         stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
         double c_ll = 0.0, c_phi = 0.0;
+        double syxb = 0.0, zty[QY];
+#pragma unroll
+        for (int dd = 0; dd < QY; ++dd) zty[dd] = 0.0;
         if (lane < ni) {
             c_ll = d.cll[r0 + lane];
             if (SCORE && F::HAS_PHI) c_phi = d.cphi[r0 + lane];
+            double* r = rec + lane * W;           // own record: written by this lane just above
+            if (F::LIN_ETA) {
+                syxb = r[0] * r[2];
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) zty[dd] = r[0] * r[L::OFF_Z + dd];
+            }
+            F::stage(r[0], r[1], A.fam);
         }
         __syncwarp();
-        // separable factor tables, stride NG per (observation, dimension)
-        if (F::NEED_EMU) {
-            const int items = ni * Q * nagq;
-            for (int t = lane; t < items; t += 32) {
-                const int a = t % nagq;
-                const int je = t / nagq;
-                const int e = je % Q;
-                const int j = je / Q;
-                const double* r = rec + j * W;
-                double c = 0.0, base = r[2];
+        // separable factor tables, stride NG per (observation, dimension): 16 lanes per
+        // (observation, dimension) pair, lane & 15 = node index (no runtime divisions)
+        {
+            const int na = lane & 15, sub = lane >> 4;
+            const bool live_a = na < nagq;
+            const double xa = live_a ? gx[na] : 0.0;
+            if (F::NEED_EMU) {
+                for (int p0 = 0; p0 < ni * Q; p0 += 2) {
+                    const int p = p0 + sub;
+                    if (p < ni * Q && live_a) {
+                        const int j = p / Q, e = p - j * Q;
+                        const double* r = rec + j * W;
+                        double c = 0.0, base = r[2];
 #pragma unroll
-                for (int dd = 0; dd < QY; ++dd) {
-                    base = fma(r[L::OFF_Z + dd], m[dd], base);
+                        for (int dd = 0; dd < QY; ++dd) {
+                            base = fma(r[L::OFF_Z + dd], m[dd], base);
 #pragma unroll
-                    for (int ee = dd; ee < Q; ++ee)
-                        if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
+                            for (int ee = dd; ee < Q; ++ee)
+                                if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
+                        }
+                        tabF[p * NG + na] = fast_exp(fma(GLMMA_SQRT2 * c, xa, e == 0 ? base : 0.0), cx);
+                    }
                 }
-                tabF[(j * Q + e) * NG + a] = fast_exp(fma(GLMMA_SQRT2 * c, gx[a], e == 0 ? base : 0.0), cx);
             }
-        }
-        if (F::HAS_ZI) {
-            constexpr int NT = FL::NT > 0 ? FL::NT : 1;
-            const int items = ni * NT * nagq;
-            for (int t = lane; t < items; t += 32) {
-                const int a = t % nagq;
-                const int je = t / nagq;
-                const int e = je % NT;
-                const int j = je / NT;
-                const double* r = rec + j * W;
-                double c = 0.0, base = r[L::OFF_XG];
+            if (F::HAS_ZI) {
+                constexpr int NT = FL::NT > 0 ? FL::NT : 1;
+                for (int p0 = 0; p0 < ni * NT; p0 += 2) {
+                    const int p = p0 + sub;
+                    if (p < ni * NT && (QZ > 0 ? live_a : na == 0)) {
+                        const int j = p / NT, e = p - j * NT;
+                        const double* r = rec + j * W;
+                        double c = 0.0, base = r[L::OFF_XG];
 #pragma unroll
-                for (int dd = 0; dd < QZ; ++dd) {
-                    base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
+                        for (int dd = 0; dd < QZ; ++dd) {
+                            base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
 #pragma unroll
-                    for (int ee = dd; ee < QZ; ++ee)
-                        if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
+                            for (int ee = dd; ee < QZ; ++ee)
+                                if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
+                        }
+                        tabL[p * NG + na] = fast_exp(fma(GLMMA_SQRT2 * c, xa, e == 0 ? base : 0.0), cx);
+                    }
                 }
-                tabL[(j * NT + e) * NG + a] = fast_exp(fma(GLMMA_SQRT2 * c, QZ > 0 ? gx[a] : 0.0, e == 0 ? base : 0.0), cx);
             }
         }
         __syncwarp();
@@ -642,15 +659,13 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
         // per-dimension extremes of the (positive) factors
         bool bad = false;
         if (lane < ni) {
+            // every factor is exp(c x_a + base), monotone in the node x_a: extremes at the end points
             if (F::NEED_EMU) {
                 double lo = 1.0, hi = 1.0;
 #pragma unroll
                 for (int e = 0; e < Q; ++e) {
-                    double mn = INFINITY, mx = 0.0;
-                    for (int a = 0; a < nagq; ++a) {
-                        const double v = tabF[(lane * Q + e) * NG + a];
-                        mn = fmin(mn, v); mx = fmax(mx, v);
-                    }
+                    const double v0 = tabF[(lane * Q + e) * NG], v1 = tabF[(lane * Q + e) * NG + nagq - 1];
+                    const double mn = fmin(v0, v1), mx = fmax(v0, v1);
                     if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
                     lo *= mn; hi *= mx;
                 }
@@ -661,11 +676,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
                 double lo = 1.0, hi = 1.0;
 #pragma unroll
                 for (int e = 0; e < NT; ++e) {
-                    double mn = INFINITY, mx = 0.0;
-                    for (int a = 0; a < (QZ > 0 ? nagq : 1); ++a) {
-                        const double v = tabL[(lane * NT + e) * NG + a];
-                        mn = fmin(mn, v); mx = fmax(mx, v);
-                    }
+                    const double v0 = tabL[(lane * NT + e) * NG], v1 = tabL[(lane * NT + e) * NG + (QZ > 0 ? nagq - 1 : 0)];
+                    const double mn = fmin(v0, v1), mx = fmax(v0, v1);
                     if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
                     lo *= mn; hi *= mx;
                 }
@@ -677,6 +689,11 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
         if (bad) continue;
         c_ll = warp_sum(c_ll);
         if (SCORE && F::HAS_PHI) c_phi = warp_sum(c_phi);
+        if (F::LIN_ETA) {
+            syxb = warp_sum(syxb);
+#pragma unroll
+            for (int dd = 0; dd < QY; ++dd) zty[dd] = warp_sum(zty[dd]);
+        }
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
@@ -702,39 +719,53 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
                 for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e) pl[e] = tabL + e * NG + (QZ > 0 ? idx[QY + (QZ > 0 ? e : 0)] : 0);
                 double vphi = 0.0;
                 double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
+                if (F::LIN_ETA) {
+                    a += syxb;
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) {
-                    se_[j] = 0.0;
-                    if (F::HAS_ZI) sz_[j] = 0.0;
-                    if (j < ni) {
-                        const double* rj = rec + j * W;
-                        double eta = rj[2];
+                    for (int dd = 0; dd < QY; ++dd) a = fma(zty[dd], b[dd], a);
+                }
+#define GLMMA_FAST_OBS(j)                                                                              \
+    {                                                                                                  \
+        const double* rj = rec + (j) * W;                                                              \
+        double eta = rj[2];                                                                            \
+        _Pragma("unroll") for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);     \
+        double ez = 0.0, emu = 0.0, elam = 0.0;                                                        \
+        if (F::NEED_EMU) {                                                                             \
+            emu = pf[0][(j) * FL::TF];                                                                 \
+            _Pragma("unroll") for (int e = 1; e < Q; ++e) emu *= pf[e][(j) * FL::TF];                   \
+        }                                                                                              \
+        if (F::HAS_ZI) {                                                                               \
+            ez = rj[L::OFF_XG];                                                                        \
+            _Pragma("unroll") for (int dd = 0; dd < QZ; ++dd)                                           \
+                ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);                                      \
+            elam = pl[0][(j) * FL::TL];                                                                \
+            _Pragma("unroll") for (int e = 1; e < QZ; ++e) elam *= pl[e][(j) * FL::TL];                 \
+        }                                                                                              \
+        double ld, se, sz, sp;                                                                         \
+        F::template point<SCORE, false>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);  \
+        a += ld;                                                                                       \
+        if (SCORE) {                                                                                   \
+            se_[j] = se;                                                                               \
+            if (F::HAS_ZI) sz_[j] = sz;                                                                \
+            if (F::HAS_PHI) vphi += sp;                                                                \
+        }                                                                                              \
+    }
 #pragma unroll
-                        for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
-                        double ez = 0.0, emu = 0.0, elam = 0.0;
-                        if (F::NEED_EMU) {
-                            emu = pf[0][j * FL::TF];
+                for (int c4 = 0; c4 < NJ / 4; ++c4) {
+                    if (ni >= 4 * c4 + 4) {
+                        // full chunk: four independent point evaluations, no branches
 #pragma unroll
-                            for (int e = 1; e < Q; ++e) emu *= pf[e][j * FL::TF];
-                        }
-                        if (F::HAS_ZI) {
-                            ez = rj[L::OFF_XG];
+                        for (int jj = 0; jj < 4; ++jj) GLMMA_FAST_OBS(4 * c4 + jj)
+                    } else {
 #pragma unroll
-                            for (int dd = 0; dd < QZ; ++dd) ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);
-                            elam = pl[0][j * FL::TL];
-#pragma unroll
-                            for (int e = 1; e < QZ; ++e) elam *= pl[e][j * FL::TL];
-                        }
-                        double ld, se, sz, sp;
-                        F::template point<SCORE, false>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
-                        a += ld;
-                        if (SCORE) {
-                            se_[j] = se;
-                            if (F::HAS_ZI) sz_[j] = sz;
-                            if (F::HAS_PHI) vphi += sp;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            se_[4 * c4 + jj] = 0.0;
+                            if (F::HAS_ZI) sz_[4 * c4 + jj] = 0.0;
+                            if (4 * c4 + jj < ni) GLMMA_FAST_OBS(4 * c4 + jj)
                         }
                     }
                 }
+#undef GLMMA_FAST_OBS
                 if (valid) amax = fmax(amax, a);
                 if (rr == 0 && attempt == 0) {
                     shift = warp_max(valid ? a : -INFINITY);
@@ -771,7 +802,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
         if (SCORE) {
             const double inv = ok ? w / sum_e : 0.0;
             if (F::HAS_PHI) {
-                tot[3] = fma(inv, gphi, tot[3]);
+                tot[3] = fma(inv * F::sp_scale(A.fam), gphi, tot[3]);
                 if (lane == 0 && ok) tot[3] = fma(w, c_phi, tot[3]);
             }
 #pragma unroll
@@ -807,7 +838,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_fast_kernel(EvalArgs 
                     s1 += acc_eta[lane * 32 + cc];
                     if (F::HAS_ZI) s2 += acc_zi[lane * 32 + cc];
                 }
-                d.zbar[r0 + lane] = inv * s1;
+                // posterior mean of the score carrier -> score (finish_se), times the cluster weight
+                const double isum = 1.0 / sum_e;
+                const double sc = F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                d.zbar[r0 + lane] = ok ? w * sc : 0.0;
                 if (F::HAS_ZI) d.zbar_zi[r0 + lane] = inv * s2;
             }
         }
@@ -858,7 +892,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx{fmtab, fmtab + 256};
+    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
     const int nrounds = (K + 31) >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
@@ -1052,7 +1086,7 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
     __shared__ double fmtab[GLMMA_FM_DOUBLES];
     for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
     __syncthreads();
-    const MathCtx cx{fmtab, fmtab + 256};
+    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
     const bool live = i < d.n;
     const int64_t r0 = live ? d.row_ptr[i] : 0;
     const int ni = live ? (int)(d.row_ptr[i + 1] - r0) : 0;

@@ -5,15 +5,18 @@
 
 extern "C" {
 void hm_log_rcp(const double* t, int n, double* L, double* r) {
-    MathCtx cx{GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST};
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) fast_log_rcp(t[i], cx, L[i], r[i]);
 }
 void hm_exp(const double* x, int n, double* out) {
-    MathCtx cx{GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST};
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) out[i] = fast_exp(x[i], cx);
 }
 void hm_l1p_sigmoid(const double* ex, int n, double* l1p, double* sig) {
-    MathCtx cx{GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST};
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) fast_l1p_sigmoid(ex[i], cx, l1p[i], sig[i]);
 }
 }

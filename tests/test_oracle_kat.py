@@ -1,0 +1,92 @@
+"""Pins the CPU oracle against the reference's published known-answer values
+(rendered vignettes) and the R RNG restatement against R's
+documented outputs (appendix E).  Runs on the CPU."""
+import numpy as np
+
+from oracle import agq, families as F, vignette_data
+from oracle.r_rng import RRng
+
+
+def test_r_rng_documented_outputs():
+    assert np.allclose(RRng(1234).runif(3), [0.1137034, 0.6222994, 0.6092747], atol=5e-8)
+    assert np.allclose(RRng(42).rnorm(3), [1.3709584, -0.5646982, 0.3631284], atol=5e-8)
+
+
+def test_gauher_matches_hermgauss():
+    for n in (7, 11, 15, 21):
+        x, w = agq.gauher(n)
+        xr, wr = np.polynomial.hermite.hermgauss(n)
+        assert np.max(np.abs(x - xr[::-1])) < 1e-14
+        assert np.max(np.abs(w / wr[::-1] - 1)) < 1e-12
+
+
+def _binary():
+    v = vignette_data.binary_data()
+    return v
+
+
+def test_kat_D1_binomial_q1():
+    v = _binary()
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"][:, :1], id=v["id"])
+    fam = F.binomial()
+    for nagq, betas, Dv, pub in [
+        (11, [-2.61816557, -1.32418678, 0.28514773, 0.04015372], 4.26266211, -374.51972108),
+        (15, [-2.61679077, -1.32349829, 0.28501148, 0.04020003], 4.26351799, -374.51983340),
+        (21, [-2.6168440, -1.3235049, 0.2850151, 0.0401995], 4.2636311, -374.5198046),
+    ]:
+        betas = np.array(betas)
+        D = np.array([[Dv]])
+        gh = agq.GHfun(np.zeros((data.n, 1)), data, fam, betas, np.linalg.inv(D), None, None, nagq, 1)
+        th = np.concatenate([betas, agq.chol_transf(D)])
+        assert abs(-agq.logLik_mixed(th, data, fam, gh) - pub) < 5e-7
+
+
+def test_kat_D2_binomial_q2_loglik_and_modes():
+    v = _binary()
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"], id=v["id"])
+    fam = F.binomial()
+    betas = np.array([-2.059256329, -1.167646870, 0.261720034, 0.001924039])
+    D = np.array([[0.47137731, 0.11092919], [0.11092919, 0.06332475]])
+    gh = agq.GHfun(np.zeros((data.n, 2)), data, fam, betas, np.linalg.inv(D), None, None, 11, 2)
+    th = np.concatenate([betas, agq.chol_transf(D)])
+    assert abs(-agq.logLik_mixed(th, data, fam, gh) - (-358.8167)) < 5e-4
+    # the score at the published (rounded, early-stopped: SURVEY H2) optimum is small
+    sc = agq.score_mixed(th, data, fam, gh)
+    assert np.max(np.abs(sc)) < 0.5
+    # head(ranef(fm)), docs/articles/Methods.html:324-330: the posterior modes of GHfun
+    pub = np.array([[-0.3764536, -0.122065606], [0.6675107, 0.289646664], [0.4843611, 0.215634477],
+                    [-0.2083419, -0.006681441], [0.2373342, 0.162463265], [-0.3690096, -0.184228112]])
+    assert np.max(np.abs(gh.post_modes[:6] - pub)) < 1e-5
+    # Newton and BFGS mode finders agree (H1: mode-finder mismatch is ~1e-5)
+    gh2 = agq.GHfun(np.zeros((data.n, 2)), data, fam, betas, np.linalg.inv(D), None, None, 11, 2, mode_finder="newton")
+    assert np.max(np.abs(gh.post_modes - gh2.post_modes)) < 1e-3
+    assert abs(agq.logLik_mixed(th, data, fam, gh2) - agq.logLik_mixed(th, data, fam, gh)) < 1e-6
+
+
+def test_kat_D4_hurdle_lognormal():
+    v = vignette_data.hurdle_lognormal_data()
+    fam = F.hurdle_lognormal()
+    # km1: random intercept only (q = 1)
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"][:, :1], id=v["id"], X_zi=v["X_zi"])
+    betas = np.array([-2.08122468, -0.24046281, 0.22303981, -0.05686286])
+    gammas = np.array([-1.6034499, 0.6713555])
+    phis = np.array([-0.3348787])
+    D = np.array([[0.9609426 ** 2]])
+    gh = agq.GHfun(np.zeros((data.n, 1)), data, fam, betas, np.linalg.inv(D), phis, gammas, 11, 1)
+    th = np.concatenate([betas, agq.chol_transf(D), phis, gammas])
+    assert abs(-agq.logLik_mixed(th, data, fam, gh) - (-1214.208)) < 5e-3
+
+
+def test_kat_D5_hurdle_poisson_q3():
+    v = vignette_data.hurdle_count_data()
+    fam = F.hurdle_poisson()
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"], id=v["id"], X_zi=v["X_zi"], Z_zi=v["Z_zi"])
+    betas = np.array([1.52792269, 0.08389745, 0.09206185, -0.08020395])
+    gammas = np.array([-1.5398382, 0.5175922])
+    sd = np.array([0.8226, 0.3644, 0.6584])
+    R = np.array([[1, -0.3125, -0.0065], [-0.3125, 1, 0.0636], [-0.0065, 0.0636, 1]])
+    D = R * np.outer(sd, sd)
+    gh = agq.GHfun(np.zeros((data.n, 3)), data, fam, betas, np.linalg.inv(D), None, gammas, 7, 3,
+                   mode_finder="newton")
+    th = np.concatenate([betas, agq.chol_transf(D), gammas])
+    assert abs(-agq.logLik_mixed(th, data, fam, gh) - (-2797.307)) < 5e-2
