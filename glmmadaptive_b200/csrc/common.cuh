@@ -80,6 +80,7 @@ struct DevData {
     double* sphi_obs;     // N (contrib only) or null
     double* ll_i;         // n (contrib only) or null
     double* S_i;          // n x q*q (contrib only) or null
+    double* csum;         // n x GLMMA_NCSUM per-cluster scalars (cluster_sums_kernel)
     int32_t* defer;       // n : 1 = cluster left to the generic eval kernel by the register variant
 };
 

@@ -25,6 +25,7 @@ struct glmma_handle {
     cudaStream_t stream;
     GridPar* d_grid;
     double* d_fmtab;
+    double* d_ytab;
     // launch shape of the eval kernel, [0] = loglik only, [1] = with score
     int jt;
     int eval_grid[2];
@@ -360,7 +361,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     glmma_handle* h = new glmma_handle();
     h->family = data->family; h->link = data->link; h->device = device; h->nagq = data->nAGQ;
     h->q = q; h->K = (int)Kd; h->y_cols = data->y_cols; h->ops = ops; h->stream = nullptr;
-    h->have_modes = false; h->launches = 0; h->sticky = 0;
+    h->have_modes = false; h->launches = 0; h->sticky = 0; h->d_ytab = nullptr;
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
     DevData& d = h->d;
@@ -429,12 +430,11 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     cudaMemcpyAsync(h->d_grid, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream);
 
     {
-        std::vector<double> fm(GLMMA_FM_DOUBLES);
+        std::vector<double> fm(320);
         for (int t = 0; t < 256; ++t) fm[t] = GLMMA_LOGTAB_HOST[t];
         for (int t = 0; t < 64; ++t) fm[256 + t] = GLMMA_EXPTAB_HOST[t];
-        fastmath_constants(fm.data() + 320);
-        TRY(dev_alloc(h, &h->d_fmtab, GLMMA_FM_DOUBLES));
-        cudaMemcpy(h->d_fmtab, fm.data(), sizeof(double) * GLMMA_FM_DOUBLES, cudaMemcpyHostToDevice);
+        TRY(dev_alloc(h, &h->d_fmtab, 320));
+        cudaMemcpy(h->d_fmtab, fm.data(), sizeof(double) * 320, cudaMemcpyHostToDevice);
     }
 
     // launch shape: the observation tile covers (nearly) all clusters; larger ones stream
@@ -474,12 +474,12 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     }
     // register variant for small clusters (eval_fast_kernel)
     h->nj = 0;
-    if (h->nagq <= GLMMA_NAGQ_FAST && jt <= 16 && !std::getenv("GLMMA_NO_FAST")) h->nj = jt <= 8 ? 8 : 16;
+    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && jt <= 16 && !std::getenv("GLMMA_NO_FAST")) h->nj = jt <= 8 ? 8 : 16;
     int max_fast = 0;
     if (h->nj) {
         for (int s = 0; s < 2; ++s) {
             int bps = 0;
-            ce = ops->fast_config(s, h->nj, &bps, &h->fast_smem[s]);
+            ce = ops->fast_config(s, h->nj, h->K, &bps, &h->fast_smem[s]);
             if (ce != cudaSuccess || bps < 1) {
                 cuda_fail(h, ce, "fast eval kernel configuration");
                 g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
@@ -489,6 +489,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
             max_fast = std::max(max_fast, h->fast_grid[s]);
         }
         TRY(dev_alloc(h, &d.defer, n));
+        TRY(dev_alloc(h, &d.csum, (size_t)n * GLMMA_NCSUM));
+        TRY(dev_alloc(h, &h->d_ytab, 2 * GLMMA_YTAB));
     }
     max_grid += max_fast;
     h->score_grid = (int)std::min<int64_t>((N + SCORE_THREADS * 8 - 1) / (SCORE_THREADS * 8), (int64_t)prop.multiProcessorCount * 4);
@@ -564,7 +566,7 @@ static int run_prep(glmma_handle* h, const double* betas, const double* phis, co
     if (rc) return rc;
     if (!fill_fampar(h->family, h->d.n_phis, phis, fp, h->error)) return GLMMA_ERR_ARG;
     PrepArgs pa;
-    pa.d = h->d; pa.fam = *fp; pa.want_score = 1;
+    pa.d = h->d; pa.fam = *fp; pa.want_score = 1; pa.ytab = h->d.csum ? h->d_ytab : nullptr;
     h->ops->prep(pa, c, h->stream);
     h->launches++;
     CU(h, cudaGetLastError());
@@ -580,7 +582,7 @@ int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, c
     rc = run_prep(h, betas, phis, gammas, &fp);
     if (rc) return rc;
     ModeArgs ma;
-    ma.d = h->d; ma.fam = fp; ma.fmtab = h->d_fmtab; ma.warm = warm && h->have_modes; ma.maxit = 100; ma.tol = 1e-10; ma.stats = h->d_stats;
+    ma.d = h->d; ma.fam = fp; ma.fmtab = h->d_fmtab; fastmath_constants(ma.fmc); ma.warm = warm && h->have_modes; ma.maxit = 100; ma.tol = 1e-10; ma.stats = h->d_stats;
     fill_prior(h, invD, true, &ma.prior);
     CU(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     const double mean_ni = (double)h->d.N / (double)h->d.n;
@@ -653,7 +655,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (rc) return rc;
     EvalArgs ea;
     ea.d = dd_override ? *dd_override : h->d;
-    ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; ea.partials = h->d_partials; ea.jt = h->jt;
+    ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt;
     rc = fill_prior(h, D, false, &ea.prior);
     if (rc) return rc;
     if (k0) CU(h, cudaEventRecord(k0, h->stream));
@@ -721,7 +723,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
     rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, &dd, nullptr, nullptr);
     if (rc == GLMMA_OK && d_sphi) {
         EvalArgs ea;
-        ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
+        ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
         fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error);
         fill_prior(h, D, false, &ea.prior);
         h->ops->sphi(ea, h->eval_grid[1], h->eval_smem[1], h->stream);

@@ -75,7 +75,18 @@ struct FamBase {
     //           posterior mean maps to the score mean by an affine per-observation map
     //           (e.g. mu instead of y - mu); finish_se(mean(c), y1, y2) undoes it.
     //  sp_scale(): factor applied once per cluster to the accumulated point<., false>().sp
+    //  FAST2: the register variant evaluates a chunk of observations stage by stage:
+    //           t = fast_arg(emu), (L, r) = (log t, 1/t) for the whole chunk at once
+    //           (fast_log_rcp_vec), then fast_finish() -- the same arithmetic as
+    //           point<., false>, arranged so that the chunk's chains are interleaved.
     static constexpr bool LIN_ETA = false;
+    static constexpr bool Y_TABLE = false;       // obs_const() depends on an integer-valued y1 only
+    static constexpr bool FAST2 = false;
+    static constexpr bool FAST2_LOG = true;      // fast_finish reads L / r
+    __device__ static __forceinline__ double fast_arg(double emu, const FamPar&) { return emu; }
+    template <bool SCORE>
+    __device__ static __forceinline__ void fast_finish(double, double, double, double, double, const FamPar&,
+                                                       double& ld, double& se, double& sp) { ld = 0.0; se = 0.0; sp = 0.0; }
     __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
     __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ double sp_scale(const FamPar&) { return 1.0; }
@@ -109,6 +120,15 @@ struct FamBinomialLogit : FamBase {
     }
     static constexpr bool LIN_ETA = true;
     __device__ static __forceinline__ double finish_se(double c, double y, double N, const FamPar&) { return fma(-N, c, y); }
+    static constexpr bool FAST2 = true;
+    __device__ static __forceinline__ double fast_arg(double emu, const FamPar&) { return 1.0 + emu; }
+    template <bool SCORE>
+    __device__ static __forceinline__ void fast_finish(double, double N, double emu, double L, double r, const FamPar&,
+                                                       double& ld, double& se, double& sp) {
+        ld = -N * L;
+        if (SCORE) se = emu * r;
+        sp = 0.0;
+    }
 };
 
 // ----- stats::binomial(), probit / cloglog -- score via (y - N mu) mu'(eta) / V(mu),
@@ -144,6 +164,7 @@ struct FamBinomialOther : FamBase {
 
 // ----- stats::poisson(), log -- R/Fit_Funs.R:440-445 ---------------------------
 struct FamPoisson : FamBase {
+    static constexpr bool Y_TABLE = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = -lgamma(y + 1.0); cphi = 0.0;
     }
@@ -162,6 +183,15 @@ struct FamPoisson : FamBase {
     }
     static constexpr bool LIN_ETA = true;
     __device__ static __forceinline__ double finish_se(double c, double y, double, const FamPar&) { return y - c; }
+    static constexpr bool FAST2 = true;
+    static constexpr bool FAST2_LOG = false;
+    template <bool SCORE>
+    __device__ static __forceinline__ void fast_finish(double, double, double emu, double, double, const FamPar&,
+                                                       double& ld, double& se, double& sp) {
+        ld = -emu;
+        if (SCORE) se = emu;
+        sp = 0.0;
+    }
 };
 
 // FamPar layout shared by the negative-binomial type families:
@@ -174,6 +204,7 @@ __device__ __forceinline__ void nb_const(double y, const FamPar& fp, double& cll
 
 // ----- negative.binomial() -- R/Fit_Funs.R:467-513 -----------------------------
 struct FamNegBin : FamBase {
+    static constexpr bool Y_TABLE = true;
     static constexpr bool HAS_PHI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         nb_const(y, fp, cll, cphi);
@@ -207,10 +238,22 @@ struct FamNegBin : FamBase {
     __device__ static __forceinline__ void stage(double& y1, double& y2, const FamPar& fp) { y2 = y1 + fp.a[0]; }
     __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar& fp) { return fp.a[0] * (c - 1.0); }
     __device__ static __forceinline__ double sp_scale(const FamPar& fp) { return -fp.a[0]; }
+    static constexpr bool FAST2 = true;
+    __device__ static __forceinline__ double fast_arg(double emu, const FamPar& fp) { return emu + fp.a[0]; }
+    template <bool SCORE>
+    __device__ static __forceinline__ void fast_finish(double, double yp_, double, double L, double r, const FamPar&,
+                                                       double& ld, double& se, double& sp) {
+        ld = -yp_ * L;
+        if (SCORE) {
+            se = yp_ * r;
+            sp = L + se;
+        }
+    }
 };
 
 // ----- zi.poisson() -- R/Fit_Funs.R:515-563 ------------------------------------
 struct FamZiPoisson : FamBase {
+    static constexpr bool Y_TABLE = true;
     static constexpr bool LIN_ETA = true;
     static constexpr bool HAS_ZI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
@@ -241,6 +284,7 @@ struct FamZiPoisson : FamBase {
 
 // ----- zi.negative.binomial() -- R/Fit_Funs.R:565-640 --------------------------
 struct FamZiNegBin : FamBase {
+    static constexpr bool Y_TABLE = true;
     static constexpr bool LIN_ETA = true;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
@@ -323,6 +367,7 @@ __device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCt
 
 // ----- hurdle.poisson() -- R/Fit_Funs.R:642-688 --------------------------------
 struct FamHurdlePoisson : FamBase {
+    static constexpr bool Y_TABLE = true;
     static constexpr bool HAS_ZI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
@@ -345,6 +390,7 @@ struct FamHurdlePoisson : FamBase {
 
 // ----- hurdle.negative.binomial() -- R/Fit_Funs.R:690-764 ----------------------
 struct FamHurdleNegBin : FamBase {
+    static constexpr bool Y_TABLE = true;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {

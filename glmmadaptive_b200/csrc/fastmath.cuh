@@ -34,22 +34,49 @@ static GLMMA_NOINLINE double fm_slow_log(double x) { return log(x); }
 static GLMMA_NOINLINE double fm_slow_rcp(double x) { return 1.0 / x; }
 
 // Tables + the polynomial / range-reduction constants that are not encodable as
-// instruction immediates.  The kernels load the constants from shared memory once, so
-// they live in registers; as literals ptxas re-materialises each of them with two
-// moves at every use (ncu: 24 of 134 instructions per 32 points were such moves).
-struct MathCtx {
-    const double* logtab;   // 128 x (invc, logc)
-    const double* exptab;   // 64 x 2^(j/64)
-    double l6, l5, l3, ln2hi, ln2lo;                          // -1/6, 1/5, 1/3, ln2 split
-    double e64ln2, emagic, ehi, elo, e120, e24, e6;           // exp: 64/ln2, 1.5*2^52, -ln2/64 split, 1/5!, 1/4!, 1/3!
-};
+// instruction immediates.  The kernels read the constants through a shared-memory
+// pointer: as literals ptxas re-materialises each of them with two moves at every use
+// (ncu: 24 of 134 instructions per 32 points were such moves); as loads it keeps the
+// hot ones in registers and re-reads the others with one LDS.
+//
+// On the device both tables are REPLICATED in shared memory so that the data-dependent
+// lookups are bank-conflict free: entry i of the log table has 8 copies, lane l reads copy
+// l & 7 (a 16-byte access is served per quarter warp: 8 lanes x 16 B = all 32 banks once);
+// entry j of the exp table has 16 copies, lane l reads copy l & 15.  With a single copy the
+// random indices made the shared-memory pipe the limiter of the whole kernel (ncu r1:
+// l1tex data-pipe wavefronts 76 %, 48 M bank conflicts per 200 k clusters).
+#ifdef __CUDA_ARCH__
+#define FM_LOG_STRIDE 16      // doubles between consecutive entries (8 copies x 2 doubles)
+#define FM_EXP_STRIDE 16      // 16 copies x 1 double
+#else
+#define FM_LOG_STRIDE 2
+#define FM_EXP_STRIDE 1
+#endif
+#define GLMMA_FM_LOG_DOUBLES (128 * 16)
+#define GLMMA_FM_EXP_DOUBLES (64 * 16)
 #define GLMMA_FM_NCONST 12
-// c must hold the GLMMA_FM_NCONST constants in this order (fastmath_constants())
+struct MathCtx {
+    const double* logtab;   // device: replicated table + 2 * (lane & 7); host: 128 x (invc, logc)
+    const double* exptab;   // device: replicated table + (lane & 15);    host: 64 x 2^(j/64)
+    double c[GLMMA_FM_NCONST];   // constants, order of fastmath_constants(); on the device they come
+                                 // from the kernel parameters (constant bank), not from shared memory
+};
+#define FMC_L6 0      // -1/6
+#define FMC_L5 1      // 1/5
+#define FMC_L3 2      // 1/3
+#define FMC_LN2HI 3
+#define FMC_LN2LO 4
+#define FMC_E64LN2 5  // 64 / ln2
+#define FMC_EMAGIC 6  // 1.5 * 2^52
+#define FMC_EHI 7     // -ln2/64 high part
+#define FMC_ELO 8     // -ln2/64 low part
+#define FMC_E120 9
+#define FMC_E24 10
+#define FMC_E6 11
 GLMMA_HD MathCtx make_mathctx(const double* logtab, const double* exptab, const double* c) {
     MathCtx m;
     m.logtab = logtab; m.exptab = exptab;
-    m.l6 = c[0]; m.l5 = c[1]; m.l3 = c[2]; m.ln2hi = c[3]; m.ln2lo = c[4];
-    m.e64ln2 = c[5]; m.emagic = c[6]; m.ehi = c[7]; m.elo = c[8]; m.e120 = c[9]; m.e24 = c[10]; m.e6 = c[11];
+    for (int i = 0; i < GLMMA_FM_NCONST; ++i) m.c[i] = c[i];
     return m;
 }
 
@@ -107,20 +134,20 @@ GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) 
     const int ke = tmp & 0xfff00000;
     const double z = fm_make(hi - ke, fm_lo(t));
 #ifdef __CUDA_ARCH__
-    const double2 tc = *reinterpret_cast<const double2*>(cx.logtab + 2 * i);
+    const double2 tc = *reinterpret_cast<const double2*>(cx.logtab + FM_LOG_STRIDE * i);
     const double invc = tc.x, logc = tc.y;
 #else
-    const double invc = cx.logtab[2 * i], logc = cx.logtab[2 * i + 1];
+    const double invc = cx.logtab[FM_LOG_STRIDE * i], logc = cx.logtab[FM_LOG_STRIDE * i + 1];
 #endif
     const double kd = (double)k;
     const double r = fma(z, invc, -1.0);
     const double r2 = r * r;
-    double q = fma(r, cx.l6, cx.l5);
+    double q = fma(r, cx.c[FMC_L6], cx.c[FMC_L5]);
     q = fma(r, q, -0.25);
-    q = fma(r, q, cx.l3);
+    q = fma(r, q, cx.c[FMC_L3]);
     q = fma(r, q, -0.5);
-    const double w = fma(kd, cx.ln2hi, logc);
-    const double s = fma(kd, cx.ln2lo, r);
+    const double w = fma(kd, cx.c[FMC_LN2HI], logc);
+    const double s = fma(kd, cx.c[FMC_LN2LO], r);
     L = w + fma(r2, q, s);
     // 1/z = invc / (1 + r) = invc (1 - r) (1 + r^2 + r^4 + r^6), |r|^8 < 6e-20
     double u = fma(r2, r2, r2);                   // r^2 + r^4
@@ -130,20 +157,72 @@ GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) 
     rcp = fm_make(fm_hi(y) - ke, fm_lo(y));       // y * 2^-k
 }
 
+// N independent fast_log_rcp evaluations, written stage by stage so that the N dependency
+// chains are interleaved in program order (DFMA latency on sm_100 is ~8 cycles at one issue
+// per 2 cycles: four chains in flight per warp keep the FP64 pipe fed without relying on the
+// scheduler to find the parallelism across separately inlined calls).  Unchecked: the caller
+// guarantees 1e-300 <= t[i] <= 1e300.
+template <int N>
+GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, double* rcp) {
+    int ke[N];
+    double z[N], kd[N], invc[N], logc[N], r[N], r2[N], q[N], u[N];
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int i = 0; i < N; ++i) {
+        const int hi = fm_hi(t[i]);
+        const int tmp = hi - 0x3FE60000;
+        const int idx = (tmp >> 13) & 127;
+        ke[i] = tmp & 0xfff00000;
+        kd[i] = (double)(tmp >> 20);
+        z[i] = fm_make(hi - ke[i], fm_lo(t[i]));
+#ifdef __CUDA_ARCH__
+        const double2 tc = *reinterpret_cast<const double2*>(cx.logtab + FM_LOG_STRIDE * idx);
+        invc[i] = tc.x; logc[i] = tc.y;
+#else
+        invc[i] = cx.logtab[FM_LOG_STRIDE * idx]; logc[i] = cx.logtab[FM_LOG_STRIDE * idx + 1];
+#endif
+    }
+    const double c6 = cx.c[FMC_L6], c5 = cx.c[FMC_L5], c3 = cx.c[FMC_L3], lh = cx.c[FMC_LN2HI], ll = cx.c[FMC_LN2LO];
+#define FM_VEC for (int i = 0; i < N; ++i)
+#ifdef __CUDACC__
+#define FM_UNROLL _Pragma("unroll")
+#else
+#define FM_UNROLL
+#endif
+    FM_UNROLL FM_VEC r[i] = fma(z[i], invc[i], -1.0);
+    FM_UNROLL FM_VEC r2[i] = r[i] * r[i];
+    FM_UNROLL FM_VEC q[i] = fma(r[i], c6, c5);
+    FM_UNROLL FM_VEC logc[i] = fma(kd[i], lh, logc[i]);          // w
+    FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.25);
+    FM_UNROLL FM_VEC u[i] = fma(r2[i], r2[i], r2[i]);
+    FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], c3);
+    FM_UNROLL FM_VEC kd[i] = fma(kd[i], ll, r[i]);               // s
+    FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.5);
+    FM_UNROLL FM_VEC u[i] = fma(u[i], r2[i], r2[i]);
+    FM_UNROLL FM_VEC invc[i] = fma(-invc[i], r[i], invc[i]);     // y0
+    FM_UNROLL FM_VEC q[i] = fma(r2[i], q[i], kd[i]);
+    FM_UNROLL FM_VEC invc[i] = fma(invc[i], u[i], invc[i]);      // y
+    FM_UNROLL FM_VEC L[i] = logc[i] + q[i];
+    FM_UNROLL FM_VEC rcp[i] = fm_make(fm_hi(invc[i]) - ke[i], fm_lo(invc[i]));
+#undef FM_VEC
+#undef FM_UNROLL
+}
+
 // exp x = 2^(n/64) exp(r), n = rint(64 x / ln2), |r| <= ln2/128
 GLMMA_HD double fast_exp(double x, const MathCtx& cx) {
     if (!(fabs(x) <= 700.0)) return fm_slow_exp(x);
-    const double kf = fma(x, cx.e64ln2, cx.emagic);
+    const double kf = fma(x, cx.c[FMC_E64LN2], cx.c[FMC_EMAGIC]);
     const int n = fm_lo(kf);
-    const double nd = kf - cx.emagic;
-    double r = fma(nd, cx.ehi, x);
-    r = fma(nd, cx.elo, r);
+    const double nd = kf - cx.c[FMC_EMAGIC];
+    double r = fma(nd, cx.c[FMC_EHI], x);
+    r = fma(nd, cx.c[FMC_ELO], r);
     const double r2 = r * r;
-    double p = fma(r, cx.e120, cx.e24);
-    p = fma(r, p, cx.e6);
+    double p = fma(r, cx.c[FMC_E120], cx.c[FMC_E24]);
+    p = fma(r, p, cx.c[FMC_E6]);
     p = fma(r, p, 0.5);
     p = fma(r2, p, r);
-    const double tj = cx.exptab[n & 63];
+    const double tj = cx.exptab[FM_EXP_STRIDE * (n & 63)];
     const double v = fma(tj, p, tj);
     return fm_make(fm_hi(v) + ((n >> 6) << 20), fm_lo(v));
 }

@@ -17,6 +17,7 @@ struct EvalArgs {
     FamPar fam;
     const GridPar* grid;     // device copy of the Gauss-Hermite table
     const double* fmtab;     // device copy of the fastmath tables (log table, then exp table)
+    double fmc[GLMMA_FM_NCONST];   // fastmath constants (constant bank)
     double* partials;        // gridDim.x * GLMMA_NACC block partial sums
     int jt;                  // observation tile held in shared memory per warp (<= GLMMA_JT_CAP)
     int only_deferred;       // eval_kernel: process only clusters flagged in d.defer
@@ -26,6 +27,7 @@ struct PrepArgs {
     DevData d;
     FamPar fam;
     int want_score;
+    double* ytab;            // 2 x GLMMA_YTAB table of obs_const(y) (count families) or null
 };
 
 struct ModeArgs {
@@ -33,6 +35,7 @@ struct ModeArgs {
     PriorPar prior;          // Dinv = invD as handed to find_modes
     FamPar fam;
     const double* fmtab;
+    double fmc[GLMMA_FM_NCONST];
     int warm;
     int maxit;
     double tol;
@@ -43,6 +46,25 @@ template <int Q> struct Tri {
     __host__ __device__ static constexpr int rm(int d, int e) { return d * Q - d * (d - 1) / 2 + (e - d); }   // row-major d<=e
     __host__ __device__ static constexpr int cm(int r, int c) { return c * (c + 1) / 2 + r; }               // R upper.tri order r<=c
 };
+
+// 8-byte asynchronous global -> shared copy (LDGSTS)
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// replicated fastmath tables (see fastmath.cuh): src is the compact global copy
+// [128 x (invc, logc) | 64 x 2^(j/64)]
+__device__ __forceinline__ void load_fmtab(double* fmtab, const double* src) {
+    for (int t = threadIdx.x; t < GLMMA_FM_LOG_DOUBLES; t += blockDim.x) {
+        const int entry = t >> 4, within = t & 1;
+        fmtab[t] = src[entry * 2 + within];
+    }
+    for (int t = threadIdx.x; t < GLMMA_FM_EXP_DOUBLES; t += blockDim.x) fmtab[GLMMA_FM_LOG_DOUBLES + t] = src[256 + (t >> 4)];
+    __syncthreads();
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs A, CoefPar C) {
 // so exp(eta) over the K = nagq^Q nodes needs only Q * nagq exponentials per observation
 // ("optional algorithmic shortcut").
 // ------------------------------------------------------------------------------
-#define GLMMA_FM_DOUBLES (256 + 64 + GLMMA_FM_NCONST)
+#define GLMMA_FM_DOUBLES (GLMMA_FM_LOG_DOUBLES + GLMMA_FM_EXP_DOUBLES)   // replicated tables in shared memory
 
 template <class F, int QY, int QZ>
 struct EvalLayout {
@@ -278,13 +300,13 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
     double* scr_zi = acc_eta + jt * 32;
     double* acc_zi = scr_zi + jt * 32;
 
-    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const double lw_const = A.grid->lw_const;
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;         // the round holding the central node
@@ -294,8 +316,19 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
     for (int a = 0; a < GLMMA_NACC; ++a) tot[a] = 0.0;
 
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
-        if (A.only_deferred && d.defer[i] == 0) continue;      // done by eval_fast_kernel
+    // only_deferred: every warp owns blocks of 32 consecutive clusters, reads their flags with
+    // one coalesced load and walks the set bits (the register variant did the others)
+    const int64_t span = A.only_deferred ? 32 : 1;
+    for (int64_t ib = ((int64_t)blockIdx.x * wpb + wib) * span; ib < d.n; ib += nwarps * span) {
+      unsigned todo = 1u;
+      if (A.only_deferred) {
+          const int64_t ci = ib + lane;
+          todo = __ballot_sync(0xffffffffu, ci < d.n && d.defer[ci] != 0);
+      }
+      while (todo) {
+        const int bit = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t i = ib + bit;
         const int64_t r0 = d.row_ptr[i];
         const int ni = (int)(d.row_ptr[i + 1] - r0);
         const double w = d.weights ? d.weights[i] : 1.0;
@@ -490,6 +523,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
             }
         }
         __syncwarp();
+      }
     }
 
     // block partials, fixed order (deterministic for a fixed launch shape)
@@ -509,16 +543,95 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 }
 
 // ------------------------------------------------------------------------------
-// eval, register variant: clusters of at most NJ observations, nagq <= GLMMA_NAGQ_FAST.
-// The observation loop is fully unrolled: per-observation score terms and their
-// posterior-weighted sums live in registers, every shared-memory operand has an
-// immediate offset, and the NJ independent point evaluations give the FP64 pipe
-// instruction-level parallelism.  The functors run with CAREFUL = false, which is
-// exact when no link clamp is active on the cluster's grid and all separable factors
-// are in range; clusters that fail that test (or are larger than NJ) are flagged in
-// d.defer and handled by eval_kernel.
+// prep + cluster sums in one pass: 8 lanes per cluster walk its rows (coalesced: a
+// cluster's rows are contiguous in every column), write xb, xg, cll, cphi and reduce
+//   csum[i] = { sum_j cll_j, sum_j cphi_j, sum_j y1_j xb_j, (Z'y1)[0..QY) }
+// (the last two feed the linear-eta hoist of the register variant).
+// ------------------------------------------------------------------------------
+#define GLMMA_NCSUM (3 + GLMMA_QMAX)
+
+// obs_const() of the count families depends on the (integer) response only: tabulate it
+// for y = 0 .. GLMMA_YTAB-1 once per evaluation instead of three lgamma/digamma calls
+// per observation (ncu r1: prep was 0.34 ms of a 4 ms evaluation, all of it special functions).
+#define GLMMA_YTAB 1024
+template <class F>
+__global__ void ytab_kernel(FamPar fam, double* ytab) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= GLMMA_YTAB) return;
+    double cll, cphi;
+    F::obs_const((double)y, 0.0, fam, cll, cphi);
+    ytab[2 * y] = cll;
+    ytab[2 * y + 1] = cphi;
+}
+template <class F>
+__device__ __forceinline__ void obs_const_tab(double y1, double y2, const FamPar& fam, const double* ytab,
+                                              double& cll, double& cphi) {
+    if (F::Y_TABLE && ytab != nullptr) {
+        const int iy = (int)y1;
+        if (y1 >= 0.0 && y1 < (double)GLMMA_YTAB && (double)iy == y1) {
+            const double2 t = *reinterpret_cast<const double2*>(ytab + 2 * iy);
+            cll = t.x; cphi = t.y;
+            return;
+        }
+    }
+    F::obs_const(y1, y2, fam, cll, cphi);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C) {
+    const DevData& d = A.d;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = gtid >> 3;
+    const int lg = (int)(gtid & 7);
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+    const bool live = i < d.n;
+    const int64_t r0 = live ? d.row_ptr[i] : 0, r1 = live ? d.row_ptr[i + 1] : 0;
+    double s[GLMMA_NCSUM];
+#pragma unroll
+    for (int t = 0; t < GLMMA_NCSUM; ++t) s[t] = 0.0;
+    for (int64_t row = r0 + lg; row < r1; row += 8) {
+        double xb = d.offset ? d.offset[row] : 0.0;
+        for (int l = 0; l < d.p; ++l) xb = fma(d.X[row + (int64_t)l * d.N], C.betas[l], xb);
+        d.xb[row] = xb;
+        if (F::HAS_ZI) {
+            double xg = d.offset_zi ? d.offset_zi[row] : 0.0;
+            for (int l = 0; l < d.p_zi; ++l) xg = fma(d.X_zi[row + (int64_t)l * d.N], C.gammas[l], xg);
+            d.xg[row] = xg;
+        }
+        const double y = d.y1[row];
+        double cll, cphi;
+        obs_const_tab<F>(y, F::USES_Y2 ? d.y2[row] : 0.0, A.fam, A.ytab, cll, cphi);
+        d.cll[row] = cll;
+        if (F::HAS_PHI) d.cphi[row] = cphi;
+        s[0] += cll;
+        if (F::HAS_PHI) s[1] += cphi;
+        if (F::LIN_ETA) {
+            s[2] = fma(y, xb, s[2]);
+            for (int dd = 0; dd < d.q_y; ++dd) s[3 + dd] = fma(y, d.Z[row + (int64_t)dd * d.N], s[3 + dd]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < GLMMA_NCSUM; ++t) s[t] = group_sum<8>(s[t], gmask);
+    if (live && lg == 0) {
+#pragma unroll
+        for (int t = 0; t < GLMMA_NCSUM; ++t) d.csum[i * GLMMA_NCSUM + t] = s[t];
+    }
+}
+
+// ------------------------------------------------------------------------------
+// eval, register variant: clusters of at most NJ observations, nagq <= GLMMA_NAGQ_FAST,
+// K <= GLMMA_K_FAST.  The observation loop is unrolled in branch-free chunks of four:
+// per-observation score terms and their posterior-weighted sums live in registers,
+// every shared-memory operand has an immediate offset, and the independent point
+// evaluations give the FP64 pipe instruction-level parallelism.  The functors run with
+// CAREFUL = false, which is exact when no link clamp is active on the cluster's grid and
+// all separable factors are in range; clusters that fail that test (or are larger than
+// NJ) are flagged in d.defer and handled by eval_kernel.
+// Shared memory per block: [fastmath | gx, glw | node table (z.., lw per node) | node idx
+// | per-warp areas: rec, tabF, tabL, acc (also scratch), totals].
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
+#define GLMMA_K_FAST 512
 #ifndef GLMMA_FAST_MINBLOCKS
 #define GLMMA_FAST_MINBLOCKS 4
 #endif
@@ -532,9 +645,14 @@ struct FastLayout {
     static constexpr int TF = Q * GLMMA_NAGQ_FAST;          // doubles of tabF per observation
     static constexpr int TL = NT * GLMMA_NAGQ_FAST;
     static constexpr int NACCS = F::HAS_ZI ? 2 : 1;
-    static constexpr int WARP_DOUBLES = NJ * (W + TF + TL) + NACCS * NJ * 32;
-    __host__ static size_t smem_bytes(int warps) {
-        return sizeof(double) * (L::head_doubles() + (size_t)warps * WARP_DOUBLES);
+    static constexpr int NTOT = 2 + Q * (Q + 1) / 2;        // per-lane totals: g_phi, (pad), S packed
+    // per-cluster scalars prefetched with the records: modes, R^-1, logdet, csum, weight
+    static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + GLMMA_NCSUM + 1;
+    static constexpr int PRE = ((NJ * W + NSC) + 1) & ~1;   // one prefetch buffer (records + scalars)
+    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJ * 32 + NTOT * 32 + 4;
+    __host__ __device__ static size_t node_doubles(int K) { return (((size_t)K * (Q + 1) + (K + 1) / 2) + 1) & ~(size_t)1; }
+    __host__ static size_t smem_bytes(int warps, int K) {
+        return sizeof(double) * (L::head_doubles() + node_doubles(K) + (size_t)warps * WARP_DOUBLES);
     }
 };
 
@@ -556,109 +674,171 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
     const int wpb = blockDim.x >> 5;
     const int nagq = A.grid->nagq;
     const int K = A.grid->K;
-    double* rec = smem + L::head_doubles() + wib * FL::WARP_DOUBLES;
-    double* tabF = rec + NJ * W;
+    double* ntab = smem + L::head_doubles();                 // K x (Q + 1): z_0.., log wGH
+    int* nidx = reinterpret_cast<int*>(ntab + (size_t)K * (Q + 1));   // K packed node indices
+    double* pre0 = smem + L::head_doubles() + FL::node_doubles(K) + wib * FL::WARP_DOUBLES;
+    double* tabF = pre0 + 2 * FL::PRE;
     double* tabL = tabF + NJ * FL::TF;
     double* acc_eta = tabL + NJ * FL::TL;
     double* acc_zi = acc_eta + NJ * 32;
+    double* totl = acc_eta + FL::NACCS * NJ * 32;            // NTOT x 32 per-lane totals
+    double* tots = totl + FL::NTOT * 32;                     // loglik, sum_w, n_nonfinite (lane 0)
 
-    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
-    const double lw_const = A.grid->lw_const;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int kk = k, packed = 0;
+        double lw = A.grid->lw_const;
+#pragma unroll
+        for (int e = 0; e < Q; ++e) {
+            const int a = kk % nagq;
+            kk /= nagq;
+            packed |= a << (8 * e);
+            ntab[k * (Q + 1) + e] = gx[a];
+            lw += glw[a];
+        }
+        ntab[k * (Q + 1) + Q] = lw;
+        nidx[k] = packed;
+    }
+    for (int t = lane; t < FL::NTOT * 32 + 4; t += 32) totl[t] = 0.0;
+    __syncthreads();
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;
+    constexpr int SC_M = 0, SC_RI = Q, SC_LD = Q + NP, SC_CS = Q + NP + 1, SC_W = Q + NP + 1 + GLMMA_NCSUM;
 
-    double tot[GLMMA_NACC];
+    // Asynchronous prefetch (cp.async, LDGSTS) of one cluster's observation columns and
+    // per-cluster scalars into a shared-memory buffer: issued one cluster ahead, so the
+    // global-memory latency is covered by the previous cluster's arithmetic.
+    auto prefetch = [&](int64_t ci, int64_t c_r0, int c_ni, double* buf) {
+        if (c_ni <= NJ) {
+            if (lane < c_ni) {
+                const int64_t row = c_r0 + lane;
+                double* r = buf + lane * W;
+                cp_async8(r + 0, d.y1 + row);
+                if (F::USES_Y2) cp_async8(r + 1, d.y2 + row);
+                cp_async8(r + 2, d.xb + row);
+                if (F::HAS_ZI) cp_async8(r + L::OFF_XG, d.xg + row);
 #pragma unroll
-    for (int a = 0; a < GLMMA_NACC; ++a) tot[a] = 0.0;
+                for (int dd = 0; dd < QY; ++dd) cp_async8(r + L::OFF_Z + dd, d.Z + row + (int64_t)dd * d.N);
+#pragma unroll
+                for (int dd = 0; dd < QZ; ++dd) cp_async8(r + L::OFF_Z + QY + dd, d.Z_zi + row + (int64_t)dd * d.N);
+            }
+            double* sc = buf + NJ * W;
+            if (lane < FL::NSC) {
+                const double* src;
+                if (lane < SC_RI) src = d.modes + ci * Q + lane;
+                else if (lane < SC_LD) src = d.rinv + ci * NP + (lane - SC_RI);
+                else if (lane < SC_CS) src = d.logdet + ci;
+                else if (lane < SC_W) src = d.csum + ci * GLMMA_NCSUM + (lane - SC_CS);
+                else src = d.weights ? d.weights + ci : nullptr;
+                if (src) cp_async8(sc + lane, src);
+            }
+        }
+        cp_async_commit();
+    };
 
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
-        const int64_t r0 = d.row_ptr[i];
-        const int ni = (int)(d.row_ptr[i + 1] - r0);
-        if (ni > NJ) {
+    const int64_t i0 = (int64_t)blockIdx.x * wpb + wib;
+    // row_ptr of the current and the next cluster are kept in registers
+    int64_t r0 = 0, r0n = 0;
+    int ni = 0, nin = 0;
+    if (i0 < d.n) { r0 = d.row_ptr[i0]; ni = (int)(d.row_ptr[i0 + 1] - r0); prefetch(i0, r0, ni, pre0); }
+    if (i0 + nwarps < d.n) { r0n = d.row_ptr[i0 + nwarps]; nin = (int)(d.row_ptr[i0 + nwarps + 1] - r0n); }
+    int pbuf = 0;
+    for (int64_t i = i0; i < d.n; i += nwarps) {
+        double* rec = pre0 + pbuf * FL::PRE;
+        const double* sc = rec + NJ * W;
+        // rotate the row_ptr pipeline and start the next cluster's copies
+        const int64_t r0c = r0;
+        const int nic = ni;
+        r0 = r0n; ni = nin;
+        const int64_t inext = i + nwarps, inext2 = i + 2 * nwarps;
+        cp_async_wait_all();
+        __syncwarp();
+        if (inext < d.n) prefetch(inext, r0, ni, pre0 + (pbuf ^ 1) * FL::PRE);
+        if (inext2 < d.n) { r0n = d.row_ptr[inext2]; nin = (int)(d.row_ptr[inext2 + 1] - r0n); }
+        pbuf ^= 1;
+        if (nic > NJ) {
             if (lane == 0) d.defer[i] = 1;
             continue;
         }
-        const double w = d.weights ? d.weights[i] : 1.0;
         double m[Q], ri[NP];
 #pragma unroll
-        for (int dd = 0; dd < Q; ++dd) m[dd] = d.modes[i * Q + dd];
+        for (int dd = 0; dd < Q; ++dd) m[dd] = sc[SC_M + dd];
 #pragma unroll
-        for (int t = 0; t < NP; ++t) ri[t] = d.rinv[i * NP + t];
-
-        __syncwarp();
-        stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
-        double c_ll = 0.0, c_phi = 0.0;
-        double syxb = 0.0, zty[QY];
-#pragma unroll
-        for (int dd = 0; dd < QY; ++dd) zty[dd] = 0.0;
-        if (lane < ni) {
-            c_ll = d.cll[r0 + lane];
-            if (SCORE && F::HAS_PHI) c_phi = d.cphi[r0 + lane];
-            double* r = rec + lane * W;           // own record: written by this lane just above
-            if (F::LIN_ETA) {
-                syxb = r[0] * r[2];
-#pragma unroll
-                for (int dd = 0; dd < QY; ++dd) zty[dd] = r[0] * r[L::OFF_Z + dd];
-            }
-            F::stage(r[0], r[1], A.fam);
+        for (int t = 0; t < NP; ++t) ri[t] = sc[SC_RI + t];
+        if (lane < nic) {
+            if (!F::USES_Y2) rec[lane * W + 1] = 0.0;
+            F::stage(rec[lane * W], rec[lane * W + 1], A.fam);     // own record
         }
         __syncwarp();
-        // separable factor tables, stride NG per (observation, dimension): 16 lanes per
-        // (observation, dimension) pair, lane & 15 = node index (no runtime divisions)
+        // coefficients of the separable factors: (sqrt(2) c_je, base) per (observation, dimension)
+        double2* coef = reinterpret_cast<double2*>(acc_eta);
+        constexpr int NTc = FL::NT > 0 ? FL::NT : 1;
+        for (int p = lane; p < nic * (Q + FL::NT); p += 32) {
+            const bool isF = p < nic * Q;
+            const int pp = isF ? p : p - nic * Q;
+            const int j = isF ? pp / Q : pp / NTc;
+            const int e = isF ? pp - j * Q : pp - j * NTc;
+            const double* r = rec + j * W;
+            double c = 0.0, base;
+            if (isF) {
+                base = r[2];
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) {
+                    base = fma(r[L::OFF_Z + dd], m[dd], base);
+#pragma unroll
+                    for (int ee = dd; ee < Q; ++ee)
+                        if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
+                }
+            } else {
+                base = r[F::HAS_ZI ? L::OFF_XG : 2];
+#pragma unroll
+                for (int dd = 0; dd < QZ; ++dd) {
+                    base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
+#pragma unroll
+                    for (int ee = dd; ee < QZ; ++ee)
+                        if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
+                }
+            }
+            coef[p] = make_double2(GLMMA_SQRT2 * c, e == 0 ? base : 0.0);
+        }
+        __syncwarp();
+        // tables: 16 lanes per (observation, dimension) pair, lane & 15 = node index
         {
             const int na = lane & 15, sub = lane >> 4;
             const bool live_a = na < nagq;
             const double xa = live_a ? gx[na] : 0.0;
             if (F::NEED_EMU) {
-                for (int p0 = 0; p0 < ni * Q; p0 += 2) {
+                // independent iterations: unrolled so that four exp chains are in flight
+#pragma unroll 4
+                for (int p0 = 0; p0 < nic * Q; p0 += 2) {
                     const int p = p0 + sub;
-                    if (p < ni * Q && live_a) {
-                        const int j = p / Q, e = p - j * Q;
-                        const double* r = rec + j * W;
-                        double c = 0.0, base = r[2];
-#pragma unroll
-                        for (int dd = 0; dd < QY; ++dd) {
-                            base = fma(r[L::OFF_Z + dd], m[dd], base);
-#pragma unroll
-                            for (int ee = dd; ee < Q; ++ee)
-                                if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
-                        }
-                        tabF[p * NG + na] = fast_exp(fma(GLMMA_SQRT2 * c, xa, e == 0 ? base : 0.0), cx);
+                    if (p < nic * Q && live_a) {
+                        const double2 cb = coef[p];
+                        tabF[p * NG + na] = fast_exp(fma(cb.x, xa, cb.y), cx);
                     }
                 }
             }
             if (F::HAS_ZI) {
-                constexpr int NT = FL::NT > 0 ? FL::NT : 1;
-                for (int p0 = 0; p0 < ni * NT; p0 += 2) {
+#pragma unroll 4
+                for (int p0 = 0; p0 < nic * NTc; p0 += 2) {
                     const int p = p0 + sub;
-                    if (p < ni * NT && (QZ > 0 ? live_a : na == 0)) {
-                        const int j = p / NT, e = p - j * NT;
-                        const double* r = rec + j * W;
-                        double c = 0.0, base = r[L::OFF_XG];
-#pragma unroll
-                        for (int dd = 0; dd < QZ; ++dd) {
-                            base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
-#pragma unroll
-                            for (int ee = dd; ee < QZ; ++ee)
-                                if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
-                        }
-                        tabL[p * NG + na] = fast_exp(fma(GLMMA_SQRT2 * c, xa, e == 0 ? base : 0.0), cx);
+                    if (p < nic * NTc && (QZ > 0 ? live_a : na == 0)) {
+                        const double2 cb = coef[nic * Q + p];
+                        tabL[p * NG + na] = fast_exp(fma(cb.x, xa, cb.y), cx);
                     }
                 }
             }
         }
         __syncwarp();
-        // range test: extremes of exp(eta) / exp(eta_zi) over the grid are products of the
-        // per-dimension extremes of the (positive) factors
         bool bad = false;
-        if (lane < ni) {
+        if (lane < nic) {
             // every factor is exp(c x_a + base), monotone in the node x_a: extremes at the end points
             if (F::NEED_EMU) {
                 double lo = 1.0, hi = 1.0;
@@ -672,11 +852,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 if (!(lo >= F::EMU_LO && hi <= F::EMU_HI)) bad = true;
             }
             if (F::HAS_ZI) {
-                constexpr int NT = FL::NT > 0 ? FL::NT : 1;
                 double lo = 1.0, hi = 1.0;
 #pragma unroll
-                for (int e = 0; e < NT; ++e) {
-                    const double v0 = tabL[(lane * NT + e) * NG], v1 = tabL[(lane * NT + e) * NG + (QZ > 0 ? nagq - 1 : 0)];
+                for (int e = 0; e < NTc; ++e) {
+                    const double v0 = tabL[(lane * NTc + e) * NG], v1 = tabL[(lane * NTc + e) * NG + (QZ > 0 ? nagq - 1 : 0)];
                     const double mn = fmin(v0, v1), mx = fmax(v0, v1);
                     if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
                     lo *= mn; hi *= mx;
@@ -687,13 +866,12 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
         bad = __any_sync(0xffffffffu, bad);
         if (lane == 0) d.defer[i] = bad ? 1 : 0;
         if (bad) continue;
-        c_ll = warp_sum(c_ll);
-        if (SCORE && F::HAS_PHI) c_phi = warp_sum(c_phi);
-        if (F::LIN_ETA) {
-            syxb = warp_sum(syxb);
+
+        const double* cs = sc + SC_CS;
+        const double syxb = F::LIN_ETA ? cs[2] : 0.0;
+        double zty[QY];
 #pragma unroll
-            for (int dd = 0; dd < QY; ++dd) zty[dd] = warp_sum(zty[dd]);
-        }
+        for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? cs[3 + dd] : 0.0;
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
@@ -708,15 +886,34 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 const int r = (rr == 0) ? rc : (rr <= rc ? rr - 1 : rr);
                 const int k = (r << 5) + lane;
                 const bool valid = k < K;
+                const int kc = valid ? k : K - 1;
+                // node: b_k = mode + sqrt(2) R^-1 z_k, a = log N(b_k; 0, D) + log wGH_k
+                const double* nt = ntab + kc * (Q + 1);
+                const int packed = nidx[kc];
                 double b[Q];
-                int idx[Q];
-                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int e = dd; e < Q; ++e) s = fma(ri[Tri<Q>::rm(dd, e)], nt[e], s);
+                    b[dd] = fma(GLMMA_SQRT2, s, m[dd]);
+                }
+                double quad = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int e = 0; e < Q; ++e) s = fma(A.prior.Dinv[dd * Q + e], b[e], s);
+                    quad = fma(b[dd], s, quad);
+                }
+                double a = fma(-0.5, quad, A.prior.logprior_const) + nt[Q];
                 const double* pf[Q];
 #pragma unroll
-                for (int e = 0; e < Q; ++e) pf[e] = tabF + e * NG + idx[e];
+                for (int e = 0; e < Q; ++e) pf[e] = tabF + e * NG + ((packed >> (8 * e)) & 0xff);
                 const double* pl[QZ > 0 ? QZ : 1];
 #pragma unroll
-                for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e) pl[e] = tabL + e * NG + (QZ > 0 ? idx[QY + (QZ > 0 ? e : 0)] : 0);
+                for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e)
+                    pl[e] = tabL + e * NG + (QZ > 0 ? ((packed >> (8 * (QY + e))) & 0xff) : 0);
                 double vphi = 0.0;
                 double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
                 if (F::LIN_ETA) {
@@ -752,16 +949,41 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
     }
 #pragma unroll
                 for (int c4 = 0; c4 < NJ / 4; ++c4) {
-                    if (ni >= 4 * c4 + 4) {
+                    if (nic >= 4 * c4 + 4) {
                         // full chunk: four independent point evaluations, no branches
+                        if (F::FAST2) {
+                            // stage-wise form (interleaved chains): exp(eta) products, log/rcp, finish
+                            double emu4[4], t4[4], L4[4], r4[4], ld4[4], sp4[4];
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) GLMMA_FAST_OBS(4 * c4 + jj)
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * c4 + jj;
+                                emu4[jj] = pf[0][j * FL::TF];
+#pragma unroll
+                                for (int e = 1; e < Q; ++e) emu4[jj] *= pf[e][j * FL::TF];
+                                t4[jj] = F::fast_arg(emu4[jj], A.fam);
+                                L4[jj] = 0.0; r4[jj] = 0.0;
+                            }
+                            if (F::FAST2_LOG) fast_log_rcp_vec<4>(t4, cx, L4, r4);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * c4 + jj;
+                                const double* rj = rec + j * W;
+                                double se;
+                                F::template fast_finish<SCORE>(rj[0], rj[1], emu4[jj], L4[jj], r4[jj], A.fam, ld4[jj], se, sp4[jj]);
+                                if (SCORE) se_[j] = se;
+                            }
+                            a += (ld4[0] + ld4[1]) + (ld4[2] + ld4[3]);
+                            if (SCORE && F::HAS_PHI) vphi += (sp4[0] + sp4[1]) + (sp4[2] + sp4[3]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) GLMMA_FAST_OBS(4 * c4 + jj)
+                        }
                     } else {
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             se_[4 * c4 + jj] = 0.0;
                             if (F::HAS_ZI) sz_[4 * c4 + jj] = 0.0;
-                            if (4 * c4 + jj < ni) GLMMA_FAST_OBS(4 * c4 + jj)
+                            if (4 * c4 + jj < nic) GLMMA_FAST_OBS(4 * c4 + jj)
                         }
                     }
                 }
@@ -776,9 +998,11 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 if (SCORE) {
                     int t = 0;
 #pragma unroll
-                    for (int dd = 0; dd < Q; ++dd)
+                    for (int dd = 0; dd < Q; ++dd) {
+                        const double eb = e * b[dd];
 #pragma unroll
-                        for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
+                        for (int ee = dd; ee < Q; ++ee) { S[t] = fma(eb, b[ee], S[t]); ++t; }
+                    }
                     if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
@@ -793,20 +1017,24 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
             shift = mx;
         }
-        const double ll = shift + log(sum_e) + d.logdet[i] + c_ll;
+        const double w = d.weights ? sc[SC_W] : 1.0;
+        double lsum, isum;
+        fast_log_rcp<true>(sum_e, cx, lsum, isum);
+        const double ll = shift + lsum + sc[SC_LD] + cs[0];
         const bool ok = fabs(ll) < INFINITY;
         if (lane == 0) {
-            if (ok) { tot[0] += w * ll; tot[1] += w; } else tot[2] += 1.0;
+            if (ok) { tots[0] += w * ll; tots[1] += w; } else tots[2] += 1.0;
             if (d.ll_i) d.ll_i[i] = w * ll;
         }
         if (SCORE) {
-            const double inv = ok ? w / sum_e : 0.0;
+            const double inv = ok ? w * isum : 0.0;
             if (F::HAS_PHI) {
-                tot[3] = fma(inv * F::sp_scale(A.fam), gphi, tot[3]);
-                if (lane == 0 && ok) tot[3] = fma(w, c_phi, tot[3]);
+                double g = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
+                if (lane == 0 && ok) g = fma(w, cs[1], g);
+                totl[lane] = g;
             }
 #pragma unroll
-            for (int t = 0; t < NP; ++t) tot[4 + t] = fma(inv, S[t], tot[4 + t]);
+            for (int t = 0; t < NP; ++t) totl[(2 + t) * 32 + lane] = fma(inv, S[t], totl[(2 + t) * 32 + lane]);
             if (d.S_i) {
                 double Sr[NP];
 #pragma unroll
@@ -823,43 +1051,68 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                         }
                 }
             }
-            // per-observation sums over the 32 lanes: through shared memory, skewed columns
+            // per-observation sums over the 32 lanes: through shared memory; lane l sums the
+            // (l / NJ)-th slice of columns of observation l % NJ, slices combined by shuffles
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 acc_eta[j * 32 + lane] = acc_e[j];
                 if (F::HAS_ZI) acc_zi[j * 32 + lane] = acc_z[j];
             }
             __syncwarp();
-            if (lane < ni) {
+            {
+                constexpr int NSL = 32 / NJ;          // slices (4 for NJ = 8, 2 for NJ = 16)
+                constexpr int CW = 32 / NSL;          // columns per slice
+                const int j = lane % NJ, sl = lane / NJ;
                 double s1 = 0.0, s2 = 0.0;
-#pragma unroll 8
-                for (int c = 0; c < 32; ++c) {
-                    const int cc = (c + lane) & 31;
-                    s1 += acc_eta[lane * 32 + cc];
-                    if (F::HAS_ZI) s2 += acc_zi[lane * 32 + cc];
+#pragma unroll
+                for (int c = 0; c < CW; ++c) {
+                    const int cc = sl * CW + ((c + j) & (CW - 1));
+                    s1 += acc_eta[j * 32 + cc];
+                    if (F::HAS_ZI) s2 += acc_zi[j * 32 + cc];
                 }
-                // posterior mean of the score carrier -> score (finish_se), times the cluster weight
-                const double isum = 1.0 / sum_e;
-                const double sc = F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
-                d.zbar[r0 + lane] = ok ? w * sc : 0.0;
-                if (F::HAS_ZI) d.zbar_zi[r0 + lane] = inv * s2;
+#pragma unroll
+                for (int o = NJ; o < 32; o <<= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                if (lane < nic) {
+                    const double sc = F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                    d.zbar[r0c + lane] = ok ? w * sc : 0.0;
+                    if (F::HAS_ZI) d.zbar_zi[r0c + lane] = inv * s2;
+                }
             }
         }
         __syncwarp();
     }
 
-    __syncthreads();
-    double* red = smem;
+    // block partials, fixed order (deterministic for a fixed launch shape)
+    __syncwarp();
+    {
+        // per-warp totals: [0] loglik [1] sum_w [2] n_nonfinite [3] g_phi [4..] S
+        double v3 = warp_sum(totl[lane]);
+        double vs[NP];
 #pragma unroll
-    for (int a = 0; a < GLMMA_NACC; ++a) {
-        const double v = warp_sum(tot[a]);
-        if (lane == 0) red[wib * GLMMA_NACC + a] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < GLMMA_NACC) {
-        double v = 0.0;
-        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
-        A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+        for (int t = 0; t < NP; ++t) vs[t] = warp_sum(totl[(2 + t) * 32 + lane]);
+        __syncwarp();
+        if (lane == 0) {
+            tots[3] = v3;      // tots has 4 slots: reuse the pad for g_phi
+        }
+        __syncthreads();
+        double* red = smem;    // wpb * NACC doubles (fastmath tables are no longer needed)
+        if (lane == 0) {
+            red[wib * GLMMA_NACC + 0] = tots[0];
+            red[wib * GLMMA_NACC + 1] = tots[1];
+            red[wib * GLMMA_NACC + 2] = tots[2];
+            red[wib * GLMMA_NACC + 3] = v3;
+#pragma unroll
+            for (int t = 0; t < GLMMA_NPACK; ++t) red[wib * GLMMA_NACC + 4 + t] = t < NP ? vs[t] : 0.0;
+        }
+        __syncthreads();
+        if (threadIdx.x < GLMMA_NACC) {
+            double v = 0.0;
+            for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
+            A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+        }
     }
 }
 
@@ -886,13 +1139,13 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A
     const int nagq = A.grid->nagq, K = A.grid->K;
     double* rec = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, true);
     double* scr = rec + jt * L::W + jt * (Q + L::NTABL) * nagq;
-    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
     }
     __syncthreads();
-    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const int nrounds = (K + 31) >> 5;
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
@@ -1084,9 +1337,9 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
     const int lane = threadIdx.x & 31;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     __shared__ double fmtab[GLMMA_FM_DOUBLES];
-    for (int t = threadIdx.x; t < GLMMA_FM_DOUBLES; t += blockDim.x) fmtab[t] = A.fmtab[t];
+    load_fmtab(fmtab, A.fmtab);
     __syncthreads();
-    const MathCtx cx = make_mathctx(fmtab, fmtab + 256, fmtab + 320);
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const bool live = i < d.n;
     const int64_t r0 = live ? d.row_ptr[i] : 0;
     const int ni = live ? (int)(d.row_ptr[i + 1] - r0) : 0;

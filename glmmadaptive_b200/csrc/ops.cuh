@@ -10,8 +10,13 @@ struct OpsImpl {
     using L = EvalLayout<F, QY, QZ>;
 
     static void prep(const PrepArgs& a, const CoefPar& c, cudaStream_t s) {
-        const int64_t blocks = (a.d.N + 255) / 256;
-        prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
+        if (F::Y_TABLE && a.ytab) ytab_kernel<F><<<GLMMA_YTAB / 256, 256, 0, s>>>(a.fam, a.ytab);
+        if (a.d.csum) {
+            prep_cluster_kernel<F><<<(unsigned)((a.d.n * 8 + 255) / 256), 256, 0, s>>>(a, c);
+        } else {
+            const int64_t blocks = (a.d.N + 255) / 256;
+            prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
+        }
     }
     static cudaError_t eval_config(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes) {
         const size_t smem = L::smem_bytes(jt, nagq, score != 0, GLMMA_EVAL_THREADS / 32);
@@ -36,8 +41,8 @@ struct OpsImpl {
     }
     // register variant (eval_fast_kernel): nj = 8 or 16 observations per cluster
     template <int NJ>
-    static cudaError_t fast_config_nj(int score, int* blocks_per_sm, size_t* smem_bytes) {
-        const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32);
+    static cudaError_t fast_config_nj(int score, int K, int* blocks_per_sm, size_t* smem_bytes) {
+        const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32, K);
         *smem_bytes = smem;
         cudaError_t e;
         if (score) {
@@ -51,8 +56,8 @@ struct OpsImpl {
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, false, NJ>,
                                                              GLMMA_EVAL_THREADS, smem);
     }
-    static cudaError_t fast_config(int score, int nj, int* blocks_per_sm, size_t* smem_bytes) {
-        return nj == 8 ? fast_config_nj<8>(score, blocks_per_sm, smem_bytes) : fast_config_nj<16>(score, blocks_per_sm, smem_bytes);
+    static cudaError_t fast_config(int score, int nj, int K, int* blocks_per_sm, size_t* smem_bytes) {
+        return nj == 8 ? fast_config_nj<8>(score, K, blocks_per_sm, smem_bytes) : fast_config_nj<16>(score, K, blocks_per_sm, smem_bytes);
     }
     static void eval_fast(const EvalArgs& a, int score, int nj, int grid, size_t smem, cudaStream_t s) {
         if (nj == 8) {

@@ -9,6 +9,11 @@ void hm_log_rcp(const double* t, int n, double* L, double* r) {
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) fast_log_rcp(t[i], cx, L[i], r[i]);
 }
+void hm_log_rcp_vec4(const double* t, int n, double* L, double* r) {
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
+    for (int i = 0; i + 4 <= n; i += 4) fast_log_rcp_vec<4>(t + i, cx, L + i, r + i);
+}
 void hm_exp(const double* x, int n, double* out) {
     double c[GLMMA_FM_NCONST]; fastmath_constants(c);
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);

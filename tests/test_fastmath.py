@@ -22,6 +22,7 @@ def hm():
     dp = C.POINTER(C.c_double)
     lib.hm_log_rcp.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_exp.argtypes = [dp, C.c_int, dp]
+    lib.hm_log_rcp_vec4.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
     return lib
 
@@ -47,6 +48,12 @@ def test_log_rcp(hm):
     eL = np.abs(L - Lref)
     assert np.all((eL <= 2 * ulp(Lref)) | (eL <= 2.3e-16)), (np.max(eL / ulp(Lref)), np.max(eL))
     assert np.max(np.abs(r - rref) / ulp(rref)) <= 2.0
+    # the stage-wise 4-vector form used by the register-variant kernel is the same arithmetic
+    n4 = len(t) // 4 * 4
+    L4 = np.empty(n4); r4 = np.empty(n4)
+    hm.hm_log_rcp_vec4(_p(t), n4, _p(L4), _p(r4))
+    assert np.all(np.abs(L4 - Lref[:n4]) <= np.maximum(2 * ulp(Lref[:n4]), 2.3e-16))
+    assert np.max(np.abs(r4 - rref[:n4]) / ulp(rref[:n4])) <= 2.0
     # out-of-range arguments take the library path
     bad = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310])
     L = np.empty_like(bad); r = np.empty_like(bad)
