@@ -75,18 +75,25 @@ struct FamBase {
     //           posterior mean maps to the score mean by an affine per-observation map
     //           (e.g. mu instead of y - mu); finish_se(mean(c), y1, y2) undoes it.
     //  sp_scale(): factor applied once per cluster to the accumulated point<., false>().sp
-    //  FAST2: the register variant evaluates a chunk of observations stage by stage:
-    //           t = fast_arg(emu), (L, r) = (log t, 1/t) for the whole chunk at once
-    //           (fast_log_rcp_vec), then fast_finish() -- the same arithmetic as
-    //           point<., false>, arranged so that the chunk's chains are interleaved.
+    //  FAST_KIND: how the register variant evaluates a chunk of observations (stage by stage, the
+    //           chunk's dependency chains interleaved):
+    //           0  generic: point<., false> per observation;
+    //           1  t = (prod of the separable factors) + fast_addend(); (L, r) = (log t, 1/t) for the
+    //              whole chunk (fast_log_rcp_vec); log f = -rec1 L (+ y eta at node level) with rec1
+    //              the staged second record field; the eta-score carrier is r; with HAS_PHI the
+    //              phi-score is sp_scale() * (L + rec1 r), whose second term needs no per-point work
+    //              (it is sum_j rec1_j * [posterior sum of r_j], formed once per cluster);
+    //           2  exp(eta) only: log f = -emu (+ y eta), carrier emu.
+    //           fast_score(mean(carrier), y1, rec1) maps the posterior mean of the carrier to the
+    //           posterior mean of the eta-score.
     static constexpr bool LIN_ETA = false;
     static constexpr bool Y_TABLE = false;       // obs_const() depends on an integer-valued y1 only
-    static constexpr bool FAST2 = false;
-    static constexpr bool FAST2_LOG = true;      // fast_finish reads L / r
-    __device__ static __forceinline__ double fast_arg(double emu, const FamPar&) { return emu; }
-    template <bool SCORE>
-    __device__ static __forceinline__ void fast_finish(double, double, double, double, double, const FamPar&,
-                                                       double& ld, double& se, double& sp) { ld = 0.0; se = 0.0; sp = 0.0; }
+    static constexpr int FAST_KIND = 0;
+    // log of [EMU_LO, EMU_HI] rounded inwards (range test on the linear predictor)
+    static constexpr double LOG_EMU_LO = -36.008;
+    static constexpr double LOG_EMU_HI = 667.7;
+    __device__ static __forceinline__ double fast_addend(const FamPar&) { return 0.0; }
+    __device__ static __forceinline__ double fast_score(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
     __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ double sp_scale(const FamPar&) { return 1.0; }
@@ -99,6 +106,8 @@ struct FamBase {
 struct FamBinomialLogit : FamBase {
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
+    static constexpr double LOG_EMU_LO = -29.93;
+    static constexpr double LOG_EMU_HI = 29.93;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar&, double& cll, double& cphi) {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
@@ -120,14 +129,11 @@ struct FamBinomialLogit : FamBase {
     }
     static constexpr bool LIN_ETA = true;
     __device__ static __forceinline__ double finish_se(double c, double y, double N, const FamPar&) { return fma(-N, c, y); }
-    static constexpr bool FAST2 = true;
-    __device__ static __forceinline__ double fast_arg(double emu, const FamPar&) { return 1.0 + emu; }
-    template <bool SCORE>
-    __device__ static __forceinline__ void fast_finish(double, double N, double emu, double L, double r, const FamPar&,
-                                                       double& ld, double& se, double& sp) {
-        ld = -N * L;
-        if (SCORE) se = emu * r;
-        sp = 0.0;
+    // t = 1 + exp(eta): log f = y eta - N log t, mu = 1 - 1/t
+    static constexpr int FAST_KIND = 1;
+    __device__ static __forceinline__ double fast_addend(const FamPar&) { return 1.0; }
+    __device__ static __forceinline__ double fast_score(double mean_r, double y, double N, const FamPar&) {
+        return fma(-N, 1.0 - mean_r, y);
     }
 };
 
@@ -183,15 +189,8 @@ struct FamPoisson : FamBase {
     }
     static constexpr bool LIN_ETA = true;
     __device__ static __forceinline__ double finish_se(double c, double y, double, const FamPar&) { return y - c; }
-    static constexpr bool FAST2 = true;
-    static constexpr bool FAST2_LOG = false;
-    template <bool SCORE>
-    __device__ static __forceinline__ void fast_finish(double, double, double emu, double, double, const FamPar&,
-                                                       double& ld, double& se, double& sp) {
-        ld = -emu;
-        if (SCORE) se = emu;
-        sp = 0.0;
-    }
+    static constexpr int FAST_KIND = 2;
+    __device__ static __forceinline__ double fast_score(double mean_mu, double y, double, const FamPar&) { return y - mean_mu; }
 };
 
 // FamPar layout shared by the negative-binomial type families:
@@ -238,16 +237,12 @@ struct FamNegBin : FamBase {
     __device__ static __forceinline__ void stage(double& y1, double& y2, const FamPar& fp) { y2 = y1 + fp.a[0]; }
     __device__ static __forceinline__ double finish_se(double c, double, double, const FamPar& fp) { return fp.a[0] * (c - 1.0); }
     __device__ static __forceinline__ double sp_scale(const FamPar& fp) { return -fp.a[0]; }
-    static constexpr bool FAST2 = true;
-    __device__ static __forceinline__ double fast_arg(double emu, const FamPar& fp) { return emu + fp.a[0]; }
-    template <bool SCORE>
-    __device__ static __forceinline__ void fast_finish(double, double yp_, double, double L, double r, const FamPar&,
-                                                       double& ld, double& se, double& sp) {
-        ld = -yp_ * L;
-        if (SCORE) {
-            se = yp_ * r;
-            sp = L + se;
-        }
+    // t = exp(eta) + phi, rec1 = y + phi: log f = y eta - rec1 log t; score_eta = phi (rec1 / t - 1);
+    // score_phi = -phi (log t + rec1 / t) + node-independent part
+    static constexpr int FAST_KIND = 1;
+    __device__ static __forceinline__ double fast_addend(const FamPar& fp) { return fp.a[0]; }
+    __device__ static __forceinline__ double fast_score(double mean_r, double, double yp_, const FamPar& fp) {
+        return fp.a[0] * fma(yp_, mean_r, -1.0);
     }
 };
 
@@ -327,6 +322,8 @@ struct FamZiBinomial : FamBase {
     static constexpr bool LIN_ETA = true;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
+    static constexpr double LOG_EMU_LO = -29.93;
+    static constexpr double LOG_EMU_HI = 29.93;
     static constexpr bool HAS_ZI = true;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar&, double& cll, double& cphi) {
@@ -471,6 +468,8 @@ __device__ __forceinline__ void beta_point(double ly, double l1y, double eta, do
 struct FamBeta : FamBase {
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
+    static constexpr double LOG_EMU_LO = -29.93;
+    static constexpr double LOG_EMU_HI = 29.93;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double ly, double l1y, const FamPar& fp, double& cll, double& cphi) {
@@ -489,6 +488,8 @@ struct FamBeta : FamBase {
 struct FamHurdleBeta : FamBase {
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
+    static constexpr double LOG_EMU_LO = -29.93;
+    static constexpr double LOG_EMU_HI = 29.93;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;

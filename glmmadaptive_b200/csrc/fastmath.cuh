@@ -54,7 +54,7 @@ static GLMMA_NOINLINE double fm_slow_rcp(double x) { return 1.0 / x; }
 #endif
 #define GLMMA_FM_LOG_DOUBLES (128 * 16)
 #define GLMMA_FM_EXP_DOUBLES (64 * 16)
-#define GLMMA_FM_NCONST 12
+#define GLMMA_FM_NCONST 13
 struct MathCtx {
     const double* logtab;   // device: replicated table + 2 * (lane & 7); host: 128 x (invc, logc)
     const double* exptab;   // device: replicated table + (lane & 15);    host: 64 x 2^(j/64)
@@ -73,6 +73,7 @@ struct MathCtx {
 #define FMC_E120 9
 #define FMC_E24 10
 #define FMC_E6 11
+#define FMC_LN2 12    // ln 2 rounded to double (stage-wise log: one fma for k ln2 + logc)
 GLMMA_HD MathCtx make_mathctx(const double* logtab, const double* exptab, const double* c) {
     MathCtx m;
     m.logtab = logtab; m.exptab = exptab;
@@ -112,6 +113,7 @@ inline void fastmath_constants(double* c) {
     c[0] = -1.0 / 6.0; c[1] = 0.2; c[2] = 1.0 / 3.0; c[3] = FM_LN2_HI; c[4] = FM_LN2_LO;
     c[5] = FM_64_LN2; c[6] = FM_MAGIC; c[7] = -FM_LN2_64_HI; c[8] = -FM_LN2_64_LO;
     c[9] = 1.0 / 120.0; c[10] = 1.0 / 24.0; c[11] = 1.0 / 6.0;
+    c[12] = 0x1.62e42fefa39efp-1;
 }
 
 // log t and 1/t for t > 0.
@@ -162,6 +164,10 @@ GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) 
 // per 2 cycles: four chains in flight per warp keep the FP64 pipe fed without relying on the
 // scheduler to find the parallelism across separately inlined calls).  Unchecked: the caller
 // guarantees 1e-300 <= t[i] <= 1e300.
+// k ln2 + logc is ONE fma with ln2 rounded to double: z lies in [0.6875, 1.375), so k != 0
+// implies |log t| >= 0.318 and the rounding error of ln2 (2.3e-17 |k|) stays below half an
+// ulp of the result; the hi/lo split of the scalar form buys nothing here (13 FP64
+// instructions per element instead of 14).
 template <int N>
 GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, double* rcp) {
     int ke[N];
@@ -183,7 +189,7 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
         invc[i] = cx.logtab[FM_LOG_STRIDE * idx]; logc[i] = cx.logtab[FM_LOG_STRIDE * idx + 1];
 #endif
     }
-    const double c6 = cx.c[FMC_L6], c5 = cx.c[FMC_L5], c3 = cx.c[FMC_L3], lh = cx.c[FMC_LN2HI], ll = cx.c[FMC_LN2LO];
+    const double c6 = cx.c[FMC_L6], c5 = cx.c[FMC_L5], c3 = cx.c[FMC_L3], ln2 = cx.c[FMC_LN2];
 #define FM_VEC for (int i = 0; i < N; ++i)
 #ifdef __CUDACC__
 #define FM_UNROLL _Pragma("unroll")
@@ -193,18 +199,39 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
     FM_UNROLL FM_VEC r[i] = fma(z[i], invc[i], -1.0);
     FM_UNROLL FM_VEC r2[i] = r[i] * r[i];
     FM_UNROLL FM_VEC q[i] = fma(r[i], c6, c5);
-    FM_UNROLL FM_VEC logc[i] = fma(kd[i], lh, logc[i]);          // w
+    FM_UNROLL FM_VEC logc[i] = fma(kd[i], ln2, logc[i]);         // w = k ln2 + logc
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.25);
     FM_UNROLL FM_VEC u[i] = fma(r2[i], r2[i], r2[i]);
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], c3);
-    FM_UNROLL FM_VEC kd[i] = fma(kd[i], ll, r[i]);               // s
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.5);
     FM_UNROLL FM_VEC u[i] = fma(u[i], r2[i], r2[i]);
     FM_UNROLL FM_VEC invc[i] = fma(-invc[i], r[i], invc[i]);     // y0
-    FM_UNROLL FM_VEC q[i] = fma(r2[i], q[i], kd[i]);
+    FM_UNROLL FM_VEC q[i] = fma(r2[i], q[i], r[i]);
     FM_UNROLL FM_VEC invc[i] = fma(invc[i], u[i], invc[i]);      // y
     FM_UNROLL FM_VEC L[i] = logc[i] + q[i];
     FM_UNROLL FM_VEC rcp[i] = fm_make(fm_hi(invc[i]) - ke[i], fm_lo(invc[i]));
+}
+
+// N independent fast_exp evaluations, stage by stage (see fast_log_rcp_vec).  Unchecked:
+// the caller guarantees |x[i]| <= 700.
+template <int N>
+GLMMA_HD void fast_exp_vec(const double* x, const MathCtx& cx, double* out) {
+    int n[N];
+    double kf[N], r[N], r2[N], p[N], tj[N];
+    const double c64 = cx.c[FMC_E64LN2], mg = cx.c[FMC_EMAGIC], ehi = cx.c[FMC_EHI], elo = cx.c[FMC_ELO];
+    const double e120 = cx.c[FMC_E120], e24 = cx.c[FMC_E24], e6 = cx.c[FMC_E6];
+    FM_UNROLL FM_VEC kf[i] = fma(x[i], c64, mg);
+    FM_UNROLL FM_VEC { n[i] = fm_lo(kf[i]); tj[i] = cx.exptab[FM_EXP_STRIDE * (n[i] & 63)]; }
+    FM_UNROLL FM_VEC kf[i] = kf[i] - mg;
+    FM_UNROLL FM_VEC r[i] = fma(kf[i], ehi, x[i]);
+    FM_UNROLL FM_VEC r[i] = fma(kf[i], elo, r[i]);
+    FM_UNROLL FM_VEC r2[i] = r[i] * r[i];
+    FM_UNROLL FM_VEC p[i] = fma(r[i], e120, e24);
+    FM_UNROLL FM_VEC p[i] = fma(r[i], p[i], e6);
+    FM_UNROLL FM_VEC p[i] = fma(r[i], p[i], 0.5);
+    FM_UNROLL FM_VEC p[i] = fma(r2[i], p[i], r[i]);
+    FM_UNROLL FM_VEC p[i] = fma(tj[i], p[i], tj[i]);
+    FM_UNROLL FM_VEC out[i] = fm_make(fm_hi(p[i]) + ((n[i] >> 6) << 20), fm_lo(p[i]));
 #undef FM_VEC
 #undef FM_UNROLL
 }

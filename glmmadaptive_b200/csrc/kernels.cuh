@@ -6,6 +6,7 @@
 // Ztb, eta_y, log_Lik, p_by ... as N x K matrices, R/Functions.R:128-134,
 // R/Fit_Funs.R:21-33,63-90).
 #pragma once
+#include <type_traits>
 #include "families.cuh"
 
 #define GLMMA_EVAL_THREADS 128
@@ -767,105 +768,112 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             if (lane == 0) d.defer[i] = 1;
             continue;
         }
+        // modes and sqrt(2) R^-1 (the factor of b_k = mode + sqrt(2) R^-1 z_k is folded in once)
         double m[Q], ri[NP];
 #pragma unroll
         for (int dd = 0; dd < Q; ++dd) m[dd] = sc[SC_M + dd];
 #pragma unroll
-        for (int t = 0; t < NP; ++t) ri[t] = sc[SC_RI + t];
-        if (lane < nic) {
-            if (!F::USES_Y2) rec[lane * W + 1] = 0.0;
-            F::stage(rec[lane * W], rec[lane * W + 1], A.fam);     // own record
-        }
-        __syncwarp();
-        // coefficients of the separable factors: (sqrt(2) c_je, base) per (observation, dimension)
+        for (int t = 0; t < NP; ++t) ri[t] = GLMMA_SQRT2 * sc[SC_RI + t];
+        // Lane j < n_i owns observation j: stages its record, forms the coefficients of its
+        // separable factors  exp(eta_jk) = prod_e exp(c_je x_{a_e(k)} + [e == 0] base_j)
+        // and tests the range of eta (and eta_zi) over the whole grid: every factor is monotone in
+        // its node, so the extremes are base -+ sum_e |c_e| x_max.  Outside the fast range (a link
+        // clamp could be active, or a factor / fast_log_rcp argument could leave its range) the
+        // cluster is left to eval_kernel.
         double2* coef = reinterpret_cast<double2*>(acc_eta);
         constexpr int NTc = FL::NT > 0 ? FL::NT : 1;
-        for (int p = lane; p < nic * (Q + FL::NT); p += 32) {
-            const bool isF = p < nic * Q;
-            const int pp = isF ? p : p - nic * Q;
-            const int j = isF ? pp / Q : pp / NTc;
-            const int e = isF ? pp - j * Q : pp - j * NTc;
-            const double* r = rec + j * W;
-            double c = 0.0, base;
-            if (isF) {
-                base = r[2];
-#pragma unroll
-                for (int dd = 0; dd < QY; ++dd) {
-                    base = fma(r[L::OFF_Z + dd], m[dd], base);
-#pragma unroll
-                    for (int ee = dd; ee < Q; ++ee)
-                        if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
-                }
-            } else {
-                base = r[F::HAS_ZI ? L::OFF_XG : 2];
-#pragma unroll
-                for (int dd = 0; dd < QZ; ++dd) {
-                    base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
-#pragma unroll
-                    for (int ee = dd; ee < QZ; ++ee)
-                        if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
-                }
-            }
-            coef[p] = make_double2(GLMMA_SQRT2 * c, e == 0 ? base : 0.0);
-        }
-        __syncwarp();
-        // tables: 16 lanes per (observation, dimension) pair, lane & 15 = node index
-        {
-            const int na = lane & 15, sub = lane >> 4;
-            const bool live_a = na < nagq;
-            const double xa = live_a ? gx[na] : 0.0;
-            if (F::NEED_EMU) {
-                // independent iterations: unrolled so that four exp chains are in flight
-#pragma unroll 4
-                for (int p0 = 0; p0 < nic * Q; p0 += 2) {
-                    const int p = p0 + sub;
-                    if (p < nic * Q && live_a) {
-                        const double2 cb = coef[p];
-                        tabF[p * NG + na] = fast_exp(fma(cb.x, xa, cb.y), cx);
-                    }
-                }
-            }
-            if (F::HAS_ZI) {
-#pragma unroll 4
-                for (int p0 = 0; p0 < nic * NTc; p0 += 2) {
-                    const int p = p0 + sub;
-                    if (p < nic * NTc && (QZ > 0 ? live_a : na == 0)) {
-                        const double2 cb = coef[nic * Q + p];
-                        tabL[p * NG + na] = fast_exp(fma(cb.x, xa, cb.y), cx);
-                    }
-                }
-            }
-        }
-        __syncwarp();
         bool bad = false;
         if (lane < nic) {
-            // every factor is exp(c x_a + base), monotone in the node x_a: extremes at the end points
+            double* r = rec + lane * W;
+            if (!F::USES_Y2) r[1] = 0.0;
+            F::stage(r[0], r[1], A.fam);
+            const double xmax = gx[0];
             if (F::NEED_EMU) {
-                double lo = 1.0, hi = 1.0;
+                double base = r[2], amp = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) base = fma(r[L::OFF_Z + dd], m[dd], base);
 #pragma unroll
                 for (int e = 0; e < Q; ++e) {
-                    const double v0 = tabF[(lane * Q + e) * NG], v1 = tabF[(lane * Q + e) * NG + nagq - 1];
-                    const double mn = fmin(v0, v1), mx = fmax(v0, v1);
-                    if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
-                    lo *= mn; hi *= mx;
+                    double c = 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd)
+                        if (dd <= e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, e)], c);
+                    coef[lane * Q + e] = make_double2(c, e == 0 ? base : 0.0);
+                    const double ae = fabs(c) * xmax;
+                    if (!(ae + (e == 0 ? fabs(base) : 0.0) <= 230.0)) bad = true;
+                    amp += ae;
                 }
-                if (!(lo >= F::EMU_LO && hi <= F::EMU_HI)) bad = true;
+                if (!(base - amp >= F::LOG_EMU_LO && base + amp <= F::LOG_EMU_HI)) bad = true;
             }
             if (F::HAS_ZI) {
-                double lo = 1.0, hi = 1.0;
+                double base = r[L::OFF_XG], amp = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < QZ; ++dd) base = fma(r[L::OFF_Z + QY + dd], m[QY + dd], base);
 #pragma unroll
                 for (int e = 0; e < NTc; ++e) {
-                    const double v0 = tabL[(lane * NTc + e) * NG], v1 = tabL[(lane * NTc + e) * NG + (QZ > 0 ? nagq - 1 : 0)];
-                    const double mn = fmin(v0, v1), mx = fmax(v0, v1);
-                    if (!(mn >= 1e-100 && mx <= 1e100)) bad = true;
-                    lo *= mn; hi *= mx;
+                    double c = 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QZ; ++dd)
+                        if (dd <= e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + e)], c);
+                    coef[NJ * Q + lane * NTc + e] = make_double2(c, e == 0 ? base : 0.0);
+                    const double ae = fabs(c) * xmax;
+                    if (!(ae + (e == 0 ? fabs(base) : 0.0) <= 230.0)) bad = true;
+                    amp += ae;
                 }
-                if (!(lo >= 1e-290 && hi <= 1e290)) bad = true;
+                if (!(base - amp >= -667.0 && base + amp <= 667.0)) bad = true;
             }
         }
         bad = __any_sync(0xffffffffu, bad);
+        __syncwarp();                              // coefficient stores -> table-building reads
         if (lane == 0) d.defer[i] = bad ? 1 : 0;
         if (bad) continue;
+        // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
+        // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
+        // test above
+        {
+            const unsigned inv_nagq = (65536u + (unsigned)nagq - 1u) / (unsigned)nagq;
+            if (F::NEED_EMU) {
+                const int items = nic * Q * nagq;
+                for (int t0 = lane; t0 < items; t0 += 96) {
+                    double x3[3], o3[3];
+                    int off[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int t = min(t0 + 32 * u, items - 1);
+                        const int p = (int)(((unsigned)t * inv_nagq) >> 16);
+                        const int na = t - p * nagq;
+                        const double2 cb = coef[p];
+                        x3[u] = fma(cb.x, gx[na], cb.y);
+                        off[u] = p * NG + na;
+                    }
+                    fast_exp_vec<3>(x3, cx, o3);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) tabF[off[u]] = o3[u];
+                }
+            }
+            if (F::HAS_ZI) {
+                const int nz = QZ > 0 ? nagq : 1;
+                const unsigned inv_nz = QZ > 0 ? inv_nagq : 65536u;
+                const int items = nic * NTc * nz;
+                for (int t0 = lane; t0 < items; t0 += 96) {
+                    double x3[3], o3[3];
+                    int off[3];
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int t = min(t0 + 32 * u, items - 1);
+                        const int p = (int)(((unsigned)t * inv_nz) >> 16);
+                        const int na = t - p * nz;
+                        const double2 cb = coef[NJ * Q + p];
+                        x3[u] = fma(cb.x, QZ > 0 ? gx[na] : 0.0, cb.y);
+                        off[u] = p * NG + na;
+                    }
+                    fast_exp_vec<3>(x3, cx, o3);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) tabL[off[u]] = o3[u];
+                }
+            }
+        }
+        __syncwarp();
 
         const double* cs = sc + SC_CS;
         const double syxb = F::LIN_ETA ? cs[2] : 0.0;
@@ -893,10 +901,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 double b[Q];
 #pragma unroll
                 for (int dd = 0; dd < Q; ++dd) {
-                    double s = 0.0;
+                    double s = m[dd];
 #pragma unroll
                     for (int e = dd; e < Q; ++e) s = fma(ri[Tri<Q>::rm(dd, e)], nt[e], s);
-                    b[dd] = fma(GLMMA_SQRT2, s, m[dd]);
+                    b[dd] = s;
                 }
                 double quad = 0.0;
 #pragma unroll
@@ -947,37 +955,76 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             if (F::HAS_PHI) vphi += sp;                                                                \
         }                                                                                              \
     }
+                if (F::FAST_KIND != 0) {
+                    // stage-wise chunks of four observations (interleaved chains): separable
+                    // product, (log t, 1/t) for the chunk, accumulation.  Two alternating
+                    // accumulators keep the sum over observations off the critical path.
+                    double a1 = 0.0;
+                    auto chunk = [&](const int c4, auto full_tag) {
+                        constexpr bool FULL = decltype(full_tag)::value;
+                        double t4[4], L4[4], r4[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * c4 + jj;
+                            double pr = pf[0][j * FL::TF];
+#pragma unroll
+                            for (int e = 1; e < Q - 1; ++e) pr *= pf[e][j * FL::TF];
+                            if (F::FAST_KIND == 1)
+                                t4[jj] = Q > 1 ? fma(pr, pf[Q - 1][j * FL::TF], F::fast_addend(A.fam)) : pr + F::fast_addend(A.fam);
+                            else
+                                t4[jj] = Q > 1 ? pr * pf[Q - 1][j * FL::TF] : pr;
+                            // rows past the cluster's end hold stale table entries: keep the argument of
+                            // the unchecked log in range (their results are discarded below)
+                            if (!FULL && j >= nic) t4[jj] = 1.0;
+                        }
+                        if (F::FAST_KIND == 1) {
+                            fast_log_rcp_vec<4>(t4, cx, L4, r4);
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * c4 + jj;
+                                const bool on = FULL || j < nic;
+                                const double wj = on ? rec[j * W + 1] : 0.0;
+                                if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
+                                if (SCORE) {
+                                    se_[j] = on ? r4[jj] : 0.0;
+                                    if (F::HAS_PHI) vphi += on ? L4[jj] : 0.0;
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const int j = 4 * c4 + jj;
+                                const double ej = (FULL || j < nic) ? t4[jj] : 0.0;
+                                if (jj & 1) a1 -= ej; else a -= ej;
+                                if (SCORE) se_[j] = ej;
+                            }
+                        }
+                    };
+                    if (nic == NJ) {
+                        // complete cluster: one branch-free block, so the chunks' chains interleave too
+#pragma unroll
+                        for (int c4 = 0; c4 < NJ / 4; ++c4) chunk(c4, std::true_type{});
+                    } else {
+#pragma unroll
+                        for (int c4 = 0; c4 < NJ / 4; ++c4) {
+                            if (nic >= 4 * c4 + 4) {
+                                chunk(c4, std::true_type{});
+                            } else if (nic > 4 * c4) {
+                                chunk(c4, std::false_type{});
+                            } else {
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) se_[4 * c4 + jj] = 0.0;
+                            }
+                        }
+                    }
+                    a += a1;
+                } else {
 #pragma unroll
                 for (int c4 = 0; c4 < NJ / 4; ++c4) {
                     if (nic >= 4 * c4 + 4) {
                         // full chunk: four independent point evaluations, no branches
-                        if (F::FAST2) {
-                            // stage-wise form (interleaved chains): exp(eta) products, log/rcp, finish
-                            double emu4[4], t4[4], L4[4], r4[4], ld4[4], sp4[4];
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = 4 * c4 + jj;
-                                emu4[jj] = pf[0][j * FL::TF];
-#pragma unroll
-                                for (int e = 1; e < Q; ++e) emu4[jj] *= pf[e][j * FL::TF];
-                                t4[jj] = F::fast_arg(emu4[jj], A.fam);
-                                L4[jj] = 0.0; r4[jj] = 0.0;
-                            }
-                            if (F::FAST2_LOG) fast_log_rcp_vec<4>(t4, cx, L4, r4);
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = 4 * c4 + jj;
-                                const double* rj = rec + j * W;
-                                double se;
-                                F::template fast_finish<SCORE>(rj[0], rj[1], emu4[jj], L4[jj], r4[jj], A.fam, ld4[jj], se, sp4[jj]);
-                                if (SCORE) se_[j] = se;
-                            }
-                            a += (ld4[0] + ld4[1]) + (ld4[2] + ld4[3]);
-                            if (SCORE && F::HAS_PHI) vphi += (sp4[0] + sp4[1]) + (sp4[2] + sp4[3]);
-                        } else {
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) GLMMA_FAST_OBS(4 * c4 + jj)
-                        }
+                        for (int jj = 0; jj < 4; ++jj) GLMMA_FAST_OBS(4 * c4 + jj)
                     } else {
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
@@ -986,6 +1033,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                             if (4 * c4 + jj < nic) GLMMA_FAST_OBS(4 * c4 + jj)
                         }
                     }
+                }
                 }
 #undef GLMMA_FAST_OBS
                 if (valid) amax = fmax(amax, a);
@@ -1029,6 +1077,12 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
         if (SCORE) {
             const double inv = ok ? w * isum : 0.0;
             if (F::HAS_PHI) {
+                if (F::FAST_KIND == 1) {
+                    // second term of the phi-score, sum_k e_k sum_j rec1_j r_jk, from the carrier sums
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        if (j < nic) gphi = fma(rec[j * W + 1], acc_e[j], gphi);
+                }
                 double g = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
                 if (lane == 0 && ok) g = fma(w, cs[1], g);
                 totl[lane] = g;
@@ -1076,7 +1130,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
                 if (lane < nic) {
-                    const double sc = F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                    const double sc = F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
+                                                        : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
                     d.zbar[r0c + lane] = ok ? w * sc : 0.0;
                     if (F::HAS_ZI) d.zbar_zi[r0c + lane] = inv * s2;
                 }

@@ -19,6 +19,11 @@ void hm_exp(const double* x, int n, double* out) {
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) out[i] = fast_exp(x[i], cx);
 }
+void hm_exp_vec3(const double* x, int n, double* out) {
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
+    for (int i = 0; i + 3 <= n; i += 3) fast_exp_vec<3>(x + i, cx, out + i);
+}
 void hm_l1p_sigmoid(const double* ex, int n, double* l1p, double* sig) {
     double c[GLMMA_FM_NCONST]; fastmath_constants(c);
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);

@@ -22,6 +22,7 @@ def hm():
     dp = C.POINTER(C.c_double)
     lib.hm_log_rcp.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_exp.argtypes = [dp, C.c_int, dp]
+    lib.hm_exp_vec3.argtypes = [dp, C.c_int, dp]
     lib.hm_log_rcp_vec4.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
     return lib
@@ -72,6 +73,11 @@ def test_exp(hm):
     hm.hm_exp(_p(x), len(x), _p(out))
     ref = np.array([float(mpexp(mpf(float(v)))) for v in x])
     assert np.max(np.abs(out - ref) / ulp(ref)) <= 2.0
+    # the stage-wise 3-vector form (table building of the register-variant kernel): same arithmetic
+    n3 = len(x) // 3 * 3
+    o3 = np.empty(n3)
+    hm.hm_exp_vec3(_p(x), n3, _p(o3))
+    np.testing.assert_array_equal(o3, out[:n3])
     far = np.array([-800.0, 720.0, np.nan, -np.inf, np.inf, -745.0])
     out = np.empty_like(far)
     hm.hm_exp(_p(far), len(far), _p(out))
