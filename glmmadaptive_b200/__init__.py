@@ -1,8 +1,9 @@
 """glmmadaptive_b200 -- B200-native engine for GLMMadaptive's adaptive
 Gauss-Hermite marginal log-likelihood / score hot path.
 
-Host-side mirror of the reference closures (GHfun, logLik_mixed, score_mixed)
-over the C ABI in include/glmma.h.  See DESIGN.md.
+Host-side mirror of the reference closures (GHfun, logLik_mixed, score_mixed) and of
+its fitting loop (mixed_model, mixed_fit) over the C ABI in include/glmma.h.  See DESIGN.md.
 """
 from .engine import Engine, GH, GHfun, logLik_mixed, score_mixed, chol_transf, family_spec  # noqa: F401
+from .fit import mixed_model, mixed_fit, starting_values  # noqa: F401
 from .sharded import ShardedEngine, shard_bounds  # noqa: F401

@@ -63,6 +63,8 @@ SIGNATURES = {
     "glmma_eval_device": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_void_p]),
     "glmma_eval_contrib": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p,
                                      c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "glmma_em_estep": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "glmma_em_score": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p]),
     "glmma_time_eval": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "glmma_measure_fp64_peak": (C.c_int, [C.c_int, c_double_p]),

@@ -38,6 +38,8 @@ struct glmma_handle {
     double* d_score_partials;  // score_grid * (p + p_zi)
     double* d_result;          // result vector
     unsigned long long* d_stats;
+    double* d_pby;             // n x K posterior node weights of the last E-step (lazily allocated)
+    bool have_pby;
     bool have_modes;
     int64_t launches;
     std::vector<void*> allocs;
@@ -362,6 +364,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->family = data->family; h->link = data->link; h->device = device; h->nagq = data->nAGQ;
     h->q = q; h->K = (int)Kd; h->y_cols = data->y_cols; h->ops = ops; h->stream = nullptr;
     h->have_modes = false; h->launches = 0; h->sticky = 0; h->d_ytab = nullptr;
+    h->d_pby = nullptr; h->have_pby = false;
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
     DevData& d = h->d;
@@ -594,6 +597,7 @@ int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, c
     CU(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_modes = true;
+    h->have_pby = false;
     if (stats) {
         stats->n_not_converged = (int64_t)st[0];
         stats->n_chol_failed = (int64_t)st[1];
@@ -646,7 +650,7 @@ int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* cho
 // enqueue one evaluation on the stream; the result vector ends up at d_out
 static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                         const double* gammas, int want_score, double* d_out, const DevData* dd_override,
-                        cudaEvent_t k0, cudaEvent_t k1) {
+                        cudaEvent_t k0, cudaEvent_t k1, int em_mode = 0) {
     if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
     if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
     const int s = want_score ? 1 : 0;
@@ -654,6 +658,8 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     int rc = run_prep(h, betas, phis, gammas, &fp);
     if (rc) return rc;
     EvalArgs ea;
+    std::memset(&ea, 0, sizeof(ea));
+    ea.em_mode = em_mode; ea.pby = h->d_pby;
     ea.d = dd_override ? *dd_override : h->d;
     ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt;
     rc = fill_prior(h, D, false, &ea.prior);
@@ -661,7 +667,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (k0) CU(h, cudaEventRecord(k0, h->stream));
     int n_blocks = 0;
     ea.only_deferred = 0;
-    if (h->nj) {
+    if (h->nj && em_mode == 0) {
         // small clusters: register variant; it flags what it leaves to the generic kernel
         h->ops->eval_fast(ea, s, h->nj, h->fast_grid[s], h->fast_smem[s], h->stream);
         h->launches++;
@@ -723,6 +729,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
     rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, &dd, nullptr, nullptr);
     if (rc == GLMMA_OK && d_sphi) {
         EvalArgs ea;
+        std::memset(&ea, 0, sizeof(ea));
         ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
         fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error);
         fill_prior(h, D, false, &ea.prior);
@@ -741,6 +748,41 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
     }
     cudaFree(d_ll); cudaFree(d_S); cudaFree(d_sphi);
     return rc;
+}
+
+// ---- EM phase of mixed_fit (R/mixed_fit.R:119-229) ---------------------------------------
+
+int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                   const double* gammas, double* result) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
+    if (!h->d_pby) {
+        rc = dev_alloc(h, &h->d_pby, (size_t)h->d.n * (size_t)h->K);
+        if (rc) return rc;
+    }
+    rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, nullptr, nullptr, nullptr, 1);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * glmma_result_len(h), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->have_pby = true;
+    return GLMMA_OK;
+}
+
+int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
+                   double* result) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
+    if (!h->have_pby) return fail(h, GLMMA_ERR_STATE, "no posterior weights yet: call glmma_em_estep first");
+    // the prior only enters the node weights, which are frozen: any positive definite D will do
+    double eye[GLMMA_QMAX * GLMMA_QMAX] = {0};
+    for (int i = 0; i < h->q; ++i) eye[i * h->q + i] = 1.0;
+    rc = enqueue_eval(h, betas, eye, phis, gammas, 1, h->d_result, nullptr, nullptr, nullptr, 2);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * glmma_result_len(h), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return GLMMA_OK;
 }
 
 int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,

@@ -22,6 +22,14 @@ struct EvalArgs {
     double* partials;        // gridDim.x * GLMMA_NACC block partial sums
     int jt;                  // observation tile held in shared memory per warp (<= GLMMA_JT_CAP)
     int only_deferred;       // eval_kernel: process only clusters flagged in d.defer
+    // EM phase of mixed_fit (R/mixed_fit.R:119-229), eval_kernel only:
+    //   em_mode 1 (E-step): also store the un-normalised posterior node weights
+    //             e_ik = exp(a_ik - shift_i) in pby (n x K; all zero for a dropped cluster);
+    //   em_mode 2 (M-step): take e_ik from pby instead of from the current theta, i.e. evaluate
+    //             the scores with p_by held fixed (score_betas / score_phis / score_gammas,
+    //             R/Fit_Funs.R:295-427); the log-likelihood slot of the result is 0.
+    int em_mode;
+    double* pby;
 };
 
 struct PrepArgs {
@@ -419,7 +427,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                     shift = warp_max(valid ? a : -INFINITY);
                     if (!(fabs(shift) < INFINITY)) shift = 0.0;
                 }
-                const double e = valid ? fast_exp(a - shift, cx) : 0.0;
+                double e = valid ? fast_exp(a - shift, cx) : 0.0;
+                if (A.em_mode == 2) e = valid ? A.pby[i * K + k] : 0.0;
+                else if (A.em_mode == 1 && valid) A.pby[i * K + k] = e;
                 sum_e += e;
                 if (SCORE) {
                     int t = 0;
@@ -469,13 +479,16 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
             sum_e = warp_sum(sum_e);
             // the shift came from the central round; if that was not enough to keep the sum
             // in range, repeat once with the true maximum over all nodes
-            if (sum_e > 0.0 && sum_e < INFINITY) break;
+            if ((sum_e > 0.0 && sum_e < INFINITY) || A.em_mode == 2) break;
             const double mx = warp_max(amax);
             if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
             shift = mx;
         }
-        const double ll = shift + log(sum_e) + d.logdet[i] + c_ll;
-        const bool ok = fabs(ll) < INFINITY;       // false for NaN and +-Inf
+        const double ll = A.em_mode == 2 ? 0.0 : shift + log(sum_e) + d.logdet[i] + c_ll;
+        // false for NaN and +-Inf; M-step: the E-step zeroed the weights of the clusters it dropped
+        const bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
+        if (A.em_mode == 1 && !ok)
+            for (int k = lane; k < K; k += 32) A.pby[i * K + k] = 0.0;
         if (lane == 0) {
             if (ok) { tot[0] += w * ll; tot[1] += w; } else tot[2] += 1.0;
             if (d.ll_i) d.ll_i[i] = w * ll;

@@ -222,6 +222,23 @@ class Engine:
         self._check(self.lib.glmma_eval_contrib(self._h, *ptrs, _dp(ll_i), _dp(zbar), _dp(zbar_zi), _dp(sphi), _dp(S_i)))
         return dict(ll_i=ll_i, zbar=zbar, zbar_zi=zbar_zi, sphi_obs=sphi, S_i=S_i)
 
+    # -- EM phase (R/mixed_fit.R:119-229) ---------------------------------------
+    def em_estep(self, betas, D, phis=None, gammas=None):
+        """E-step on the current grid: glmma_eval's result (loglik = lgLik[it], S = sum_i w_i
+        E[b b' | y_i]) and the posterior node weights p_by kept on the device."""
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        res = np.zeros(self.result_len)
+        self._check(self.lib.glmma_em_estep(self._h, *ptrs, _dp(res)))
+        return self.unpack(res, True)
+
+    def em_score(self, betas, phis=None, gammas=None):
+        """Scores at (betas, phis, gammas) with p_by frozen at the last E-step
+        (score_betas / score_phis / score_gammas, R/Fit_Funs.R:295-427, up to sign)."""
+        keep, ptrs = self._theta_ptrs(betas, np.eye(self.q), phis, gammas)
+        res = np.zeros(self.result_len)
+        self._check(self.lib.glmma_em_score(self._h, ptrs[0], ptrs[2], ptrs[3], _dp(res)))
+        return self.unpack(res, True)
+
     def time_eval(self, betas, D, phis=None, gammas=None, want_score=True, iters=10):
         keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
         a, b = C.c_float(), C.c_float()

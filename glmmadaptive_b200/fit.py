@@ -1,0 +1,409 @@
+"""Host-side mirror of the reference's fitting entry points over the CUDA engine:
+
+  mixed_model()   R/mixed_model.R:1-340   (design matrices in, fitted object out; the formula /
+                                           model.frame layer of the reference stays with the caller)
+  mixed_fit()     R/mixed_fit.R:1-349     (EM phase, quasi-Newton phase, final Hessian)
+
+Everything of size N or n runs on the GPU through libglmma.so (GHfun -> glmma_find_modes, the
+E-step -> glmma_em_estep, the M-step scores with p_by held fixed -> glmma_em_score, optim's
+fn/gr -> glmma_eval); this module holds the loop logic mixed_fit() keeps in R: the tiny
+dense algebra on p-, q- and nparams-sized objects (numeric Hessians of the M-step scores,
+nearPD, the Newton updates, optim's BFGS `vmmin`, the convergence rules).  No CPU fallback:
+without the CUDA library nothing here can run.
+
+Deviations from the reference, all documented in DESIGN.md:
+  * find_modes uses the engine's damped Newton instead of optim(BFGS);
+  * the phis M-step uses cluster weights (the reference's score_phis() drops them when the family
+    has a score_phis_fun, R/Fit_Funs.R:392-394); identical without weights.
+"""
+import time
+
+import numpy as np
+
+from .engine import Engine, GHfun, chol_transf, logLik_mixed, score_mixed, split_thetas
+
+_EPS = np.finfo(float).eps
+
+# control defaults of mixed_model(), R/mixed_model.R:150-156
+CONTROL = dict(iter_EM=30, iter_qN_outer=15, iter_qN=10, iter_qN_incr=10, optimizer="optim",
+               optim_method="BFGS", parscale_betas=0.1, parscale_D=0.01, parscale_phis=0.01,
+               parscale_gammas=0.01, tol1=1e-4, tol2=1e-5, tol3=1e-8, numeric_deriv="fd", nAGQ=None,
+               update_GH_every=10, max_coef_value=12.0, max_phis_value=float(np.exp(10.0)), verbose=False)
+
+
+# ------------------------------------------------------------------------------------------
+# starting values: stats::glm.fit as mixed_model() calls it (R/mixed_model.R:162-194)
+# ------------------------------------------------------------------------------------------
+class _GlmFamily:
+    """initialize / link / variance / deviance pieces of the four stats families used for starts."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def start(self, y, w):
+        if self.name == "binomial":
+            return (w * y + 0.5) / (w + 1.0)
+        return y + 0.1 if self.name == "poisson" else y
+
+    def link(self, mu):
+        return {"binomial": lambda m: np.log(m / (1 - m)), "poisson": np.log,
+                "Gamma": lambda m: 1 / m, "gaussian": lambda m: m}[self.name](mu)
+
+    def inv(self, eta):
+        if self.name == "binomial":
+            return 1 / (1 + np.exp(-np.clip(eta, -30.0, 30.0)))
+        if self.name == "poisson":
+            return np.maximum(np.exp(eta), _EPS)
+        return 1 / eta if self.name == "Gamma" else eta
+
+    def dmu(self, eta):
+        if self.name == "binomial":
+            e = np.exp(-np.abs(eta))
+            return np.maximum(e / (1 + e) ** 2, _EPS)
+        if self.name == "poisson":
+            return np.maximum(np.exp(eta), _EPS)
+        return -1 / eta ** 2 if self.name == "Gamma" else np.ones_like(eta)
+
+    def var(self, mu):
+        return {"binomial": mu * (1 - mu), "poisson": mu, "Gamma": mu * mu, "gaussian": np.ones_like(mu)}[self.name]
+
+    def deviance(self, y, mu, w):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            if self.name == "binomial":
+                r = np.where(y > 0, y * np.log(y / mu), 0.0) + np.where(y < 1, (1 - y) * np.log((1 - y) / (1 - mu)), 0.0)
+            elif self.name == "poisson":
+                r = np.where(y > 0, y * np.log(y / mu), 0.0) - (y - mu)
+            elif self.name == "Gamma":
+                r = -(np.log(np.where(y == 0, 1.0, y / mu)) - (y - mu) / mu)
+            else:
+                return float(np.sum(w * (y - mu) ** 2))
+        return float(2 * np.sum(w * r))
+
+
+def glm_fit(X, y, family, offset=None, epsilon=1e-8, maxit=25):
+    """Iteratively reweighted least squares with glm.fit's starts and stopping rule."""
+    X = np.asarray(X, float)
+    y = np.asarray(y, float)
+    fam = _GlmFamily(family)
+    w = np.ones(len(X))
+    if family == "binomial" and y.ndim == 2:
+        w = y.sum(axis=1)
+        y = np.divide(y[:, 0], w, out=np.zeros(len(X)), where=w > 0)
+    off = 0.0 if offset is None else np.asarray(offset, float)
+    eta = fam.link(fam.start(y, w))
+    mu = fam.inv(eta)
+    dev_old = fam.deviance(y, mu, w)
+    beta = np.zeros(X.shape[1])
+    for _ in range(maxit):
+        g = fam.dmu(eta)
+        sw = np.sqrt(w * g * g / fam.var(mu))
+        beta = np.linalg.lstsq(X * sw[:, None], ((eta - off) + (y - mu) / g) * sw, rcond=None)[0]
+        eta = X @ beta + off
+        mu = fam.inv(eta)
+        dev = fam.deviance(y, mu, w)
+        if abs(dev - dev_old) / (abs(dev) + 0.1) < epsilon:
+            break
+        dev_old = dev
+    return beta
+
+
+def starting_values(y, X, X_zi, family, nRE, n_phis, diag_D=False, offset=None, offset_zi=None):
+    """R/mixed_model.R:157-194, 251-263: glm coefficients * sqrt(1.346) for the families the
+    reference calls `known`, zeros otherwise; identity D; phis = 0; logistic fit of y == 0 for gammas."""
+    fam = family
+    starts = {"binomial": "binomial", "poisson": "poisson", "negative binomial": "poisson", "Gamma": "Gamma"}
+    if fam in starts:
+        betas = glm_fit(X, y, starts[fam], offset) * np.sqrt(1.346)
+    else:
+        betas = np.zeros(np.shape(X)[1])
+    out = dict(betas=betas, D=np.ones(nRE) if diag_D else np.eye(nRE))
+    if X_zi is not None:
+        y1 = np.asarray(y, float)
+        y1 = y1[:, 0] if y1.ndim == 2 else y1
+        out["gammas"] = glm_fit(X_zi, (y1 == 0).astype(float), "binomial", offset_zi)
+        if fam in ("zero-inflated poisson", "zero-inflated negative binomial", "hurdle poisson",
+                   "hurdle negative binomial"):
+            out["betas"] = glm_fit(X, y, "poisson")
+    if n_phis:
+        out["phis"] = np.zeros(n_phis)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# small dense helpers (R/Functions.R:219-262, 343-382; optim's vmmin)
+# ------------------------------------------------------------------------------------------
+def fd_vec(x, f, eps=_EPS ** 0.25):
+    x = np.asarray(x, float)
+    f0 = np.asarray(f(x), float)
+    J = np.empty((len(x), len(x)))
+    for i in range(len(x)):
+        xi = x.copy()
+        xi[i] += eps * max(abs(x[i]), 1.0)
+        J[:, i] = (np.asarray(f(xi), float) - f0) / (xi[i] - x[i])
+    return (J + J.T) / 2
+
+
+def cd_vec(x, f, eps=1e-3):
+    x = np.asarray(x, float)
+    J = np.empty((len(x), len(x)))
+    for i in range(len(x)):
+        hi, lo = x.copy(), x.copy()
+        h = eps * max(abs(x[i]), 1.0)
+        hi[i] += h
+        lo[i] -= h
+        J[:, i] = (np.asarray(f(hi), float) - np.asarray(f(lo), float)) / (hi[i] - lo[i])
+    return (J + J.T) / 2
+
+
+def _eig_desc(A):
+    w, V = np.linalg.eigh(A)
+    return w[::-1], V[:, ::-1]
+
+
+def nearPD(M, eig_tol=1e-6, conv_tol=1e-7, posd_tol=1e-8, maxits=100):
+    """Higham's alternating projections as the reference codes it (R/Functions.R:343-382)."""
+    M = np.asarray(M, float)
+    k = len(M)
+    norm = lambda A: np.abs(A).sum(axis=1).max()
+    X, U = M.copy(), np.zeros_like(M)
+    for _ in range(maxits):
+        Y = X
+        T = Y - U
+        w, V = _eig_desc(Y)
+        keep = w > eig_tol * w[0]
+        X = (V[:, keep] * w[keep]) @ V[:, keep].T
+        U = X - T
+        X = (X + X.T) / 2
+        if norm(Y - X) / norm(Y) <= conv_tol:
+            break
+    X = (X + X.T) / 2
+    w, V = _eig_desc(X)
+    floor = posd_tol * abs(w[0])
+    if w[k - 1] < floor:
+        d0 = np.diag(X).copy()
+        X = (V * np.where(w < floor, floor, w)) @ V.T
+        s = np.sqrt(np.maximum(floor, d0) / np.diag(X))
+        X = s[:, None] * X * s[None, :]
+    return (X + X.T) / 2
+
+
+def vmmin(par, fn, gr, maxit, reltol, parscale):
+    """optim(method = "BFGS"): R's variable-metric minimiser (src/appl/optim.c `vmmin`, restated from
+    its published algorithm) on the parscale-d parameters.
+    Returns (par, value, convergence, n_fn, n_gr)."""
+    ps = np.asarray(parscale, float)
+    F = lambda u: float(fn(u * ps))
+    G = lambda u: np.asarray(gr(u * ps), float) * ps
+    u = np.asarray(par, float) / ps
+    k = len(u)
+    if maxit <= 0:
+        return u * ps, F(u), 0, 0, 0
+    fmin = f = F(u)
+    if not np.isfinite(f):
+        raise FloatingPointError("initial value in 'vmmin' is not finite")
+    g = G(u)
+    nf = ng = 1
+    it, last_reset = 1, 1
+    H = np.eye(k)
+    while True:
+        if last_reset == ng:
+            H = np.eye(k)
+        u0, g0 = u.copy(), g.copy()
+        step_dir = -H @ g
+        slope = float(step_dir @ g)
+        if slope < 0.0:
+            s, ok = 1.0, False
+            while True:
+                u = u0 + s * step_dir
+                unchanged = int(np.sum((10.0 + u0) == (10.0 + u)))
+                if unchanged < k:
+                    f = F(u)
+                    nf += 1
+                    ok = np.isfinite(f) and f <= fmin + slope * s * 1e-4
+                    if not ok:
+                        s *= 0.2
+                if unchanged == k or ok:
+                    break
+            if not (abs(f - fmin) > reltol * (abs(fmin) + reltol)):
+                unchanged = k
+                fmin = f
+            if unchanged < k:
+                fmin = f
+                g = G(u)
+                ng += 1
+                it += 1
+                dx = s * step_dir
+                dg = g - g0
+                curv = float(dx @ dg)
+                if curv > 0:
+                    Hdg = H @ dg
+                    H = H + ((1.0 + float(Hdg @ dg) / curv) * np.outer(dx, dx) - np.outer(Hdg, dx) - np.outer(dx, Hdg)) / curv
+                else:
+                    last_reset = ng
+            elif last_reset < ng:
+                unchanged = 0
+                last_reset = ng
+        else:
+            unchanged = 0
+            if last_reset == ng:
+                unchanged = k
+            else:
+                last_reset = ng
+        if it >= maxit:
+            break
+        if ng - last_reset > 2 * k:
+            last_reset = ng
+        if unchanged == k and last_reset == ng:
+            break
+    return u * ps, fmin, (0 if it < maxit else 1), nf, ng
+
+
+# ------------------------------------------------------------------------------------------
+# mixed_fit
+# ------------------------------------------------------------------------------------------
+def _params_row(betas, D, phis, gammas, diag_D):
+    q = len(D)
+    Dv = np.diag(D) if diag_D else np.array([D[r, c] for c in range(q) for r in range(c, q)])
+    return np.concatenate([np.atleast_1d(v) for v in (betas, Dv, phis, gammas) if v is not None])
+
+
+def _thetas(betas, D, phis, gammas, diag_D):
+    Dv = np.log(np.diag(D)) if diag_D else chol_transf(D)
+    return np.concatenate([np.atleast_1d(v) for v in (betas, Dv, phis, gammas) if v is not None])
+
+
+def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, trace=None):
+    """R/mixed_fit.R:62-349 on a device-resident data set.  Returns the list mixed_fit() returns
+    (coefficients, phis, D, gammas, post_modes, post_vars, logLik, Hessian, converged) plus timing
+    and evaluation counters."""
+    con = dict(CONTROL)
+    con.update(control or {})
+    eng = engine
+    q, n = eng.q, eng.n
+    betas = np.array(initial_values["betas"], float)
+    D = np.array(initial_values["D"], float)
+    D = np.diag(D) if D.ndim == 1 else D
+    phis = None if initial_values.get("phis") is None else np.array(initial_values["phis"], float)
+    gammas = None if initial_values.get("gammas") is None else np.array(initial_values["gammas"], float)
+    nderiv = fd_vec if con["numeric_deriv"] == "fd" else cd_vec
+    counts = dict(find_modes=0, estep=0, em_score=0, eval=0)
+    t_start = time.perf_counter()
+
+    def new_grid(cold=False):
+        counts["find_modes"] += 1
+        return GHfun(eng, np.zeros((n, q)) if cold else None, betas, np.linalg.inv(D), phis, gammas)
+
+    def too_large():
+        return bool(np.any(np.abs(betas[1:]) > con["max_coef_value"]) or
+                    (gammas is not None and np.any(np.abs(gammas) > con["max_coef_value"])))
+
+    def em_sc(key, bt, ph, gm):
+        counts["em_score"] += 1
+        return -eng.em_score(bt, ph, gm)[key]
+
+    converged, during_EM = False, False
+    gh = None
+    if con["iter_EM"] > 0:
+        refresh = set(range(0, con["iter_EM"] + 1, con["update_GH_every"]))
+        rows, lls = [], []
+        gh = new_grid(cold=True)
+        for it in range(1, con["iter_EM"] + 1):
+            if it in refresh:
+                gh = new_grid()
+            rows.append(_params_row(betas, D, phis, gammas, diag_D))
+            es = eng.em_estep(betas, D, phis, gammas)
+            counts["estep"] += 1
+            lls.append(es["loglik"])
+            if trace is not None:
+                trace.append(("EM", it, es["loglik"], betas.copy()))
+            if it > 4 and lls[-1] > lls[-2]:
+                c1 = np.max(np.abs(rows[-1] - rows[-2]) / (np.abs(rows[-2]) + con["tol1"])) < con["tol2"]
+                c2 = (lls[-1] - lls[-2]) < con["tol3"] * (abs(lls[-2]) + con["tol3"])
+                if c1 or c2:
+                    converged = during_EM = True
+                    break
+            # D <- colMeans(post_b2, na.rm = TRUE), symmetrised (R/mixed_fit.R:186-190)
+            D = es["S"] / max(n - es["n_nonfinite"], 1)
+            D = (D + D.T) / 2
+            if diag_D:
+                D = np.diag(np.diag(D))
+            # one Newton step per block with numerically differentiated M-step scores, p_by fixed
+            if phis is not None:
+                f = lambda v: em_sc("g_phi", betas, v, gammas)
+                phis = phis - np.linalg.solve(nearPD(nderiv(phis, f)), f(phis))
+            f = lambda v: em_sc("g_beta", v, phis, gammas)
+            betas = betas - np.linalg.solve(nearPD(nderiv(betas, f)), f(betas))
+            if gammas is not None:
+                f = lambda v: em_sc("g_gamma", betas, phis, v)
+                gammas = gammas - np.linalg.solve(nearPD(nderiv(gammas, f)), f(gammas))
+            if too_large():
+                raise FloatingPointError("A large coefficient value has been detected during the optimization "
+                                         "(R/mixed_fit.R:70-77); re-scale covariates or set iter_EM = 0")
+            if eng.spec.family in ("negative binomial", "zero-inflated negative binomial") and \
+                    np.exp(phis[0]) > con["max_phis_value"]:
+                raise FloatingPointError("shape/size parameter of the negative binomial above max_phis_value")
+    t_em = time.perf_counter() - t_start
+
+    tht = _thetas(betas, D, phis, gammas, diag_D)
+    n_outer = 0
+    if not converged and con["iter_qN_outer"] > 0:
+        nD = q if diag_D else eng.npack
+        parscale = np.concatenate([np.full(eng.p, con["parscale_betas"]), np.full(nD, con["parscale_D"]),
+                                   np.full(eng.n_phis, con["parscale_phis"]), np.full(eng.p_zi, con["parscale_gammas"])])
+        iter_qN = con["iter_qN"]
+
+        def fn(t):
+            counts["eval"] += 1
+            return logLik_mixed(t, eng, gh, diag_D)
+
+        for it in range(1, con["iter_qN_outer"] + 1):
+            n_outer = it
+            gh = new_grid(cold=(gh is None))
+            tht, val, conv, _, _ = vmmin(tht, fn, lambda t: score_mixed(t, eng, gh, diag_D), iter_qN, con["tol3"], parscale)
+            betas, D, _, phis, gammas = split_thetas(tht, eng, diag_D)
+            betas = betas.copy()
+            phis = None if phis is None else phis.copy()
+            gammas = None if gammas is None else gammas.copy()
+            if trace is not None:
+                trace.append(("qN", it, -val, betas.copy()))
+            if too_large():
+                raise FloatingPointError("A large coefficient value has been detected during the optimization")
+            if conv == 0:
+                converged = True
+                break
+            iter_qN += con["iter_qN_incr"]
+    t_qn = time.perf_counter() - t_start - t_em
+
+    tht = _thetas(betas, D, phis, gammas, diag_D)
+    gh = new_grid(cold=(gh is None))
+    out = dict(coefficients=betas, phis=phis, D=D, gammas=gammas, post_modes=gh.post_modes, gh=gh,
+               logLik=-logLik_mixed(tht, eng, gh, diag_D), converged=converged, converged_during_EM=during_EM,
+               thetas=tht, n_outer=n_outer, counts=counts)
+    if hessian:
+        out["Hessian"] = cd_vec(tht, lambda t: score_mixed(t, eng, gh, diag_D))
+        counts["eval"] += 2 * len(tht)
+    out["seconds"] = dict(EM=t_em, quasi_newton=t_qn, total=time.perf_counter() - t_start)
+    return out
+
+
+def mixed_model(y, X, Z, id, family, link=None, X_zi=None, Z_zi=None, offset=None, offset_zi=None,
+                weights=None, initial_values=None, control=None, diag_D=False, device=0, hessian=True,
+                engine=None):
+    """mixed_model() from design matrices.  Rows must be grouped by `id` (the reference sorts its
+    data frame by the grouping factor, R/mixed_model.R:50).  Returns mixed_fit()'s list."""
+    con = dict(control or {})
+    own = engine is None
+    if own:
+        engine = Engine(y, X, Z, id, family, link=link, nAGQ=con.get("nAGQ"), X_zi=X_zi, Z_zi=Z_zi,
+                        offset=offset, offset_zi=offset_zi, weights=weights, device=device)
+    try:
+        inits = starting_values(y, X, X_zi, engine.spec.family, engine.q, engine.n_phis, diag_D, offset, offset_zi)
+        if initial_values:
+            inits.update(initial_values)
+        fit = mixed_fit(engine, inits, con, diag_D, hessian)
+        fit["post_vars"] = fit["gh"].post_vars if engine.n <= 100_000 else None
+        fit["nAGQ"] = engine.nAGQ
+    finally:
+        if own:
+            engine.close()
+    return fit

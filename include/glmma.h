@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLMMA_VERSION 100
+#define GLMMA_VERSION 110
 
 #if defined(__GNUC__)
 #define GLMMA_API __attribute__((visibility("default")))
@@ -194,6 +194,26 @@ GLMMA_API int glmma_eval_device(glmma_handle* h, const double* betas, const doub
 GLMMA_API int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
                        const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
                        double* sphi_obs, double* S_i);
+
+/* ---- EM phase of mixed_fit (R/mixed_fit.R:119-229; score_betas / score_phis /
+ *      score_gammas, R/Fit_Funs.R:295-427) ---------------------------------- */
+
+/* E-step on the current grid: the same result vector as glmma_eval(want_score = 1)
+ * (loglik = lgLik[it] of R/mixed_fit.R:155; S / n = the D update of :186-190), and the
+ * posterior node weights  p_by[i, k] * wGH[k]  (R/mixed_fit.R:141-143) are kept on the
+ * device (n x K doubles) for the M-step calls that follow. */
+GLMMA_API int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                   const double* gammas, double* result);
+
+/* M-step scores with p_by held fixed at the last E-step's value:
+ *   g_beta  = -score_betas(betas, ..., p_by)    (R/Fit_Funs.R:295-365)
+ *   g_phi   = -score_phis(phis, ..., p_by)      (R/Fit_Funs.R:367-396)
+ *   g_gamma = -score_gammas(gammas, ..., p_by)  (R/Fit_Funs.R:398-427)
+ * evaluated at the (betas, phis, gammas) passed here, in glmma_eval's result layout
+ * ([0] = 0, S = sum_i w_i E_p_by[b b'] on the frozen weights).  mixed_fit() differentiates these numerically
+ * for its Newton updates, so one EM iteration makes 3 + 2 * (p + n_phis + p_zi) such calls at most. */
+GLMMA_API int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
+                   double* result);
 
 /* ---- measurement helpers (bench.py; not part of the reference seam) ----- */
 

@@ -1,0 +1,95 @@
+"""GPU: the EM-phase entry points and full mixed_model() fits of the engine against the oracle's
+restatement of R/mixed_fit.R, and against the coefficients the reference's vignette publishes.
+
+Tolerances: E-step / M-step scores with shared grid: relative 1e-10 (as eval); fitted
+coefficients: 1e-6 (north_star) against the oracle's fit with the same mode finder, and every
+printed digit of the published `fm1` estimates."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import agq, families as F, vignette_data, fit as ofit
+import glmmadaptive_b200 as gb
+from glmmadaptive_b200 import synth
+from helpers import oracle_data, oracle_family, oracle_grid, pack_chol, thetas_vec, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vignette_kat.json")
+
+
+def _case(name, n, **kw):
+    d, th = synth.make(name, n=n, ni=6, seed=21, ragged=True, **kw)
+    fam_name = d.pop("family")
+    return d, th, fam_name
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "C4"])
+def test_em_estep_and_frozen_scores(name):
+    d, th, fam_name = _case(name, 40)
+    if name == "C3":
+        d["weights"] = np.random.default_rng(1).uniform(0.5, 2.0, 40)
+    fam = oracle_family(fam_name)
+    od, gh = oracle_grid(d, th, fam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d.get("X_zi"),
+                    Z_zi=d.get("Z_zi"), weights=d.get("weights"))
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    betas, D, phis, gammas = th["betas"], th["D"], th.get("phis"), th.get("gammas")
+    p_by, post_b2, ll, eta_zi = ofit.e_step(od, fam, gh, betas, D, phis, gammas)
+    es = eng.em_estep(betas, D, phis, gammas)
+    assert relerr(es["loglik"], ll) < 1e-10
+    assert relerr(es["S"].reshape(-1), np.sum(post_b2, axis=0)) < 1e-10
+    # the E-step result is the fused evaluation's
+    ev = eng.eval(betas, D, phis, gammas)
+    assert relerr(es["loglik"], ev["loglik"]) < 1e-13 and relerr(es["g_beta"], ev["g_beta"]) < 1e-9
+    # scores at a DIFFERENT theta with the posterior weights frozen at the E-step's theta
+    b2 = betas + np.array([0.05, -0.03, 0.02])
+    ph2 = None if phis is None else phis + 0.07
+    g2 = None if gammas is None else gammas + np.array([0.04, -0.06])
+    sc = eng.em_score(b2, ph2, g2)
+    ref_b = ofit.score_betas(b2, od, fam, gh, ph2, eta_zi if g2 is None else ofit._etas(od, gh, b2, g2)[1], p_by)
+    assert np.max(np.abs(-sc["g_beta"] - ref_b)) < 1e-10 * max(1.0, np.max(np.abs(ref_b))) * 10
+    if phis is not None:
+        ref_p = ofit.score_phis(ph2, od, fam, gh, b2, eta_zi, p_by)
+        if d.get("weights") is None:       # the reference drops the weights here (Fit_Funs.R:392-394)
+            assert abs(-sc["g_phi"][0] - ref_p[0]) < 1e-9 * max(1.0, abs(ref_p[0]))
+    if gammas is not None:
+        ref_g = ofit.score_gammas(g2, od, fam, gh, b2, ph2, p_by)
+        assert np.max(np.abs(-sc["g_gamma"] - ref_g)) < 1e-9 * max(1.0, np.max(np.abs(ref_g)))
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["D1_nAGQ11", "D1_nAGQ15"])
+def test_mixed_model_reproduces_published_fm1(name):
+    """mixed_model(y ~ sex * time, random = ~ 1 | id, family = binomial()) on the vignette data:
+    the engine's fit prints the same digits as the reference's rendered vignette."""
+    k = [r for r in json.load(open(GOLD))["kats"] if r["name"] == name][0]
+    v = vignette_data.binary_data()
+    fit = gb.mixed_model(v["y"], v["X"], v["Z"][:, :1], v["id"], "binomial", control=dict(nAGQ=k["nAGQ"]))
+    assert fit["converged"]
+    assert np.max(np.abs(fit["coefficients"] - np.array(k["betas"]))) < 1e-6
+    assert abs(fit["D"][0, 0] - k["D"][0][0]) < 1e-6
+    assert abs(fit["logLik"] - k["loglik"]) < 5e-7
+    # standard errors from the engine's Hessian: sqrt(diag(solve(Hessian))) is finite and positive
+    se = np.sqrt(np.diag(np.linalg.inv(fit["Hessian"])))
+    assert np.all(np.isfinite(se)) and np.all(se > 0)
+
+
+@pytest.mark.parametrize("name,n", [("C3", 60), ("C2", 50), ("C4", 60)])
+def test_mixed_model_vs_oracle_fit(name, n):
+    d, th, fam_name = _case(name, n)
+    fam = oracle_family(fam_name)
+    od = oracle_data(d)
+    con = dict(nAGQ=7 if name == "C4" else 9, iter_EM=12, iter_qN_outer=4)
+    ref = ofit.mixed_fit(od, fam, control=con, mode_finder="newton", hessian=False)
+    fit = gb.mixed_model(d["y"], d["X"], d["Z"], d["id"], fam_name, X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"),
+                         control=con, hessian=False)
+    assert fit["converged"] == ref["converged"]
+    assert np.max(np.abs(fit["coefficients"] - ref["coefficients"])) < 1e-6
+    assert np.max(np.abs(fit["D"] - ref["D"])) < 1e-6
+    if ref["phis"] is not None:
+        assert np.max(np.abs(fit["phis"] - ref["phis"])) < 1e-6
+    if ref["gammas"] is not None:
+        assert np.max(np.abs(fit["gammas"] - ref["gammas"])) < 1e-6
+    assert abs(fit["logLik"] - ref["logLik"]) < 1e-7 * abs(ref["logLik"])
