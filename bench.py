@@ -289,6 +289,29 @@ def run_ours(args):
     h2d = 8 * (len(betas) + D.size + (0 if phis is None else len(phis)) + (0 if gammas is None else len(gammas)))
     d2h = 8 * eng.result_len
 
+    # ---- second half of BASELINE's metric: wall seconds of a whole mixed_model() fit (default
+    # control: 30 EM iterations, then optim-BFGS outer iterations, then the cd_vec Hessian) on the
+    # same data, clusters sharded over the ranks, starting values from glm.fit run on the device (IRLS passes)
+    fit_info = None
+    if not args.no_fit:
+        barrier()
+        t0 = time.perf_counter()
+        inits = gb.starting_values_device(sh)
+        t_inits = time.perf_counter() - t0
+        l0 = eng.launch_count
+        fit = gb.mixed_fit(sh, inits, {}, hessian=True)
+        barrier()
+        t_fit = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if world > 1:
+            dist.all_reduce(t_fit, op=dist.ReduceOp.MAX)
+        fit_info = {"seconds": float(t_fit.item()), "starting_values_s": t_inits, "phases_s": fit["seconds"],
+                    "converged": bool(fit["converged"]), "outer_iterations": fit["n_outer"],
+                    "calls": fit["counts"], "gpu_launches": eng.launch_count - l0,
+                    "logLik": fit["logLik"], "coefficients": [float(v) for v in fit["coefficients"]],
+                    "true_betas": [float(v) for v in betas],
+                    "what": "glmmadaptive_b200.mixed_fit (host mirror of R/mixed_fit.R with default control) on "
+                            "the resident data set; excludes data generation and glmma_create (create_s)"}
+
     # ---- kernel-level timing of the dominant kernel (rank-local) and the roofline
     ms_eval, ms_kernel = eng.time_eval(betas, D, phis, gammas, True, iters=max(3, min(args.steps, 10)))
     barrier()
@@ -355,6 +378,7 @@ def run_ours(args):
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "find_modes": {"cold_clusters_per_s": n_total / t_modes_cold, "warm_clusters_per_s": n_total / t_modes_warm,
                               "mean_iterations_cold": st["mean_iterations"], "not_converged": st["n_not_converged"]},
+               "mixed_model": fit_info,
                "ms_per_eval_local": ms_eval,
                "check": {"loglik": res["loglik"], "n_nonfinite": res["n_nonfinite"]}}
     eng.close()
@@ -373,6 +397,7 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--clusters", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fit", action="store_true", help="skip the whole-fit (mixed_model() seconds) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,5 +1,5 @@
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fit 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):

@@ -231,6 +231,97 @@ __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* e
     }
 }
 
+
+// ------------------------------------------------------------------------------
+// starting values: one IRLS step of stats::glm.fit (as mixed_model() calls it,
+// R/mixed_model.R:162-194) as one pass over the rows: the p x p normal equations
+//   A = X' W X,  r = X' W z,  deviance
+// with W = mu.eta^2 / V(mu) * prior weight and z = (eta - offset) + (y - mu) / mu.eta.
+// first = 1: eta from family$initialize's mustart instead of X beta.
+// fam: 0 binomial(logit), 1 poisson(log), 2 Gamma(inverse), 3 gaussian(identity).
+// resp: 0 the model response (y1; binomial: y1 / y2 with prior weight y2), 1 the zero indicator.
+// ------------------------------------------------------------------------------
+#define GLM_PMAX 8
+#define GLM_NACC (GLM_PMAX * (GLM_PMAX + 1) / 2 + GLM_PMAX + 1)
+#define GLM_THREADS 128
+struct GlmArgs {
+    const double* X; const double* y1; const double* y2; const double* offset;
+    int64_t N; int p; int fam; int resp; int first; int y1_is_log;
+    double beta[GLM_PMAX];
+    double* partials;     // gridDim.x * GLM_NACC
+};
+
+__global__ void __launch_bounds__(GLM_THREADS) glm_irls_kernel(GlmArgs A) {
+    __shared__ double sh[GLM_THREADS / 32];
+    double acc[GLM_NACC];
+#pragma unroll
+    for (int t = 0; t < GLM_NACC; ++t) acc[t] = 0.0;
+    const int p = A.p;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < A.N; row += (int64_t)gridDim.x * blockDim.x) {
+        double x[GLM_PMAX];
+#pragma unroll
+        for (int l = 0; l < GLM_PMAX; ++l) x[l] = l < p ? A.X[row + (int64_t)l * A.N] : 0.0;
+        double y = A.y1[row], pw = 1.0;
+        if (A.resp == 1) {
+            y = ((A.y1_is_log ? y == -INFINITY : y == 0.0)) ? 1.0 : 0.0;
+        } else if (A.fam == 0 && A.y2) {
+            pw = A.y2[row];
+            y = pw > 0.0 ? y / pw : 0.0;
+        }
+        const double off = A.offset ? A.offset[row] : 0.0;
+        double eta, mu;
+        if (A.first) {
+            mu = A.fam == 0 ? (pw * y + 0.5) / (pw + 1.0) : (A.fam == 1 ? y + 0.1 : y);
+            eta = A.fam == 0 ? log(mu / (1.0 - mu)) : (A.fam == 1 ? log(mu) : (A.fam == 2 ? 1.0 / mu : mu));
+        } else {
+            eta = off;
+#pragma unroll
+            for (int l = 0; l < GLM_PMAX; ++l) eta = fma(x[l], A.beta[l], eta);
+        }
+        double g, var;
+        if (A.fam == 0) {
+            const double ec = fmin(fmax(eta, -30.0), 30.0);
+            mu = 1.0 / (1.0 + exp(-ec));
+            const double e = exp(-fabs(eta));
+            g = fmax(e / ((1.0 + e) * (1.0 + e)), GLMMA_DBL_EPS);
+            var = mu * (1.0 - mu);
+        } else if (A.fam == 1) {
+            mu = fmax(exp(eta), GLMMA_DBL_EPS);
+            g = mu; var = mu;
+        } else if (A.fam == 2) {
+            mu = 1.0 / eta; g = -1.0 / (eta * eta); var = mu * mu;
+        } else {
+            mu = eta; g = 1.0; var = 1.0;
+        }
+        const double ww = pw * g * g / var;
+        const double zz = (eta - off) + (y - mu) / g;
+        int t = 0;
+#pragma unroll
+        for (int l = 0; l < GLM_PMAX; ++l) {
+            const double wx = ww * x[l];
+#pragma unroll
+            for (int m = l; m < GLM_PMAX; ++m) { acc[t] = fma(wx, x[m], acc[t]); ++t; }
+            acc[GLM_PMAX * (GLM_PMAX + 1) / 2 + l] = fma(wx, zz, acc[GLM_PMAX * (GLM_PMAX + 1) / 2 + l]);
+        }
+        // deviance of the CURRENT mu (glm.fit's convergence test)
+        double dv;
+        if (A.fam == 0) {
+            dv = 2.0 * pw * ((y > 0.0 ? y * log(y / mu) : 0.0) + (y < 1.0 ? (1.0 - y) * log((1.0 - y) / (1.0 - mu)) : 0.0));
+        } else if (A.fam == 1) {
+            dv = 2.0 * ((y > 0.0 ? y * log(y / mu) : 0.0) - (y - mu));
+        } else if (A.fam == 2) {
+            dv = -2.0 * (log(y == 0.0 ? 1.0 : y / mu) - (y - mu) / mu);
+        } else {
+            dv = (y - mu) * (y - mu);
+        }
+        acc[GLM_NACC - 1] += dv;
+    }
+    for (int t = 0; t < GLM_NACC; ++t) {
+        const double v = block_sum(acc[t], sh);
+        if (threadIdx.x == 0) A.partials[(int64_t)blockIdx.x * GLM_NACC + t] = v;
+    }
+}
+
 __global__ void fp64_peak_kernel(double* out, int iters) {
     // 8 independent DFMA chains per thread
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -667,7 +758,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (k0) CU(h, cudaEventRecord(k0, h->stream));
     int n_blocks = 0;
     ea.only_deferred = 0;
-    if (h->nj && em_mode == 0) {
+    if (h->nj) {
         // small clusters: register variant; it flags what it leaves to the generic kernel
         h->ops->eval_fast(ea, s, h->nj, h->fast_grid[s], h->fast_smem[s], h->stream);
         h->launches++;
@@ -782,6 +873,54 @@ int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, con
     if (rc) return rc;
     CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * glmma_result_len(h), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
+    return GLMMA_OK;
+}
+
+// ---- starting values of mixed_model() (R/mixed_model.R:157-194) --------------------------
+
+int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
+                   const double* beta, double* out) {
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!out || (!first && !beta)) return fail(h, GLMMA_ERR_ARG, "null argument");
+    const DevData& d = h->d;
+    if (design != 0 && design != 1) return fail(h, GLMMA_ERR_ARG, "design must be 0 (X) or 1 (X_zi)");
+    const int p = design == 0 ? d.p : d.p_zi;
+    if (p < 1 || p > GLM_PMAX) return fail(h, GLMMA_ERR_ARG, "glmma_glm_pass supports 1..8 columns");
+    if (glm_family < 0 || glm_family > 3) return fail(h, GLMMA_ERR_ARG, "glm_family must be 0..3");
+    const bool y1_is_log = h->family == GLMMA_BETA || h->family == GLMMA_HURDLE_BETA;
+    if (response == 0 && y1_is_log) return fail(h, GLMMA_ERR_ARG, "no glm start for the beta families' response");
+    GlmArgs ga;
+    std::memset(&ga, 0, sizeof(ga));
+    ga.X = design == 0 ? d.X : d.X_zi;
+    ga.y1 = d.y1;
+    ga.y2 = (h->family == GLMMA_BINOMIAL || h->family == GLMMA_ZI_BINOMIAL) ? d.y2 : nullptr;
+    ga.offset = use_offset ? (design == 0 ? d.offset : d.offset_zi) : nullptr;
+    ga.N = d.N; ga.p = p; ga.fam = glm_family; ga.resp = response; ga.y1_is_log = y1_is_log ? 1 : 0;
+    ga.first = first ? 1 : 0;
+    for (int l = 0; l < GLM_PMAX; ++l) ga.beta[l] = (!first && l < p) ? beta[l] : 0.0;
+    const int blocks = (int)std::min<int64_t>((d.N + GLM_THREADS - 1) / GLM_THREADS, 148 * 8);
+    double* d_part = nullptr;
+    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * (size_t)blocks * GLM_NACC);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc (glm)");
+    ga.partials = d_part;
+    std::vector<double> part((size_t)blocks * GLM_NACC), tot(GLM_NACC, 0.0);
+    glm_irls_kernel<<<blocks, GLM_THREADS, 0, h->stream>>>(ga);
+    h->launches++;
+    e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return cuda_fail(h, e, "glm_irls_kernel");
+    for (int b = 0; b < blocks; ++b)          // fixed order: deterministic
+        for (int t = 0; t < GLM_NACC; ++t) tot[t] += part[(size_t)b * GLM_NACC + t];
+    out[0] = tot[GLM_NACC - 1];
+    for (int l = 0; l < p; ++l) out[1 + l] = tot[GLM_PMAX * (GLM_PMAX + 1) / 2 + l];
+    int t = 0;
+    for (int l = 0; l < GLM_PMAX; ++l)
+        for (int m = l; m < GLM_PMAX; ++m) {
+            if (l < p && m < p) { out[1 + p + l + m * p] = tot[t]; out[1 + p + m + l * p] = tot[t]; }
+            ++t;
+        }
     return GLMMA_OK;
 }
 

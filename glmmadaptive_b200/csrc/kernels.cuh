@@ -1054,7 +1054,11 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                     shift = warp_max(valid ? a : -INFINITY);
                     if (!(fabs(shift) < INFINITY)) shift = 0.0;
                 }
-                const double e = valid ? fast_exp(a - shift, cx) : 0.0;
+                double e = valid ? fast_exp(a - shift, cx) : 0.0;
+                if (A.em_mode) {             // EM phase: store (E-step) / replace (M-step) the node weights
+                    if (A.em_mode == 2) e = valid ? A.pby[i * K + k] : 0.0;
+                    else if (valid) A.pby[i * K + k] = e;
+                }
                 sum_e += e;
                 if (SCORE) {
                     int t = 0;
@@ -1073,7 +1077,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 }
             }
             sum_e = warp_sum(sum_e);
-            if (sum_e > 0.0 && sum_e < INFINITY) break;
+            if ((sum_e > 0.0 && sum_e < INFINITY) || A.em_mode == 2) break;
             const double mx = warp_max(amax);
             if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
             shift = mx;
@@ -1081,8 +1085,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
         const double w = d.weights ? sc[SC_W] : 1.0;
         double lsum, isum;
         fast_log_rcp<true>(sum_e, cx, lsum, isum);
-        const double ll = shift + lsum + sc[SC_LD] + cs[0];
-        const bool ok = fabs(ll) < INFINITY;
+        const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD] + cs[0];
+        const bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
+        if (A.em_mode == 1 && !ok)
+            for (int k = lane; k < K; k += 32) A.pby[i * K + k] = 0.0;
         if (lane == 0) {
             if (ok) { tots[0] += w * ll; tots[1] += w; } else tots[2] += 1.0;
             if (d.ll_i) d.ll_i[i] = w * ll;

@@ -226,18 +226,37 @@ class Engine:
     def em_estep(self, betas, D, phis=None, gammas=None):
         """E-step on the current grid: glmma_eval's result (loglik = lgLik[it], S = sum_i w_i
         E[b b' | y_i]) and the posterior node weights p_by kept on the device."""
+        return self.unpack(self.em_estep_raw(betas, D, phis, gammas), True)
+
+    def em_estep_raw(self, betas, D, phis=None, gammas=None):
         keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
         res = np.zeros(self.result_len)
         self._check(self.lib.glmma_em_estep(self._h, *ptrs, _dp(res)))
-        return self.unpack(res, True)
+        return res
 
     def em_score(self, betas, phis=None, gammas=None):
         """Scores at (betas, phis, gammas) with p_by frozen at the last E-step
         (score_betas / score_phis / score_gammas, R/Fit_Funs.R:295-427, up to sign)."""
+        return self.unpack(self.em_score_raw(betas, phis, gammas), True)
+
+    def em_score_raw(self, betas, phis=None, gammas=None):
         keep, ptrs = self._theta_ptrs(betas, np.eye(self.q), phis, gammas)
         res = np.zeros(self.result_len)
         self._check(self.lib.glmma_em_score(self._h, ptrs[0], ptrs[2], ptrs[3], _dp(res)))
-        return self.unpack(res, True)
+        return res
+
+    # -- starting values (R/mixed_model.R:157-194) ---------------------------------
+    GLM_FAMILIES = {"binomial": 0, "poisson": 1, "Gamma": 2, "gaussian": 3}
+
+    def glm_pass(self, glm_family, design="X", response="y", use_offset=True, beta=None):
+        """One IRLS pass of stats::glm.fit on the resident rows: [deviance, X'Wz (p), X'WX (p x p)]."""
+        ncol = self.p if design == "X" else self.p_zi
+        out = np.zeros(1 + ncol + ncol * ncol)
+        b = None if beta is None else _f(np.atleast_1d(beta), "C")
+        self._check(self.lib.glmma_glm_pass(self._h, 0 if design == "X" else 1, self.GLM_FAMILIES[glm_family],
+                                            0 if response == "y" else 1, int(bool(use_offset)),
+                                            int(beta is None), _dp(b), _dp(out)))
+        return out
 
     def time_eval(self, betas, D, phis=None, gammas=None, want_score=True, iters=10):
         keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
@@ -340,8 +359,8 @@ class GH:
     def post_vars(self):
         """lapply(post_hessians, solve): (R'R)^-1 per cluster."""
         q = self.engine.q
-        out = np.empty((self.engine.n, q, q))
-        for i in range(self.engine.n):
+        out = np.empty((len(self.post_modes), q, q))
+        for i in range(len(self.post_modes)):
             R = np.zeros((q, q))
             for v, (r, c) in zip(self.chol[i], _upper_tri_colmajor(q)):
                 R[r, c] = v
@@ -367,14 +386,16 @@ def GHfun(engine, b, betas, inv_D, phis=None, gammas=None):
     R/mixed_fit.R:100,117,287); zeros give the reference's cold start."""
     warm = True
     if b is not None:
-        b = np.asarray(b, float).reshape(engine.n, engine.q)
-        if np.any(b != 0.0):
-            eye = np.zeros((engine.n, engine.npack))
+        b = np.asarray(b, float)
+        if not np.any(b != 0.0):
+            warm = False
+        else:
+            n_loc = getattr(engine, "n_local", engine.n)      # a ShardedEngine holds its own clusters only
+            b = b.reshape(n_loc, engine.q)
+            eye = np.zeros((n_loc, engine.npack))
             for t, (r, c) in enumerate(_upper_tri_colmajor(engine.q)):
                 eye[:, t] = 1.0 if r == c else 0.0
             engine.set_modes(b, eye)
-        else:
-            warm = False
     stats = engine.find_modes(betas, inv_D, phis, gammas, warm=warm)
     modes, chol, logdet = engine.get_modes()
     return GH(engine, modes, chol, logdet, gauss_hermite_wGH(engine.nAGQ, engine.q), stats,

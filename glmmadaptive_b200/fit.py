@@ -20,6 +20,7 @@ import time
 
 import numpy as np
 
+from ._lib import GlmmaError, ERR_NUMERIC
 from .engine import Engine, GHfun, chol_transf, logLik_mixed, score_mixed, split_thetas
 
 _EPS = np.finfo(float).eps
@@ -96,8 +97,12 @@ def glm_fit(X, y, family, offset=None, epsilon=1e-8, maxit=25):
     beta = np.zeros(X.shape[1])
     for _ in range(maxit):
         g = fam.dmu(eta)
-        sw = np.sqrt(w * g * g / fam.var(mu))
-        beta = np.linalg.lstsq(X * sw[:, None], ((eta - off) + (y - mu) / g) * sw, rcond=None)[0]
+        # weighted least squares through the p x p normal equations (Cholesky): the design has
+        # millions of rows and a handful of columns, so a QR of X costs seconds where this costs
+        # milliseconds; glm.fit's own QR agrees to the conditioning of X'WX
+        ww = w * g * g / fam.var(mu)
+        Xw = X * ww[:, None]
+        beta = np.linalg.solve(Xw.T @ X, Xw.T @ ((eta - off) + (y - mu) / g))
         eta = X @ beta + off
         mu = fam.inv(eta)
         dev = fam.deviance(y, mu, w)
@@ -126,6 +131,43 @@ def starting_values(y, X, X_zi, family, nRE, n_phis, diag_D=False, offset=None, 
             out["betas"] = glm_fit(X, y, "poisson")
     if n_phis:
         out["phis"] = np.zeros(n_phis)
+    return out
+
+
+def glm_fit_device(engine, family, design="X", response="y", use_offset=True, epsilon=1e-8, maxit=25):
+    """glm.fit on the data the engine holds: every IRLS iteration is one device pass
+    (glmma_glm_pass) returning the deviance and the p x p normal equations; works unchanged on a
+    ShardedEngine (the pass results are all-reduced)."""
+    p = engine.p if design == "X" else engine.p_zi
+    beta, dev_old = None, None
+    for it in range(maxit + 1):
+        out = engine.glm_pass(family, design, response, use_offset, beta)
+        dev = out[0]
+        if it > 0 and abs(dev - dev_old) / (abs(dev) + 0.1) < epsilon:
+            break
+        dev_old = dev
+        if it == maxit:
+            break
+        beta = np.linalg.solve(out[1 + p:].reshape(p, p), out[1:1 + p])
+    return beta
+
+
+def starting_values_device(engine, diag_D=False):
+    """starting_values() with the glm.fit calls run on the device-resident data."""
+    fam = engine.spec.family
+    starts = {"binomial": "binomial", "poisson": "poisson", "negative binomial": "poisson", "Gamma": "Gamma"}
+    if fam in starts:
+        betas = glm_fit_device(engine, starts[fam]) * np.sqrt(1.346)
+    else:
+        betas = np.zeros(engine.p)
+    out = dict(betas=betas, D=np.ones(engine.q) if diag_D else np.eye(engine.q))
+    if engine.p_zi:
+        out["gammas"] = glm_fit_device(engine, "binomial", design="X_zi", response="zero")
+        if fam in ("zero-inflated poisson", "zero-inflated negative binomial", "hurdle poisson",
+                   "hurdle negative binomial"):
+            out["betas"] = glm_fit_device(engine, "poisson", use_offset=False)
+    if engine.n_phis:
+        out["phis"] = np.zeros(engine.n_phis)
     return out
 
 
@@ -291,15 +333,22 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
 
     def new_grid(cold=False):
         counts["find_modes"] += 1
-        return GHfun(eng, np.zeros((n, q)) if cold else None, betas, np.linalg.inv(D), phis, gammas)
+        return GHfun(eng, 0.0 if cold else None, betas, np.linalg.inv(D), phis, gammas)
 
     def too_large():
         return bool(np.any(np.abs(betas[1:]) > con["max_coef_value"]) or
                     (gammas is not None and np.any(np.abs(gammas) > con["max_coef_value"])))
 
+    last = {}
+
     def em_sc(key, bt, ph, gm):
-        counts["em_score"] += 1
-        return -eng.em_score(bt, ph, gm)[key]
+        # the reference evaluates the score at the expansion point twice (inside numer_deriv_vec and
+        # again for the Newton step); the second call is answered from the first
+        sig = tuple(None if v is None else np.asarray(v, float).tobytes() for v in (bt, ph, gm))
+        if sig not in last:
+            counts["em_score"] += 1
+            last[sig] = eng.em_score(bt, ph, gm)
+        return -last[sig][key]
 
     converged, during_EM = False, False
     gh = None
@@ -313,6 +362,7 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
             rows.append(_params_row(betas, D, phis, gammas, diag_D))
             es = eng.em_estep(betas, D, phis, gammas)
             counts["estep"] += 1
+            last.clear()
             lls.append(es["loglik"])
             if trace is not None:
                 trace.append(("EM", it, es["loglik"], betas.copy()))
@@ -353,8 +403,18 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
         iter_qN = con["iter_qN"]
 
         def fn(t):
+            # a trial step of the line search can leave the region where D = U'U is numerically
+            # positive definite (or finite); R's logLik_mixed returns a non-finite value there and
+            # vmmin shortens the step (accpoint needs a finite f) -- same here
             counts["eval"] += 1
-            return logLik_mixed(t, eng, gh, diag_D)
+            try:
+                with np.errstate(over="ignore", invalid="ignore"):
+                    v = logLik_mixed(t, eng, gh, diag_D)
+            except GlmmaError as e:
+                if e.code != ERR_NUMERIC:
+                    raise
+                return np.inf
+            return v if np.isfinite(v) else np.inf
 
         for it in range(1, con["iter_qN_outer"] + 1):
             n_outer = it
@@ -397,7 +457,10 @@ def mixed_model(y, X, Z, id, family, link=None, X_zi=None, Z_zi=None, offset=Non
         engine = Engine(y, X, Z, id, family, link=link, nAGQ=con.get("nAGQ"), X_zi=X_zi, Z_zi=Z_zi,
                         offset=offset, offset_zi=offset_zi, weights=weights, device=device)
     try:
-        inits = starting_values(y, X, X_zi, engine.spec.family, engine.q, engine.n_phis, diag_D, offset, offset_zi)
+        if engine.p <= 8 and engine.p_zi <= 8 and hasattr(engine, "glm_pass"):
+            inits = starting_values_device(engine, diag_D)
+        else:
+            inits = starting_values(y, X, X_zi, engine.spec.family, engine.q, engine.n_phis, diag_D, offset, offset_zi)
         if initial_values:
             inits.update(initial_values)
         fit = mixed_fit(engine, inits, con, diag_D, hessian)

@@ -49,19 +49,47 @@ def shard_arrays(arrays, ids, rank, world_size):
 
 
 class ShardedEngine:
-    """The Engine interface over ``world_size`` ranks.  ``local`` is this rank's
-    Engine (built from :func:`shard_arrays`); evaluations are all-reduced (sum)
-    over ``group`` so every rank returns the whole-data result, exactly what a
-    single Engine over all clusters returns."""
+    """The Engine interface over ``world_size`` ranks.  ``local`` is this rank's Engine (built
+    from :func:`shard_arrays`); every evaluation (eval, E-step, frozen-weight M-step scores) is
+    all-reduced (sum) over ``group`` so that each rank holds the whole-data result, exactly what a
+    single Engine over all clusters returns.  GHfun / logLik_mixed / score_mixed / mixed_fit take
+    a ShardedEngine wherever they take an Engine: every rank runs the same (deterministic) host
+    loop on identical reduced numbers, so no parameter broadcast is needed.  Modes stay on the
+    owning GPU; ``n`` is the global number of clusters (it enters the D update and score.D)."""
 
-    def __init__(self, local, dist=None, group=None, device_tensor_factory=None):
+    _SIZES = ("p", "q", "q_y", "q_zi", "p_zi", "n_phis", "npack", "nAGQ", "K", "result_len", "spec", "device")
+
+    def __init__(self, local, dist=None, group=None, reduce_on_host=False):
         self.local = local
-        self.dist = dist
+        self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1) else None
         self.group = group
+        self.reduce_on_host = reduce_on_host      # gloo (CPU tests): reduce host vectors
         self._buf = None
-        self._factory = device_tensor_factory
-        for k in ("p", "q", "q_y", "q_zi", "p_zi", "n_phis", "npack", "nAGQ", "K", "result_len"):
+        for k in self._SIZES:
             setattr(self, k, getattr(local, k))
+        self.n_local = local.n
+        self.n = int(self._reduce_host(np.array([float(local.n)]))[0])
+        self.N = int(self._reduce_host(np.array([float(local.N)]))[0])
+        self._cache_key, self._cache_val = None, None
+
+    # grid bookkeeping lives on the local engine (GHfun / _ensure_grid read and write it there)
+    @property
+    def _modes_version(self):
+        return self.local._modes_version
+
+    @property
+    def launch_count(self):
+        return self.local.launch_count
+
+    def _reduce_host(self, vec):
+        if self.dist is None:
+            return np.asarray(vec, float)
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float64).copy())
+        if not self.reduce_on_host:
+            t = t.to(f"cuda:{self.local.device}")
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
 
     def _buffer(self):
         if self._buf is None:
@@ -71,21 +99,55 @@ class ShardedEngine:
         return self._buf
 
     def find_modes(self, betas, invD, phis=None, gammas=None, warm=True):
-        # no collective needed: modes are per cluster and stay on the owning GPU
-        return self.local.find_modes(betas, invD, phis, gammas, warm)
+        # no data-path collective: modes are per cluster and stay on the owning GPU; only the
+        # convergence counters are summed
+        st = self.local.find_modes(betas, invD, phis, gammas, warm)
+        self._cache_key = None
+        tot = self._reduce_host(np.array([st["n_not_converged"], st["n_chol_failed"],
+                                          st["mean_iterations"] * self.n_local], float))
+        return dict(n_not_converged=int(tot[0]), n_chol_failed=int(tot[1]),
+                    max_iterations=st["max_iterations"], mean_iterations=tot[2] / max(self.n, 1))
+
+    def get_modes(self):
+        return self.local.get_modes()
+
+    def set_modes(self, post_modes, chol_upper):
+        self.local.set_modes(post_modes, chol_upper)
+        self._cache_key = None
+
+    def unpack(self, r, want_score=True):
+        return self.local.unpack(r, want_score)
 
     def eval_enqueue(self, betas, D, phis=None, gammas=None, want_score=True):
         """Local kernels + all-reduce, all asynchronous on the current stream; returns
         the device tensor holding the reduced result vector."""
         buf = self._buffer()
         self.local.eval_device(betas, D, phis, gammas, want_score, buf.data_ptr())
-        if self.dist is not None and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+        if self.dist is not None:
             self.dist.all_reduce(buf, group=self.group)
         return buf
 
     def eval(self, betas, D, phis=None, gammas=None, want_score=True):
+        if self.reduce_on_host:
+            r = self._reduce_host(self.local.eval_raw(betas, D, phis, gammas, want_score))
+            return self.local.unpack(r, want_score)
         buf = self.eval_enqueue(betas, D, phis, gammas, want_score)
         return self.local.unpack(buf.cpu().numpy(), want_score)
+
+    def em_estep(self, betas, D, phis=None, gammas=None):
+        return self.local.unpack(self._reduce_host(self.local.em_estep_raw(betas, D, phis, gammas)), True)
+
+    def em_score(self, betas, phis=None, gammas=None):
+        return self.local.unpack(self._reduce_host(self.local.em_score_raw(betas, phis, gammas)), True)
+
+    def glm_pass(self, *a, **k):
+        return self._reduce_host(self.local.glm_pass(*a, **k))
+
+    def eval_contrib(self, *a, **k):
+        return self.local.eval_contrib(*a, **k)      # per-cluster / per-observation pieces stay local
+
+    def close(self):
+        self.local.close()
 
 
 def allreduce_results(vec, dist, group=None):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLMMA_VERSION 110
+#define GLMMA_VERSION 120
 
 #if defined(__GNUC__)
 #define GLMMA_API __attribute__((visibility("default")))
@@ -214,6 +214,23 @@ GLMMA_API int glmma_em_estep(glmma_handle* h, const double* betas, const double*
  * for its Newton updates, so one EM iteration makes 3 + 2 * (p + n_phis + p_zi) such calls at most. */
 GLMMA_API int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
                    double* result);
+
+/* ---- starting values of mixed_model() (R/mixed_model.R:157-194) ------------ */
+
+/* One iteration of stats::glm.fit (IRLS) on the resident data, as one pass over the rows:
+ *   design     0: X (ncol p), 1: X_zi (ncol p_zi); at most 8 columns
+ *   glm_family 0 binomial(logit), 1 poisson(log), 2 Gamma(inverse), 3 gaussian(identity)
+ *   response   0: the model response (two-column binomial: successes / trials with prior weights
+ *                 trials), 1: the zero indicator as.numeric(y == 0) (the gammas start, :181-186)
+ *   use_offset 1: the design's offset enters (mixed_model passes `offset` / `offset_zi`)
+ *   first      1: eta from family$initialize's mustart (beta ignored), 0: eta = X beta + offset
+ * out (1 + p + p*p doubles): [0] deviance at the current mu, [1..p] X'Wz, then X'WX (column-major),
+ * with W = prior * mu.eta^2 / V(mu), z = (eta - offset) + (y - mu) / mu.eta.  The caller solves the
+ * p x p system and applies glm.fit's stopping rule |dev - dev_old| / (|dev| + 0.1) < 1e-8, maxit 25
+ * (glmmadaptive_b200/fit.py: glm_fit_device); sums over cluster shards add, so the ranks of a
+ * sharded fit all-reduce `out` before solving. */
+GLMMA_API int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset,
+                   int first, const double* beta, double* out);
 
 /* ---- measurement helpers (bench.py; not part of the reference seam) ----- */
 

@@ -93,3 +93,27 @@ def test_mixed_model_vs_oracle_fit(name, n):
     if ref["gammas"] is not None:
         assert np.max(np.abs(fit["gammas"] - ref["gammas"])) < 1e-6
     assert abs(fit["logLik"] - ref["logLik"]) < 1e-7 * abs(ref["logLik"])
+
+
+def test_device_glm_starts_match_host_glm_fit():
+    """glm.fit starting values computed by IRLS passes on the device (glmma_glm_pass) against the
+    host restatement of stats::glm.fit, for every start mixed_model() computes
+    (R/mixed_model.R:157-194)."""
+    from glmmadaptive_b200 import fit as hf
+    from family_cases import build_case
+    for case in [("binomial", "logit", 2, 0, None), ("binomial2", "logit", 2, 0, None), ("poisson", None, 1, 0, None),
+                 ("negative.binomial", None, 1, 0, [0.4]), ("Gamma.fam", None, 2, 0, [1.0]),
+                 ("zi.poisson", None, 2, 1, None), ("hurdle.negative.binomial", None, 2, 1, [0.6]),
+                 ("hurdle.lognormal", None, 1, 1, [-0.3]), ("hurdle.beta.fam", None, 1, 1, [1.5]),
+                 ("zi.binomial", None, 1, 1, None)]:
+        fam_name, d, th = build_case(*case, n=200)
+        rng = np.random.default_rng(5)
+        off = rng.normal(0, 0.2, len(d["X"]))
+        eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, link=case[1], nAGQ=5, X_zi=d.get("X_zi"),
+                        Z_zi=d.get("Z_zi"), offset=off, offset_zi=None if d.get("X_zi") is None else 0.5 * off)
+        dev = hf.starting_values_device(eng)
+        host = hf.starting_values(d["y"], d["X"], d.get("X_zi"), eng.spec.family, eng.q, eng.n_phis, False,
+                                  off, None if d.get("X_zi") is None else 0.5 * off)
+        for k in host:
+            assert np.max(np.abs(np.asarray(dev[k]) - np.asarray(host[k]))) < 1e-8, (case[0], k)
+        eng.close()
