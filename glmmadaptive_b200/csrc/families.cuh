@@ -546,6 +546,39 @@ struct FamCensoredNormal : FamBase {
     template <bool SCORE, bool CAREFUL>
     __device__ static __forceinline__ void point(double y, double ind, GLMMA_POINT_ARGS) {
         const double sigma = fp.a[0], isig = fp.a[2];
+        if (!CAREFUL) {
+            // Register variant: the same quantities from the table-based Gaussian tail functions
+            // (fast_gauss_tail), with x = t (left-censored) or -t (right-censored), B = Phi(x),
+            // Bf = max(B, sqrt(eps)) where the reference floors it:
+            //   left :  score_eta = -lambda(x) / sigma,                  score_phi = -t phi / max(B, sqrt(eps))
+            //   right:  score_eta = (sigma phi - eta (Bf - B)) / (Bf sigma^2),  score_phi = (B - Bf + t phi) / Bf
+            // which are the reference's expressions with P = 1 - B substituted (they differ from its
+            // floating-point evaluation by rounding noise only, and agree exactly when no floor is active).
+            const double t = (y - eta) * isig;
+            sz = 0.0;
+            if (ind == 0.0) {
+                ld = -0.5 * t * t;
+                if (SCORE) { se = t * isig; sp = t * t; } else { se = 0.0; sp = 0.0; }
+            } else {
+                const bool left = ind == 1.0;
+                const double x = left ? t : -t;
+                double lam, dn, B;
+                fast_gauss_tail(x, cx, ld, lam, dn, B);
+                const double Bf = fmax(B, GLMMA_SQRT_DBL_EPS);
+                if (B >= GLMMA_SQRT_DBL_EPS) {
+                    se = (left ? -lam : lam) * isig;
+                    sp = -x * lam;
+                } else if (left) {
+                    se = -lam * isig;
+                    sp = -t * dn / Bf;
+                } else {
+                    se = (sigma * dn - eta * (Bf - B)) / Bf * isig * isig;
+                    sp = (B - Bf + t * dn) / Bf;
+                }
+            }
+            return;
+        }
+
         const double t = (y - eta) * isig;
         sz = 0.0; se = 0.0; sp = 0.0;
         if (ind == 0.0) {

@@ -254,6 +254,113 @@ GLMMA_HD double fast_exp(double x, const MathCtx& cx) {
     return fm_make(fm_hi(v) + ((n >> 6) << 20), fm_lo(v));
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Gaussian tail functions for censored.normal (R/Fit_Funs.R:1360-1435): log Phi(x) and the inverse
+// Mills ratio phi(x) / Phi(x), without libm's erfc / erfcx / log / exp (about 600 instructions per
+// censored point and, inlined eight times, an instruction-cache problem: profiles/README.md).
+//
+//   erfcx(u) = exp(u^2) erfc(u), u >= 0:   (1 + 2u) erfcx(u) = p26(t),  t = (u - 4) / (u + 4)
+// p26: Chebyshev interpolant of degree 26 converted to the monomial basis (coefficients of
+// magnitude <= 1.24; generated with mpmath at 60 digits, truncation error 2e-19, fp64 evaluation
+// error <= 4 ulp -- tests/test_fastmath.py).
+//   x <= 0:  Phi(x) = erfcx(-x/sqrt2) exp(-x^2/2) / 2  =>  log Phi = -x^2/2 - ln2 + log c,  phi/Phi = sqrt(2/pi) / c
+//   x >  0:  Phi(x) = 1 - erfcx(x/sqrt2) exp(-x^2/2) / 2 = P  =>  log Phi = log P,  phi/Phi = exp(-x^2/2) / (sqrt(2 pi) P)
+// one fast_log_rcp serves the logarithm and the reciprocal in both cases.
+// ------------------------------------------------------------------------------------------
+#define GLMMA_ERFCX_DEG 26
+#ifdef __CUDA_ARCH__
+static __constant__ double GLMMA_ERFCX_C[GLMMA_ERFCX_DEG + 1] = {
+#else
+static const double GLMMA_ERFCX_C[GLMMA_ERFCX_DEG + 1] = {
+#endif
+    1.23299511862555256e+00,
+    -1.39621116840562498e-01,
+    1.53796521026200415e-02,
+    6.80970542546903562e-02,
+    -1.01039066036325037e-01,
+    9.37328349984395126e-02,
+    -6.63303658116485007e-02,
+    3.71675155359114107e-02,
+    -1.61977340659525300e-02,
+    5.03196999281092534e-03,
+    -7.57773219535229294e-04,
+    -1.99256776457919693e-04,
+    1.50621307463917777e-04,
+    -2.43989423090698060e-05,
+    -1.12207534527254248e-05,
+    5.70920121222635183e-06,
+    2.90906296837142686e-07,
+    -8.24912743496457224e-07,
+    7.89343963476141997e-08,
+    1.10090415607283036e-07,
+    -2.19171286847767334e-08,
+    -1.47051875523876298e-08,
+    3.97990820993533376e-09,
+    1.78874921890775359e-09,
+    -5.47796315403793008e-10,
+    -1.37212432109557996e-10,
+    4.33574469688012796e-11};
+
+// 1 / t, unchecked (1e-300 <= t <= 1e300): the reciprocal half of fast_log_rcp (6 FP64 instructions)
+GLMMA_HD double fast_rcp(double t, const MathCtx& cx) {
+    const int hi = fm_hi(t);
+    const int tmp = hi - 0x3FE60000;
+    const int i = (tmp >> 13) & 127;
+    const int ke = tmp & 0xfff00000;
+    const double z = fm_make(hi - ke, fm_lo(t));
+    const double invc = cx.logtab[FM_LOG_STRIDE * i];
+    const double r = fma(z, invc, -1.0);
+    const double r2 = r * r;
+    double u = fma(r2, r2, r2);
+    u = fma(u, r2, r2);
+    const double y0 = fma(-invc, r, invc);
+    const double y = fma(y0, u, y0);
+    return fm_make(fm_hi(y) - ke, fm_lo(y));
+}
+
+// erfcx(u) for 0 <= u <= 1e100
+GLMMA_HD double fast_erfcx(double u, const MathCtx& cx) {
+    const double d1 = u + 4.0, d2 = fma(2.0, u, 1.0);
+    const double rp = fast_rcp(d1 * d2, cx);          // one reciprocal for both denominators
+    const double t = (u - 4.0) * (rp * d2);            // (u - 4) / (u + 4)
+    const double t2 = t * t;
+    // even / odd halves: two Horner chains of 13 instead of one of 26
+    double pe = GLMMA_ERFCX_C[26], po = GLMMA_ERFCX_C[25];
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int k = 24; k >= 0; k -= 2) {
+        pe = fma(pe, t2, GLMMA_ERFCX_C[k]);
+        if (k >= 2) po = fma(po, t2, GLMMA_ERFCX_C[k - 1]);
+    }
+    return fma(t, po, pe) * (rp * d1);                 // / (1 + 2u)
+}
+
+// log Phi(x), phi(x) / Phi(x), phi(x) and Phi(x); branch-free, |x| <= 37 (beyond, exp takes its
+// library path and the results stay correct: phi and, for x < 0, Phi underflow to 0)
+GLMMA_HD void fast_gauss_tail(double x, const MathCtx& cx, double& logphi, double& mills, double& dens, double& cdf) {
+    const double c = fast_erfcx(fabs(x) * 0.70710678118654752, cx);
+    const double hx = -0.5 * x;
+    const double h = hx * x;
+    const double hl = fma(hx, x, -h);                  // exact rounding residual of -x^2/2
+    double E = fast_exp(h, cx);
+    E = fma(E, hl, E);                                 // exp(h + hl): keeps exp(-x^2/2) at ~3 ulp for large |x|
+    const bool neg = x <= 0.0;
+    const double q = 0.5 * E * c;                      // Phi(-|x|)
+    const double P = 1.0 - q;                          // Phi(|x|)
+    double L, r;
+    fast_log_rcp<false>(neg ? c : P, cx, L, r);
+    logphi = neg ? (h - 0.69314718055994531) + L : L;
+    dens = 0.39894228040143268 * E;
+    mills = neg ? 0.79788456080286536 * r : dens * r;
+    cdf = neg ? q : P;
+}
+GLMMA_HD void fast_logphi_mills(double x, const MathCtx& cx, double& logphi, double& mills) {
+    double dens, cdf;
+    fast_gauss_tail(x, cx, logphi, mills, dens, cdf);
+}
+
 // log(1 + exp(x)) and plogis(x) from exp(x) = ex (any finite positive value, or 0/inf)
 // CHECK = false: the caller guarantees 1e-300 <= ex <= 1e300
 template <bool CHECK = true>

@@ -24,6 +24,16 @@ void hm_exp_vec3(const double* x, int n, double* out) {
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i + 3 <= n; i += 3) fast_exp_vec<3>(x + i, cx, out + i);
 }
+void hm_logphi_mills(const double* x, int n, double* lp, double* ml) {
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
+    for (int i = 0; i < n; ++i) fast_logphi_mills(x[i], cx, lp[i], ml[i]);
+}
+void hm_erfcx(const double* u, int n, double* out) {
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
+    for (int i = 0; i < n; ++i) out[i] = fast_erfcx(u[i], cx);
+}
 void hm_l1p_sigmoid(const double* ex, int n, double* l1p, double* sig) {
     double c[GLMMA_FM_NCONST]; fastmath_constants(c);
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);

@@ -25,6 +25,8 @@ def hm():
     lib.hm_exp_vec3.argtypes = [dp, C.c_int, dp]
     lib.hm_log_rcp_vec4.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
+    lib.hm_logphi_mills.argtypes = [dp, C.c_int, dp, dp]
+    lib.hm_erfcx.argtypes = [dp, C.c_int, dp]
     return lib
 
 
@@ -97,3 +99,27 @@ def test_l1p_sigmoid(hm):
     assert np.max(np.abs(l1p - ref_l)) <= 4e-16 + 2 * np.max(ulp(ref_l))
     assert np.all(np.abs(l1p - ref_l) <= np.maximum(3 * ulp(ref_l), 2.3e-16))
     assert np.all(np.abs(sig - ref_s) <= np.maximum(3 * ulp(ref_s), 1e-300))
+
+
+def test_erfcx_logphi_mills(hm):
+    """Gaussian tail functions of the censored-normal fast path against mpmath."""
+    from mpmath import erfc, ncdf, npdf, sqrt as mpsqrt
+    mp.dps = 50
+    rng = np.random.default_rng(3)
+    u = np.concatenate([rng.uniform(0, 8, 6000), rng.uniform(0, 0.05, 500), np.exp(rng.uniform(0, 6, 500)), [0.0, 4.0, 1e3]])
+    out = np.empty_like(u)
+    hm.hm_erfcx(_p(u), len(u), _p(out))
+
+    def erfcx_ref(v):
+        v = mpf(float(v))
+        return mpexp(v * v) * erfc(v) if v < 20 else sum((-1) ** k * mp.rf(mpf(1) / 2, k) / v ** (2 * k) for k in range(30)) / (v * mpsqrt(mp.pi))
+    ref = np.array([float(erfcx_ref(v)) for v in u])
+    assert np.max(np.abs(out - ref) / ulp(ref)) <= 6.0
+    x = np.concatenate([rng.uniform(-8, 8, 8000), rng.uniform(-0.01, 0.01, 300), [0.0, -30.0, 8.0, -4.5, 4.5]])
+    lp = np.empty_like(x); ml = np.empty_like(x)
+    hm.hm_logphi_mills(_p(x), len(x), _p(lp), _p(ml))
+    lref = np.array([float(mplog(ncdf(mpf(float(v))))) for v in x])
+    mref = np.array([float(npdf(mpf(float(v))) / ncdf(mpf(float(v)))) for v in x])
+    # log Phi: 8 ulp or 3e-16 absolute (x > 0: log of a number next to 1); Mills ratio: 8 ulp
+    assert np.all(np.abs(lp - lref) <= np.maximum(8 * ulp(lref), 3e-16)), np.max(np.abs(lp - lref))
+    assert np.max(np.abs(ml - mref) / np.maximum(ulp(mref), 1e-300)) <= 8.0

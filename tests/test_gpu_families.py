@@ -121,3 +121,40 @@ def test_kat_hurdle_poisson_q3():
     # sds/correlations are published with 4 digits only
     assert abs(-gb.logLik_mixed(tv, eng, gh) - (-2797.307)) < 5e-2
     eng.close()
+
+
+def test_censored_normal_floor_regimes():
+    """censored.normal with censoring points far in the tails (|t| up to ~9): the sqrt(eps) floors of
+    the reference's score functions (R/Fit_Funs.R:1395, 1413, 1421) become active; the register
+    variant's table-based Gaussian tail functions must reproduce them (and the plain regime) to 1e-10."""
+    rng = np.random.default_rng(17)
+    ofam = oracle_family("censored.normal")
+    d, N = design(rng, 40, 6, 2)
+    betas = np.array([0.3, 0.5, -0.4])
+    D = np.array([[0.3, 0.05], [0.05, 0.2]])
+    eta = d["X"] @ betas
+    sigma = 0.7
+    v = eta + sigma * rng.standard_normal(N)
+    ind = rng.integers(0, 3, N).astype(float)
+    # push a third of the censored observations deep into either tail
+    shift = np.where(rng.random(N) < 0.35, rng.choice([-1.0, 1.0], N) * rng.uniform(3.5, 6.0, N), 0.0)
+    y = np.column_stack([v + np.where(ind > 0, shift, 0.0), ind])
+    d["y"] = y
+    th = dict(betas=betas, D=D, phis=np.array([np.log(sigma)]), gammas=None, nAGQ=11)
+    od, gh = oracle_grid(d, th, ofam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], "censored.normal", nAGQ=11)
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    tv = thetas_vec(th)
+    ref = agq.suff_stats(tv, od, ofam, gh)
+    got = eng.eval(th["betas"], th["D"], th["phis"], None)
+    assert got["n_nonfinite"] == ref["n_nonfinite"] == 0
+    assert relerr(got["loglik"], ref["loglik"]) < RTOL
+    for key in ("g_beta", "g_phi"):
+        sc = max(1.0, np.max(np.abs(ref[key])))
+        assert np.max(np.abs(got[key] - ref[key])) < 10 * RTOL * sc, key
+    assert relerr(got["S"], ref["S"]) < RTOL
+    # some grid points really are in the floored regime
+    tmin = np.min(np.abs((y[ind > 0, 0][:, None] - (od.X[ind > 0] @ betas)[:, None] - gh.Ztb[ind > 0]) / sigma))
+    tmax = np.max(np.abs((y[ind > 0, 0][:, None] - (od.X[ind > 0] @ betas)[:, None] - gh.Ztb[ind > 0]) / sigma))
+    assert tmax > 6.0
+    eng.close()
