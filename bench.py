@@ -374,7 +374,10 @@ def run_ours(args):
                        "what": "glmma_eval through the C ABI: host theta in (kernel parameters), result vector "
                                "copied back and synchronised every step; the data set is uploaded once by "
                                "glmma_create, as the R glue does",
-                       "create_s": t_create, "upload_bytes": eng.input_bytes},
+                       "create_s": t_create, "upload_bytes": eng.input_bytes,
+                       "cold_first_eval_s": t_create + t_modes_cold + 1.0 / e2e_value,
+                       "cold_what": "from host arrays to the first result: glmma_create (host->device copy of the "
+                                    "whole data set, upload_bytes) + cold mode search + one evaluation"},
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "find_modes": {"cold_clusters_per_s": n_total / t_modes_cold, "warm_clusters_per_s": n_total / t_modes_warm,
                               "mean_iterations_cold": st["mean_iterations"], "not_converged": st["n_not_converged"]},

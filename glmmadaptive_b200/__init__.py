@@ -5,5 +5,6 @@ Host-side mirror of the reference closures (GHfun, logLik_mixed, score_mixed) an
 its fitting loop (mixed_model, mixed_fit) over the C ABI in include/glmma.h.  See DESIGN.md.
 """
 from .engine import Engine, GH, GHfun, logLik_mixed, score_mixed, chol_transf, family_spec  # noqa: F401
-from .fit import mixed_model, mixed_fit, starting_values, starting_values_device, glm_fit_device  # noqa: F401
+from .fit import (mixed_model, mixed_fit, starting_values, starting_values_device, glm_fit_device,  # noqa: F401
+                  predict_subject_specific)
 from .sharded import ShardedEngine, shard_bounds  # noqa: F401

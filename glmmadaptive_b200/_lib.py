@@ -16,7 +16,7 @@ FAMILY_IDS = {
     "binomial": 0, "poisson": 1, "negative binomial": 2, "zero-inflated poisson": 3,
     "zero-inflated negative binomial": 4, "zero-inflated binomial": 5, "hurdle poisson": 6,
     "hurdle negative binomial": 7, "hurdle log-normal": 8, "beta": 9, "hurdle beta": 10,
-    "Gamma": 11, "censored normal": 12,
+    "Gamma": 11, "censored normal": 12, "Student's-t": 13, "beta binomial": 14,
 }
 LINK_IDS = {None: 0, "default": 0, "logit": 1, "log": 2, "identity": 3, "probit": 4, "cloglog": 5}
 
@@ -32,6 +32,7 @@ class GlmmaData(C.Structure):
         ("y", c_double_p), ("X", c_double_p), ("Z", c_double_p), ("X_zi", c_double_p),
         ("Z_zi", c_double_p), ("offset", c_double_p), ("offset_zi", c_double_p),
         ("weights", c_double_p), ("id", C.POINTER(C.c_int32)), ("row_ptr", C.POINTER(C.c_int64)),
+        ("family_df", C.c_double),
     ]
 
 

@@ -21,6 +21,7 @@ static thread_local std::string g_create_error;
 struct glmma_handle {
     DevData d;                 // device pointers + sizes
     int family, link, device, nagq, q, K, y_cols;
+    double family_df;          // students.t(df)
     const FamOps* ops;
     cudaStream_t stream;
     GridPar* d_grid;
@@ -115,9 +116,9 @@ static bool spd_inverse(const double* A, int q, double* Ainv, double* logdet) {
     return true;
 }
 
-static bool fill_fampar(int family, int n_phis, const double* phis, FamPar* fp, std::string& err) {
+static bool fill_fampar(int family, int n_phis, const double* phis, FamPar* fp, std::string& err, double df = 0.0) {
     std::memset(fp, 0, sizeof(*fp));
-    const bool needs = family == GLMMA_NEGBIN || family == GLMMA_ZI_NEGBIN || family == GLMMA_HURDLE_NEGBIN ||
+    const bool needs = family == GLMMA_STUDENTS_T || family == GLMMA_BETA_BINOMIAL || family == GLMMA_NEGBIN || family == GLMMA_ZI_NEGBIN || family == GLMMA_HURDLE_NEGBIN ||
                        family == GLMMA_HURDLE_LOGNORMAL || family == GLMMA_BETA || family == GLMMA_HURDLE_BETA ||
                        family == GLMMA_GAMMA || family == GLMMA_CENSORED_NORMAL;
     if (!needs) return true;
@@ -128,8 +129,12 @@ static bool fill_fampar(int family, int n_phis, const double* phis, FamPar* fp, 
             fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = std::lgamma(ph); fp->a[3] = glmma_digamma(ph); break;
         case GLMMA_HURDLE_LOGNORMAL:
             fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = 1.0 / (ph * ph); break;
-        case GLMMA_BETA: case GLMMA_HURDLE_BETA:
+        case GLMMA_BETA: case GLMMA_HURDLE_BETA: case GLMMA_BETA_BINOMIAL:
             fp->a[0] = ph; fp->a[1] = std::lgamma(ph); fp->a[2] = glmma_digamma(ph); break;
+        case GLMMA_STUDENTS_T:
+            fp->a[0] = ph; fp->a[2] = 1.0 / ph; fp->a[3] = df + 1.0; fp->a[4] = 1.0 / df; fp->a[5] = 0.5 * (df + 1.0);
+            fp->a[1] = std::lgamma(0.5 * (df + 1.0)) - std::lgamma(0.5 * df) - 0.5 * std::log(df * 3.14159265358979323846) - phis[0];
+            break;
         case GLMMA_CENSORED_NORMAL:
             fp->a[0] = ph; fp->a[1] = phis[0]; fp->a[2] = 1.0 / ph; break;
     }
@@ -152,6 +157,8 @@ static const FamOps* lookup_ops(int family, int link, int qy, int qz) {
         case GLMMA_HURDLE_BETA: return glmma_ops_hurdle_beta(qy, qz);
         case GLMMA_GAMMA: return glmma_ops_gamma(qy, qz);
         case GLMMA_CENSORED_NORMAL: return glmma_ops_censored_normal(qy, qz);
+        case GLMMA_STUDENTS_T: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_IDENTITY) ? glmma_ops_students_t(qy, qz) : nullptr;
+        case GLMMA_BETA_BINOMIAL: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_LOGIT) ? glmma_ops_beta_binomial(qy, qz) : nullptr;
 #endif
     }
     return nullptr;
@@ -381,7 +388,8 @@ int glmma_family_id(const char* name) {
         {"zero-inflated binomial", GLMMA_ZI_BINOMIAL}, {"hurdle poisson", GLMMA_HURDLE_POISSON},
         {"hurdle negative binomial", GLMMA_HURDLE_NEGBIN}, {"hurdle log-normal", GLMMA_HURDLE_LOGNORMAL},
         {"beta", GLMMA_BETA}, {"hurdle beta", GLMMA_HURDLE_BETA}, {"Gamma", GLMMA_GAMMA},
-        {"censored normal", GLMMA_CENSORED_NORMAL}};
+        {"censored normal", GLMMA_CENSORED_NORMAL}, {"Student's-t", GLMMA_STUDENTS_T},
+        {"beta binomial", GLMMA_BETA_BINOMIAL}};
     for (auto& t : tab) if (std::strcmp(t.n, name) == 0) return t.id;
     return -1;
 }
@@ -411,6 +419,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     if (data->y_cols != 1 && data->y_cols != 2) return fail(nullptr, GLMMA_ERR_ARG, "y_cols must be 1 or 2");
     if (data->family == GLMMA_CENSORED_NORMAL && data->y_cols != 2)
         return fail(nullptr, GLMMA_ERR_ARG, "censored normal needs a two-column response");
+    if (data->family == GLMMA_STUDENTS_T && !(data->family_df > 0.0))
+        return fail(nullptr, GLMMA_ERR_ARG, "students.t needs family_df > 0 (the df of the family object)");
     if ((data->q_zi > 0 && !data->Z_zi) || (data->p_zi > 0 && !data->X_zi))
         return fail(nullptr, GLMMA_ERR_ARG, "X_zi / Z_zi missing");
     const FamOps* ops = lookup_ops(data->family, data->link, data->q_y, data->q_zi);
@@ -455,6 +465,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->family = data->family; h->link = data->link; h->device = device; h->nagq = data->nAGQ;
     h->q = q; h->K = (int)Kd; h->y_cols = data->y_cols; h->ops = ops; h->stream = nullptr;
     h->have_modes = false; h->launches = 0; h->sticky = 0; h->d_ytab = nullptr;
+    h->family_df = data->family_df;
     h->d_pby = nullptr; h->have_pby = false;
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
@@ -468,7 +479,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     const double* ya = data->y;
     const double* yb = data->y_cols == 2 ? data->y + N : nullptr;
     switch (data->family) {
-        case GLMMA_BINOMIAL: case GLMMA_ZI_BINOMIAL:
+        case GLMMA_BINOMIAL: case GLMMA_ZI_BINOMIAL: case GLMMA_BETA_BINOMIAL:
             y2.resize(N);
             for (int64_t r = 0; r < N; ++r) { y1[r] = ya[r]; y2[r] = yb ? ya[r] + yb[r] : 1.0; }
             break;
@@ -658,7 +669,7 @@ static int run_prep(glmma_handle* h, const double* betas, const double* phis, co
     CoefPar c;
     int rc = fill_coef(h, betas, gammas, &c);
     if (rc) return rc;
-    if (!fill_fampar(h->family, h->d.n_phis, phis, fp, h->error)) return GLMMA_ERR_ARG;
+    if (!fill_fampar(h->family, h->d.n_phis, phis, fp, h->error, h->family_df)) return GLMMA_ERR_ARG;
     PrepArgs pa;
     pa.d = h->d; pa.fam = *fp; pa.want_score = 1; pa.ytab = h->d.csum ? h->d_ytab : nullptr;
     h->ops->prep(pa, c, h->stream);
@@ -822,7 +833,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
         EvalArgs ea;
         std::memset(&ea, 0, sizeof(ea));
         ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
-        fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error);
+        fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error, h->family_df);
         fill_prior(h, D, false, &ea.prior);
         h->ops->sphi(ea, h->eval_grid[1], h->eval_smem[1], h->stream);
         h->launches++;
@@ -894,7 +905,7 @@ int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, in
     std::memset(&ga, 0, sizeof(ga));
     ga.X = design == 0 ? d.X : d.X_zi;
     ga.y1 = d.y1;
-    ga.y2 = (h->family == GLMMA_BINOMIAL || h->family == GLMMA_ZI_BINOMIAL) ? d.y2 : nullptr;
+    ga.y2 = (h->family == GLMMA_BINOMIAL || h->family == GLMMA_ZI_BINOMIAL || h->family == GLMMA_BETA_BINOMIAL) ? d.y2 : nullptr;
     ga.offset = use_offset ? (design == 0 ? d.offset : d.offset_zi) : nullptr;
     ga.N = d.N; ga.p = p; ga.fam = glm_family; ga.resp = response; ga.y1_is_log = y1_is_log ? 1 : 0;
     ga.first = first ? 1 : 0;

@@ -606,3 +606,80 @@ struct FamCensoredNormal : FamBase {
         }
     }
 };
+
+// ----- students.t(df) -- R/Fit_Funs.R:1006-1041; identity link, df fixed by the family object.
+// a[0] = sigma, a[1] = lgamma((df+1)/2) - lgamma(df/2) - log(df pi)/2 - log sigma, a[2] = 1/sigma,
+// a[3] = df + 1, a[4] = 1/df, a[5] = (df + 1)/2 --------------------------------------------------
+struct FamStudentsT : FamBase {
+    static constexpr bool HAS_PHI = true;
+    static constexpr bool NEED_EMU = false;
+    __device__ static __forceinline__ void obs_const(double, double, const FamPar& fp, double& cll, double& cphi) {
+        cll = fp.a[1]; cphi = -1.0;
+    }
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
+        const double d = y - eta;
+        const double t = d * fp.a[2];
+        const double w = t * t * fp.a[4];               // (y - mu)^2 / (df sigma^2)
+        double L, r;
+        fast_log_rcp<CAREFUL>(1.0 + w, cx, L, r);
+        ld = -fp.a[5] * L;
+        if (SCORE) {
+            se = d * fp.a[2] * fp.a[2] * fp.a[3] * fp.a[4] * r;
+            sp = fp.a[3] * w * r;
+        } else { se = 0.0; sp = 0.0; }
+        sz = 0.0;
+    }
+};
+
+// ----- beta.binomial(), logit -- R/Fit_Funs.R:1245-1321.  y1 = successes, y2 = trials N.
+// a[0] = phi, a[1] = lgamma(phi), a[2] = digamma(phi).  With A = phi mu, B = phi (1 - mu):
+//   log f = lchoose(N, y) + [lgamma(y + A) - lgamma(A)] + [lgamma(N - y + B) - lgamma(B)] + lgamma(phi) - lgamma(N + phi)
+// For integer counts the bracketed differences are finite sums  sum_{i < y} log(A + i)  and their
+// derivatives  sum_{i < y} 1 / (A + i), i.e. one fast_log_rcp per unit of y (Bernoulli data: one per
+// point); counts above GLMMA_BB_SUM_MAX (or non-integer responses) take lgamma / digamma. -----------
+#define GLMMA_BB_SUM_MAX 24
+__device__ __forceinline__ void bb_rising(double x, double cnt, const MathCtx& cx, double& dlg, double& dpsi) {
+    // lgamma(x + cnt) - lgamma(x) and digamma(x + cnt) - digamma(x), cnt >= 0
+    const int n = (int)cnt;
+    if ((double)n == cnt && n <= GLMMA_BB_SUM_MAX && x >= 1e-290) {
+        dlg = 0.0; dpsi = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double L, r;
+            fast_log_rcp<true>(x + (double)i, cx, L, r);
+            dlg += L; dpsi += r;
+        }
+    } else {
+        dlg = lgamma(x + cnt) - lgamma(x);
+        dpsi = glmma_digamma(x + cnt) - glmma_digamma(x);
+    }
+}
+struct FamBetaBinomial : FamBase {
+    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
+    static constexpr double EMU_HI = 1e13;
+    static constexpr double LOG_EMU_LO = -29.93;
+    static constexpr double LOG_EMU_HI = 29.93;
+    static constexpr bool HAS_PHI = true;
+    static constexpr bool USES_Y2 = true;
+    __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
+        const double lch = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
+        cll = lch + fp.a[1] - lgamma(N + fp.a[0]);
+        cphi = fp.a[0] * (fp.a[2] - glmma_digamma(N + fp.a[0]));
+    }
+    template <bool SCORE, bool CAREFUL>
+    __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
+        const double phi = fp.a[0];
+        double mu, lt, L;
+        link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
+        const double A = phi * mu, B = phi - A;
+        double lgA, psA, lgB, psB;
+        bb_rising(A, y, cx, lgA, psA);
+        bb_rising(B, N - y, cx, lgB, psB);
+        ld = lgA + lgB;
+        if (SCORE) {
+            se = phi * (psA - psB) * (mu - mu * mu);
+            sp = phi * (mu * psA + (1.0 - mu) * psB);
+        } else { se = 0.0; sp = 0.0; }
+        sz = 0.0;
+    }
+};

@@ -38,6 +38,8 @@ _SPECS = {
     "hurdle.beta.fam": ("hurdle beta", "logit", 1, True, 1),
     "Gamma.fam": ("Gamma", "log", 1, False, 1),
     "censored.normal": ("censored normal", "identity", 1, False, 2),
+    "students.t": ("Student's-t", "identity", 1, False, 1),
+    "beta.binomial": ("beta binomial", "logit", 1, False, None),
 }
 _BY_FAMILY_STRING = {v[0]: v for v in _SPECS.values()}
 
@@ -79,7 +81,7 @@ class Engine:
     (R/mixed_fit.R:1-25), uploaded once.  Wraps one ``glmma_handle``."""
 
     def __init__(self, y, X, Z, id, family, link=None, nAGQ=None, X_zi=None, Z_zi=None, offset=None,
-                 offset_zi=None, weights=None, device=0):
+                 offset_zi=None, weights=None, device=0, df=None):
         self.lib = _lib.load()
         self.spec = family_spec(family, link) if not isinstance(family, FamilySpec) else family
         y = _f(y)
@@ -107,6 +109,7 @@ class Engine:
         d.offset, d.offset_zi, d.weights = _dp(offset), _dp(offset_zi), _dp(weights)
         d.id = ids.ctypes.data_as(C.POINTER(C.c_int32))
         d.row_ptr = None
+        d.family_df = 0.0 if df is None else float(df)      # students.t(df)
         h = C.c_void_p()
         rc = self.lib.glmma_create(C.byref(d), int(device), C.byref(h))
         if rc != 0:

@@ -470,3 +470,65 @@ def mixed_model(y, X, Z, id, family, link=None, X_zi=None, Z_zi=None, offset=Non
         if own:
             engine.close()
     return fit
+
+
+# ------------------------------------------------------------------------------------------
+# predict(type = "subject_specific") point predictions (R/methods.R:976-1012)
+# ------------------------------------------------------------------------------------------
+def _linkinv(link, eta):
+    """family$linkinv with stats::make.link's clamps (SURVEY appendix C)."""
+    if link == "logit":
+        e = np.clip(eta, -30.0, 30.0)       # R: .Call(C_logit_linkinv): exp(eta) clamped to [eps, 1/eps]
+        t = np.where(eta < -30, _EPS, np.where(eta > 30, 1.0 / _EPS, np.exp(e)))
+        return t / (1.0 + t)
+    if link == "log":
+        return np.maximum(np.exp(eta), _EPS)
+    if link == "probit":
+        from math import sqrt
+        from scipy.special import ndtr
+        thresh = 8.125890664701906        # -qnorm(.Machine$double.eps)
+        return ndtr(np.clip(eta, -thresh, thresh))
+    if link == "cloglog":
+        return np.clip(-np.expm1(-np.exp(eta)), _EPS, 1.0 - _EPS)
+    return eta
+
+
+def predict_subject_specific(fit, y, X, Z, id, family, link=None, X_zi=None, Z_zi=None, offset=None,
+                             offset_zi=None, type_pred="response", nAGQ=None, device=0, df=None):
+    """predict(object, newdata, type = "subject_specific", se.fit = FALSE): empirical Bayes modes of
+    the random effects of the clusters in `newdata` at the fitted parameters -- the device mode search
+    of find_modes(), R/methods.R:984-997 -- then eta = X beta + rowSums(Z * b_hat[id, ]) (:998-1003),
+    the response-scale prediction and, for families with a zero part, the multiplication by
+    1 - plogis(eta_zi) (:1004-1010).  The Monte-Carlo standard errors (:1013-1142) stay with the caller."""
+    eng = Engine(y, X, Z, id, family, link=link, nAGQ=nAGQ, X_zi=X_zi, Z_zi=Z_zi, offset=offset,
+                 offset_zi=offset_zi, device=device, df=df)
+    try:
+        betas, D = np.asarray(fit["coefficients"], float), np.asarray(fit["D"], float)
+        phis, gammas = fit.get("phis"), fit.get("gammas")
+        gh = GHfun(eng, 0.0, betas, np.linalg.inv(D), phis, gammas)
+        ids = np.asarray(id)
+        idx = np.concatenate(([0], np.cumsum(ids[1:] != ids[:-1])))        # 0-based cluster index per row
+        X = np.asarray(X, float)
+        Zm = np.asarray(Z, float).reshape(len(X), -1)
+        eta = X @ betas + np.sum(Zm * gh.post_modes[idx, :eng.q_y], axis=1)
+        if offset is not None:
+            eta = eta + np.asarray(offset, float)
+        pred = eta if type_pred == "link" else _linkinv(eng.spec.link, eta)
+        out = dict(post_modes=gh.post_modes, stats=gh.stats, eta=eta)
+        if eng.p_zi:
+            eta_zi = np.asarray(X_zi, float).reshape(len(X), -1) @ np.asarray(gammas, float)
+            if offset_zi is not None:
+                eta_zi = eta_zi + np.asarray(offset_zi, float)
+            if eng.q_zi:
+                eta_zi = eta_zi + np.sum(np.asarray(Z_zi, float).reshape(len(X), -1) * gh.post_modes[idx, eng.q_y:], axis=1)
+            if eng.spec.family == "hurdle log-normal":
+                pred = np.exp(pred + 0.5 * np.exp(np.asarray(phis, float)[0]) ** 2)
+            zi_probs = 1.0 / (1.0 + np.exp(-eta_zi))
+            pred = (1.0 - zi_probs) * pred
+            out.update(eta_zi=eta_zi, zi_probs=zi_probs)
+        out["pred"] = pred
+        if eng.n <= 100_000:
+            out["post_vars"] = gh.post_vars
+        return out
+    finally:
+        eng.close()

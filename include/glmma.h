@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLMMA_VERSION 120
+#define GLMMA_VERSION 130
 
 #if defined(__GNUC__)
 #define GLMMA_API __attribute__((visibility("default")))
@@ -59,7 +59,9 @@ enum glmma_family {
     GLMMA_HURDLE_BETA = 10,      /* hurdle.beta.fam()            R/Fit_Funs.R:932-1004  */
     GLMMA_GAMMA = 11,            /* Gamma.fam()                  R/Fit_Funs.R:1323-1358 */
     GLMMA_CENSORED_NORMAL = 12,  /* censored.normal()            R/Fit_Funs.R:1360-1435 */
-    GLMMA_N_FAMILIES = 13
+    GLMMA_STUDENTS_T = 13,       /* students.t(df)               R/Fit_Funs.R:1006-1041 */
+    GLMMA_BETA_BINOMIAL = 14,    /* beta.binomial() (logit)      R/Fit_Funs.R:1245-1321 */
+    GLMMA_N_FAMILIES = 15
 };
 
 /* family$link; only the link each family object is built with is accelerated
@@ -101,6 +103,7 @@ typedef struct glmma_data {
     const int32_t* id;      /* N cluster labels, equal values contiguous (R's `id`);
                                used when row_ptr is NULL                                 */
     const int64_t* row_ptr; /* n+1 CSR offsets into the rows, or NULL                    */
+    double family_df;       /* students.t: family$df (fixed by the family object); else 0 */
 } glmma_data;
 
 /* Per-call statistics of the mode search (replaces the silent behaviour of

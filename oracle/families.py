@@ -806,3 +806,82 @@ ALL_FAMILIES = {
     "Gamma.fam": Gamma_fam,
     "censored.normal": censored_normal,
 }
+
+
+class students_t(Family):
+    """R/Fit_Funs.R:1006-1041; identity link, df fixed by the family object."""
+    family = "Student's-t"
+    link = "identity"
+    has_phis = True
+    n_phis = 1
+
+    def __init__(self, df):
+        self.df = float(df)
+
+    def linkinv(self, eta):
+        return identity_linkinv(eta)
+
+    def variance(self, mu):
+        return np.ones_like(mu)
+
+    def log_dens(self, y, eta, phis, eta_zi=None):
+        sigma = np.exp(phis[0])
+        yc = _colv(y, eta)
+        df = self.df
+        t = (yc - eta) / sigma
+        out = sp.gammaln((df + 1) / 2) - sp.gammaln(df / 2) - 0.5 * np.log(df * np.pi) \
+            - (df + 1) / 2 * np.log1p(t * t / df) - np.log(sigma)        # dt(t, df, log = TRUE) - log(sigma)
+        return out, eta
+
+    def score_eta_fun(self, y, mu, phis, eta_zi=None):
+        sigma2 = np.exp(phis[0]) ** 2
+        y_mu = _colv(y, mu) - mu
+        return (y_mu * (self.df + 1) / (self.df * sigma2)) / (1 + y_mu ** 2 / (self.df * sigma2))
+
+    def score_phis_fun(self, y, mu, phis, eta_zi=None):
+        sigma = np.exp(phis[0])
+        y_mu2_df = (_colv(y, mu) - mu) ** 2 / self.df
+        return (self.df + 1) * y_mu2_df * sigma ** -2 / (1 + y_mu2_df / sigma ** 2) - 1
+
+
+class beta_binomial(Family):
+    """R/Fit_Funs.R:1245-1321 (logit link)."""
+    family = "beta binomial"
+    link = "logit"
+    has_phis = True
+    n_phis = 1
+
+    def linkinv(self, eta):
+        return logit_linkinv(eta)
+
+    def _size_y(self, y, like):
+        y = np.asarray(y, float)
+        if y.ndim == 2:
+            return _colv(y[:, 0] + y[:, 1], like), _colv(y[:, 0], like)
+        return _colv(np.ones(len(y)), like), _colv(y, like)
+
+    def log_dens(self, y, eta, phis, eta_zi=None):
+        phi = np.exp(phis[0])
+        mu_y = self.mu_fun(eta)
+        size, x = self._size_y(y, mu_y)
+        A, B = phi * mu_y, phi * (1 - mu_y)
+        lbeta = lambda a, b: sp.gammaln(a) + sp.gammaln(b) - sp.gammaln(a + b)
+        lchoose = sp.gammaln(size + 1) - sp.gammaln(x + 1) - sp.gammaln(size - x + 1)
+        return lchoose + lbeta(x + A, size - x + B) - lbeta(A, B), mu_y
+
+    def score_eta_fun(self, y, mu, phis, eta_zi=None):
+        phi = np.exp(phis[0])
+        size, x = self._size_y(y, mu)
+        phi_mu, phi_1mu = phi * mu, phi * (1 - mu)
+        comp1 = (sp.digamma(x + phi_mu) - sp.digamma(size - x + phi_1mu)) * phi
+        comp2 = (sp.digamma(phi_mu) - sp.digamma(phi_1mu)) * phi
+        return (comp1 - comp2) * (mu - mu * mu)
+
+    def score_phis_fun(self, y, mu, phis, eta_zi=None):
+        phi = np.exp(phis[0])
+        size, x = self._size_y(y, mu)
+        mu1 = 1 - mu
+        phi_mu, phi_1mu = phi * mu, phi * mu1
+        comp1 = sp.digamma(x + phi_mu) * mu + sp.digamma(size - x + phi_1mu) * mu1 - sp.digamma(size + phi)
+        comp2 = sp.digamma(phi_mu) * mu + sp.digamma(phi_1mu) * mu1 - sp.digamma(phi)
+        return (comp1 - comp2) * phi

@@ -62,6 +62,16 @@ def response(fam, rng, N, eta):
         hi, lo = np.quantile(v, 0.8), np.quantile(v, 0.1)
         ind = np.where(v > hi, 2.0, np.where(v < lo, 1.0, 0.0))
         return np.column_stack([np.clip(v, lo, hi), ind])
+    if fam == "students.t":
+        return eta + 0.6 * rng.standard_t(4.0, N)
+    if fam in ("beta.binomial", "beta.binomial2"):
+        m = 1 / (1 + np.exp(-eta))
+        pr = rng.beta(m * 3.0, (1 - m) * 3.0)
+        if fam == "beta.binomial":
+            return (rng.random(N) < pr).astype(float)
+        trials = rng.integers(1, 7, N)
+        s = rng.binomial(trials, pr)
+        return np.column_stack([s, trials - s]).astype(float)
     raise ValueError(fam)
 
 
@@ -90,26 +100,30 @@ CASES = [
     ("hurdle.beta.fam", None, 1, 1, [1.5]),
     ("Gamma.fam", None, 2, 0, [1.0]),
     ("censored.normal", None, 2, 0, [-0.3]),
+    ("students.t", None, 2, 0, [-0.4]),
+    ("beta.binomial", None, 1, 0, [1.1]),
+    ("beta.binomial2", None, 2, 0, [1.1]),
 ]
 
 
 def build_case(fam, link, q_y, q_zi, phis, n=36):
     """Returns (fam_name, data dict, theta dict) of one CASES row (seeded)."""
     rng = np.random.default_rng(sum(map(ord, fam)) * 100 + 10 * q_y + q_zi)
-    fam_name = "binomial" if fam == "binomial2" else fam
+    fam_name = {"binomial2": "binomial", "beta.binomial2": "beta.binomial"}.get(fam, fam)
     zi = fam_name.startswith("zi.") or fam_name.startswith("hurdle.")
     d, N = design(rng, n, 6, q_y, zi=zi, q_zi=q_zi)
     q = q_y + q_zi
     A = rng.standard_normal((q, q)) * 0.3
     D = A @ A.T + 0.3 * np.eye(q)
     betas = np.array([0.3, 0.5, -0.4])
-    if fam in ("beta.fam", "hurdle.beta.fam", "binomial", "binomial2", "zi.binomial"):
+    if fam in ("beta.fam", "hurdle.beta.fam", "binomial", "binomial2", "zi.binomial", "beta.binomial", "beta.binomial2"):
         betas = np.array([-0.2, 0.6, -0.3])
     b = rng.standard_normal((n, q)) @ np.linalg.cholesky(D).T
     eta = d["X"] @ betas + np.sum(d["Z"] * b[d["id"], :q_y], axis=1)
     d["y"] = response(fam, rng, N, eta)
     th = dict(betas=betas, D=D, phis=None if phis is None else np.array(phis),
-              gammas=np.array([-0.8, 0.4]) if zi else None, nAGQ=7 if q >= 3 else 9)
+              gammas=np.array([-0.8, 0.4]) if zi else None, nAGQ=7 if q >= 3 else 9,
+              df=4.0 if fam == "students.t" else None)
     return fam_name, d, th
 
 

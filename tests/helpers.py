@@ -11,8 +11,10 @@ ORACLE_FAMILIES = {
     "zi.binomial": F.zi_binomial, "hurdle.poisson": F.hurdle_poisson,
     "hurdle.negative.binomial": F.hurdle_negative_binomial, "hurdle.lognormal": F.hurdle_lognormal,
     "beta.fam": F.beta_fam, "hurdle.beta.fam": F.hurdle_beta_fam, "Gamma.fam": F.Gamma_fam,
-    "censored.normal": F.censored_normal,
+    "censored.normal": F.censored_normal, "students.t": lambda: F.students_t(TEST_DF),
+    "beta.binomial": F.beta_binomial,
 }
+TEST_DF = 4.0      # df of the students.t family object used throughout the tests
 
 
 def oracle_data(d):

@@ -23,7 +23,7 @@ def test_family_parity(fam, link, q_y, q_zi, phis):
     D = th["D"]
     od, gh = oracle_grid(d, th, ofam)
     eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, link=link, nAGQ=th["nAGQ"],
-                    X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"))
+                    X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"), df=th.get("df"))
     eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
     tv = thetas_vec(th)
     ref = agq.suff_stats(tv, od, ofam, gh)

@@ -117,3 +117,23 @@ def test_device_glm_starts_match_host_glm_fit():
         for k in host:
             assert np.max(np.abs(np.asarray(dev[k]) - np.asarray(host[k]))) < 1e-8, (case[0], k)
         eng.close()
+
+
+def test_predict_subject_specific_vs_oracle():
+    """predict(type = "subject_specific") point predictions for new clusters: EB modes from the
+    device mode search, then the reference's formulas (R/methods.R:976-1012)."""
+    for name in ("C3", "C4"):
+        d, th, fam_name = _case(name, 30)
+        fam = oracle_family(fam_name)
+        od, gh = oracle_grid(d, th, fam, mode_finder="newton")
+        fit = dict(coefficients=th["betas"], D=th["D"], phis=th.get("phis"), gammas=th.get("gammas"))
+        pr = gb.predict_subject_specific(fit, d["y"], d["X"], d["Z"], d["id"], fam_name, X_zi=d.get("X_zi"),
+                                         Z_zi=d.get("Z_zi"), nAGQ=th["nAGQ"])
+        assert np.max(np.abs(pr["post_modes"] - gh.post_modes)) < 1e-7
+        idx = np.repeat(np.arange(od.n), np.diff(od.row_ptr))
+        eta = od.X @ th["betas"] + np.sum(od.Z * gh.post_modes[idx, :od.q_y], axis=1)
+        ref = np.exp(eta)
+        if name == "C4":
+            ez = od.X_zi @ th["gammas"] + od.Z_zi[:, 0] * gh.post_modes[idx, 2]
+            ref = ref / (1 + np.exp(ez))
+        assert np.max(np.abs(pr["pred"] - ref) / ref) < 1e-6

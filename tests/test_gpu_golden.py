@@ -27,9 +27,9 @@ def npz():
 def test_engine_matches_fixture(npz, case):
     fam, link, q_y, q_zi, phis = case
     g = load_case(npz, case_id(*case))
-    fam_name = "binomial" if fam == "binomial2" else fam
+    fam_name = {"binomial2": "binomial", "beta.binomial2": "beta.binomial"}.get(fam, fam)
     eng = gb.Engine(g["y"], g["X"], g["Z"], g["id"], fam_name, link=link, nAGQ=int(g["nAGQ"]),
-                    X_zi=g.get("X_zi"), Z_zi=g.get("Z_zi"))
+                    X_zi=g.get("X_zi"), Z_zi=g.get("Z_zi"), df=4.0 if fam == "students.t" else None)
     eng.set_modes(g["post_modes"], g["chol"])
     got = eng.eval(g["betas"], g["D"], g.get("phis"), g.get("gammas"))
     assert got["n_nonfinite"] == 0
