@@ -1,0 +1,144 @@
+"""GPU: edge cases of the hot path through the C ABI, each against the oracle (1e-10 relative):
+single-observation clusters, one very large cluster among tiny ones (ragged CSR, streaming path),
+a single cluster, the largest grids the engine accepts (nAGQ = 32 for q = 1; nAGQ = 21 for q = 2,
+the vignette's setting), zero cluster weights, offsets in both linear predictors, extreme linear
+predictors that activate R's link clamps, and argument errors."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import agq
+import glmmadaptive_b200 as gb
+from glmmadaptive_b200 import _lib
+from helpers import oracle_data, oracle_family, oracle_grid, pack_chol, thetas_vec, relerr
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _mk(rng, sizes, q_y, fam, zi=False):
+    ids = np.repeat(np.arange(len(sizes)), sizes)
+    N = len(ids)
+    x = rng.random(N)
+    g = rng.integers(0, 2, len(sizes)).astype(float)[ids]
+    d = dict(id=ids, X=np.column_stack([np.ones(N), x, g]), Z=np.column_stack([np.ones(N), x])[:, :q_y])
+    if zi:
+        d["X_zi"] = np.column_stack([np.ones(N), g])
+    return d, N
+
+
+def _check(d, th, fam_name, **kw):
+    fam = oracle_family(fam_name)
+    od, gh = oracle_grid(d, th, fam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d.get("X_zi"),
+                    Z_zi=d.get("Z_zi"), offset=d.get("offset"), offset_zi=d.get("offset_zi"),
+                    weights=d.get("weights"))
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    ref = agq.suff_stats(thetas_vec(th), od, fam, gh)
+    got = eng.eval(th["betas"], th["D"], th.get("phis"), th.get("gammas"))
+    assert got["n_nonfinite"] == ref["n_nonfinite"]
+    assert relerr(got["loglik"], ref["loglik"]) < RTOL
+    for key in ("g_beta", "g_phi", "g_gamma"):
+        if key in ref:
+            assert np.max(np.abs(got[key] - ref[key])) < 10 * RTOL * max(1.0, np.max(np.abs(ref[key]))), key
+    assert np.max(np.abs(got["S"] - ref["S"])) < RTOL * max(1.0, np.max(np.abs(ref["S"])))
+    st = eng.find_modes(th["betas"], np.linalg.inv(th["D"]), th.get("phis"), th.get("gammas"), warm=False)
+    assert st["n_chol_failed"] == 0
+    modes, _, _ = eng.get_modes()
+    assert np.max(np.abs(modes - gh.post_modes)) < 1e-7
+    eng.close()
+    return got, ref
+
+
+def test_single_observation_clusters_and_single_cluster():
+    rng = np.random.default_rng(1)
+    betas, D = np.array([0.2, 0.4, -0.3]), np.array([[0.5, 0.1], [0.1, 0.3]])
+    d, N = _mk(rng, np.ones(50, int), 2, "poisson")
+    d["y"] = rng.poisson(np.exp(d["X"] @ betas)).astype(float)
+    _check(d, dict(betas=betas, D=D, nAGQ=11), "poisson")
+    d, N = _mk(rng, np.array([7]), 2, "poisson")
+    d["y"] = rng.poisson(np.exp(d["X"] @ betas)).astype(float)
+    _check(d, dict(betas=betas, D=D, nAGQ=11), "poisson")
+
+
+def test_one_huge_cluster_among_tiny_ones():
+    rng = np.random.default_rng(2)
+    sizes = np.array([1, 2, 600, 1, 3, 33, 2, 17, 1, 9])
+    betas, D = np.array([0.1, 0.3, -0.2]), np.array([[0.4, 0.05], [0.05, 0.2]])
+    d, N = _mk(rng, sizes, 2, "negative.binomial")
+    mu = np.exp(d["X"] @ betas)
+    d["y"] = rng.negative_binomial(2.0, 2.0 / (2.0 + mu)).astype(float)
+    _check(d, dict(betas=betas, D=D, phis=np.array([np.log(2.0)]), nAGQ=9), "negative.binomial")
+
+
+@pytest.mark.parametrize("q_y,nagq", [(1, 32), (2, 21), (1, 1), (2, 16)])
+def test_largest_and_smallest_grids(q_y, nagq):
+    rng = np.random.default_rng(3)
+    betas = np.array([-0.3, 0.6, -0.2])
+    D = np.array([[0.8, 0.1], [0.1, 0.3]])[:q_y, :q_y]
+    d, N = _mk(rng, 1 + rng.poisson(4, 25), q_y, "binomial")
+    d["y"] = (rng.random(N) < 1 / (1 + np.exp(-(d["X"] @ betas)))).astype(float)
+    _check(d, dict(betas=betas, D=D, nAGQ=nagq), "binomial")
+
+
+def test_zero_weights_offsets_and_zero_part():
+    rng = np.random.default_rng(4)
+    betas, gammas = np.array([0.4, 0.3, -0.2]), np.array([-1.0, 0.5])
+    D = np.array([[0.4, 0.1], [0.1, 0.2]])
+    d, N = _mk(rng, 1 + rng.poisson(5, 30), 2, "zi.poisson", zi=True)
+    y = rng.poisson(np.exp(d["X"] @ betas)).astype(float)
+    y[rng.random(N) < 0.3] = 0.0
+    d["y"] = y
+    w = rng.uniform(0.5, 2.0, 30)
+    w[[3, 11]] = 0.0
+    d["weights"] = w
+    d["offset"] = rng.normal(0, 0.3, N)
+    d["offset_zi"] = rng.normal(0, 0.3, N)
+    got, ref = _check(d, dict(betas=betas, D=D, gammas=gammas, nAGQ=11), "zi.poisson")
+    assert abs(got["sum_w"] - w.sum()) < 1e-12
+
+
+def test_link_clamps_on_extreme_linear_predictors():
+    """|eta| beyond 30 (logit) and eta below log(eps) (log link): R's make.link clamps are active and
+    the register variant must hand these clusters to the careful kernel."""
+    rng = np.random.default_rng(5)
+    D = np.array([[0.5]])
+    d, N = _mk(rng, 1 + rng.poisson(4, 30), 1, "binomial")
+    d["X"][:, 1] = rng.normal(0, 25, N)              # wild covariate
+    betas = np.array([0.5, 1.5, -0.2])
+    d["y"] = (rng.random(N) < 1 / (1 + np.exp(-np.clip(d["X"] @ betas, -40, 40)))).astype(float)
+    _check(d, dict(betas=betas, D=D, nAGQ=11), "binomial")
+    d2, N2 = _mk(rng, 1 + rng.poisson(4, 30), 1, "poisson")
+    d2["X"][:, 1] = rng.normal(0, 1, N2)
+    betas2 = np.array([-38.0, 0.5, 0.1])              # exp(eta) < eps: mu clamps to eps
+    d2["y"] = np.zeros(N2)
+    d2["y"][rng.random(N2) < 0.05] = 1.0
+    _check(d2, dict(betas=betas2, D=D, nAGQ=11), "poisson")
+
+
+def test_argument_errors_are_reported_not_crashed():
+    lib = _lib.load()
+    rng = np.random.default_rng(6)
+    d, N = _mk(rng, np.array([3, 4]), 1, "poisson")
+    y = rng.poisson(1.0, N).astype(float)
+    with pytest.raises(ValueError):
+        gb.Engine(y, d["X"], d["Z"], d["id"], "compoisson")
+    with pytest.raises(_lib.GlmmaError):
+        gb.Engine(y, d["X"], d["Z"], d["id"], "poisson", nAGQ=99)
+    with pytest.raises(_lib.GlmmaError):               # zero part family without X_zi
+        gb.Engine(y, d["X"], d["Z"], d["id"], "zi.poisson")
+    with pytest.raises(_lib.GlmmaError):               # students.t needs its df
+        gb.Engine(y, d["X"], d["Z"], d["id"], "students.t")
+    eng = gb.Engine(y, d["X"], d["Z"], d["id"], "poisson")
+    with pytest.raises(_lib.GlmmaError) as e:          # eval before any grid exists
+        eng.eval(np.zeros(3), np.eye(1))
+    assert e.value.code == _lib.ERR_STATE
+    eng.find_modes(np.zeros(3), np.eye(1))
+    with pytest.raises(_lib.GlmmaError) as e:          # D not positive definite
+        eng.eval(np.zeros(3), np.array([[-1.0]]))
+    assert e.value.code == _lib.ERR_NUMERIC
+    with pytest.raises(_lib.GlmmaError) as e:          # M-step before an E-step
+        eng.em_score(np.zeros(3))
+    assert e.value.code == _lib.ERR_STATE
+    eng.close()
