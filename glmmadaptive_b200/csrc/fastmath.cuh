@@ -54,7 +54,7 @@ static GLMMA_NOINLINE double fm_slow_rcp(double x) { return 1.0 / x; }
 #endif
 #define GLMMA_FM_LOG_DOUBLES (128 * 16)
 #define GLMMA_FM_EXP_DOUBLES (64 * 16)
-#define GLMMA_FM_NCONST 13
+#define GLMMA_FM_NCONST 14
 struct MathCtx {
     const double* logtab;   // device: replicated table + 2 * (lane & 7); host: 128 x (invc, logc)
     const double* exptab;   // device: replicated table + (lane & 15);    host: 64 x 2^(j/64)
@@ -73,7 +73,8 @@ struct MathCtx {
 #define FMC_E120 9
 #define FMC_E24 10
 #define FMC_E6 11
-#define FMC_LN2 12    // ln 2 rounded to double (stage-wise log: one fma for k ln2 + logc)
+#define FMC_LN2 12    // ln 2 rounded to double
+#define FMC_LN2S 13   // ln 2 * 2^-20 (stage-wise log: one fma for k ln2 + logc from k * 2^20)
 GLMMA_HD MathCtx make_mathctx(const double* logtab, const double* exptab, const double* c) {
     MathCtx m;
     m.logtab = logtab; m.exptab = exptab;
@@ -114,6 +115,7 @@ inline void fastmath_constants(double* c) {
     c[5] = FM_64_LN2; c[6] = FM_MAGIC; c[7] = -FM_LN2_64_HI; c[8] = -FM_LN2_64_LO;
     c[9] = 1.0 / 120.0; c[10] = 1.0 / 24.0; c[11] = 1.0 / 6.0;
     c[12] = 0x1.62e42fefa39efp-1;
+    c[13] = 0x1.62e42fefa39efp-21;
 }
 
 // log t and 1/t for t > 0.
@@ -166,8 +168,8 @@ GLMMA_HD void fast_log_rcp(double t, const MathCtx& cx, double& L, double& rcp) 
 // guarantees 1e-300 <= t[i] <= 1e300.
 // k ln2 + logc is ONE fma with ln2 rounded to double: z lies in [0.6875, 1.375), so k != 0
 // implies |log t| >= 0.318 and the rounding error of ln2 (2.3e-17 |k|) stays below half an
-// ulp of the result; the hi/lo split of the scalar form buys nothing here (13 FP64
-// instructions per element instead of 14).
+// ulp of the result; the hi/lo split of the scalar form buys nothing here.  12 FP64
+// instructions per element (scalar form: 14); k enters as (double)(k 2^20) times ln2 2^-20.
 template <int N>
 GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, double* rcp) {
     int ke[N];
@@ -180,7 +182,7 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
         const int tmp = hi - 0x3FE60000;
         const int idx = (tmp >> 13) & 127;
         ke[i] = tmp & 0xfff00000;
-        kd[i] = (double)(tmp >> 20);
+        kd[i] = (double)ke[i];                      // k * 2^20: the shift is folded into the constant below
         z[i] = fm_make(hi - ke[i], fm_lo(t[i]));
 #ifdef __CUDA_ARCH__
         const double2 tc = *reinterpret_cast<const double2*>(cx.logtab + FM_LOG_STRIDE * idx);
@@ -189,7 +191,7 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
         invc[i] = cx.logtab[FM_LOG_STRIDE * idx]; logc[i] = cx.logtab[FM_LOG_STRIDE * idx + 1];
 #endif
     }
-    const double c6 = cx.c[FMC_L6], c5 = cx.c[FMC_L5], c3 = cx.c[FMC_L3], ln2 = cx.c[FMC_LN2];
+    const double c6 = cx.c[FMC_L6], c5 = cx.c[FMC_L5], c3 = cx.c[FMC_L3], ln2s = cx.c[FMC_LN2S];
 #define FM_VEC for (int i = 0; i < N; ++i)
 #ifdef __CUDACC__
 #define FM_UNROLL _Pragma("unroll")
@@ -199,14 +201,15 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
     FM_UNROLL FM_VEC r[i] = fma(z[i], invc[i], -1.0);
     FM_UNROLL FM_VEC r2[i] = r[i] * r[i];
     FM_UNROLL FM_VEC q[i] = fma(r[i], c6, c5);
-    FM_UNROLL FM_VEC logc[i] = fma(kd[i], ln2, logc[i]);         // w = k ln2 + logc
+    FM_UNROLL FM_VEC logc[i] = fma(kd[i], ln2s, logc[i]);        // w = k ln2 + logc
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.25);
-    FM_UNROLL FM_VEC u[i] = fma(r2[i], r2[i], r2[i]);
+    FM_UNROLL FM_VEC u[i] = fma(r2[i], r2[i], r2[i]);            // r^2 + r^4
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], c3);
     FM_UNROLL FM_VEC q[i] = fma(r[i], q[i], -0.5);
-    FM_UNROLL FM_VEC u[i] = fma(u[i], r2[i], r2[i]);
-    FM_UNROLL FM_VEC invc[i] = fma(-invc[i], r[i], invc[i]);     // y0
+    FM_UNROLL FM_VEC invc[i] = fma(-invc[i], r[i], invc[i]);     // y0 = invc (1 - r)
     FM_UNROLL FM_VEC q[i] = fma(r2[i], q[i], r[i]);
+    // 1/z = y0 (1 + r^2 + r^4) up to r^6 <= 3.6e-15 relative: the reciprocal only feeds score
+    // carriers (tolerance 1e-10), the logarithm keeps its full series
     FM_UNROLL FM_VEC invc[i] = fma(invc[i], u[i], invc[i]);      // y
     FM_UNROLL FM_VEC L[i] = logc[i] + q[i];
     FM_UNROLL FM_VEC rcp[i] = fm_make(fm_hi(invc[i]) - ke[i], fm_lo(invc[i]));

