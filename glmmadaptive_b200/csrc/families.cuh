@@ -55,8 +55,12 @@ __device__ __forceinline__ void zero_part(double ez, double elam, const MathCtx&
     fast_l1p_sigmoid<CAREFUL>(elam, cx, l1p, pi);
 }
 
+// zl1p / zpi: log(1 + exp(eta_zi)) and plogis(eta_zi) when the caller has them already (ZT = true: the
+// register variant tabulates them per (observation, zero-part node index) -- eta_zi depends on the
+// node only through the zero-part random effect, so with q_zi <= 1 there are n_i * nAGQ distinct
+// values per cluster instead of n_i * nAGQ^q)
 #define GLMMA_POINT_ARGS double eta, double ez, double emu, double elam, const FamPar& fp, const MathCtx& cx, \
-                         double& ld, double& se, double& sz, double& sp
+                         double& ld, double& se, double& sz, double& sp, double zl1p = 0.0, double zpi = 0.0
 
 struct FamBase {
     static constexpr bool HAS_ZI = false;    // family has a zero part (eta_zi)
@@ -113,7 +117,7 @@ struct FamBinomialLogit : FamBase {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, lt, L;
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
@@ -146,7 +150,7 @@ struct FamBinomialOther : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
         FamBinomialLogit::obs_const(y, N, fp, cll, cphi);
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, dmu;
         if (LINK == 4) {
@@ -174,7 +178,7 @@ struct FamPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = -lgamma(y + 1.0); cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu;
         link_log<CAREFUL>(eta, emu, mu, lmu);
@@ -208,7 +212,7 @@ struct FamNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         nb_const(y, fp, cll, cphi);
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double yp_, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu, L, r;
@@ -254,11 +258,11 @@ struct FamZiPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu, pi, l1p;
         link_log<CAREFUL>(eta, emu, mu, lmu);
-        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);          // plogis(eta_zi), log(1 + lambda)
+        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);   // log(1 + lambda), plogis(eta_zi)
         if (y > 0.0) {
             ld = (CAREFUL ? fma(y, lmu, -mu) : -mu) - l1p;     // fast variant: + y eta at node level
             if (SCORE) { se = y - mu; sz = -pi; }
@@ -286,13 +290,13 @@ struct FamZiNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu, L, r, pi, l1p;
         link_log<CAREFUL>(eta, emu, mu, lmu);
         fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
-        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
             const double yp = y + phi;
             ld = (CAREFUL ? fma(y, lmu, -yp * L) : -yp * L) - l1p;     // fast variant: + y eta at node level
@@ -330,11 +334,11 @@ struct FamZiBinomial : FamBase {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, lt, L, pi, l1p;
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
-        zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
         if (y > 0.0) {
             ld = (CAREFUL ? fma(y, lt, -N * L) : -N * L) - l1p;        // fast variant: + y eta at node level
             if (SCORE) { se = fma(-N, mu, y); sz = -pi; }
@@ -353,10 +357,11 @@ struct FamZiBinomial : FamBase {
 };
 
 // zero part shared by the hurdle families (e.g. R/Fit_Funs.R:652-655, 670-676)
-template <bool CAREFUL>
-__device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCtx& cx, bool pos, double& lz, double& sz) {
+template <bool CAREFUL, bool ZT = false>
+__device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCtx& cx, bool pos, double& lz, double& sz,
+                                            double zl1p = 0.0, double zpi = 0.0) {
     double pi, l1p;
-    zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+    if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
     // positive: log(1 - pi) = -log(1 + e^ez); zero: log pi = ez - log(1 + e^ez)
     lz = pos ? -l1p : ez - l1p;
     sz = pos ? -pi : 1.0 - pi;
@@ -369,11 +374,11 @@ struct FamHurdlePoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
+        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double mu, lmu;
@@ -393,11 +398,11 @@ struct FamHurdleNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
+        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double phi = fp.a[0];
@@ -430,11 +435,11 @@ struct FamHurdleLogNormal : FamBase {
         if (y > 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double ly, GLMMA_POINT_ARGS) {
         const bool pos = y > 0.0;
         double lz;
-        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
+        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double d = ly - eta;
@@ -476,7 +481,7 @@ struct FamBeta : FamBase {
         cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y;
         cphi = fp.a[0] * fp.a[2];
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
         beta_point<SCORE, CAREFUL>(ly, l1y, eta, emu, fp, cx, ld, se, sp);
         sz = 0.0;
@@ -497,11 +502,11 @@ struct FamHurdleBeta : FamBase {
         if (ly > -INFINITY) { cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y; cphi = fp.a[0] * fp.a[2]; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
         const bool pos = ly > -INFINITY;
         double lz;
-        hurdle_zero<CAREFUL>(ez, elam, cx, pos, lz, sz);
+        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double l2;
@@ -521,7 +526,7 @@ struct FamGamma : FamBase {
         cll = (phi - 1.0) * ly - fp.a[2] + phi * fp.a[1];
         cphi = phi * (ly + fp.a[1] + 1.0 - fp.a[3]);
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu;
@@ -543,7 +548,7 @@ struct FamCensoredNormal : FamBase {
         if (ind == 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double ind, GLMMA_POINT_ARGS) {
         const double sigma = fp.a[0], isig = fp.a[2];
         if (!CAREFUL) {
@@ -616,7 +621,7 @@ struct FamStudentsT : FamBase {
     __device__ static __forceinline__ void obs_const(double, double, const FamPar& fp, double& cll, double& cphi) {
         cll = fp.a[1]; cphi = -1.0;
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double d = y - eta;
         const double t = d * fp.a[2];
@@ -666,7 +671,7 @@ struct FamBetaBinomial : FamBase {
         cll = lch + fp.a[1] - lgamma(N + fp.a[0]);
         cphi = fp.a[0] * (fp.a[2] - glmma_digamma(N + fp.a[0]));
     }
-    template <bool SCORE, bool CAREFUL>
+    template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lt, L;

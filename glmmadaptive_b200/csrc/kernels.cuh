@@ -646,6 +646,7 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
 #define GLMMA_K_FAST 512
+#define GLMMA_NTAB_MAX_K 256
 #ifndef GLMMA_FAST_MINBLOCKS
 #define GLMMA_FAST_MINBLOCKS 4
 #endif
@@ -664,7 +665,13 @@ struct FastLayout {
     static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + GLMMA_NCSUM + 1;
     static constexpr int PRE = ((NJ * W + NSC) + 1) & ~1;   // one prefetch buffer (records + scalars)
     static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJ * 32 + NTOT * 32 + 4;
-    __host__ __device__ static size_t node_doubles(int K) { return (((size_t)K * (Q + 1) + (K + 1) / 2) + 1) & ~(size_t)1; }
+    // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed node indices (K ints).  For
+    // large grids the double part is dropped (the round loop then reads gx / glw through the packed
+    // indices): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
+    __host__ __device__ static bool has_ntab(int K) { return K <= GLMMA_NTAB_MAX_K; }
+    __host__ __device__ static size_t node_doubles(int K) {
+        return (((has_ntab(K) ? (size_t)K * (Q + 1) : 0) + (K + 1) / 2) + 1) & ~(size_t)1;
+    }
     __host__ static size_t smem_bytes(int warps, int K) {
         return sizeof(double) * (L::head_doubles() + node_doubles(K) + (size_t)warps * WARP_DOUBLES);
     }
@@ -688,8 +695,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
     const int wpb = blockDim.x >> 5;
     const int nagq = A.grid->nagq;
     const int K = A.grid->K;
-    double* ntab = smem + L::head_doubles();                 // K x (Q + 1): z_0.., log wGH
-    int* nidx = reinterpret_cast<int*>(ntab + (size_t)K * (Q + 1));   // K packed node indices
+    // K > GLMMA_NTAB_MAX_K needs nagq^Q > 256 with nagq <= 16, i.e. Q >= 3: for Q < 3 the test folds away
+    const bool has_ntab = Q < 3 || FL::has_ntab(K);
+    double* ntab = smem + L::head_doubles();                 // K x (Q + 1): z_0.., log wGH (small grids)
+    int* nidx = reinterpret_cast<int*>(ntab + (has_ntab ? (size_t)K * (Q + 1) : 0));   // K packed node indices
     double* pre0 = smem + L::head_doubles() + FL::node_doubles(K) + wib * FL::WARP_DOUBLES;
     double* tabF = pre0 + 2 * FL::PRE;
     double* tabL = tabF + NJ * FL::TF;
@@ -712,10 +721,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             const int a = kk % nagq;
             kk /= nagq;
             packed |= a << (8 * e);
-            ntab[k * (Q + 1) + e] = gx[a];
+            if (has_ntab) ntab[k * (Q + 1) + e] = gx[a];
             lw += glw[a];
         }
-        ntab[k * (Q + 1) + Q] = lw;
+        if (has_ntab) ntab[k * (Q + 1) + Q] = lw;
         nidx[k] = packed;
     }
     for (int t = lane; t < FL::NTOT * 32 + 4; t += 32) totl[t] = 0.0;
@@ -795,6 +804,11 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
         // cluster is left to eval_kernel.
         double2* coef = reinterpret_cast<double2*>(acc_eta);
         constexpr int NTc = FL::NT > 0 ? FL::NT : 1;
+        // zero part tabulated (families.cuh, GLMMA_POINT_ARGS): lives in the accumulator scratch, past
+        // the coefficients, until the rounds are over
+        constexpr bool ZT = F::HAS_ZI && QZ <= 1;
+        double2* tabZ = reinterpret_cast<double2*>(acc_eta + 2 * (NJ * Q + NJ * NTc));
+        static_assert(!ZT || 2 * (NJ * Q + NJ * NTc) + 2 * NJ * NG <= FL::NACCS * NJ * 32, "zero-part table does not fit");
         bool bad = false;
         if (lane < nic) {
             double* r = rec + lane * W;
@@ -887,6 +901,19 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             }
         }
         __syncwarp();
+        if (ZT) {
+            // zero-part pieces per (observation, zero-part node index): log(1 + lambda), plogis(eta_zi)
+            const int nz = QZ > 0 ? nagq : 1;
+            const unsigned inv_nz = QZ > 0 ? (65536u + (unsigned)nagq - 1u) / (unsigned)nagq : 65536u;
+            for (int t = lane; t < nic * nz; t += 32) {
+                const int j = (int)(((unsigned)t * inv_nz) >> 16);
+                const int na = t - j * nz;
+                double l1p, pi;
+                fast_l1p_sigmoid<false>(tabL[j * FL::TL + na], cx, l1p, pi);
+                tabZ[j * NG + na] = make_double2(l1p, pi);
+            }
+            __syncwarp();
+        }
 
         const double* cs = sc + SC_CS;
         const double syxb = F::LIN_ETA ? cs[2] : 0.0;
@@ -909,8 +936,20 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 const bool valid = k < K;
                 const int kc = valid ? k : K - 1;
                 // node: b_k = mode + sqrt(2) R^-1 z_k, a = log N(b_k; 0, D) + log wGH_k
-                const double* nt = ntab + kc * (Q + 1);
                 const int packed = nidx[kc];
+                double nt[Q + 1];
+                if (has_ntab) {
+#pragma unroll
+                    for (int e = 0; e <= Q; ++e) nt[e] = ntab[kc * (Q + 1) + e];
+                } else {
+                    nt[Q] = A.grid->lw_const;
+#pragma unroll
+                    for (int e = 0; e < Q; ++e) {
+                        const int ae = (packed >> (8 * e)) & 0xff;
+                        nt[e] = gx[ae];
+                        nt[Q] += glw[ae];
+                    }
+                }
                 double b[Q];
 #pragma unroll
                 for (int dd = 0; dd < Q; ++dd) {
@@ -935,6 +974,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
 #pragma unroll
                 for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e)
                     pl[e] = tabL + e * NG + (QZ > 0 ? ((packed >> (8 * (QY + e))) & 0xff) : 0);
+                const double2* pz = tabZ + (QZ > 0 ? ((packed >> (8 * QY)) & 0xff) : 0);
                 double vphi = 0.0;
                 double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
                 if (F::LIN_ETA) {
@@ -960,7 +1000,12 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             _Pragma("unroll") for (int e = 1; e < QZ; ++e) elam *= pl[e][(j) * FL::TL];                 \
         }                                                                                              \
         double ld, se, sz, sp;                                                                         \
-        F::template point<SCORE, false>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);  \
+        if (ZT) {                                                                                      \
+            const double2 zt = pz[(j) * NG];                                                           \
+            F::template point<SCORE, false, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp, zt.x, zt.y); \
+        } else {                                                                                       \
+            F::template point<SCORE, false>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp); \
+        }                                                                                              \
         a += ld;                                                                                       \
         if (SCORE) {                                                                                   \
             se_[j] = se;                                                                               \
