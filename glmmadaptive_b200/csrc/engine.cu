@@ -198,32 +198,42 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_reduce_kernel(DevData d, 
     }
 }
 
-// result vector (include/glmma.h, glmma_eval) from the block partials, one block
+// result vector (include/glmma.h, glmma_eval) from the block partials, one block: warp w reduces
+// accumulator w (then score column w, w + 8, ...) -- lanes stride the blocks, a fixed shuffle tree
+// finishes, so the sum order is fixed (deterministic) and nothing is serialised behind block barriers
 __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* eval_partials, int n_eval_blocks,
                                                                   const double* score_partials, int n_score_blocks,
                                                                   int p, int n_phis, int p_zi, int q, int want_score,
                                                                   double* result) {
-    __shared__ double sh[FINAL_THREADS / 32];
+    __shared__ double acc[GLMMA_NACC];
+    __shared__ double col[GLMMA_PMAX + GLMMA_PZIMAX];
     const int np = q * (q + 1) / 2;
-    double acc[GLMMA_NACC];
-    for (int a = 0; a < 4 + np; ++a) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < n_eval_blocks; b += FINAL_THREADS) s += eval_partials[(int64_t)b * GLMMA_NACC + a];
-        acc[a] = block_sum(s, sh);
-    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = FINAL_THREADS / 32;
     const int ncol = p + p_zi;
+    for (int a = w; a < 4 + np; a += nw) {
+        double s = 0.0;
+        for (int b = lane; b < n_eval_blocks; b += 32) s += eval_partials[(int64_t)b * GLMMA_NACC + a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) acc[a] = s;
+    }
+    if (want_score) {
+        for (int l = w; l < ncol; l += nw) {
+            double s = 0.0;
+            for (int b = lane; b < n_score_blocks; b += 32) s += score_partials[(int64_t)b * ncol + l];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) col[l] = s;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
     }
     if (!want_score) return;
-    for (int l = 0; l < ncol; ++l) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < n_score_blocks; b += FINAL_THREADS) s += score_partials[(int64_t)b * ncol + l];
-        const double t = block_sum(s, sh);
-        if (threadIdx.x == 0) {
-            if (l < p) result[4 + l] = t;
-            else result[4 + p + n_phis + (l - p)] = t;
-        }
+    for (int l = threadIdx.x; l < ncol; l += FINAL_THREADS) {
+        if (l < p) result[4 + l] = col[l];
+        else result[4 + p + n_phis + (l - p)] = col[l];
     }
     if (threadIdx.x == 0) {
         for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3];
@@ -237,7 +247,6 @@ __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* e
             }
     }
 }
-
 
 // ------------------------------------------------------------------------------
 // starting values: one IRLS step of stats::glm.fit (as mixed_model() calls it,

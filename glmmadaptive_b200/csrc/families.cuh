@@ -460,10 +460,18 @@ __device__ __forceinline__ void beta_point(double ly, double l1y, double eta, do
     const double a = mu * phi;
     const double b = phi - a;
     const double dl = ly - l1y;
-    ld = a * dl - lgamma(a) - lgamma(b);
+    double lga, lgb, pa, pb;
+    if (fmin(a, b) >= 1e-290 && fmax(a, b) <= 1e25) {
+        // joint table-based lgamma / digamma (fastmath.cuh); warp-uniform in practice
+        fast_lgamma_digamma(a, cx, lga, pa);
+        fast_lgamma_digamma(b, cx, lgb, pb);
+    } else {
+        lga = lgamma(a); lgb = lgamma(b);
+        pa = SCORE ? glmma_digamma(a) : 0.0;
+        pb = SCORE ? glmma_digamma(b) : 0.0;
+    }
+    ld = a * dl - lga - lgb;
     if (SCORE) {
-        const double pa = glmma_digamma(a);
-        const double pb = glmma_digamma(b);
         se = phi * (pb - pa + dl) * (mu - mu * mu);
         sp = phi * (mu * (ly - pa) + (1.0 - mu) * (l1y - pb));
     }

@@ -364,6 +364,59 @@ GLMMA_HD void fast_logphi_mills(double x, const MathCtx& cx, double& logphi, dou
     fast_gauss_tail(x, cx, logphi, mills, dens, cdf);
 }
 
+
+// two independent fast_log_rcp evaluations (full series for both results), interleaved; unchecked
+GLMMA_HD void fast_log_rcp_pair(const double* t, const MathCtx& cx, double* L, double* rcp) {
+    double L0, r0, L1, r1;
+    fast_log_rcp<false>(t[0], cx, L0, r0);
+    fast_log_rcp<false>(t[1], cx, L1, r1);
+    L[0] = L0; rcp[0] = r0; L[1] = L1; rcp[1] = r1;
+}
+
+// ------------------------------------------------------------------------------------------
+// lgamma(x) and digamma(x) together, 1e-290 <= x <= 1e25 (beta.fam / hurdle.beta.fam evaluate both at
+// a = mu phi and b = (1 - mu) phi at every quadrature point; libm's lgamma + a digamma with a
+// data-dependent shift loop cost ~1000 instructions per point there).
+//   shift by 10:  P(x) = x (x+1) ... (x+9) = s (s+8) (s+14) (s+18) (s+20),  s = x (x + 9)
+//   lgamma(x)  = lgamma(x + 10) - log P,   digamma(x) = digamma(x + 10) - P'(x) / P(x)
+//   Stirling series at z = x + 10 >= 10 (7 terms: truncation < 1e-16 absolute)
+// Two fast_log_rcp (z and P) supply both logarithms and both reciprocals.  Error: lgamma 12 ulp or
+// 1.5e-14 absolute (a difference of two terms of size 13..25), digamma 8 ulp or 4e-15 absolute
+// (tests/test_fastmath.py).
+// ------------------------------------------------------------------------------------------
+GLMMA_HD void fast_lgamma_digamma(double x, const MathCtx& cx, double& lg, double& psi) {
+    const double s = x * (x + 9.0);
+    const double f1 = s + 8.0, f2 = s + 14.0, f3 = s + 18.0, f4 = s + 20.0;
+    const double t34 = f3 * f4, s34 = f3 + f4;
+    const double u2 = fma(f2, s34, t34);          // d/ds of f2 f3 f4
+    const double p234 = f2 * t34;
+    const double u1 = fma(f1, u2, p234);          // d/ds of f1 f2 f3 f4
+    const double p1234 = f1 * p234;
+    const double u0 = fma(s, u1, p1234);          // dP/ds
+    const double P = s * p1234;
+    const double dP = u0 * fma(2.0, x, 9.0);      // P'(x)
+    const double z = x + 10.0;
+    double tt[2] = {z, P}, LL[2], rr[2];
+    fast_log_rcp_pair(tt, cx, LL, rr);
+    const double Lz = LL[0], rz = rr[0], w = rz * rz;
+    double a = fma(w, 6.41025641025641025641e-03, -1.91752691752691752692e-03);    // 1/156, -691/360360
+    a = fma(w, a, 8.41750841750841750842e-04);     // 1/1188
+    a = fma(w, a, -5.95238095238095238095e-04);    // -1/1680
+    a = fma(w, a, 7.93650793650793650794e-04);     // 1/1260
+    a = fma(w, a, -2.77777777777777777778e-03);    // -1/360
+    a = fma(w, a, 8.33333333333333333333e-02);     // 1/12
+    const double lgz = fma(z - 0.5, Lz, fma(rz, a, 0.91893853320467274178 - z));
+    double b = fma(w, -8.33333333333333333333e-02, 2.10927960927960927961e-02);      // -1/12, 691/32760
+    b = fma(w, b, -7.57575757575757575758e-03);    // -1/132
+    b = fma(w, b, 4.16666666666666666667e-03);     // 1/240
+    b = fma(w, b, -3.96825396825396825397e-03);    // -1/252
+    b = fma(w, b, 8.33333333333333333333e-03);     // 1/120
+    b = fma(w, b, -8.33333333333333333333e-02);    // -1/12
+    const double psz = fma(w, b, fma(-0.5, rz, Lz));
+    lg = lgz - LL[1];
+    psi = fma(-dP, rr[1], psz);
+}
+
 // log(1 + exp(x)) and plogis(x) from exp(x) = ex (any finite positive value, or 0/inf)
 // CHECK = false: the caller guarantees 1e-300 <= ex <= 1e300
 template <bool CHECK = true>

@@ -27,6 +27,7 @@ def hm():
     lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_logphi_mills.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_erfcx.argtypes = [dp, C.c_int, dp]
+    lib.hm_lgamma_digamma.argtypes = [dp, C.c_int, dp, dp]
     return lib
 
 
@@ -124,3 +125,20 @@ def test_erfcx_logphi_mills(hm):
     # log Phi: 8 ulp or 3e-16 absolute (x > 0: log of a number next to 1); Mills ratio: 8 ulp
     assert np.all(np.abs(lp - lref) <= np.maximum(8 * ulp(lref), 3e-16)), np.max(np.abs(lp - lref))
     assert np.max(np.abs(ml - mref) / np.maximum(ulp(mref), 1e-300)) <= 8.0
+
+
+def test_lgamma_digamma(hm):
+    """Joint lgamma / digamma of the beta families' fast path against mpmath."""
+    from mpmath import loggamma, digamma
+    mp.dps = 50
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.uniform(0, 12, 6000), np.exp(rng.uniform(-25, 10, 4000)), rng.uniform(0.9, 2.1, 1500),
+                        [1.0, 2.0, 1.4616321449683623, 1e-12, 0.5, 10.0, 1e4, 1e8]])
+    lg = np.empty_like(x); ps = np.empty_like(x)
+    hm.hm_lgamma_digamma(_p(x), len(x), _p(lg), _p(ps))
+    lref = np.array([float(loggamma(mpf(float(v)))) for v in x])
+    pref = np.array([float(digamma(mpf(float(v)))) for v in x])
+    # lgamma(x + 10) - log P(x): the two terms are of size 13..25 for x < 12, so the absolute error is
+    # a few ulps OF THOSE (1.5e-14), whatever the size of the result; 12 ulp for larger arguments
+    assert np.all(np.abs(lg - lref) <= np.maximum(12 * ulp(lref), 1.5e-14)), np.max(np.abs(lg - lref))
+    assert np.all(np.abs(ps - pref) <= np.maximum(8 * ulp(pref), 4e-15)), np.max(np.abs(ps - pref))
