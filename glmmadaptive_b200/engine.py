@@ -90,7 +90,15 @@ class Engine:
         X_zi = None if X_zi is None else _f(np.asarray(X_zi, float).reshape(len(X), -1))
         Z_zi = None if Z_zi is None else _f(np.asarray(Z_zi, float).reshape(len(X), -1))
         offset, offset_zi, weights = _f(offset), _f(offset_zi), _f(weights)
-        ids = np.ascontiguousarray(np.asarray(id).astype(np.int32))
+        # Cluster index: rows of one cluster must be contiguous (the reference sorts its data frame by
+        # the grouping factor, R/mixed_model.R:50).  Any label type works: only label changes matter.
+        labels = np.asarray(id).reshape(-1)
+        if len(labels) != X.shape[0]:
+            raise ValueError("id must have one entry per row of X")
+        change = np.flatnonzero(labels[1:] != labels[:-1]) + 1
+        row_ptr = np.ascontiguousarray(np.concatenate(([0], change, [len(labels)])), dtype=np.int64)
+        if len(labels) <= 2_000_000 and len(np.unique(labels)) != len(row_ptr) - 1:
+            raise ValueError("rows are not grouped by id: sort the data by the grouping factor first")
         N = X.shape[0]
         self.N, self.p, self.q_y = N, X.shape[1], Z.shape[1]
         self.p_zi = 0 if X_zi is None else X_zi.shape[1]
@@ -107,8 +115,9 @@ class Engine:
         d.n_phis, d.y_cols, d.nAGQ = self.n_phis, (2 if y.ndim == 2 and y.shape[1] == 2 else 1), self.nAGQ
         d.y, d.X, d.Z, d.X_zi, d.Z_zi = _dp(y), _dp(X), _dp(Z), _dp(X_zi), _dp(Z_zi)
         d.offset, d.offset_zi, d.weights = _dp(offset), _dp(offset_zi), _dp(weights)
-        d.id = ids.ctypes.data_as(C.POINTER(C.c_int32))
-        d.row_ptr = None
+        d.id = None
+        d.row_ptr = row_ptr.ctypes.data_as(C.POINTER(C.c_int64))
+        d.n_clusters = len(row_ptr) - 1
         d.family_df = 0.0 if df is None else float(df)      # students.t(df)
         h = C.c_void_p()
         rc = self.lib.glmma_create(C.byref(d), int(device), C.byref(h))
@@ -123,7 +132,8 @@ class Engine:
         self._modes_version = None
         self._cache_key, self._cache_val = None, None
         self._X_host, self._X_zi_host = X, X_zi
-        self.input_bytes = sum(a.nbytes for a in (y, X, Z, X_zi, Z_zi, offset, offset_zi, weights, ids) if a is not None)
+        self.input_bytes = sum(a.nbytes for a in (y, X, Z, X_zi, Z_zi, offset, offset_zi, weights) if a is not None) + \
+            4 * len(row_ptr)
 
     # -- lifetime -----------------------------------------------------------
     def close(self):

@@ -113,7 +113,7 @@ def to_bytes(val, unit):
     return float(val.replace(",", "")) * m[unit]
 
 
-m = re.search(r"--clusters (\d+)", open(os.path.join(ROOT, "devprof.sh")).read())
+m = re.search(r"--clusters (\d+)", open(os.path.join(ROOT, "scripts", "ncu_full_capture.sh")).read())
 clusters = int(m.group(1)) if m else None
 traffic = {"kernels": [{
     "kernel": src[0][1].replace("void ", "").replace("(int)", "").replace("(bool)", "").split("(")[0],

@@ -142,3 +142,21 @@ def test_argument_errors_are_reported_not_crashed():
         eng.em_score(np.zeros(3))
     assert e.value.code == _lib.ERR_STATE
     eng.close()
+
+
+def test_id_labels_of_any_type_and_ungrouped_rows():
+    rng = np.random.default_rng(7)
+    d, N = _mk(rng, np.array([3, 2, 4]), 1, "poisson")
+    y = rng.poisson(1.0, N).astype(float)
+    th = (np.array([0.1, 0.2, -0.1]), np.array([[0.5]]))
+    ref = None
+    for ids in (d["id"], np.array(list("aaabbcccc")), np.repeat([10**12, 5, -3], [3, 2, 4]), np.repeat([2.5, 0.1, 7.0], [3, 2, 4])):
+        eng = gb.Engine(y, d["X"], d["Z"], ids, "poisson", nAGQ=7)
+        assert eng.n == 3
+        eng.find_modes(th[0], np.linalg.inv(th[1]), warm=False)
+        r = eng.eval_raw(th[0], th[1])
+        ref = r if ref is None else ref
+        assert np.array_equal(r, ref)
+        eng.close()
+    with pytest.raises(ValueError):
+        gb.Engine(y, d["X"], d["Z"], np.array([0, 1, 0, 1, 2, 2, 2, 2, 2]), "poisson")
