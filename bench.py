@@ -8,7 +8,14 @@ One "step" = one fused evaluation (logLik_mixed value + full score_mixed vector,
 reference R/Fit_Funs.R:1-293) of the BASELINE.json config-3 workload -- negative
 binomial, random intercepts + slopes (q = 2), nAGQ = 11 (K = 121 nodes), 1e6 clusters x 8
 observations -- on a fixed quadrature grid, clusters sharded over the N GPUs ("strong"
-scaling: the metric is quoted at 1M clusters for every N).  Prints ONE JSON line.
+scaling: the metric is quoted at 1M clusters for every N).  Prints ONE JSON line with
+  value         evaluations/s, data resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e           the same through the C ABI with host theta in / host result out per step (+ cold-start figure)
+  roofline      dominant kernel vs the FP64 peak measured in the same run (flops by SURVEY.md 8(d) convention
+                v1, for the separable algorithm and for the dense grid), HBM sub-object, ncu dram traffic
+  cpu_baseline  the numpy port of the R code on one host core (bounded sample, extrapolated linearly)
+  mixed_model   wall seconds of a whole fit (EM + BFGS + Hessian, default control) on the same data
+--workload C2|C4|C5a|C5b and --clusters select the other BASELINE configurations (profiles/*.jsonl).
 """
 import argparse
 import json
