@@ -224,10 +224,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_total = args.clusters
-    d, th = synth.make(args.workload, n=n_total, seed=None)
+    d, th = synth.make(args.workload, n=n_total, ni=args.ni, seed=None, ragged=args.ragged)
     fam_name = d.pop("family")
     cfg = synth.CONFIGS[args.workload]
-    ni = cfg["ni"]
+    ni = cfg["ni"] if args.ni is None else args.ni
     arrays = {k: d.get(k) for k in ("y", "X", "Z", "X_zi", "Z_zi")}
     loc, (c0, c1), (r0, r1) = sharded.shard_arrays(arrays, d["id"], rank, world)
     stream = torch.cuda.current_stream()
@@ -373,7 +373,8 @@ def run_ours(args):
                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": f"{args.workload}: {fam_name}, q={eng.q}, nAGQ={eng.nAGQ} (K={eng.K}), "
-                                      f"{n_total} clusters x {ni} obs, clusters sharded over {world} GPU(s)",
+                                      f"{n_total} clusters x {ni} obs{' (ragged: 1 + Poisson)' if args.ragged else ''}, "
+                                      f"clusters sharded over {world} GPU(s)",
                           "l2": "inputs larger than L2 (0.43 GB data + work arrays per evaluation)",
                           "cluster_evals_per_s": n_total * 1e3 / ms_step,
                           "point_evals_per_s": n_total * ni * eng.K * 1e3 / ms_step},
@@ -406,6 +407,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--clusters", type=int, default=1_000_000)
+    ap.add_argument("--ni", type=int, default=None, help="observations per cluster (default: the configuration's)")
+    ap.add_argument("--ragged", action="store_true", help="cluster sizes 1 + Poisson(ni - 1) instead of fixed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fit", action="store_true", help="skip the whole-fit (mixed_model() seconds) leg")
     args = ap.parse_args()

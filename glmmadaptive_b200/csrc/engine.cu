@@ -17,6 +17,7 @@
 #define FINAL_THREADS 256
 
 static thread_local std::string g_create_error;
+static const int kTile[3] = {8, 12, 16};       // observation tiles of the register variant
 
 struct glmma_handle {
     DevData d;                 // device pointers + sizes
@@ -31,9 +32,11 @@ struct glmma_handle {
     int jt;
     int eval_grid[2];
     size_t eval_smem[2];
-    int nj;                    // register-variant tile (8 / 16), 0 = generic kernel only
-    int fast_grid[2];
-    size_t fast_smem[2];
+    int nj;                    // register-variant tiles in use: bit v = tile kTile[v] (8, 12, 16); 0 = generic kernel only
+    int fast_grid[3][2];       // [tile][loglik only / with score]
+    size_t fast_smem[3][2];
+    int4* d_order[3];          // cluster lists of the tiles: {cluster, first row, n_i, 0}
+    int64_t n_order[3];
     int score_grid;
     double* d_partials;        // eval block partials
     double* d_score_partials;  // score_grid * (p + p_zi)
@@ -476,6 +479,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->have_modes = false; h->launches = 0; h->sticky = 0; h->d_ytab = nullptr;
     h->family_df = data->family_df;
     h->d_pby = nullptr; h->have_pby = false;
+    for (int v = 0; v < 3; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
     DevData& d = h->d;
@@ -587,24 +591,67 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         max_grid = std::max(max_grid, h->eval_grid[s]);
     }
     // register variant for small clusters (eval_fast_kernel)
+    // Register variant (eval_fast_kernel) by cluster size: tiles of 8, 12 and 16 observations, the
+    // generic kernel beyond.  A tile is only used when it serves a worthwhile share of the clusters;
+    // ragged data run several tiles back to back, each on its own list of clusters.
     h->nj = 0;
-    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && jt <= 16 && !std::getenv("GLMMA_NO_FAST")) h->nj = jt <= 8 ? 8 : 16;
     int max_fast = 0;
+    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && !std::getenv("GLMMA_NO_FAST")) {
+        int64_t n_le8 = 0, n_9_12 = 0, n_13_16 = 0;
+        for (int v = 1; v <= 8; ++v) n_le8 += cnt[v];
+        for (int v = 9; v <= 12; ++v) n_9_12 += cnt[v];
+        for (int v = 13; v <= 16; ++v) n_13_16 += cnt[v];
+        const int64_t few = (int64_t)(0.005 * (double)n);
+        const bool use12 = n_9_12 > 0 && n_9_12 >= (int64_t)(0.05 * (double)n);
+        const bool use16 = (n_13_16 > 0 && n_13_16 >= few) || (!use12 && n_9_12 > 0 && n_9_12 >= few);
+        const bool use8 = n_le8 > 0 && (n_le8 >= (int64_t)(0.1 * (double)n) || !(use12 || use16));
+        h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0);
+    }
     if (h->nj) {
-        for (int s = 0; s < 2; ++s) {
-            int bps = 0;
-            ce = ops->fast_config(s, h->nj, h->K, &bps, &h->fast_smem[s]);
-            if (ce != cudaSuccess || bps < 1) {
-                cuda_fail(h, ce, "fast eval kernel configuration");
-                g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
+        for (int v = 0; v < 3; ++v) {
+            if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
+            for (int s = 0; s < 2; ++s) {
+                int bps = 0;
+                ce = ops->fast_config(s, kTile[v], h->K, &bps, &h->fast_smem[v][s]);
+                if (ce != cudaSuccess || bps < 1) {
+                    cuda_fail(h, ce, "fast eval kernel configuration");
+                    g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
+                }
+                const int64_t want = (n + wpb - 1) / wpb;
+                h->fast_grid[v][s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
             }
-            const int64_t want = (n + wpb - 1) / wpb;
-            h->fast_grid[s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
-            max_fast = std::max(max_fast, h->fast_grid[s]);
+            max_fast += std::max(h->fast_grid[v][0], h->fast_grid[v][1]);
         }
         TRY(dev_alloc(h, &d.defer, n));
         TRY(dev_alloc(h, &d.csum, (size_t)n * GLMMA_NCSUM));
         TRY(dev_alloc(h, &h->d_ytab, 2 * GLMMA_YTAB));
+        // Size classes.  Each tile in use gets the list of the clusters it is the smallest fit for (the
+        // identity when all clusters fit one tile) and the clusters beyond the largest tile are flagged
+        // for eval_kernel once and for all (no launch of the register variant ever visits them).
+        int top = 0;
+        for (int v = 0; v < 3; ++v) if (h->nj & (1 << v)) top = kTile[v];
+        {
+            std::vector<int4> lists[3];
+            std::vector<int32_t> flags(n, 0);
+            for (int64_t i = 0; i < n; ++i) {
+                const int ni = row_ptr[i + 1] - row_ptr[i];
+                if (ni > top) { flags[i] = 1; continue; }
+                for (int v = 0; v < 3; ++v)           // the smallest tile in use that holds the cluster
+                    if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); break; }
+            }
+            for (int v = 0; v < 3; ++v) {
+                if (!(h->nj & (1 << v))) continue;
+                h->n_order[v] = (int64_t)lists[v].size();
+                const int4* tmp = nullptr;
+                if (lists[v].empty()) lists[v].push_back(make_int4(0, 0, 0, 0));
+                TRY(dev_upload(h, &tmp, lists[v].data(), lists[v].size()));
+                h->d_order[v] = const_cast<int4*>(tmp);
+                const int64_t want = (h->n_order[v] + wpb - 1) / wpb;
+                for (int s = 0; s < 2; ++s) h->fast_grid[v][s] = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][s]));
+            }
+            cudaMemcpyAsync(d.defer, flags.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream);
+            cudaStreamSynchronize(h->stream);      // lists / flags are block-local; errors surface at the final check
+        }
     }
     max_grid += max_fast;
     h->score_grid = (int)std::min<int64_t>((N + SCORE_THREADS * 8 - 1) / (SCORE_THREADS * 8), (int64_t)prop.multiProcessorCount * 4);
@@ -779,10 +826,16 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     int n_blocks = 0;
     ea.only_deferred = 0;
     if (h->nj) {
-        // small clusters: register variant; it flags what it leaves to the generic kernel
-        h->ops->eval_fast(ea, s, h->nj, h->fast_grid[s], h->fast_smem[s], h->stream);
-        h->launches++;
-        n_blocks = h->fast_grid[s];
+        // register variant, smaller tile first; each launch flags what it leaves to the next one
+        for (int v = 0; v < 3; ++v) {
+            if (!(h->nj & (1 << v))) continue;
+            ea.order = h->d_order[v];
+            ea.n_order = h->n_order[v];
+            ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
+            h->ops->eval_fast(ea, s, kTile[v], h->fast_grid[v][s], h->fast_smem[v][s], h->stream);
+            h->launches++;
+            n_blocks += h->fast_grid[v][s];
+        }
         ea.only_deferred = 1;
         ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
     }

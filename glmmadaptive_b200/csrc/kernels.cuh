@@ -30,6 +30,12 @@ struct EvalArgs {
     //             R/Fit_Funs.R:295-427); the log-likelihood slot of the result is 0.
     int em_mode;
     double* pby;
+    // eval_fast_kernel, dispatch on cluster size (ragged data): the launch walks the n_order clusters
+    // listed in `order` (one size class, built once by glmma_create; the identity for data whose
+    // clusters all fit one tile); the other classes belong to the launch with the other tile / to
+    // eval_kernel.
+    const int4* order;       // {cluster, first row, n_i, 0} per listed cluster: one 16-byte load
+    int64_t n_order;
 };
 
 struct PrepArgs {
@@ -664,7 +670,8 @@ struct FastLayout {
     // per-cluster scalars prefetched with the records: modes, R^-1, logdet, csum, weight
     static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + GLMMA_NCSUM + 1;
     static constexpr int PRE = ((NJ * W + NSC) + 1) & ~1;   // one prefetch buffer (records + scalars)
-    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJ * 32 + NTOT * 32 + 4;
+    static constexpr int NJR = NJ <= 8 ? 8 : 16;            // rows of the per-observation reduction scratch (power of two)
+    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJR * 32 + NTOT * 32 + 4;
     // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed node indices (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
     // indices): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
@@ -703,8 +710,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
     double* tabF = pre0 + 2 * FL::PRE;
     double* tabL = tabF + NJ * FL::TF;
     double* acc_eta = tabL + NJ * FL::TL;
-    double* acc_zi = acc_eta + NJ * 32;
-    double* totl = acc_eta + FL::NACCS * NJ * 32;            // NTOT x 32 per-lane totals
+    double* acc_zi = acc_eta + FL::NJR * 32;
+    double* totl = acc_eta + FL::NACCS * FL::NJR * 32;       // NTOT x 32 per-lane totals
     double* tots = totl + FL::NTOT * 32;                     // loglik, sum_w, n_nonfinite (lane 0)
 
     load_fmtab(fmtab, A.fmtab);
@@ -766,25 +773,30 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
     };
 
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    const int64_t i0 = (int64_t)blockIdx.x * wpb + wib;
-    // row_ptr of the current and the next cluster are kept in registers
-    int64_t r0 = 0, r0n = 0;
-    int ni = 0, nin = 0;
-    if (i0 < d.n) { r0 = d.row_ptr[i0]; ni = (int)(d.row_ptr[i0 + 1] - r0); prefetch(i0, r0, ni, pre0); }
-    if (i0 + nwarps < d.n) { r0n = d.row_ptr[i0 + nwarps]; nin = (int)(d.row_ptr[i0 + nwarps + 1] - r0n); }
+    const int64_t p0 = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t n_pos = A.n_order;
+    const int4* __restrict__ order = A.order;
+    // cluster id, first row and size of the current and the next cluster are kept in registers
+    int4 cur = make_int4(0, 0, 0, 0), nxt = make_int4(0, 0, 0, 0);
+    if (p0 < n_pos) {
+        cur = order[p0];
+        prefetch(cur.x, cur.y, cur.z, pre0);
+    }
+    if (p0 + nwarps < n_pos) nxt = order[p0 + nwarps];
     int pbuf = 0;
-    for (int64_t i = i0; i < d.n; i += nwarps) {
+    for (int64_t pos = p0; pos < n_pos; pos += nwarps) {
         double* rec = pre0 + pbuf * FL::PRE;
         const double* sc = rec + NJ * W;
-        // rotate the row_ptr pipeline and start the next cluster's copies
-        const int64_t r0c = r0;
-        const int nic = ni;
-        r0 = r0n; ni = nin;
-        const int64_t inext = i + nwarps, inext2 = i + 2 * nwarps;
+        // rotate the pipeline and start the next cluster's copies
+        const int64_t i = cur.x;      // 64-bit: i * K, i * Q ... index arrays of up to n * K elements
+        const int64_t r0c = cur.y;
+        const int nic = cur.z;
+        cur = nxt;
+        const int64_t pnext = pos + nwarps, pnext2 = pos + 2 * nwarps;
         cp_async_wait_all();
         __syncwarp();
-        if (inext < d.n) prefetch(inext, r0, ni, pre0 + (pbuf ^ 1) * FL::PRE);
-        if (inext2 < d.n) { r0n = d.row_ptr[inext2]; nin = (int)(d.row_ptr[inext2 + 1] - r0n); }
+        if (pnext < n_pos) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * FL::PRE);
+        if (pnext2 < n_pos) nxt = order[pnext2];
         pbuf ^= 1;
         if (nic > NJ) {
             if (lane == 0) d.defer[i] = 1;
@@ -808,7 +820,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
         // the coefficients, until the rounds are over
         constexpr bool ZT = F::HAS_ZI && QZ <= 1;
         double2* tabZ = reinterpret_cast<double2*>(acc_eta + 2 * (NJ * Q + NJ * NTc));
-        static_assert(!ZT || 2 * (NJ * Q + NJ * NTc) + 2 * NJ * NG <= FL::NACCS * NJ * 32, "zero-part table does not fit");
+        static_assert(!ZT || 2 * (NJ * Q + NJ * NTc) + 2 * NJ * NG <= FL::NACCS * FL::NJR * 32, "zero-part table does not fit");
         bool bad = false;
         if (lane < nic) {
             double* r = rec + lane * W;
@@ -1170,7 +1182,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                 }
             }
             // per-observation sums over the 32 lanes: through shared memory; lane l sums the
-            // (l / NJ)-th slice of columns of observation l % NJ, slices combined by shuffles
+            // (l / NJR)-th slice of columns of observation l % NJR, slices combined by shuffles
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 acc_eta[j * 32 + lane] = acc_e[j];
@@ -1178,9 +1190,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
             }
             __syncwarp();
             {
-                constexpr int NSL = 32 / NJ;          // slices (4 for NJ = 8, 2 for NJ = 16)
+                constexpr int NJR = FL::NJR;          // rows NJ .. NJR - 1 (tile 12) hold stale data: their lanes write nothing
+                constexpr int NSL = 32 / NJR;         // slices (4 for 8 rows, 2 for 16)
                 constexpr int CW = 32 / NSL;          // columns per slice
-                const int j = lane % NJ, sl = lane / NJ;
+                const int j = lane % NJR, sl = lane / NJR;
                 double s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int c = 0; c < CW; ++c) {
@@ -1189,7 +1202,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                     if (F::HAS_ZI) s2 += acc_zi[j * 32 + cc];
                 }
 #pragma unroll
-                for (int o = NJ; o < 32; o <<= 1) {
+                for (int o = NJR; o < 32; o <<= 1) {
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }

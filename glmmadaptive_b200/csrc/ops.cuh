@@ -57,12 +57,17 @@ struct OpsImpl {
                                                              GLMMA_EVAL_THREADS, smem);
     }
     static cudaError_t fast_config(int score, int nj, int K, int* blocks_per_sm, size_t* smem_bytes) {
-        return nj == 8 ? fast_config_nj<8>(score, K, blocks_per_sm, smem_bytes) : fast_config_nj<16>(score, K, blocks_per_sm, smem_bytes);
+        return nj == 8 ? fast_config_nj<8>(score, K, blocks_per_sm, smem_bytes)
+             : nj == 12 ? fast_config_nj<12>(score, K, blocks_per_sm, smem_bytes)
+                        : fast_config_nj<16>(score, K, blocks_per_sm, smem_bytes);
     }
     static void eval_fast(const EvalArgs& a, int score, int nj, int grid, size_t smem, cudaStream_t s) {
         if (nj == 8) {
             if (score) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
             else eval_fast_kernel<F, QY, QZ, false, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        } else if (nj == 12) {
+            if (score) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+            else eval_fast_kernel<F, QY, QZ, false, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
         } else {
             if (score) eval_fast_kernel<F, QY, QZ, true, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
             else eval_fast_kernel<F, QY, QZ, false, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);

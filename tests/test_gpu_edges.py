@@ -160,3 +160,32 @@ def test_id_labels_of_any_type_and_ungrouped_rows():
         eng.close()
     with pytest.raises(ValueError):
         gb.Engine(y, d["X"], d["Z"], np.array([0, 1, 0, 1, 2, 2, 2, 2, 2]), "poisson")
+
+
+@pytest.mark.parametrize("fam_name", ["negative.binomial", "zi.poisson", "censored.normal"])
+def test_all_size_classes_in_one_data_set(fam_name):
+    """Cluster sizes 1..40 in one data set: the register variant's three tiles (8, 12, 16 observations,
+    each on its own cluster list) and the generic kernel all contribute to one evaluation."""
+    rng = np.random.default_rng(11)
+    sizes = np.concatenate([rng.integers(1, 9, 40), rng.integers(9, 13, 30), rng.integers(13, 17, 20), rng.integers(17, 41, 10)])
+    rng.shuffle(sizes)
+    betas, D = np.array([0.2, 0.4, -0.3]), np.array([[0.4, 0.08], [0.08, 0.25]])
+    zi = fam_name == "zi.poisson"
+    d, N = _mk(rng, sizes, 2, fam_name, zi=zi)
+    eta = d["X"] @ betas
+    th = dict(betas=betas, D=D, nAGQ=9)
+    if fam_name == "negative.binomial":
+        d["y"] = rng.negative_binomial(2.0, 2.0 / (2.0 + np.exp(eta))).astype(float)
+        th["phis"] = np.array([np.log(2.0)])
+    elif zi:
+        y = rng.poisson(np.exp(eta)).astype(float)
+        y[rng.random(N) < 0.3] = 0.0
+        d["y"] = y
+        th["gammas"] = np.array([-1.0, 0.5])
+    else:
+        v = eta + 0.7 * rng.standard_normal(N)
+        hi, lo = np.quantile(v, 0.8), np.quantile(v, 0.1)
+        d["y"] = np.column_stack([np.clip(v, lo, hi), np.where(v > hi, 2.0, np.where(v < lo, 1.0, 0.0))])
+        th["phis"] = np.array([np.log(0.7)])
+    d["weights"] = rng.uniform(0.5, 1.5, len(sizes))
+    _check(d, th, fam_name)
