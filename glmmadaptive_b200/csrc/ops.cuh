@@ -39,39 +39,28 @@ struct OpsImpl {
         if (score) eval_kernel<F, QY, QZ, true><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
         else eval_kernel<F, QY, QZ, false><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
     }
-    // register variant (eval_fast_kernel): nj = 8 or 16 observations per cluster
+    // register variant (eval_fast_kernel): tiles of nj = 8, 12 or 16 observations per cluster.  Only the
+    // fused (log-likelihood + score) form is instantiated: optim's fn and gr are answered from one fused
+    // pass anyway (engine.py: _fused_eval), and a log-likelihood-only call simply ignores the score
+    // outputs -- the loglik-only instantiations would add a quarter to build time and binary size.
     template <int NJ>
-    static cudaError_t fast_config_nj(int score, int K, int* blocks_per_sm, size_t* smem_bytes) {
+    static cudaError_t fast_config_nj(int K, int* blocks_per_sm, size_t* smem_bytes) {
         const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32, K);
         *smem_bytes = smem;
-        cudaError_t e;
-        if (score) {
-            e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, true, NJ>,
-                                                                 GLMMA_EVAL_THREADS, smem);
-        }
-        e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, false, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, false, NJ>,
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, true, NJ>,
                                                              GLMMA_EVAL_THREADS, smem);
     }
-    static cudaError_t fast_config(int score, int nj, int K, int* blocks_per_sm, size_t* smem_bytes) {
-        return nj == 8 ? fast_config_nj<8>(score, K, blocks_per_sm, smem_bytes)
-             : nj == 12 ? fast_config_nj<12>(score, K, blocks_per_sm, smem_bytes)
-                        : fast_config_nj<16>(score, K, blocks_per_sm, smem_bytes);
+    static cudaError_t fast_config(int /*score*/, int nj, int K, int* blocks_per_sm, size_t* smem_bytes) {
+        return nj == 8 ? fast_config_nj<8>(K, blocks_per_sm, smem_bytes)
+             : nj == 12 ? fast_config_nj<12>(K, blocks_per_sm, smem_bytes)
+                        : fast_config_nj<16>(K, blocks_per_sm, smem_bytes);
     }
-    static void eval_fast(const EvalArgs& a, int score, int nj, int grid, size_t smem, cudaStream_t s) {
-        if (nj == 8) {
-            if (score) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-            else eval_fast_kernel<F, QY, QZ, false, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        } else if (nj == 12) {
-            if (score) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-            else eval_fast_kernel<F, QY, QZ, false, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        } else {
-            if (score) eval_fast_kernel<F, QY, QZ, true, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-            else eval_fast_kernel<F, QY, QZ, false, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        }
+    static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, size_t smem, cudaStream_t s) {
+        if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+        else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
     }
     static void sphi(const EvalArgs& a, int grid, size_t smem, cudaStream_t s) {
         sphi_obs_kernel<F, QY, QZ><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
