@@ -96,6 +96,10 @@ struct FamBase {
     // log of [EMU_LO, EMU_HI] rounded inwards (range test on the linear predictor)
     static constexpr double LOG_EMU_LO = -36.008;
     static constexpr double LOG_EMU_HI = 667.7;
+    // families that do not read exp(eta) can still restrict the register variant to clusters whose
+    // linear predictor stays inside [ETA_LO, ETA_HI] on the whole grid (a link clamp outside)
+    static constexpr bool HAS_ETA_RANGE = false;
+    static constexpr double ETA_LO = -1e300, ETA_HI = 1e300;
     __device__ static __forceinline__ double fast_addend(const FamPar&) { return 0.0; }
     __device__ static __forceinline__ double fast_score(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
@@ -146,12 +150,50 @@ struct FamBinomialLogit : FamBase {
 template <int LINK>   // 4 probit, 5 cloglog (enum glmma_link)
 struct FamBinomialOther : FamBase {
     static constexpr bool USES_Y2 = true;
-    static constexpr bool NEED_EMU = false;
+    // cloglog reads exp(eta) from the separable tables; probit works on eta itself
+    static constexpr bool NEED_EMU = LINK == 5;
+    // Register variant where no clamp of R's make.link() is active on the grid:
+    //   probit : |eta| <= 8 (thresh = -qnorm(eps) = 8.126, dnorm(eta) >= eps)
+    //   cloglog: eps <= mu <= 1 - eps and mu.eta >= eps  <=>  1e-15 <= exp(eta) <= 35
+    // It evaluates the reference's own expressions -- mu, then q = 1 - mu from the ROUNDED mu, then
+    // log mu, log q and (y - N mu) mu.eta / (mu q) -- with the table-based primitives, so that where
+    // the reference is ill conditioned (q below 1e-6 depends on the last bits of mu) both variants of
+    // the engine are ill conditioned in the same way.
+    static constexpr bool HAS_ETA_RANGE = LINK == 4;
+    static constexpr double ETA_LO = -8.0, ETA_HI = 8.0;
+    static constexpr double EMU_LO = 1e-15, EMU_HI = 35.0;
+    static constexpr double LOG_EMU_LO = -34.5, LOG_EMU_HI = 3.55;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
         FamBinomialLogit::obs_const(y, N, fp, cll, cphi);
     }
     template <bool SCORE, bool CAREFUL, bool ZT = false>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
+        sz = 0.0; sp = 0.0;
+        if (!CAREFUL) {
+            double mu, dmu;
+            if (LINK == 4) {
+                // Phi(-|eta|) = erfcx(|eta| / sqrt2) exp(-eta^2 / 2) / 2
+                const double c = fast_erfcx(fabs(eta) * 0.70710678118654752, cx);
+                const double hx = -0.5 * eta, h = hx * eta;
+                double E = fast_exp(h, cx);
+                E = fma(E, fma(hx, eta, -h), E);
+                const double tail = 0.5 * E * c;
+                mu = eta >= 0.0 ? 1.0 - tail : tail;
+                dmu = 0.39894228040143268 * E;
+            } else {
+                // mu = 1 - exp(-e^eta), mu.eta = e^eta exp(-e^eta)
+                mu = fast_one_minus_expneg(emu, cx);
+                dmu = emu * fast_exp(-emu, cx);
+            }
+            const double q = 1.0 - mu;
+            double Lp, rp, Lq, rq;
+            fast_log_rcp<false>(mu, cx, Lp, rp);
+            fast_log_rcp<false>(q, cx, Lq, rq);
+            ld = fma(y, Lp, (N - y) * Lq);
+            if (SCORE) se = fma(-N, mu, y) * dmu * (rp * rq);
+            else se = 0.0;
+            return;
+        }
         double mu, dmu;
         if (LINK == 4) {
             const double thresh = 8.125890664701906;   // -qnorm(.Machine$double.eps)
@@ -168,7 +210,6 @@ struct FamBinomialOther : FamBase {
         const double lp = (q < 0.1) ? log1p(-q) : log(mu);
         ld = (y == 0.0 ? 0.0 : y * lp) + (N - y == 0.0 ? 0.0 : (N - y) * lq);
         if (SCORE) se = (y - N * mu) * dmu / (mu * q);
-        sz = 0.0; sp = 0.0;
     }
 };
 
@@ -383,9 +424,18 @@ struct FamHurdlePoisson : FamBase {
         if (pos) {
             double mu, lmu;
             link_log<CAREFUL>(eta, emu, mu, lmu);
-            const double em1 = expm1(-mu);            // -(1 - e^-mu)
-            ld += -mu + y * eta - log(-em1);
-            if (SCORE) se = -mu + y + (em1 + 1.0) * mu / em1;
+            if (!CAREFUL) {
+                // zero-truncated poisson: log f = y eta - mu - log(1 - e^-mu); score = y - mu / (1 - e^-mu)
+                const double om = fast_one_minus_expneg(mu, cx);
+                double Lo, ro;
+                fast_log_rcp<false>(om, cx, Lo, ro);
+                ld += fma(y, eta, -mu) - Lo;
+                if (SCORE) se = fma(-mu, ro, y);
+            } else {
+                const double em1 = expm1(-mu);            // -(1 - e^-mu)
+                ld += -mu + y * eta - log(-em1);
+                if (SCORE) se = -mu + y + (em1 + 1.0) * mu / em1;
+            }
         }
     }
 };
@@ -411,12 +461,20 @@ struct FamHurdleNegBin : FamBase {
             fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
             const double yp = y + phi;
             const double lt = fp.a[1] - L;            // log(phi / (phi + mu)) = -log(1 + mu/phi)
-            const double em1 = expm1(phi * lt);       // (1 + mu/phi)^-phi - 1
-            const double tphi = em1 + 1.0;
-            ld += y * lmu - yp * L - log(-em1);
+            double lom, ratio;                        // log(1 - t^phi) and t^phi / (1 - t^phi), t = phi / (phi + mu)
+            if (!CAREFUL) {
+                const double om = fast_one_minus_expneg(-phi * lt, cx);
+                double ro;
+                fast_log_rcp<false>(om, cx, lom, ro);
+                ratio = (1.0 - om) * ro;
+            } else {
+                const double em1 = expm1(phi * lt);   // (1 + mu/phi)^-phi - 1
+                lom = log(-em1);
+                ratio = -(em1 + 1.0) / em1;
+            }
+            ld += y * lmu - yp * L - lom;
             if (SCORE) {
                 const double m = mu * r;
-                const double ratio = -tphi / em1;
                 se = y - yp * m - mu * (phi * r) * ratio;
                 sp = phi * (-L - yp * r + ratio * (m + lt));
             }

@@ -843,6 +843,19 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval
                     amp += ae;
                 }
                 if (!(base - amp >= F::LOG_EMU_LO && base + amp <= F::LOG_EMU_HI)) bad = true;
+            } else if (F::HAS_ETA_RANGE) {
+                double base = r[2], amp = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) base = fma(r[L::OFF_Z + dd], m[dd], base);
+#pragma unroll
+                for (int e = 0; e < Q; ++e) {
+                    double c = 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd)
+                        if (dd <= e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, e)], c);
+                    amp += fabs(c) * xmax;
+                }
+                if (!(base - amp >= F::ETA_LO && base + amp <= F::ETA_HI)) bad = true;
             }
             if (F::HAS_ZI) {
                 double base = r[L::OFF_XG], amp = 0.0;

@@ -39,6 +39,11 @@ void hm_lgamma_digamma(const double* x, int n, double* lg, double* ps) {
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
     for (int i = 0; i < n; ++i) fast_lgamma_digamma(x[i], cx, lg[i], ps[i]);
 }
+void hm_one_minus_expneg(const double* x, int n, double* out) {
+    double c[GLMMA_FM_NCONST]; fastmath_constants(c);
+    MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);
+    for (int i = 0; i < n; ++i) out[i] = fast_one_minus_expneg(x[i], cx);
+}
 void hm_l1p_sigmoid(const double* ex, int n, double* l1p, double* sig) {
     double c[GLMMA_FM_NCONST]; fastmath_constants(c);
     MathCtx cx = make_mathctx(GLMMA_LOGTAB_HOST, GLMMA_EXPTAB_HOST, c);

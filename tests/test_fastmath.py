@@ -27,6 +27,7 @@ def hm():
     lib.hm_l1p_sigmoid.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_logphi_mills.argtypes = [dp, C.c_int, dp, dp]
     lib.hm_erfcx.argtypes = [dp, C.c_int, dp]
+    lib.hm_one_minus_expneg.argtypes = [dp, C.c_int, dp]
     lib.hm_lgamma_digamma.argtypes = [dp, C.c_int, dp, dp]
     return lib
 
@@ -142,3 +143,17 @@ def test_lgamma_digamma(hm):
     # a few ulps OF THOSE (1.5e-14), whatever the size of the result; 12 ulp for larger arguments
     assert np.all(np.abs(lg - lref) <= np.maximum(12 * ulp(lref), 1.5e-14)), np.max(np.abs(lg - lref))
     assert np.all(np.abs(ps - pref) <= np.maximum(8 * ulp(pref), 4e-15)), np.max(np.abs(ps - pref))
+
+
+def test_one_minus_expneg(hm):
+    """1 - exp(-x) of the zero-truncated count densities and the cloglog link: relative 3e-13."""
+    from mpmath import expm1
+    mp.dps = 40
+    rng = np.random.default_rng(5)
+    x = np.concatenate([np.exp(rng.uniform(-36, 6, 20000)), rng.uniform(5e-4, 2e-3, 2000), [9.765625e-4, 0.0, 700.0, 1e-300]])
+    out = np.empty_like(x)
+    hm.hm_one_minus_expneg(_p(x), len(x), _p(out))
+    ref = np.array([float(-expm1(-mpf(float(v)))) for v in x])
+    nz = ref > 0
+    assert np.max(np.abs(out[nz] - ref[nz]) / ref[nz]) <= 3e-13
+    assert out[~nz].tolist() == [0.0] * int((~nz).sum())
