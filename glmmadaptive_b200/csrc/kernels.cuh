@@ -1554,13 +1554,17 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
         }
         if (!done) {
             ++iters;
+            // converged when the Newton step is below the tolerance -- also when rounding noise in f
+            // (a few 1e-14 with the table-based lgamma) makes the line search shorten or refuse such a
+            // step; without an acceptable step otherwise, the cluster stays flagged as not converged
             if (!moved) {
-                done = true;          // no acceptable step: leave the cluster flagged as not converged
+                done = true;
+                if (pd && dmax <= A.tol) conv = true;
             } else {
 #pragma unroll
                 for (int dd = 0; dd < Q; ++dd) { x[dd] = xn[dd]; g[dd] = gn[dd]; }
                 fx = fn;
-                if (step == 1.0 && dmax <= A.tol) { conv = true; done = true; }
+                if (dmax <= A.tol) { conv = true; done = true; }
             }
         }
     }

@@ -437,7 +437,7 @@ def find_modes_newton(b, data, family, betas, invD, phis, gammas, tol=1e-10, max
     (:21-65); the Newton matrix is the reference's own cd_vec Hessian of that
     gradient (:90, :249-262), Levenberg-shifted if not PD, Armijo backtracking
     (c = 1e-4, halving, plus a rounding slack of 1e-14 (|f| + 1) so that full steps
-    inside the quadratic region are not rejected by noise in f).  Stops when the max-norm of an accepted full step is
+    inside the quadratic region are not rejected by noise in f).  Stops when the max-norm of the Newton step is
     <= tol.  Returns modes, Hessians (cd_vec at the mode) and a convergence flag."""
     n = data.n
     post_modes = np.array(b, float, copy=True)
@@ -469,9 +469,10 @@ def find_modes_newton(b, data, family, betas, invD, phis, gammas, tol=1e-10, max
                     break
                 step *= 0.5
             if not ok:
+                conv[i] = np.max(np.abs(d)) <= tol      # a step below tol that rounding noise refuses
                 break
             x, fx = xn, fnew
-            if step == 1.0 and np.max(np.abs(d)) <= tol:
+            if np.max(np.abs(d)) <= tol:
                 conv[i] = True
                 break
         post_modes[i] = x
