@@ -729,7 +729,7 @@ static int run_prep(glmma_handle* h, const double* betas, const double* phis, co
     PrepArgs pa;
     pa.d = h->d; pa.fam = *fp; pa.want_score = 1; pa.ytab = h->d.csum ? h->d_ytab : nullptr;
     h->ops->prep(pa, c, h->stream);
-    h->launches++;
+    h->launches += (pa.ytab && h->ops->y_table) ? 2 : 1;      // ytab_kernel + prep_cluster_kernel
     CU(h, cudaGetLastError());
     return GLMMA_OK;
 }

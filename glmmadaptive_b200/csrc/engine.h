@@ -17,6 +17,7 @@ struct FamOps {
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
     bool has_zi, has_phi, uses_y2;
+    bool y_table;      // prep launches ytab_kernel too (count families)
 };
 
 // one lookup per family translation unit (nullptr: dimensions not compiled in)

@@ -77,7 +77,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2};
+        static const FamOps ops = {prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE};
         return &ops;
     }
 };
