@@ -158,3 +158,33 @@ def test_censored_normal_floor_regimes():
     tmax = np.max(np.abs((y[ind > 0, 0][:, None] - (od.X[ind > 0] @ betas)[:, None] - gh.Ztb[ind > 0]) / sigma))
     assert tmax > 6.0
     eng.close()
+
+
+def test_contributions_zero_inflated_q3_diag():
+    """i_contributions = TRUE pieces (per-cluster logLik, per-observation beta / gamma score rows,
+    per-cluster D rows) and the diagonal-D parameterisation for a zero-inflated family with a random
+    effect in the zero part (q = 3)."""
+    fam_name, d, th = build_case("zi.poisson", None, 2, 1, None, n=30)
+    ofam = oracle_family(fam_name)
+    th["D"] = np.diag(np.diag(th["D"]))
+    od, gh = oracle_grid(d, th, ofam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d["X_zi"], Z_zi=d["Z_zi"])
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    for diag in (True, False):
+        tv = thetas_vec(th, diag_D=diag)
+        assert relerr(gb.logLik_mixed(tv, eng, None, diag_D=diag), agq.logLik_mixed(tv, od, ofam, gh, diag_D=diag)) < RTOL
+        ref = agq.score_mixed(tv, od, ofam, gh, diag_D=diag)
+        got = gb.score_mixed(tv, eng, None, diag_D=diag)
+        assert np.max(np.abs(got - ref)) < 10 * RTOL * max(1.0, np.max(np.abs(ref)))
+    tv = thetas_vec(th)
+    ll_i = gb.logLik_mixed(tv, eng, None, i_contributions=True)
+    assert relerr(ll_i, agq.logLik_mixed(tv, od, ofam, gh, i_contributions=True)) < RTOL
+    cr = agq.score_mixed(tv, od, ofam, gh, i_contributions=True)
+    cg = gb.score_mixed(tv, eng, None, i_contributions=True)
+    assert np.max(np.abs(cg["score_betas"] - cr["score_betas"])) < 1e-9
+    assert np.max(np.abs(cg["score_gammas"] - cr["score_gammas"])) < 1e-9
+    assert np.max(np.abs(cg["score_D"] - cr["score_D"])) < 1e-9
+    # the rows add up to the totals
+    tot = gb.score_mixed(tv, eng, None)
+    assert np.max(np.abs(cg["score_betas"].sum(axis=0) - tot[:3])) < 1e-9
+    eng.close()
