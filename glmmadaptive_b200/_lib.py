@@ -46,6 +46,8 @@ class GlmmaModeStats(C.Structure):
 _H = C.c_void_p
 SIGNATURES = {
     "glmma_create": (C.c_int, [C.POINTER(GlmmaData), C.c_int, C.POINTER(_H)]),
+    "glmma_create_multi": (C.c_int, [C.POINTER(GlmmaData), C.POINTER(C.c_int), C.c_int, C.POINTER(_H)]),
+    "glmma_n_devices": (C.c_int, [_H]),
     "glmma_destroy": (None, [_H]),
     "glmma_last_error": (C.c_char_p, [_H]),
     "glmma_version": (C.c_int, []),

@@ -50,6 +50,13 @@ struct glmma_handle {
     std::string error;
     int sticky;                // sticky CUDA error status
     cudaEvent_t ev[4];
+    // single-process multi-GPU handle (glmma_create_multi): one sub-handle per device over a
+    // contiguous range of clusters; this handle itself then owns no device memory
+    std::vector<glmma_handle*> parts;
+    std::vector<int64_t> part_c0, part_r0;     // first cluster / first row of each part (+ total at the end)
+    double* h_pinned = nullptr;                // sub-handle: pinned host copy of the result vector
+    unsigned long long* h_stats = nullptr;     // sub-handle: pinned host copy of the mode statistics
+    int multi_p = 0, multi_pzi = 0, multi_nphis = 0;
 };
 
 // ------------------------------------------------------------------------------
@@ -410,6 +417,13 @@ const char* glmma_last_error(const glmma_handle* h) { return h ? h->error.c_str(
 
 void glmma_destroy(glmma_handle* h) {
     if (!h) return;
+    if (!h->parts.empty()) {
+        for (glmma_handle* p : h->parts) glmma_destroy(p);
+        delete h;
+        return;
+    }
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
@@ -672,16 +686,27 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
 
 int glmma_set_stream(glmma_handle* h, void* cuda_stream) {
     if (!h) return GLMMA_ERR_ARG;
+    if (!h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "a multi-device handle runs on each device's default stream");
     h->stream = (cudaStream_t)cuda_stream;
     return GLMMA_OK;
 }
 
-int64_t glmma_n_clusters(const glmma_handle* h) { return h ? h->d.n : 0; }
-int64_t glmma_n_obs(const glmma_handle* h) { return h ? h->d.N : 0; }
+int64_t glmma_n_clusters(const glmma_handle* h) { return !h ? 0 : (h->parts.empty() ? h->d.n : h->part_c0.back()); }
+int64_t glmma_n_obs(const glmma_handle* h) { return !h ? 0 : (h->parts.empty() ? h->d.N : h->part_r0.back()); }
 int glmma_nre(const glmma_handle* h) { return h ? h->q : 0; }
 int glmma_n_nodes(const glmma_handle* h) { return h ? h->K : 0; }
-int glmma_result_len(const glmma_handle* h) { return h ? 4 + h->d.p + h->d.n_phis + h->d.p_zi + h->q * h->q : 0; }
-int64_t glmma_launch_count(const glmma_handle* h) { return h ? h->launches : 0; }
+int glmma_result_len(const glmma_handle* h) {
+    if (!h) return 0;
+    if (!h->parts.empty()) return glmma_result_len(h->parts[0]);
+    return 4 + h->d.p + h->d.n_phis + h->d.p_zi + h->q * h->q;
+}
+int64_t glmma_launch_count(const glmma_handle* h) {
+    if (!h) return 0;
+    int64_t t = h->launches;
+    for (const glmma_handle* p : h->parts) t += p->launches;
+    return t;
+}
+int glmma_n_devices(const glmma_handle* h) { return !h ? 0 : (h->parts.empty() ? 1 : (int)h->parts.size()); }
 
 static int enter(glmma_handle* h) {
     if (!h) return GLMMA_ERR_ARG;
@@ -734,8 +759,9 @@ static int run_prep(glmma_handle* h, const double* betas, const double* phis, co
     return GLMMA_OK;
 }
 
-int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
-                     const double* gammas, int warm, glmma_mode_stats* stats) {
+// launches the mode search and the copy of its statistics into st_host (no synchronisation)
+static int find_modes_enqueue(glmma_handle* h, const double* betas, const double* invD, const double* phis,
+                              const double* gammas, int warm, unsigned long long* st_host) {
     int rc = enter(h);
     if (rc) return rc;
     if (!invD) return fail(h, GLMMA_ERR_ARG, "invD is null");
@@ -751,11 +777,22 @@ int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, c
     h->ops->modes(ma, G, h->stream);
     h->launches++;
     CU(h, cudaGetLastError());
-    unsigned long long st[4];
-    CU(h, cudaMemcpyAsync(st, h->d_stats, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, cudaMemcpyAsync(st_host, h->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     h->have_modes = true;
     h->have_pby = false;
+    return GLMMA_OK;
+}
+
+static int multi_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
+                            const double* gammas, int warm, glmma_mode_stats* stats);
+
+int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
+                     const double* gammas, int warm, glmma_mode_stats* stats) {
+    if (h && !h->parts.empty()) return multi_find_modes(h, betas, invD, phis, gammas, warm, stats);
+    unsigned long long st[4];
+    int rc = find_modes_enqueue(h, betas, invD, phis, gammas, warm, st);
+    if (rc) return rc;
+    CU(h, cudaStreamSynchronize(h->stream));
     if (stats) {
         stats->n_not_converged = (int64_t)st[0];
         stats->n_chol_failed = (int64_t)st[1];
@@ -766,7 +803,18 @@ int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, c
     return GLMMA_OK;
 }
 
+static int multi_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets);
+static int multi_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper);
+static int multi_eval(glmma_handle* h, const double* betas, const double* D, const double* phis, const double* gammas,
+                      int want_score, double* result, int em_mode);
+static int multi_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                              const double* gammas, double* ll_i, double* zbar, double* zbar_zi, double* sphi_obs,
+                              double* S_i);
+static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
+                          const double* beta, double* out);
+
 int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
+    if (h && !h->parts.empty()) return multi_get_modes(h, post_modes, chol_upper, log_dets);
     int rc = enter(h);
     if (rc) return rc;
     if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
@@ -787,6 +835,7 @@ int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, dou
 }
 
 int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper) {
+    if (h && !h->parts.empty()) return multi_set_modes(h, post_modes, chol_upper);
     int rc = enter(h);
     if (rc) return rc;
     if (!post_modes || !chol_upper) return fail(h, GLMMA_ERR_ARG, "null argument");
@@ -857,6 +906,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
 
 int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, const double* phis,
                       const double* gammas, int want_score, double* d_result) {
+    if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "glmma_eval_device needs a single-device handle");
     int rc = enter(h);
     if (rc) return rc;
     if (!d_result) return fail(h, GLMMA_ERR_ARG, "d_result is null");
@@ -865,6 +915,7 @@ int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, con
 
 int glmma_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                const double* gammas, int want_score, double* result) {
+    if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, want_score, result, 0);
     int rc = enter(h);
     if (rc) return rc;
     if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
@@ -879,6 +930,7 @@ int glmma_eval(glmma_handle* h, const double* betas, const double* D, const doub
 int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
                        const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
                        double* sphi_obs, double* S_i) {
+    if (h && !h->parts.empty()) return multi_eval_contrib(h, betas, D, phis, gammas, ll_i, zbar, zbar_zi, sphi_obs, S_i);
     int rc = enter(h);
     if (rc) return rc;
     const int64_t n = h->d.n, N = h->d.N;
@@ -918,6 +970,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
 
 int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const double* phis,
                    const double* gammas, double* result) {
+    if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, 1, result, 1);
     int rc = enter(h);
     if (rc) return rc;
     if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
@@ -935,6 +988,7 @@ int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const 
 
 int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
                    double* result) {
+    if (h && !h->parts.empty()) return multi_eval(h, betas, nullptr, phis, gammas, 1, result, 2);
     int rc = enter(h);
     if (rc) return rc;
     if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
@@ -953,6 +1007,7 @@ int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, con
 
 int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
                    const double* beta, double* out) {
+    if (h && !h->parts.empty()) return multi_glm_pass(h, design, glm_family, response, use_offset, first, beta, out);
     int rc = enter(h);
     if (rc) return rc;
     if (!out || (!first && !beta)) return fail(h, GLMMA_ERR_ARG, "null argument");
@@ -997,8 +1052,226 @@ int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, in
     return GLMMA_OK;
 }
 
+// ---- one process, several GPUs (R is single-process): glmma_create_multi ------------------------
+// Clusters are conditionally independent, so the log-likelihood and every score component are plain
+// sums over shards (R/Fit_Funs.R:33-37,105,194,231,244-247,271-278).  Each device holds a contiguous
+// range of clusters behind its own sub-handle; an evaluation is enqueued on every device (kernels and
+// the copy of the ~100-byte result into pinned host memory are asynchronous), then the host waits for
+// each device in turn and adds the vectors in device order (fixed order: deterministic).  No
+// collective, no peer access.
+
+static int multi_fail(glmma_handle* h, const glmma_handle* p, int rc) {
+    h->error = "device " + std::to_string(p->device) + ": " + p->error;
+    return rc;
+}
+
+int glmma_create_multi(const glmma_data* data, const int* devices, int ndev, glmma_handle** out) {
+    if (!data || !out || !devices || ndev < 1) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (ndev == 1) return glmma_create(data, devices[0], out);
+    const int64_t N = data->n_obs;
+    if (N <= 0 || !data->y || !data->X || !data->Z) return fail(nullptr, GLMMA_ERR_ARG, "y, X, Z and positive sizes are required");
+    // global CSR index
+    std::vector<int64_t> rp;
+    if (data->row_ptr) {
+        if (data->n_clusters <= 0) return fail(nullptr, GLMMA_ERR_ARG, "n_clusters must be positive");
+        rp.assign(data->row_ptr, data->row_ptr + data->n_clusters + 1);
+    } else if (data->id) {
+        rp.push_back(0);
+        for (int64_t r = 1; r < N; ++r)
+            if (data->id[r] != data->id[r - 1]) rp.push_back(r);
+        rp.push_back(N);
+    } else {
+        return fail(nullptr, GLMMA_ERR_ARG, "id or row_ptr is required");
+    }
+    const int64_t n = (int64_t)rp.size() - 1;
+    if (n < ndev) return fail(nullptr, GLMMA_ERR_ARG, "fewer clusters than devices");
+    // contiguous cluster ranges balanced on observations
+    std::vector<int64_t> cut(ndev + 1, 0);
+    cut[ndev] = n;
+    for (int k = 1; k < ndev; ++k) {
+        const int64_t target = (N * k) / ndev;
+        int64_t c = std::lower_bound(rp.begin(), rp.end(), target) - rp.begin();
+        c = std::max<int64_t>(c, cut[k - 1] + 1);
+        c = std::min<int64_t>(c, n - (ndev - k));
+        cut[k] = c;
+    }
+    glmma_handle* h = new glmma_handle();
+    h->sticky = 0; h->launches = 0; h->ops = nullptr; h->stream = nullptr; h->device = devices[0];
+    for (auto& e : h->ev) e = nullptr;
+    std::memset(&h->d, 0, sizeof(h->d));
+    auto slice = [&](const double* src, int ncol, int64_t r0, int64_t r1, std::vector<double>& buf) -> const double* {
+        if (!src || ncol <= 0) return nullptr;
+        const int64_t m = r1 - r0;
+        buf.resize((size_t)m * ncol);
+        for (int c = 0; c < ncol; ++c) std::memcpy(buf.data() + (size_t)c * m, src + (size_t)c * N + r0, sizeof(double) * m);
+        return buf.data();
+    };
+    for (int k = 0; k < ndev; ++k) {
+        const int64_t c0 = cut[k], c1 = cut[k + 1], r0 = rp[c0], r1 = rp[c1];
+        std::vector<double> by, bX, bZ, bXz, bZz, bo, boz;
+        std::vector<int64_t> prp((size_t)(c1 - c0 + 1));
+        for (int64_t i = c0; i <= c1; ++i) prp[i - c0] = rp[i] - r0;
+        glmma_data dp = *data;
+        dp.n_obs = r1 - r0; dp.n_clusters = c1 - c0; dp.id = nullptr; dp.row_ptr = prp.data();
+        dp.y = slice(data->y, data->y_cols, r0, r1, by);
+        dp.X = slice(data->X, data->p, r0, r1, bX);
+        dp.Z = slice(data->Z, data->q_y, r0, r1, bZ);
+        dp.X_zi = slice(data->X_zi, data->p_zi, r0, r1, bXz);
+        dp.Z_zi = slice(data->Z_zi, data->q_zi, r0, r1, bZz);
+        dp.offset = slice(data->offset, 1, r0, r1, bo);
+        dp.offset_zi = slice(data->offset_zi, 1, r0, r1, boz);
+        dp.weights = data->weights ? data->weights + c0 : nullptr;
+        glmma_handle* part = nullptr;
+        int rc = glmma_create(&dp, devices[k], &part);
+        if (rc == GLMMA_OK) {
+            cudaSetDevice(devices[k]);
+            if (cudaMallocHost(&part->h_pinned, sizeof(double) * glmma_result_len(part)) != cudaSuccess ||
+                cudaMallocHost(&part->h_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+                g_create_error = "cudaMallocHost failed";
+                glmma_destroy(part);
+                rc = GLMMA_ERR_CUDA;
+            }
+        }
+        if (rc != GLMMA_OK) {
+            const std::string msg = "device " + std::to_string(devices[k]) + ": " + g_create_error;
+            glmma_destroy(h);
+            g_create_error = msg;
+            return rc;
+        }
+        h->parts.push_back(part);
+        h->part_c0.push_back(c0);
+        h->part_r0.push_back(r0);
+    }
+    h->part_c0.push_back(n);
+    h->part_r0.push_back(N);
+    const glmma_handle* p0 = h->parts[0];
+    h->family = p0->family; h->link = p0->link; h->nagq = p0->nagq; h->q = p0->q; h->K = p0->K; h->y_cols = p0->y_cols;
+    h->multi_p = data->p; h->multi_pzi = data->p_zi; h->multi_nphis = data->n_phis;
+    h->have_modes = false; h->have_pby = false;
+    *out = h;
+    return GLMMA_OK;
+}
+
+static int multi_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
+                            const double* gammas, int warm, glmma_mode_stats* stats) {
+    for (glmma_handle* p : h->parts) {
+        int rc = find_modes_enqueue(p, betas, invD, phis, gammas, warm, p->h_stats);
+        if (rc) return multi_fail(h, p, rc);
+    }
+    unsigned long long nc = 0, cf = 0, it = 0, mx = 0;
+    for (glmma_handle* p : h->parts) {
+        cudaSetDevice(p->device);
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) { cuda_fail(p, e, "find_modes"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
+        nc += p->h_stats[0]; cf += p->h_stats[1]; it += p->h_stats[2]; mx = std::max(mx, p->h_stats[3]);
+    }
+    h->have_modes = true;
+    if (stats) {
+        stats->n_not_converged = (int64_t)nc; stats->n_chol_failed = (int64_t)cf;
+        stats->max_iterations = (int32_t)mx; stats->reserved = 0;
+        stats->mean_iterations = (double)it / (double)h->part_c0.back();
+    }
+    return GLMMA_OK;
+}
+
+static int multi_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
+    const int64_t n = h->part_c0.back();
+    const int q = h->q, np = q * (q + 1) / 2;
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        glmma_handle* p = h->parts[k];
+        const int64_t c0 = h->part_c0[k], m = p->d.n;
+        std::vector<double> tmp(post_modes ? (size_t)m * q : 0);
+        int rc = glmma_get_modes(p, post_modes ? tmp.data() : nullptr, chol_upper ? chol_upper + (size_t)c0 * np : nullptr,
+                                 log_dets ? log_dets + c0 : nullptr);
+        if (rc) return multi_fail(h, p, rc);
+        if (post_modes)
+            for (int dd = 0; dd < q; ++dd) std::memcpy(post_modes + (size_t)dd * n + c0, tmp.data() + (size_t)dd * m, sizeof(double) * m);
+    }
+    return GLMMA_OK;
+}
+
+static int multi_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper) {
+    if (!post_modes || !chol_upper) return fail(h, GLMMA_ERR_ARG, "null argument");
+    const int64_t n = h->part_c0.back();
+    const int q = h->q, np = q * (q + 1) / 2;
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        glmma_handle* p = h->parts[k];
+        const int64_t c0 = h->part_c0[k], m = p->d.n;
+        std::vector<double> tmp((size_t)m * q);
+        for (int dd = 0; dd < q; ++dd) std::memcpy(tmp.data() + (size_t)dd * m, post_modes + (size_t)dd * n + c0, sizeof(double) * m);
+        int rc = glmma_set_modes(p, tmp.data(), chol_upper + (size_t)c0 * np);
+        if (rc) return multi_fail(h, p, rc);
+    }
+    h->have_modes = true;
+    return GLMMA_OK;
+}
+
+static int multi_eval(glmma_handle* h, const double* betas, const double* D, const double* phis, const double* gammas,
+                      int want_score, double* result, int em_mode) {
+    if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
+    const int rl = glmma_result_len(h), len = want_score ? rl : 4;
+    double eye[GLMMA_QMAX * GLMMA_QMAX] = {0};
+    for (int i = 0; i < h->q; ++i) eye[i * h->q + i] = 1.0;
+    for (glmma_handle* p : h->parts) {
+        int rc = enter(p);
+        if (rc) return multi_fail(h, p, rc);
+        if (em_mode == 1 && !p->d_pby) {
+            rc = dev_alloc(p, &p->d_pby, (size_t)p->d.n * (size_t)p->K);
+            if (rc) return multi_fail(h, p, rc);
+        }
+        if (em_mode == 2 && !p->have_pby) return fail(h, GLMMA_ERR_STATE, "no posterior weights yet: call glmma_em_estep first");
+        rc = enqueue_eval(p, betas, em_mode == 2 ? eye : D, phis, gammas, want_score, p->d_result, nullptr, nullptr, nullptr, em_mode);
+        if (rc) return multi_fail(h, p, rc);
+        cudaError_t e = cudaMemcpyAsync(p->h_pinned, p->d_result, sizeof(double) * len, cudaMemcpyDeviceToHost, p->stream);
+        if (e != cudaSuccess) { cuda_fail(p, e, "cudaMemcpyAsync"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
+        if (em_mode == 1) p->have_pby = true;
+    }
+    for (int t = 0; t < rl; ++t) result[t] = 0.0;
+    for (glmma_handle* p : h->parts) {
+        cudaSetDevice(p->device);
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) { cuda_fail(p, e, "eval"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
+        for (int t = 0; t < len; ++t) result[t] += p->h_pinned[t];
+    }
+    result[3] = 0.0;
+    return GLMMA_OK;
+}
+
+static int multi_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                              const double* gammas, double* ll_i, double* zbar, double* zbar_zi, double* sphi_obs,
+                              double* S_i) {
+    const int q = h->q;
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        glmma_handle* p = h->parts[k];
+        const int64_t c0 = h->part_c0[k], r0 = h->part_r0[k];
+        int rc = glmma_eval_contrib(p, betas, D, phis, gammas, ll_i ? ll_i + c0 : nullptr, zbar ? zbar + r0 : nullptr,
+                                    zbar_zi ? zbar_zi + r0 : nullptr, sphi_obs ? sphi_obs + r0 : nullptr,
+                                    S_i ? S_i + (size_t)c0 * q * q : nullptr);
+        if (rc) return multi_fail(h, p, rc);
+    }
+    return GLMMA_OK;
+}
+
+static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
+                          const double* beta, double* out) {
+    if (!out) return fail(h, GLMMA_ERR_ARG, "null argument");
+    const int p_ = design == 0 ? h->multi_p : h->multi_pzi;
+    const int len = 1 + p_ + p_ * p_;
+    if (p_ < 1) return fail(h, GLMMA_ERR_ARG, "design has no columns");
+    std::vector<double> tmp(len);
+    for (int t = 0; t < len; ++t) out[t] = 0.0;
+    for (glmma_handle* p : h->parts) {
+        int rc = glmma_glm_pass(p, design, glm_family, response, use_offset, first, beta, tmp.data());
+        if (rc) return multi_fail(h, p, rc);
+        for (int t = 0; t < len; ++t) out[t] += tmp[t];
+    }
+    return GLMMA_OK;
+}
+
 int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                     const double* gammas, int want_score, int iters, float* ms_per_eval, float* ms_main_kernel) {
+    if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "glmma_time_eval needs a single-device handle");
     int rc = enter(h);
     if (rc) return rc;
     if (iters < 1) return fail(h, GLMMA_ERR_ARG, "iters must be positive");

@@ -5,6 +5,16 @@
 #include "kernels.cuh"
 #include "engine.h"
 
+// The dynamic shared-memory limit of a kernel is a per-device property of the FUNCTION, shared by every
+// handle in the process: always raise it to the device's opt-in maximum, so that a handle created later
+// with a smaller tile cannot lower it under the launches of an earlier one.
+static inline int glmma_optin_smem() {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+}
+
 template <class F, int QY, int QZ>
 struct OpsImpl {
     using L = EvalLayout<F, QY, QZ>;
@@ -23,14 +33,14 @@ struct OpsImpl {
         *smem_bytes = smem;
         cudaError_t e;
         if (score) {
-            e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
             if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
             if (e != cudaSuccess) return e;
             return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, true>,
                                                                  GLMMA_EVAL_THREADS, smem);
         }
-        e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, false>,
                                                              GLMMA_EVAL_THREADS, smem);
@@ -47,7 +57,7 @@ struct OpsImpl {
     static cudaError_t fast_config_nj(int K, int* blocks_per_sm, size_t* smem_bytes) {
         const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32, K);
         *smem_bytes = smem;
-        cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, true, NJ>,
                                                              GLMMA_EVAL_THREADS, smem);

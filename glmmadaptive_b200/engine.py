@@ -82,6 +82,8 @@ class Engine:
 
     def __init__(self, y, X, Z, id, family, link=None, nAGQ=None, X_zi=None, Z_zi=None, offset=None,
                  offset_zi=None, weights=None, device=0, df=None):
+        """``device``: a CUDA device index, or a list of indices to spread the clusters over several
+        GPUs of this process (glmma_create_multi)."""
         self.lib = _lib.load()
         self.spec = family_spec(family, link) if not isinstance(family, FamilySpec) else family
         y = _f(y)
@@ -120,11 +122,18 @@ class Engine:
         d.n_clusters = len(row_ptr) - 1
         d.family_df = 0.0 if df is None else float(df)      # students.t(df)
         h = C.c_void_p()
-        rc = self.lib.glmma_create(C.byref(d), int(device), C.byref(h))
+        if isinstance(device, (list, tuple)):
+            # one process, several GPUs: contiguous cluster ranges per device behind one handle
+            devs = (C.c_int * len(device))(*[int(v) for v in device])
+            rc = self.lib.glmma_create_multi(C.byref(d), devs, len(device), C.byref(h))
+            device = device[0]
+        else:
+            rc = self.lib.glmma_create(C.byref(d), int(device), C.byref(h))
         if rc != 0:
             raise GlmmaError(rc, self.lib.glmma_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        self.n_devices = int(self.lib.glmma_n_devices(h))
         self.n = int(self.lib.glmma_n_clusters(h))
         self.K = int(self.lib.glmma_n_nodes(h))
         self.result_len = int(self.lib.glmma_result_len(h))

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLMMA_VERSION 130
+#define GLMMA_VERSION 140
 
 #if defined(__GNUC__)
 #define GLMMA_API __attribute__((visibility("default")))
@@ -125,6 +125,13 @@ typedef struct glmma_handle glmma_handle;
  * Gauss-Hermite table (gauher(nAGQ), R/Functions.R:306-341).  Modes start at
  * 0 (post_modes <- matrix(0, n, nRE), R/mixed_fit.R:63). */
 GLMMA_API int glmma_create(const glmma_data* data, int device, glmma_handle** out);
+/* One process, several GPUs (R is single-process): the clusters are split into `ndev` contiguous
+ * ranges balanced on observations, one per device in `devices`; every entry point below then works on
+ * the returned handle as on a single-device one (results are the sums over the devices, added on the
+ * host in device order; per-cluster / per-observation outputs are concatenated).  glmma_eval_device,
+ * glmma_set_stream and glmma_time_eval need a single-device handle.  ndev = 1 is glmma_create. */
+GLMMA_API int glmma_create_multi(const glmma_data* data, const int* devices, int ndev, glmma_handle** out);
+GLMMA_API int glmma_n_devices(const glmma_handle* h);
 GLMMA_API void glmma_destroy(glmma_handle* h);
 GLMMA_API const char* glmma_last_error(const glmma_handle* h);   /* h may be NULL: last create() error */
 GLMMA_API int glmma_version(void);

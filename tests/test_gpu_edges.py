@@ -189,3 +189,21 @@ def test_all_size_classes_in_one_data_set(fam_name):
         th["phis"] = np.array([np.log(0.7)])
     d["weights"] = rng.uniform(0.5, 1.5, len(sizes))
     _check(d, th, fam_name)
+
+
+def test_two_engines_with_different_tiles_on_one_device():
+    """Two handles alive on the same device whose launches need different amounts of dynamic shared
+    memory (the limit is a per-device property of the kernel function, not of the handle)."""
+    rng = np.random.default_rng(12)
+    betas, D = np.array([0.2, 0.4, -0.3]), np.array([[0.4, 0.08], [0.08, 0.25]])
+    engines, refs = [], []
+    for sizes in (np.full(20, 30), np.full(40, 3), np.full(20, 22)):
+        d, N = _mk(rng, sizes, 2, "poisson")
+        d["y"] = rng.poisson(np.exp(d["X"] @ betas)).astype(float)
+        e = gb.Engine(d["y"], d["X"], d["Z"], d["id"], "poisson", nAGQ=9)
+        e.find_modes(betas, np.linalg.inv(D), warm=False)
+        engines.append(e)
+        refs.append(e.eval_raw(betas, D))
+    for e, r in zip(engines, refs):          # the earlier handles still launch after the later ones were created
+        assert np.array_equal(e.eval_raw(betas, D), r)
+        e.close()
