@@ -8,6 +8,11 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include "../../include/glmma.h"
 #include "kernels.cuh"
 #include "engine.h"
@@ -18,6 +23,46 @@
 
 static thread_local std::string g_create_error;
 static const int kTile[3] = {8, 12, 16};       // observation tiles of the register variant
+
+// One host thread per device of a multi-device handle: the per-evaluation enqueue work (six kernel
+// launches and a copy per device) runs in parallel instead of serialising on the caller's thread.
+// The workers only ever touch CUDA and their own sub-handle -- never the caller's runtime (R).
+struct PartWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, stop = false;
+    int rc = 0;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_job || stop; });
+            if (stop) return;
+            lk.unlock();
+            const int r = job();
+            lk.lock();
+            rc = r;
+            has_job = false;
+            cv.notify_all();
+        }
+    }
+    void submit(std::function<int()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f);
+        has_job = true;
+        cv.notify_all();
+    }
+    int wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return !has_job; });
+        return rc;
+    }
+    void shutdown() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+};
 
 struct glmma_handle {
     DevData d;                 // device pointers + sizes
@@ -53,6 +98,7 @@ struct glmma_handle {
     // single-process multi-GPU handle (glmma_create_multi): one sub-handle per device over a
     // contiguous range of clusters; this handle itself then owns no device memory
     std::vector<glmma_handle*> parts;
+    std::vector<std::unique_ptr<PartWorker>> workers;
     std::vector<int64_t> part_c0, part_r0;     // first cluster / first row of each part (+ total at the end)
     double* h_pinned = nullptr;                // sub-handle: pinned host copy of the result vector
     unsigned long long* h_stats = nullptr;     // sub-handle: pinned host copy of the mode statistics
@@ -418,6 +464,7 @@ const char* glmma_last_error(const glmma_handle* h) { return h ? h->error.c_str(
 void glmma_destroy(glmma_handle* h) {
     if (!h) return;
     if (!h->parts.empty()) {
+        for (auto& w : h->workers) w->shutdown();
         for (glmma_handle* p : h->parts) glmma_destroy(p);
         delete h;
         return;
@@ -1149,21 +1196,41 @@ int glmma_create_multi(const glmma_data* data, const int* devices, int ndev, glm
     h->family = p0->family; h->link = p0->link; h->nagq = p0->nagq; h->q = p0->q; h->K = p0->K; h->y_cols = p0->y_cols;
     h->multi_p = data->p; h->multi_pzi = data->p_zi; h->multi_nphis = data->n_phis;
     h->have_modes = false; h->have_pby = false;
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        h->workers.emplace_back(new PartWorker());
+        PartWorker* w = h->workers.back().get();
+        w->th = std::thread([w] { w->loop(); });
+    }
     *out = h;
     return GLMMA_OK;
 }
 
+// runs fn(part) for every part on the part's worker thread; returns the first non-zero status
+static int run_parts(glmma_handle* h, const std::function<int(glmma_handle*)>& fn) {
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        glmma_handle* p = h->parts[k];
+        h->workers[k]->submit([&fn, p] { return fn(p); });
+    }
+    int first = GLMMA_OK;
+    for (size_t k = 0; k < h->parts.size(); ++k) {
+        const int rc = h->workers[k]->wait();
+        if (rc != GLMMA_OK && first == GLMMA_OK) first = multi_fail(h, h->parts[k], rc);
+    }
+    return first;
+}
+
 static int multi_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
                             const double* gammas, int warm, glmma_mode_stats* stats) {
-    for (glmma_handle* p : h->parts) {
-        int rc = find_modes_enqueue(p, betas, invD, phis, gammas, warm, p->h_stats);
-        if (rc) return multi_fail(h, p, rc);
-    }
+    int rc = run_parts(h, [&](glmma_handle* p) -> int {
+        int r = find_modes_enqueue(p, betas, invD, phis, gammas, warm, p->h_stats);
+        if (r) return r;
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return cuda_fail(p, e, "find_modes");
+        return GLMMA_OK;
+    });
+    if (rc) return rc;
     unsigned long long nc = 0, cf = 0, it = 0, mx = 0;
     for (glmma_handle* p : h->parts) {
-        cudaSetDevice(p->device);
-        cudaError_t e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) { cuda_fail(p, e, "find_modes"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
         nc += p->h_stats[0]; cf += p->h_stats[1]; it += p->h_stats[2]; mx = std::max(mx, p->h_stats[3]);
     }
     h->have_modes = true;
@@ -1213,27 +1280,26 @@ static int multi_eval(glmma_handle* h, const double* betas, const double* D, con
     const int rl = glmma_result_len(h), len = want_score ? rl : 4;
     double eye[GLMMA_QMAX * GLMMA_QMAX] = {0};
     for (int i = 0; i < h->q; ++i) eye[i * h->q + i] = 1.0;
-    for (glmma_handle* p : h->parts) {
-        int rc = enter(p);
-        if (rc) return multi_fail(h, p, rc);
+    int rc = run_parts(h, [&](glmma_handle* p) -> int {
+        int r = enter(p);
+        if (r) return r;
         if (em_mode == 1 && !p->d_pby) {
-            rc = dev_alloc(p, &p->d_pby, (size_t)p->d.n * (size_t)p->K);
-            if (rc) return multi_fail(h, p, rc);
+            r = dev_alloc(p, &p->d_pby, (size_t)p->d.n * (size_t)p->K);
+            if (r) return r;
         }
-        if (em_mode == 2 && !p->have_pby) return fail(h, GLMMA_ERR_STATE, "no posterior weights yet: call glmma_em_estep first");
-        rc = enqueue_eval(p, betas, em_mode == 2 ? eye : D, phis, gammas, want_score, p->d_result, nullptr, nullptr, nullptr, em_mode);
-        if (rc) return multi_fail(h, p, rc);
+        if (em_mode == 2 && !p->have_pby) return fail(p, GLMMA_ERR_STATE, "no posterior weights yet: call glmma_em_estep first");
+        r = enqueue_eval(p, betas, em_mode == 2 ? eye : D, phis, gammas, want_score, p->d_result, nullptr, nullptr, nullptr, em_mode);
+        if (r) return r;
         cudaError_t e = cudaMemcpyAsync(p->h_pinned, p->d_result, sizeof(double) * len, cudaMemcpyDeviceToHost, p->stream);
-        if (e != cudaSuccess) { cuda_fail(p, e, "cudaMemcpyAsync"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return cuda_fail(p, e, "eval");
         if (em_mode == 1) p->have_pby = true;
-    }
+        return GLMMA_OK;
+    });
+    if (rc) return rc;
     for (int t = 0; t < rl; ++t) result[t] = 0.0;
-    for (glmma_handle* p : h->parts) {
-        cudaSetDevice(p->device);
-        cudaError_t e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) { cuda_fail(p, e, "eval"); return multi_fail(h, p, GLMMA_ERR_CUDA); }
+    for (glmma_handle* p : h->parts)          // device order: deterministic
         for (int t = 0; t < len; ++t) result[t] += p->h_pinned[t];
-    }
     result[3] = 0.0;
     return GLMMA_OK;
 }
