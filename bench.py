@@ -347,6 +347,13 @@ def run_ours(args):
                     "kernel": f"eval_fast_kernel<{fam_name}, q_y={eng.q_y}, q_zi={eng.q_zi}, score, NJ=8> "
                               "(+ eval_kernel for deferred clusters; both between the two events)",
                     "kernel_ms": ms_kernel,
+                    "ncu": None if traffic is None else {k: traffic.get(k) for k in
+                                                         ("fp64_pipe_busy_pct", "issue_slots_busy_pct",
+                                                          "shared_mem_pipe_pct", "registers_per_thread")},
+                    "ncu_note": "hardware counters of the committed ncu capture (profiles/): the FP64 pipe is busy "
+                                "that share of cycles; `frac` credits the convention's flop weights (log = 30, "
+                                "division = 10 ...) to a kernel that spends 12 FP64 instructions on log and 1/t "
+                                "together, so it is higher than the pipe utilisation (profiles/README.md)",
                     "flops_per_launch": flops,
                     "flop_convention": "SURVEY.md 8(d) v1 weights applied to the separable-exp algorithm the engine "
                                        "runs (bench.py needed_flops); dense-grid figure alongside",

@@ -122,6 +122,10 @@ traffic = {"kernels": [{
     "dram_bytes_per_launch": to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) +
     to_bytes(r["dram__bytes_write.sum"], units["dram__bytes_write.sum"]),
     "duration_us_under_ncu": float(r["gpu__time_duration.sum"].replace(",", "")),
+    "fp64_pipe_busy_pct": float(r["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]),
+    "issue_slots_busy_pct": float(r["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
+    "shared_mem_pipe_pct": float(r["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]),
+    "registers_per_thread": int(float(r["launch__registers_per_thread"])),
 }]}
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(open(out("eval_fast_hotspots.txt")).read())
