@@ -81,3 +81,16 @@ def test_starting_values_product_vs_oracle():
     b = ofit.initial_values(data, fam)
     for key in ("betas", "gammas", "D"):
         assert np.max(np.abs(np.asarray(a[key]) - np.asarray(b[key]))) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["km1", "km2", "hm1", "hm2"])
+def test_oracle_fit_reproduces_published_two_part_fits(name):
+    """Whole fits of the two-part vignette (hurdle log-normal q = 1 and q = 2 with a diagonal D, hurdle
+    negative binomial q = 2 and q = 3): glm.fit starts for betas and gammas, phis, the EM phase and
+    optim's BFGS all have to be right for the oracle to print the vignette's digits."""
+    from kat_hurdle import FIT_KATS, kat_inputs, check_fit_against_kat
+    from helpers import oracle_family
+    k = [r for r in FIT_KATS if r["name"] == name][0]
+    data = agq.Data(**kat_inputs(k))
+    out = ofit.mixed_fit(data, oracle_family(k["family"]), control=dict(nAGQ=k["nAGQ"]), diag_D=k["diag_D"], hessian=False)
+    check_fit_against_kat(k, out)

@@ -188,3 +188,20 @@ def test_contributions_zero_inflated_q3_diag():
     tot = gb.score_mixed(tv, eng, None)
     assert np.max(np.abs(cg["score_betas"].sum(axis=0) - tot[:3])) < 1e-9
     eng.close()
+
+
+def test_kat_hurdle_fits_published_loglik():
+    """KATs km2 / hm1 / hm2 (tests/kat_hurdle.py): the ENGINE, with its own mode search, at the
+    published estimates of the reference's two-part vignette."""
+    from kat_hurdle import HURDLE_KATS, kat_inputs
+    for k in HURDLE_KATS:
+        d = kat_inputs(k)
+        q = k["q_y"] + k["q_zi"]
+        betas, gammas, phis, D = map(np.array, (k["betas"], k["gammas"], k["phis"], k["D"]))
+        eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], k["family"], nAGQ=k["nAGQ"], X_zi=d["X_zi"], Z_zi=d["Z_zi"])
+        gh = gb.GHfun(eng, np.zeros((eng.n, q)), betas, np.linalg.inv(D), phis, gammas)
+        assert gh.stats["n_not_converged"] == 0
+        tv = np.concatenate([betas, np.log(np.diag(D)) if k["diag_D"] else gb.chol_transf(D), phis, gammas])
+        ll = -gb.logLik_mixed(tv, eng, gh, diag_D=k["diag_D"])
+        assert abs(ll - k["loglik"]) < k["tol"], (k["name"], ll)
+        eng.close()

@@ -90,3 +90,22 @@ def test_kat_D5_hurdle_poisson_q3():
                    mode_finder="newton")
     th = np.concatenate([betas, agq.chol_transf(D), gammas])
     assert abs(-agq.logLik_mixed(th, data, fam, gh) - (-2797.307)) < 5e-2
+
+
+def test_kat_hurdle_lognormal_q2_and_hurdle_negative_binomial():
+    """km2 (hurdle log-normal, random intercepts in both parts, diagonal D), hm1 and hm2 (hurdle
+    negative binomial, q = 2 and q = 3): the published logLik at the published estimates."""
+    import pytest
+    from kat_hurdle import HURDLE_KATS, kat_inputs
+    from helpers import oracle_family
+    for k in HURDLE_KATS:
+        d = kat_inputs(k)
+        data = agq.Data(**d)
+        fam = oracle_family(k["family"])
+        q = k["q_y"] + k["q_zi"]
+        betas, gammas, phis, D = map(np.array, (k["betas"], k["gammas"], k["phis"], k["D"]))
+        gh = agq.GHfun(np.zeros((data.n, q)), data, fam, betas, np.linalg.inv(D), phis, gammas, k["nAGQ"], q,
+                       mode_finder="newton")
+        th = np.concatenate([betas, np.log(np.diag(D)) if k["diag_D"] else agq.chol_transf(D), phis, gammas])
+        ll = -agq.logLik_mixed(th, data, fam, gh, diag_D=k["diag_D"])
+        assert abs(ll - k["loglik"]) < k["tol"], (k["name"], ll)
