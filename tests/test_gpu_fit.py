@@ -149,3 +149,19 @@ def test_mixed_model_reproduces_published_two_part_fits(name):
     fit = gb.mixed_model(d["y"], d["X"], d["Z"], d["id"], k["family"], X_zi=d["X_zi"], Z_zi=d["Z_zi"],
                          control=dict(nAGQ=k["nAGQ"]), diag_D=k["diag_D"], hessian=False)
     check_fit_against_kat(k, fit)
+
+
+def test_predictions_match_published_vignette_values():
+    """docs/articles/Methods.html of the reference: head(fitted(fm, type = "subject_specific")) (:389-394)
+    and predict(fm, newdata = pred_DF, type = "subject_specific") for subject 1's first four visits as a
+    new patient (:546-551), at the published estimates of fm (binomial, random intercepts and slopes).
+    The fitted values agree to every printed digit; the prediction to 5e-6 (the reference finds the new
+    patient's mode with optim's default BFGS tolerance, the engine with Newton to 1e-10)."""
+    v = vignette_data.binary_data()
+    fm = dict(coefficients=np.array([-2.059256329, -1.167646870, 0.261720034, 0.001924039]),
+              D=np.array([[0.47137731, 0.11092919], [0.11092919, 0.06332475]]), phis=None, gammas=None)
+    pr = gb.predict_subject_specific(fm, v["y"], v["X"], v["Z"], v["id"], "binomial", nAGQ=11)
+    pub = np.array([0.08048986, 0.08197442, 0.09997322, 0.23877793, 0.24377249, 0.24418982])
+    assert np.max(np.abs(pr["pred"][:6] - pub)) < 2e-8
+    new = gb.predict_subject_specific(fm, v["y"][:4], v["X"][:4], v["Z"][:4], np.zeros(4, int), "binomial", nAGQ=11)
+    assert np.max(np.abs(new["pred"] - np.array([0.07876144, 0.07981214, 0.09220958, 0.17714850]))) < 5e-6
