@@ -80,3 +80,20 @@ def hurdle_count_data():
     zero = rng.rbinom1(n * K, expit(eta_zi)).astype(bool)
     y[zero] = 0.0
     return dict(id=ids, time=time, sex=sex, X=X, Z=Z, X_zi=X_zi, Z_zi=Z_zi, y=y)
+
+
+def multcomp_binary_data():
+    """vignettes/Multiple_Comparisons.Rmd:30-54: binary outcome at K = 4 categorical time points,
+    300 subjects, random intercepts (rnorm and rbinom(., 1, .) only)."""
+    rng = RRng(1234)
+    n, K = 300, 4
+    ids = np.repeat(np.arange(n), K)
+    timef = np.tile(np.arange(K), n)                               # gl(K, 1, n * K)
+    sex = np.repeat((np.arange(n) >= n // 2).astype(float), K)     # gl(2, n / 2): first half "male"
+    T = np.column_stack([(timef == k).astype(float) for k in range(1, K)])
+    X_gen = np.column_stack([np.ones(n * K), sex, T, sex[:, None] * T])       # ~ sex * time
+    betas = np.array([-2.13, 1.0] + [1.2, -1.2] * (K - 1))
+    b = rng.rnorm(n, sd=1.0)
+    y = rng.rbinom1(n * K, expit(X_gen @ betas + b[ids]))
+    X_main = np.column_stack([np.ones(n * K), sex, T])                        # ~ sex + time
+    return dict(id=ids, sex=sex, time=timef, X=X_main, X_interaction=X_gen, Z=np.ones((n * K, 1)), y=y)

@@ -94,3 +94,24 @@ def test_oracle_fit_reproduces_published_two_part_fits(name):
     data = agq.Data(**kat_inputs(k))
     out = ofit.mixed_fit(data, oracle_family(k["family"]), control=dict(nAGQ=k["nAGQ"]), diag_D=k["diag_D"], hessian=False)
     check_fit_against_kat(k, out)
+
+
+# summary(fm) of docs/articles/Multiple_Comparisons.html:60-105 of the reference: estimates, STANDARD
+# ERRORS (sqrt(diag(solve(Hessian))), the cd_vec Hessian of score_mixed), random-intercept sd, logLik
+MULTCOMP_FM = dict(est=[-2.2865, 0.8860, 0.3066, -0.5053, 0.5632], se=[0.2496, 0.2447, 0.2266, 0.2463, 0.2237],
+                   sd=1.447826, loglik=-583.4797)
+
+
+def check_multcomp(out):
+    k = MULTCOMP_FM
+    assert np.max(np.abs(np.asarray(out["coefficients"]) - np.array(k["est"]))) < 6e-5
+    se = np.sqrt(np.diag(np.linalg.inv(out["Hessian"])))[:5]
+    assert np.max(np.abs(se - np.array(k["se"]))) < 6e-5
+    assert abs(np.sqrt(out["D"][0, 0]) - k["sd"]) < 6e-7
+    assert abs(out["logLik"] - k["loglik"]) < 6e-5
+
+
+def test_oracle_fit_reproduces_published_standard_errors():
+    v = vignette_data.multcomp_binary_data()
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"], id=v["id"])
+    check_multcomp(ofit.mixed_fit(data, F.binomial(), hessian=True))

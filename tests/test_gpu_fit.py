@@ -165,3 +165,11 @@ def test_predictions_match_published_vignette_values():
     assert np.max(np.abs(pr["pred"][:6] - pub)) < 2e-8
     new = gb.predict_subject_specific(fm, v["y"][:4], v["X"][:4], v["Z"][:4], np.zeros(4, int), "binomial", nAGQ=11)
     assert np.max(np.abs(new["pred"] - np.array([0.07876144, 0.07981214, 0.09220958, 0.17714850]))) < 5e-6
+
+
+def test_mixed_model_reproduces_published_standard_errors():
+    """summary(fm) of the Multiple_Comparisons vignette: the engine's estimates, the standard errors from
+    its Hessian (cd_vec of score_mixed, 2 * nparams fused evaluations), sd and logLik."""
+    from test_fit_oracle import check_multcomp
+    v = vignette_data.multcomp_binary_data()
+    check_multcomp(gb.mixed_model(v["y"], v["X"], v["Z"], v["id"], "binomial", hessian=True))
