@@ -9,6 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libglmma.so")
+LIB_PATH = os.environ.get("GLMMA_LIB", LIB_PATH)      # development builds: make DEV=1 -> libglmma_dev.so
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_NUMERIC = 0, 1, 2, 3, 4
 

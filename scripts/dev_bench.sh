@@ -1,3 +1,5 @@
+# development loop: `make -C glmmadaptive_b200/csrc DEV=1` builds libglmma_dev.so (negative binomial only)
+export GLMMA_LIB=${GLMMA_LIB:-$PWD/glmmadaptive_b200/libglmma_dev.so}
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-fit 2>&1 | python -c "
 import sys, json
