@@ -80,6 +80,7 @@ struct glmma_handle {
     int nj;                    // register-variant tiles in use: bit v = tile kTile[v] (8, 12, 16); 0 = generic kernel only
     int fast_grid[3][2];       // [tile][loglik only / with score]
     size_t fast_smem[3][2];
+    int fast_threads[3][2];    // block shape of the register variant (chosen for resident warps per SM)
     int4* d_order[3];          // cluster lists of the tiles: {cluster, first row, n_i, 0}
     int64_t n_order[3];
     int score_grid;
@@ -673,13 +674,12 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
             if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
             for (int s = 0; s < 2; ++s) {
                 int bps = 0;
-                ce = ops->fast_config(s, kTile[v], h->K, &bps, &h->fast_smem[v][s]);
+                ce = ops->fast_config(s, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
                 if (ce != cudaSuccess || bps < 1) {
                     cuda_fail(h, ce, "fast eval kernel configuration");
                     g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
                 }
-                const int64_t want = (n + wpb - 1) / wpb;
-                h->fast_grid[v][s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
+                h->fast_grid[v][s] = prop.multiProcessorCount * bps;      // trimmed to the tile's list below
             }
             max_fast += std::max(h->fast_grid[v][0], h->fast_grid[v][1]);
         }
@@ -707,8 +707,11 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                 if (lists[v].empty()) lists[v].push_back(make_int4(0, 0, 0, 0));
                 TRY(dev_upload(h, &tmp, lists[v].data(), lists[v].size()));
                 h->d_order[v] = const_cast<int4*>(tmp);
-                const int64_t want = (h->n_order[v] + wpb - 1) / wpb;
-                for (int s = 0; s < 2; ++s) h->fast_grid[v][s] = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][s]));
+                for (int s = 0; s < 2; ++s) {
+                    const int fwpb = h->fast_threads[v][s] / 32;
+                    const int64_t want = (h->n_order[v] + fwpb - 1) / fwpb;
+                    h->fast_grid[v][s] = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][s]));
+                }
             }
             cudaMemcpyAsync(d.defer, flags.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream);
             cudaStreamSynchronize(h->stream);      // lists / flags are block-local; errors surface at the final check
@@ -928,7 +931,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
             ea.order = h->d_order[v];
             ea.n_order = h->n_order[v];
             ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
-            h->ops->eval_fast(ea, s, kTile[v], h->fast_grid[v][s], h->fast_smem[v][s], h->stream);
+            h->ops->eval_fast(ea, s, kTile[v], h->fast_grid[v][s], h->fast_threads[v][s], h->fast_smem[v][s], h->stream);
             h->launches++;
             n_blocks += h->fast_grid[v][s];
         }

@@ -653,9 +653,9 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 #define GLMMA_NAGQ_FAST 16
 #define GLMMA_K_FAST 512
 #define GLMMA_NTAB_MAX_K 256
-#ifndef GLMMA_FAST_MINBLOCKS
-#define GLMMA_FAST_MINBLOCKS 4
-#endif
+// Launch shape: 128 registers per thread at any block size from GLMMA_EVAL_THREADS (four blocks per
+// SM) to GLMMA_FAST_MAX_THREADS (one); the host picks the shape that keeps most warps resident.
+#define GLMMA_FAST_MAX_THREADS 512
 
 template <class F, int QY, int QZ, int NJ>
 struct FastLayout {
@@ -685,7 +685,7 @@ struct FastLayout {
 };
 
 template <class F, int QY, int QZ, bool SCORE, int NJ>
-__global__ void __launch_bounds__(GLMMA_EVAL_THREADS, GLMMA_FAST_MINBLOCKS) eval_fast_kernel(EvalArgs A) {
+__global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(EvalArgs A) {
     using FL = FastLayout<F, QY, QZ, NJ>;
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;

@@ -53,24 +53,34 @@ struct OpsImpl {
     // fused (log-likelihood + score) form is instantiated: optim's fn and gr are answered from one fused
     // pass anyway (engine.py: _fused_eval), and a log-likelihood-only call simply ignores the score
     // outputs -- the loglik-only instantiations would add a quarter to build time and binary size.
+    // Block shape of the register variant: the fastmath tables (24 KB) are per block, so families with
+    // large per-warp areas (zero-inflated, q = 3) keep more warps resident with fewer, larger blocks.
+    // Picks the shape with the most resident warps per SM; ties go to the smaller block.
     template <int NJ>
-    static cudaError_t fast_config_nj(int K, int* blocks_per_sm, size_t* smem_bytes) {
-        const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(GLMMA_EVAL_THREADS / 32, K);
-        *smem_bytes = smem;
+    static cudaError_t fast_config_nj(int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_fast_kernel<F, QY, QZ, true, NJ>,
-                                                             GLMMA_EVAL_THREADS, smem);
+        int best = 0;
+        *blocks_per_sm = 0;
+        for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t *= 2) {
+            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K);
+            if (smem > (size_t)glmma_optin_smem()) break;
+            int bps = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ>, t, smem);
+            if (e != cudaSuccess) return e;
+            if (bps * t > best) { best = bps * t; *blocks_per_sm = bps; *smem_bytes = smem; *threads = t; }
+        }
+        return cudaSuccess;
     }
-    static cudaError_t fast_config(int /*score*/, int nj, int K, int* blocks_per_sm, size_t* smem_bytes) {
-        return nj == 8 ? fast_config_nj<8>(K, blocks_per_sm, smem_bytes)
-             : nj == 12 ? fast_config_nj<12>(K, blocks_per_sm, smem_bytes)
-                        : fast_config_nj<16>(K, blocks_per_sm, smem_bytes);
+    static cudaError_t fast_config(int /*score*/, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+        return nj == 8 ? fast_config_nj<8>(K, blocks_per_sm, smem_bytes, threads)
+             : nj == 12 ? fast_config_nj<12>(K, blocks_per_sm, smem_bytes, threads)
+                        : fast_config_nj<16>(K, blocks_per_sm, smem_bytes, threads);
     }
-    static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, size_t smem, cudaStream_t s) {
-        if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+    static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, int threads, size_t smem, cudaStream_t s) {
+        if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
+        else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, threads, smem, s>>>(a);
+        else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
     }
     static void sphi(const EvalArgs& a, int grid, size_t smem, cudaStream_t s) {
         sphi_obs_kernel<F, QY, QZ><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);

@@ -20,9 +20,10 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.argv = [a for a in sys.argv if a != "--no-traffic"] + (["--no-traffic"] if "--no-traffic" in sys.argv else [])
 tag = sys.argv[1]
-rep = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "prof_dev.ncu-rep")
-launches = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "launches_dev.csv")
+rep = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else os.path.join(ROOT, "gpurun_out", "prof_dev.ncu-rep")
+launches = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else os.path.join(ROOT, "gpurun_out", "launches_dev.csv")
 out = lambda name: os.path.join(ROOT, "profiles", f"{tag}_{name}")
 
 
@@ -127,7 +128,8 @@ traffic = {"kernels": [{
     "shared_mem_pipe_pct": float(r["l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"]),
     "registers_per_thread": int(float(r["launch__registers_per_thread"])),
 }]}
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+if "--no-traffic" not in sys.argv:          # traffic.json describes the headline kernel only
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 print(open(out("eval_fast_hotspots.txt")).read())
 print(open(out("launch_shares.txt")).read() if os.path.exists(out("launch_shares.txt")) else "")
 print(json.dumps(traffic))
