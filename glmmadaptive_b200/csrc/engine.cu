@@ -77,6 +77,7 @@ struct glmma_handle {
     int jt;
     int eval_grid[2];
     size_t eval_smem[2];
+    int eval_threads[2];       // block shape of the generic kernel
     int nj;                    // register-variant tiles in use: bit v = tile kTile[v] (8, 12, 16); 0 = generic kernel only
     int fast_grid[3][2];       // [tile][loglik only / with score]
     size_t fast_smem[3][2];
@@ -639,15 +640,15 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);
     if (ce != cudaSuccess) { cuda_fail(h, ce, "cudaGetDeviceProperties"); g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA; }
-    const int wpb = GLMMA_EVAL_THREADS / 32;
     int max_grid = 1;
     for (int s = 0; s < 2; ++s) {
         int bps = 0;
-        ce = ops->eval_config(s, jt, h->nagq, &bps, &h->eval_smem[s]);
+        ce = ops->eval_config(s, jt, h->nagq, &bps, &h->eval_smem[s], &h->eval_threads[s]);
         if (ce != cudaSuccess || bps < 1) {
             cuda_fail(h, ce, "eval kernel configuration");
             g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
         }
+        const int wpb = h->eval_threads[s] / 32;
         const int64_t want = (n + wpb - 1) / wpb;
         h->eval_grid[s] = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * bps);
         max_grid = std::max(max_grid, h->eval_grid[s]);
@@ -938,7 +939,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         ea.only_deferred = 1;
         ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
     }
-    h->ops->eval(ea, s, h->eval_grid[s], h->eval_smem[s], h->stream);
+    h->ops->eval(ea, s, h->eval_grid[s], h->eval_threads[s], h->eval_smem[s], h->stream);
     n_blocks += h->eval_grid[s];
     if (k1) CU(h, cudaEventRecord(k1, h->stream));
     h->launches++;
@@ -999,7 +1000,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
         ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
         fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error, h->family_df);
         fill_prior(h, D, false, &ea.prior);
-        h->ops->sphi(ea, h->eval_grid[1], h->eval_smem[1], h->stream);
+        h->ops->sphi(ea, h->eval_grid[1], h->eval_threads[1], h->eval_smem[1], h->stream);
         h->launches++;
     }
     if (rc == GLMMA_OK) {

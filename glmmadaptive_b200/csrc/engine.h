@@ -9,11 +9,11 @@ struct ModeArgs;
 
 struct FamOps {
     void (*prep)(const PrepArgs&, const CoefPar&, cudaStream_t);
-    cudaError_t (*eval_config)(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes);
-    void (*eval)(const EvalArgs&, int score, int grid, size_t smem, cudaStream_t);
+    cudaError_t (*eval_config)(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads);
+    void (*eval)(const EvalArgs&, int score, int grid, int threads, size_t smem, cudaStream_t);
     cudaError_t (*fast_config)(int score, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
-    void (*sphi)(const EvalArgs&, int grid, size_t smem, cudaStream_t);
+    void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
     bool has_zi, has_phi, uses_y2;

@@ -10,6 +10,7 @@
 #include "families.cuh"
 
 #define GLMMA_EVAL_THREADS 128
+#define GLMMA_EVAL_MAX_THREADS 384     // generic kernel: 128, 256 or 384 threads per block (170 registers)
 #define GLMMA_JT_CAP 32
 
 struct EvalArgs {
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs A, CoefPar C) {
 // Per warp: rec  (jt x W)            observation records y1, y2, xb, (xg), z.., zzi..
 //           tabF (jt x Q x nagq)     separable factors of exp(eta):   exp(eta_jk)    = prod_e tabF[j][e][a_e(k)]
 //           tabL (jt x QZ x nagq)    separable factors of exp(eta_zi) (zero-part families)
-//           scr_eta, acc_eta (jt x 32) [, scr_zi, acc_zi]   per-lane score scratch / accumulators
+//           scr_eta [, scr_zi] (jt x 32), ev (32)           per-lane score terms and node weights of a round
 // The separable tables use that R^-1 is triangular: eta_jk = base_j + sum_e c_je x_{a_e},
 // so exp(eta) over the K = nagq^Q nodes needs only Q * nagq exponentials per observation
 // ("optional algorithmic shortcut").
@@ -137,10 +138,11 @@ struct EvalLayout {
     static constexpr int OFF_Z = F::HAS_ZI ? 4 : 3;
     static constexpr int W0 = OFF_Z + QY + QZ;
     static constexpr int W = (W0 + 1) & ~1;                      // even: records stay 16-byte aligned
-    static constexpr int NSCR = F::HAS_ZI ? 4 : 2;               // scr_eta, acc_eta [, scr_zi, acc_zi]
+    static constexpr int NSCR = F::HAS_ZI ? 2 : 1;               // scr_eta [, scr_zi]
+    static constexpr int NTJ = (GLMMA_JT_CAP + 31) / 32;         // observations per lane of a staged tile
     static constexpr int NTABL = F::HAS_ZI ? (QZ > 0 ? QZ : 1) : 0;
     __host__ __device__ static size_t warp_doubles(int jt, int nagq, bool score) {
-        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * 32 : 0);
+        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * 32 + 32 : 0);
     }
     __host__ __device__ static size_t head_doubles() { return GLMMA_FM_DOUBLES + 2 * GLMMA_NAGQ_MAX; }
     __host__ static size_t smem_bytes(int jt, int nagq, bool score, int warps) {
@@ -291,7 +293,7 @@ __device__ __forceinline__ void lin_pred(const double* r, const double* b, const
 }
 
 template <class F, int QY, int QZ, bool SCORE>
-__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
+__global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A) {
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
     constexpr int NP = L::NP;
@@ -311,9 +313,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
     double* tabF = rec + jt * L::W;
     double* tabL = tabF + jt * Q * nagq;
     double* scr_eta = tabL + jt * L::NTABL * nagq;
-    double* acc_eta = scr_eta + jt * 32;
-    double* scr_zi = acc_eta + jt * 32;
-    double* acc_zi = scr_zi + jt * 32;
+    double* scr_zi = scr_eta + jt * 32;
+    double* ev = scr_eta + L::NSCR * jt * 32;
 
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
@@ -372,16 +373,18 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
+        // posterior-weighted score sums of the staged observations lane, lane + 32, ..: after every
+        // round lane j adds up row j of the (observation x node) scratch, so the sums need registers,
+        // not a second jt x 32 array (shared memory per warp is what bounds the resident warps here)
+        double zacc[L::NTJ], zacc_zi[L::NTJ];
         for (int attempt = 0; attempt < 2; ++attempt) {
             sum_e = 0.0; gphi = 0.0;
 #pragma unroll
             for (int t = 0; t < NP; ++t) S[t] = 0.0;
             if (SCORE) {
                 if (fast) {
-                    for (int t = lane; t < ni * 32; t += 32) {
-                        acc_eta[t] = 0.0;
-                        if (F::HAS_ZI) acc_zi[t] = 0.0;
-                    }
+#pragma unroll
+                    for (int t = 0; t < L::NTJ; ++t) { zacc[t] = 0.0; zacc_zi[t] = 0.0; }
                 } else {
                     for (int j = lane; j < ni; j += 32) {
                         d.zbar[r0 + j] = 0.0;
@@ -445,11 +448,25 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
                         for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
                     if (fast) {
                         if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
-#pragma unroll 2
-                        for (int j = 0; j < ni; ++j) {
-                            acc_eta[j * 32 + lane] = fma(e, scr_eta[j * 32 + lane], acc_eta[j * 32 + lane]);
-                            if (F::HAS_ZI) acc_zi[j * 32 + lane] = fma(e, scr_zi[j * 32 + lane], acc_zi[j * 32 + lane]);
+                        ev[lane] = e;
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < L::NTJ; ++t) {
+                            const int j = lane + 32 * t;
+                            if (j < ni) {
+                                double s1 = 0.0, s2 = 0.0;
+#pragma unroll 4
+                                for (int c = 0; c < 32; ++c) {
+                                    const int cc = (c + lane) & 31;      // rotated: conflict-free
+                                    const double ec = ev[cc];
+                                    s1 = fma(ec, scr_eta[j * 32 + cc], s1);
+                                    if (F::HAS_ZI) s2 = fma(ec, scr_zi[j * 32 + cc], s2);
+                                }
+                                zacc[t] += s1;
+                                if (F::HAS_ZI) zacc_zi[t] += s2;
+                            }
                         }
+                        __syncwarp();
                     } else {
                         for (int j0 = 0; j0 < ni; j0 += jt) {
                             const int cnt = min(jt, ni - j0);
@@ -525,15 +542,13 @@ __global__ void __launch_bounds__(GLMMA_EVAL_THREADS) eval_kernel(EvalArgs A) {
             }
             __syncwarp();
             if (fast) {
-                for (int j = lane; j < ni; j += 32) {
-                    double s1 = 0.0, s2 = 0.0;
-                    for (int c = 0; c < 32; ++c) {
-                        const int cc = (c + lane) & 31;
-                        s1 += acc_eta[j * 32 + cc];
-                        if (F::HAS_ZI) s2 += acc_zi[j * 32 + cc];
+#pragma unroll
+                for (int t = 0; t < L::NTJ; ++t) {
+                    const int j = lane + 32 * t;
+                    if (j < ni) {
+                        d.zbar[r0 + j] = inv * zacc[t];
+                        if (F::HAS_ZI) d.zbar_zi[r0 + j] = inv * zacc_zi[t];
                     }
-                    d.zbar[r0 + j] = inv * s1;
-                    if (F::HAS_ZI) d.zbar_zi[r0 + j] = inv * s2;
                 }
             } else {
                 for (int j = lane; j < ni; j += 32) {
@@ -1268,7 +1283,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 // recomputes the node weights from ll_i of a preceding eval.
 // ------------------------------------------------------------------------------
 template <class F, int QY, int QZ>
-__global__ void __launch_bounds__(GLMMA_EVAL_THREADS) sphi_obs_kernel(EvalArgs A) {
+__global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalArgs A) {
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
     constexpr int NP = L::NP;

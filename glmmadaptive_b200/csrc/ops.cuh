@@ -28,26 +28,36 @@ struct OpsImpl {
             prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
         }
     }
-    static cudaError_t eval_config(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes) {
-        const size_t smem = L::smem_bytes(jt, nagq, score != 0, GLMMA_EVAL_THREADS / 32);
-        *smem_bytes = smem;
-        cudaError_t e;
-        if (score) {
-            e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
-            if (e != cudaSuccess) return e;
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, true>,
-                                                                 GLMMA_EVAL_THREADS, smem);
-        }
-        e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
+    // Block shape of the generic kernel: its per-warp area grows with the observation tile jt, and the
+    // fastmath tables (24 KB) are per block, so larger blocks keep more warps resident when jt is large.
+    template <bool SCORE>
+    static cudaError_t eval_config_s(int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+        cudaError_t e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, eval_kernel<F, QY, QZ, false>,
-                                                             GLMMA_EVAL_THREADS, smem);
+        int best = 0;
+        *blocks_per_sm = 0;
+        for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_EVAL_MAX_THREADS; t += GLMMA_EVAL_THREADS) {
+            const size_t smem = L::smem_bytes(jt, nagq, SCORE, t / 32);
+            if (smem > (size_t)glmma_optin_smem()) break;
+            int bps = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_kernel<F, QY, QZ, SCORE>, t, smem);
+            if (e != cudaSuccess) return e;
+            if (bps * t > best) { best = bps * t; *blocks_per_sm = bps; *smem_bytes = smem; *threads = t; }
+        }
+        return cudaSuccess;
     }
-    static void eval(const EvalArgs& a, int score, int grid, size_t smem, cudaStream_t s) {
-        if (score) eval_kernel<F, QY, QZ, true><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
-        else eval_kernel<F, QY, QZ, false><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+    static cudaError_t eval_config(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+        if (score) {
+            // sphi_obs_kernel shares the scoring layout and launch shape
+            cudaError_t e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
+            if (e != cudaSuccess) return e;
+            return eval_config_s<true>(jt, nagq, blocks_per_sm, smem_bytes, threads);
+        }
+        return eval_config_s<false>(jt, nagq, blocks_per_sm, smem_bytes, threads);
+    }
+    static void eval(const EvalArgs& a, int score, int grid, int threads, size_t smem, cudaStream_t s) {
+        if (score) eval_kernel<F, QY, QZ, true><<<grid, threads, smem, s>>>(a);
+        else eval_kernel<F, QY, QZ, false><<<grid, threads, smem, s>>>(a);
     }
     // register variant (eval_fast_kernel): tiles of nj = 8, 12 or 16 observations per cluster.  Only the
     // fused (log-likelihood + score) form is instantiated: optim's fn and gr are answered from one fused
@@ -82,8 +92,8 @@ struct OpsImpl {
         else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, threads, smem, s>>>(a);
         else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
     }
-    static void sphi(const EvalArgs& a, int grid, size_t smem, cudaStream_t s) {
-        sphi_obs_kernel<F, QY, QZ><<<grid, GLMMA_EVAL_THREADS, smem, s>>>(a);
+    static void sphi(const EvalArgs& a, int grid, int threads, size_t smem, cudaStream_t s) {
+        sphi_obs_kernel<F, QY, QZ><<<grid, threads, smem, s>>>(a);
     }
     static void modes(const ModeArgs& a, int G, cudaStream_t s) {
         const int64_t threads = a.d.n * G;
