@@ -140,9 +140,11 @@ struct EvalLayout {
     static constexpr int W = (W0 + 1) & ~1;                      // even: records stay 16-byte aligned
     static constexpr int NSCR = F::HAS_ZI ? 2 : 1;               // scr_eta [, scr_zi]
     static constexpr int NTJ = (GLMMA_JT_CAP + 31) / 32;         // observations per lane of a staged tile
+    static constexpr int SCRW = 33;                              // row pitch of the score scratch: rows (one per
+                                                                 // observation) are written by columns and summed by rows
     static constexpr int NTABL = F::HAS_ZI ? (QZ > 0 ? QZ : 1) : 0;
     __host__ __device__ static size_t warp_doubles(int jt, int nagq, bool score) {
-        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * 32 + 32 : 0);
+        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * SCRW + 32 : 0);
     }
     __host__ __device__ static size_t head_doubles() { return GLMMA_FM_DOUBLES + 2 * GLMMA_NAGQ_MAX; }
     __host__ static size_t smem_bytes(int jt, int nagq, bool score, int warps) {
@@ -150,17 +152,25 @@ struct EvalLayout {
     }
 };
 
+// t / nagq for 0 <= t < 2^27 without an integer division: rcp = ceil(2^32 / nagq) errs by less than
+// nagq <= 32 parts in 2^32 (nagq == 1, the Laplace grid, is flagged by rcp == 0)
+__device__ __forceinline__ unsigned nagq_rcp(int nagq) {
+    return nagq > 1 ? (unsigned)((0x100000000ull + (unsigned)nagq - 1u) / (unsigned)nagq) : 0u;
+}
+__device__ __forceinline__ int div_nagq(int t, unsigned rcp) { return rcp ? (int)__umulhi((unsigned)t, rcp) : t; }
+
 // decode node k -> b_k = mode + sqrt(2) R^-1 z_k, returns log prior + log wGH; idx[e] = a_e(k)
 template <int Q>
-__device__ __forceinline__ double node_setup(int k, int nagq, const double* gx, const double* glw, double lw_const,
+__device__ __forceinline__ double node_setup(int k, int nagq, unsigned rcp, const double* gx, const double* glw, double lw_const,
                                              const double* m, const double* ri, const PriorPar& pr, double* b, int* idx) {
     double z[Q];
     double lw = lw_const;
     int kk = k;
 #pragma unroll
     for (int dd = 0; dd < Q; ++dd) {
-        const int a = kk % nagq;
-        kk /= nagq;
+        const int qd = div_nagq(kk, rcp);
+        const int a = kk - qd * nagq;
+        kk = qd;
         idx[dd] = a;
         z[dd] = gx[a];
         lw += glw[a];
@@ -202,7 +212,7 @@ __device__ __forceinline__ void stage_tile(const DevData& d, int64_t r0, int cnt
 
 // separable exp tables of one staged tile (lanes over (observation, dimension, node index))
 template <class F, int QY, int QZ>
-__device__ __forceinline__ void build_tables(const double* rec, int cnt, int lane, int nagq, const double* gx,
+__device__ __forceinline__ void build_tables(const double* rec, int cnt, int lane, int nagq, unsigned rcp, const double* gx,
                                              const double* m, const double* ri, const MathCtx& cx,
                                              double* tabF, double* tabL) {
     using L = EvalLayout<F, QY, QZ>;
@@ -210,8 +220,8 @@ __device__ __forceinline__ void build_tables(const double* rec, int cnt, int lan
     if (F::NEED_EMU) {
         const int items = cnt * Q * nagq;
         for (int t = lane; t < items; t += 32) {
-            const int a = t % nagq;
-            const int je = t / nagq;
+            const int je = div_nagq(t, rcp);
+            const int a = t - je * nagq;
             const int e = je % Q;
             const int j = je / Q;
             const double* r = rec + j * L::W;
@@ -232,8 +242,8 @@ __device__ __forceinline__ void build_tables(const double* rec, int cnt, int lan
         constexpr int NT = L::NTABL > 0 ? L::NTABL : 1;
         const int items = cnt * NT * nagq;
         for (int t = lane; t < items; t += 32) {
-            const int a = t % nagq;
-            const int je = t / nagq;
+            const int je = div_nagq(t, rcp);
+            const int a = t - je * nagq;
             const int e = je % NT;            // table e <-> random-effect dimension QY + e
             const int j = je / NT;
             const double* r = rec + j * L::W;
@@ -293,7 +303,7 @@ __device__ __forceinline__ void lin_pred(const double* r, const double* b, const
 }
 
 template <class F, int QY, int QZ, bool SCORE>
-__global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A) {
+__global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArgs A) {
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
     constexpr int NP = L::NP;
@@ -308,13 +318,14 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A
     const int jt = A.jt;
     const int nagq = A.grid->nagq;
     const int K = A.grid->K;
+    const unsigned rcp_nagq = nagq_rcp(nagq);
     double* wbase = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, SCORE);
     double* rec = wbase;
     double* tabF = rec + jt * L::W;
     double* tabL = tabF + jt * Q * nagq;
     double* scr_eta = tabL + jt * L::NTABL * nagq;
-    double* scr_zi = scr_eta + jt * 32;
-    double* ev = scr_eta + L::NSCR * jt * 32;
+    double* scr_zi = scr_eta + jt * L::SCRW;
+    double* ev = scr_eta + L::NSCR * jt * L::SCRW;
 
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A
         if (fast) {
             stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
             __syncwarp();
-            build_tables<F, QY, QZ>(rec, ni, lane, nagq, gx, m, ri, cx, tabF, tabL);
+            build_tables<F, QY, QZ>(rec, ni, lane, nagq, rcp_nagq, gx, m, ri, cx, tabF, tabL);
         }
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A
                 const bool valid = k < K;
                 double b[Q];
                 int idx[Q];
-                double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+                double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
                 double vphi = 0.0;
                 if (fast) {
 #pragma unroll 2
@@ -410,8 +421,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A
                         F::template point<SCORE, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
                         a += ld;
                         if (SCORE) {
-                            scr_eta[j * 32 + lane] = se;
-                            if (F::HAS_ZI) scr_zi[j * 32 + lane] = sz;
+                            scr_eta[j * L::SCRW + lane] = se;
+                            if (F::HAS_ZI) scr_zi[j * L::SCRW + lane] = sz;
                             if (F::HAS_PHI) vphi += sp;
                         }
                     }
@@ -454,14 +465,19 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) eval_kernel(EvalArgs A
                         for (int t = 0; t < L::NTJ; ++t) {
                             const int j = lane + 32 * t;
                             if (j < ni) {
-                                double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
+                                // row j against the node weights: ev[c] is a broadcast, the odd row
+                                // pitch keeps the lanes' row reads on distinct banks
+                                const double* re = scr_eta + j * L::SCRW;
+                                const double* rz = scr_zi + j * L::SCRW;
+                                double p1[4] = {0.0, 0.0, 0.0, 0.0}, p2[4] = {0.0, 0.0, 0.0, 0.0};   // four chains: latency
+#pragma unroll
                                 for (int c = 0; c < 32; ++c) {
-                                    const int cc = (c + lane) & 31;      // rotated: conflict-free
-                                    const double ec = ev[cc];
-                                    s1 = fma(ec, scr_eta[j * 32 + cc], s1);
-                                    if (F::HAS_ZI) s2 = fma(ec, scr_zi[j * 32 + cc], s2);
+                                    const double ec = ev[c];
+                                    p1[c & 3] = fma(ec, re[c], p1[c & 3]);
+                                    if (F::HAS_ZI) p2[c & 3] = fma(ec, rz[c], p2[c & 3]);
                                 }
+                                const double s1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                                const double s2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
                                 zacc[t] += s1;
                                 if (F::HAS_ZI) zacc_zi[t] += s2;
                             }
@@ -1297,6 +1313,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
     const int wpb = blockDim.x >> 5;
     const int jt = A.jt;
     const int nagq = A.grid->nagq, K = A.grid->K;
+    const unsigned rcp_nagq = nagq_rcp(nagq);
     double* rec = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, true);
     double* scr = rec + jt * L::W + jt * (Q + L::NTABL) * nagq;
     load_fmtab(fmtab, A.fmtab);
@@ -1329,7 +1346,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
             const bool valid = k < K;
             double b[Q];
             int idx[Q];
-            double a = node_setup<Q>(valid ? k : K - 1, nagq, gx, glw, A.grid->lw_const, m, ri, A.prior, b, idx);
+            double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, A.grid->lw_const, m, ri, A.prior, b, idx);
             for (int j0 = 0; j0 < ni; j0 += jt) {
                 const int cnt = min(jt, ni - j0);
                 __syncwarp();
