@@ -100,6 +100,9 @@ struct FamBase {
     // linear predictor stays inside [ETA_LO, ETA_HI] on the whole grid (a link clamp outside)
     static constexpr bool HAS_ETA_RANGE = false;
     static constexpr double ETA_LO = -1e300, ETA_HI = 1e300;
+    // generic kernel: observations evaluated per trip of its point loop (independent chains for the FP64
+    // pipe); 2 for the functors whose careful form is long (beta, censored normal, probit / cloglog)
+    static constexpr int GENERIC_UNROLL = 4;
     __device__ static __forceinline__ double fast_addend(const FamPar&) { return 0.0; }
     __device__ static __forceinline__ double fast_score(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
@@ -149,6 +152,7 @@ struct FamBinomialLogit : FamBase {
 // R/Fit_Funs.R:150-167 ---------------------------------------------------------
 template <int LINK>   // 4 probit, 5 cloglog (enum glmma_link)
 struct FamBinomialOther : FamBase {
+    static constexpr int GENERIC_UNROLL = 2;
     static constexpr bool USES_Y2 = true;
     // cloglog reads exp(eta) from the separable tables; probit works on eta itself
     static constexpr bool NEED_EMU = LINK == 5;
@@ -537,6 +541,7 @@ __device__ __forceinline__ void beta_point(double ly, double l1y, double eta, do
 
 // ----- beta.fam() -- R/Fit_Funs.R:887-930 ---------------------------------------
 struct FamBeta : FamBase {
+    static constexpr int GENERIC_UNROLL = 2;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
     static constexpr double LOG_EMU_LO = -29.93;
@@ -557,6 +562,7 @@ struct FamBeta : FamBase {
 // ----- hurdle.beta.fam() -- R/Fit_Funs.R:932-1004 (scores evaluated at the true mu;
 // the reference's attr(mu_y) <- eta slip, SURVEY appendix G, is not replicated) ---
 struct FamHurdleBeta : FamBase {
+    static constexpr int GENERIC_UNROLL = 2;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
     static constexpr double LOG_EMU_LO = -29.93;
@@ -607,6 +613,7 @@ struct FamGamma : FamBase {
 // ----- censored.normal() -- R/Fit_Funs.R:1360-1435; a[0] = sigma, a[1] = log sigma,
 // a[2] = 1/sigma ------------------------------------------------------------------
 struct FamCensoredNormal : FamBase {
+    static constexpr int GENERIC_UNROLL = 2;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
     static constexpr bool NEED_EMU = false;
@@ -726,6 +733,7 @@ __device__ __forceinline__ void bb_rising(double x, double cnt, const MathCtx& c
     }
 }
 struct FamBetaBinomial : FamBase {
+    static constexpr int GENERIC_UNROLL = 2;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
     static constexpr double LOG_EMU_LO = -29.93;

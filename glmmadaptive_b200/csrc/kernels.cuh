@@ -210,13 +210,16 @@ __device__ __forceinline__ void stage_tile(const DevData& d, int64_t r0, int cnt
     }
 }
 
-// separable exp tables of one staged tile (lanes over (observation, dimension, node index))
+// separable exp tables of one staged tile (lanes over (observation, dimension, node index)).
+// Returns whether every factor's argument is within +-230, so that no product of up to three
+// factors can under- or overflow (warp-uniform); the caller streams the cluster otherwise.
 template <class F, int QY, int QZ>
-__device__ __forceinline__ void build_tables(const double* rec, int cnt, int lane, int nagq, unsigned rcp, const double* gx,
+__device__ __forceinline__ bool build_tables(const double* rec, int cnt, int lane, int nagq, unsigned rcp, const double* gx,
                                              const double* m, const double* ri, const MathCtx& cx,
                                              double* tabF, double* tabL) {
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
+    bool ok = true;
     if (F::NEED_EMU) {
         const int items = cnt * Q * nagq;
         for (int t = lane; t < items; t += 32) {
@@ -235,6 +238,7 @@ __device__ __forceinline__ void build_tables(const double* rec, int cnt, int lan
                     if (ee == e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, ee)], c);
             }
             const double arg = fma(GLMMA_SQRT2 * c, gx[a], e == 0 ? base : 0.0);
+            if (!(fabs(arg) <= 230.0)) ok = false;
             tabF[t] = fast_exp(arg, cx);
         }
     }
@@ -256,9 +260,11 @@ __device__ __forceinline__ void build_tables(const double* rec, int cnt, int lan
                     if (ee == e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + ee)], c);
             }
             const double arg = fma(GLMMA_SQRT2 * c, QZ > 0 ? gx[a] : 0.0, e == 0 ? base : 0.0);
+            if (!(fabs(arg) <= 230.0)) ok = false;
             tabL[t] = fast_exp(arg, cx);
         }
     }
+    return __all_sync(0xffffffffu, ok);
 }
 
 // eta, eta_zi and (SEP: from the tables; else by fast_exp) exp(eta), exp(eta_zi) of one point
@@ -282,8 +288,7 @@ __device__ __forceinline__ void lin_pred(const double* r, const double* b, const
             const double* tf = tabF + j * Q * nagq;
             emu = tf[idx[0]];
 #pragma unroll
-            for (int e = 1; e < Q; ++e) emu *= tf[e * nagq + idx[e]];
-            if (!(emu > 1e-300 && emu < 1e300)) emu = exp(eta);       // a factor under/overflowed
+            for (int e = 1; e < Q; ++e) emu *= tf[e * nagq + idx[e]];     // in range: build_tables
         } else {
             emu = fast_exp(eta, cx);
         }
@@ -295,7 +300,6 @@ __device__ __forceinline__ void lin_pred(const double* r, const double* b, const
             elam = tl[QZ > 0 ? idx[QY] : 0];
 #pragma unroll
             for (int e = 1; e < QZ; ++e) elam *= tl[e * nagq + idx[QY + e]];
-            if (!(elam > 1e-300 && elam < 1e300)) elam = exp(fmin(fmax(ez, -690.0), 690.0));
         } else {
             elam = fast_exp(fmin(fmax(ez, -690.0), 690.0), cx);
         }
@@ -374,12 +378,13 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
         c_ll = warp_sum(c_ll);
         if (SCORE && F::HAS_PHI) c_phi = warp_sum(c_phi);
 
-        const bool fast = ni <= jt;
+        bool fast = ni <= jt;
         __syncwarp();
         if (fast) {
             stage_tile<F, QY, QZ>(d, r0, ni, lane, rec);
             __syncwarp();
-            build_tables<F, QY, QZ>(rec, ni, lane, nagq, rcp_nagq, gx, m, ri, cx, tabF, tabL);
+            // a factor that could under- or overflow: the streaming path forms exp(eta) per point
+            fast = build_tables<F, QY, QZ>(rec, ni, lane, nagq, rcp_nagq, gx, m, ri, cx, tabF, tabL);
         }
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
                 double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
                 double vphi = 0.0;
                 if (fast) {
-#pragma unroll 2
+#pragma unroll (F::GENERIC_UNROLL)
                     for (int j = 0; j < ni; ++j) {
                         const double* rj = rec + j * L::W;
                         double eta, ez, emu, elam, ld, se, sz, sp;
