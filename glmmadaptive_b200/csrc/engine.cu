@@ -78,6 +78,7 @@ struct glmma_handle {
     int eval_grid[2];
     size_t eval_smem[2];
     int eval_threads[2];       // block shape of the generic kernel
+    int asum_doubles;          // per-warp node sums of the generic kernel's tile-outer path (0: no cluster needs it)
     int nj;                    // register-variant tiles in use: bit v = tile kTile[v] (8, 12, 16); 0 = generic kernel only
     int fast_grid[3][2];       // [tile][loglik only / with score]
     size_t fast_smem[3][2];
@@ -637,13 +638,15 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         }
     }
     h->jt = jt;
+    // clusters larger than the staged tile: K node sums per warp (kernels.cuh, tile-outer path)
+    h->asum_doubles = (max_ni > jt && h->K <= GLMMA_ASUM_MAX_K) ? ((h->K + 1) & ~1) : 0;
     cudaDeviceProp prop;
     ce = cudaGetDeviceProperties(&prop, device);
     if (ce != cudaSuccess) { cuda_fail(h, ce, "cudaGetDeviceProperties"); g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA; }
     int max_grid = 1;
     for (int s = 0; s < 2; ++s) {
         int bps = 0;
-        ce = ops->eval_config(s, jt, h->nagq, &bps, &h->eval_smem[s], &h->eval_threads[s]);
+        ce = ops->eval_config(s, jt, h->nagq, h->asum_doubles, &bps, &h->eval_smem[s], &h->eval_threads[s]);
         if (ce != cudaSuccess || bps < 1) {
             cuda_fail(h, ce, "eval kernel configuration");
             g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
@@ -919,7 +922,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     std::memset(&ea, 0, sizeof(ea));
     ea.em_mode = em_mode; ea.pby = h->d_pby;
     ea.d = dd_override ? *dd_override : h->d;
-    ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt;
+    ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.asum_doubles = h->asum_doubles;
     rc = fill_prior(h, D, false, &ea.prior);
     if (rc) return rc;
     if (k0) CU(h, cudaEventRecord(k0, h->stream));
@@ -997,7 +1000,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
     if (rc == GLMMA_OK && d_sphi) {
         EvalArgs ea;
         std::memset(&ea, 0, sizeof(ea));
-        ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.only_deferred = 0;
+        ea.d = dd; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.asum_doubles = h->asum_doubles; ea.only_deferred = 0;
         fill_fampar(h->family, h->d.n_phis, phis, &ea.fam, h->error, h->family_df);
         fill_prior(h, D, false, &ea.prior);
         h->ops->sphi(ea, h->eval_grid[1], h->eval_threads[1], h->eval_smem[1], h->stream);

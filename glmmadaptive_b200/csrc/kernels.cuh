@@ -12,6 +12,7 @@
 #define GLMMA_EVAL_THREADS 128
 #define GLMMA_EVAL_MAX_THREADS 384     // generic kernel: 128, 256 or 384 threads per block (170 registers)
 #define GLMMA_JT_CAP 32
+#define GLMMA_ASUM_MAX_K 1024          // eval_kernel: largest grid whose node sums are kept per warp (tile-outer path)
 
 struct EvalArgs {
     DevData d;
@@ -23,6 +24,7 @@ struct EvalArgs {
     double* partials;        // gridDim.x * GLMMA_NACC block partial sums
     int jt;                  // observation tile held in shared memory per warp (<= GLMMA_JT_CAP)
     int only_deferred;       // eval_kernel: process only clusters flagged in d.defer
+    int asum_doubles;        // eval_kernel: per-warp node sums (K doubles, 0 = none) for clusters larger than jt
     // EM phase of mixed_fit (R/mixed_fit.R:119-229), eval_kernel only:
     //   em_mode 1 (E-step): also store the un-normalised posterior node weights
     //             e_ik = exp(a_ik - shift_i) in pby (n x K; all zero for a dropped cluster);
@@ -144,11 +146,11 @@ struct EvalLayout {
                                                                  // observation) are written by columns and summed by rows
     static constexpr int NTABL = F::HAS_ZI ? (QZ > 0 ? QZ : 1) : 0;
     __host__ __device__ static size_t warp_doubles(int jt, int nagq, bool score) {
-        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (size_t)NSCR * jt * SCRW + 32 : 0);
+        return (size_t)jt * W + (size_t)jt * (Q + NTABL) * nagq + (score ? (((size_t)NSCR * jt * SCRW + 1) & ~(size_t)1) + 32 : 0);   // even where it can be: the compiler pairs record loads
     }
     __host__ __device__ static size_t head_doubles() { return GLMMA_FM_DOUBLES + 2 * GLMMA_NAGQ_MAX; }
-    __host__ static size_t smem_bytes(int jt, int nagq, bool score, int warps) {
-        return sizeof(double) * (head_doubles() + warps * warp_doubles(jt, nagq, score));
+    __host__ static size_t smem_bytes(int jt, int nagq, bool score, int warps, int extra = 0) {
+        return sizeof(double) * (head_doubles() + warps * (warp_doubles(jt, nagq, score) + (size_t)extra));
     }
 };
 
@@ -323,13 +325,14 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
     const int nagq = A.grid->nagq;
     const int K = A.grid->K;
     const unsigned rcp_nagq = nagq_rcp(nagq);
-    double* wbase = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, SCORE);
+    double* wbase = smem + L::head_doubles() + wib * (L::warp_doubles(jt, nagq, SCORE) + (A.asum_doubles & ~1));
+    double* asum = wbase + L::warp_doubles(jt, nagq, SCORE);     // K node sums (clusters larger than jt)
     double* rec = wbase;
     double* tabF = rec + jt * L::W;
     double* tabL = tabF + jt * Q * nagq;
     double* scr_eta = tabL + jt * L::NTABL * nagq;
     double* scr_zi = scr_eta + jt * L::SCRW;
-    double* ev = scr_eta + L::NSCR * jt * L::SCRW;
+    double* ev = scr_eta + ((L::NSCR * jt * L::SCRW + 1) & ~1);
 
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
@@ -393,7 +396,130 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
         // round lane j adds up row j of the (observation x node) scratch, so the sums need registers,
         // not a second jt x 32 array (shared memory per warp is what bounds the resident warps here)
         double zacc[L::NTJ], zacc_zi[L::NTJ];
-        for (int attempt = 0; attempt < 2; ++attempt) {
+        // Clusters larger than the staged tile, tile-outer form: pass A walks the tiles once (records
+        // staged, separable tables built per tile) and sums the log-densities per node into asum;
+        // then the node weights are known and pass B walks the tiles again for the scores, with the
+        // same per-round row sums as the staged path.  Every point is evaluated twice, from the tables;
+        // zbar is written un-normalised (the epilogue below scales it, as for the streaming path).
+        static_assert(GLMMA_JT_CAP <= 32, "a lane owns one observation of a staged tile in the row sums");
+        bool tiled_done = false;
+        if (!fast && ni > jt && A.asum_doubles > 0) {
+            bool tok = true;
+            if (A.em_mode != 2) {
+                for (int j0 = 0; j0 < ni; j0 += jt) {
+                    const int cnt = min(jt, ni - j0);
+                    __syncwarp();
+                    stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                    __syncwarp();
+                    tok = build_tables<F, QY, QZ>(rec, cnt, lane, nagq, rcp_nagq, gx, m, ri, cx, tabF, tabL);
+                    __syncwarp();
+                    if (!tok) break;
+                    for (int r = 0; r < nrounds; ++r) {
+                        const int k = (r << 5) + lane;
+                        const bool valid = k < K;
+                        double b[Q];
+                        int idx[Q];
+                        double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+                        if (j0 > 0) a = 0.0;
+#pragma unroll (F::GENERIC_UNROLL)
+                        for (int j = 0; j < cnt; ++j) {
+                            const double* rj = rec + j * L::W;
+                            double eta, ez, emu, elam, ld, se, sz, sp;
+                            lin_pred<F, QY, QZ, true>(rj, b, idx, j, nagq, tabF, tabL, cx, eta, ez, emu, elam);
+                            F::template point<false, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
+                            a += ld;
+                        }
+                        if (valid) asum[k] = j0 > 0 ? asum[k] + a : a;
+                    }
+                }
+            }
+            if (tok) {
+                // node weights (kept in asum), their sum and the shift (the true maximum)
+                __syncwarp();
+                sum_e = 0.0;
+                if (A.em_mode == 2) {
+                    for (int k = lane; k < K; k += 32) { const double e = A.pby[i * K + k]; asum[k] = e; sum_e += e; }
+                } else {
+                    double mx = -INFINITY;
+                    for (int k = lane; k < K; k += 32) mx = fmax(mx, asum[k]);
+                    mx = warp_max(mx);
+                    shift = fabs(mx) < INFINITY ? mx : 0.0;
+                    for (int k = lane; k < K; k += 32) {
+                        const double e = fast_exp(asum[k] - shift, cx);
+                        asum[k] = e;
+                        sum_e += e;
+                        if (A.em_mode == 1) A.pby[i * K + k] = e;
+                    }
+                }
+                sum_e = warp_sum(sum_e);
+                __syncwarp();
+                gphi = 0.0;
+#pragma unroll
+                for (int t = 0; t < NP; ++t) S[t] = 0.0;
+                if (SCORE) {
+                    for (int j0 = 0; j0 < ni; j0 += jt) {
+                        const int cnt = min(jt, ni - j0);
+                        __syncwarp();
+                        stage_tile<F, QY, QZ>(d, r0 + j0, cnt, lane, rec);
+                        __syncwarp();
+                        tok = build_tables<F, QY, QZ>(rec, cnt, lane, nagq, rcp_nagq, gx, m, ri, cx, tabF, tabL);
+                        __syncwarp();
+                        if (!tok) break;          // M-step on a cluster whose tables leave the range: streaming path
+                        double za = 0.0, zz = 0.0;
+                        for (int r = 0; r < nrounds; ++r) {
+                            const int k = (r << 5) + lane;
+                            const bool valid = k < K;
+                            double b[Q];
+                            int idx[Q];
+                            node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+                            const double e = valid ? asum[k] : 0.0;
+                            if (j0 == 0) {
+                                int t = 0;
+#pragma unroll
+                                for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                                    for (int ee = dd; ee < Q; ++ee) { S[t] = fma(e * b[dd], b[ee], S[t]); ++t; }
+                            }
+                            double vphi = 0.0;
+#pragma unroll (F::GENERIC_UNROLL)
+                            for (int j = 0; j < cnt; ++j) {
+                                const double* rj = rec + j * L::W;
+                                double eta, ez, emu, elam, ld, se, sz, sp;
+                                lin_pred<F, QY, QZ, true>(rj, b, idx, j, nagq, tabF, tabL, cx, eta, ez, emu, elam);
+                                F::template point<true, true>(rj[0], rj[1], eta, ez, emu, elam, A.fam, cx, ld, se, sz, sp);
+                                scr_eta[j * L::SCRW + lane] = se;
+                                if (F::HAS_ZI) scr_zi[j * L::SCRW + lane] = sz;
+                                if (F::HAS_PHI) vphi += sp;
+                            }
+                            if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+                            ev[lane] = e;
+                            __syncwarp();
+                            if (lane < cnt) {
+                                const double* re = scr_eta + lane * L::SCRW;
+                                const double* rz = scr_zi + lane * L::SCRW;
+                                double p1[4] = {0.0, 0.0, 0.0, 0.0}, p2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) {
+                                    const double ec = ev[c];
+                                    p1[c & 3] = fma(ec, re[c], p1[c & 3]);
+                                    if (F::HAS_ZI) p2[c & 3] = fma(ec, rz[c], p2[c & 3]);
+                                }
+                                za += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+                                if (F::HAS_ZI) zz += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+                            }
+                            __syncwarp();
+                        }
+                        if (lane < cnt) {
+                            d.zbar[r0 + j0 + lane] = za;
+                            if (F::HAS_ZI) d.zbar_zi[r0 + j0 + lane] = zz;
+                        }
+                    }
+                }
+                tiled_done = tok;
+            }
+            __syncwarp();
+        }
+        for (int attempt = 0; attempt < 2 && !tiled_done; ++attempt) {
             sum_e = 0.0; gphi = 0.0;
 #pragma unroll
             for (int t = 0; t < NP; ++t) S[t] = 0.0;
@@ -1319,7 +1445,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
     const int jt = A.jt;
     const int nagq = A.grid->nagq, K = A.grid->K;
     const unsigned rcp_nagq = nagq_rcp(nagq);
-    double* rec = smem + L::head_doubles() + wib * L::warp_doubles(jt, nagq, true);
+    double* rec = smem + L::head_doubles() + wib * (L::warp_doubles(jt, nagq, true) + (A.asum_doubles & ~1));
     double* scr = rec + jt * L::W + jt * (Q + L::NTABL) * nagq;
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {

@@ -31,13 +31,13 @@ struct OpsImpl {
     // Block shape of the generic kernel: its per-warp area grows with the observation tile jt, and the
     // fastmath tables (24 KB) are per block, so larger blocks keep more warps resident when jt is large.
     template <bool SCORE>
-    static cudaError_t eval_config_s(int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+    static cudaError_t eval_config_s(int jt, int nagq, int extra, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_kernel<F, QY, QZ, SCORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
         for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_EVAL_MAX_THREADS; t += GLMMA_EVAL_THREADS) {
-            const size_t smem = L::smem_bytes(jt, nagq, SCORE, t / 32);
+            const size_t smem = L::smem_bytes(jt, nagq, SCORE, t / 32, extra);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_kernel<F, QY, QZ, SCORE>, t, smem);
@@ -46,14 +46,14 @@ struct OpsImpl {
         }
         return cudaSuccess;
     }
-    static cudaError_t eval_config(int score, int jt, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+    static cudaError_t eval_config(int score, int jt, int nagq, int extra, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         if (score) {
             // sphi_obs_kernel shares the scoring layout and launch shape
             cudaError_t e = cudaFuncSetAttribute(sphi_obs_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
             if (e != cudaSuccess) return e;
-            return eval_config_s<true>(jt, nagq, blocks_per_sm, smem_bytes, threads);
+            return eval_config_s<true>(jt, nagq, extra, blocks_per_sm, smem_bytes, threads);
         }
-        return eval_config_s<false>(jt, nagq, blocks_per_sm, smem_bytes, threads);
+        return eval_config_s<false>(jt, nagq, extra, blocks_per_sm, smem_bytes, threads);
     }
     static void eval(const EvalArgs& a, int score, int grid, int threads, size_t smem, cudaStream_t s) {
         if (score) eval_kernel<F, QY, QZ, true><<<grid, threads, smem, s>>>(a);

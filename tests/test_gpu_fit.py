@@ -19,8 +19,8 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vignette_kat.json")
 
 
-def _case(name, n, **kw):
-    d, th = synth.make(name, n=n, ni=6, seed=21, ragged=True, **kw)
+def _case(name, n, ni=6, **kw):
+    d, th = synth.make(name, n=n, ni=ni, seed=21, ragged=True, **kw)
     fam_name = d.pop("family")
     return d, th, fam_name
 
@@ -30,6 +30,20 @@ def test_em_estep_and_frozen_scores(name):
     d, th, fam_name = _case(name, 40)
     if name == "C3":
         d["weights"] = np.random.default_rng(1).uniform(0.5, 2.0, 40)
+    _em_check(d, th, fam_name)
+
+
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_em_passes_on_clusters_larger_than_the_staged_tile(name):
+    """Cluster sizes 1 + Poisson(44): nearly all beyond the generic kernel's 32 staged observations
+    (tile-outer path: node sums per warp, two passes over the tiles), E-step and frozen-weight scores."""
+    d, th, fam_name = _case(name, 14, ni=45)
+    sizes = np.bincount(np.unique(d["id"], return_inverse=True)[1])
+    assert (sizes > 32).sum() >= 10
+    _em_check(d, th, fam_name)
+
+
+def _em_check(d, th, fam_name):
     fam = oracle_family(fam_name)
     od, gh = oracle_grid(d, th, fam)
     eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d.get("X_zi"),
