@@ -97,3 +97,68 @@ def multcomp_binary_data():
     y = rng.rbinom1(n * K, expit(X_gen @ betas + b[ids]))
     X_main = np.column_stack([np.ones(n * K), sex, T])                        # ~ sex + time
     return dict(id=ids, sex=sex, time=timef, X=X_main, X_interaction=X_gen, Z=np.ones((n * K, 1)), y=y)
+
+
+# ---- data sets that need R's rpois / rgamma / rnbinom / rbeta (oracle/r_rng.py: RScalarRng) ----
+def poisson_data():
+    """vignettes/GLMMadaptive.Rmd:201-226 (gm1, gm2): rpois(n * K, exp(eta_y))."""
+    from .r_rng import RScalarRng
+    rng = RScalarRng(1234)
+    n, K, t_max = 100, 8, 15
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    betas = np.array([2.13, -0.25, 0.24, -0.05])
+    b = rng.rnorm(n, sd=np.sqrt(0.48))
+    y = rng.rpois(n * K, np.exp(X @ betas + b[ids]))
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z[:, :1], y=y)
+
+
+def zi_count_data():
+    """vignettes/ZeroInflated_and_TwoPart_Models.Rmd:43-79 (fm1, fm2, gm1):
+    rnbinom(n * K, size = 2, mu = exp(eta_y)) with extra zeros by rbinom(., 1, plogis(eta_zi))."""
+    from .r_rng import RScalarRng
+    rng = RScalarRng(1234)
+    n, K, t_max = 100, 8, 5
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    X_zi = np.column_stack([np.ones(n * K), sex])
+    Z_zi = np.ones((n * K, 1))
+    betas = np.array([1.5, 0.05, 0.05, -0.03])
+    gammas = np.array([-1.5, 0.5])
+    b = np.column_stack([rng.rnorm(n, sd=np.sqrt(0.5)), rng.rnorm(n, sd=np.sqrt(0.4))])
+    eta_y = X @ betas + b[ids, 0]
+    eta_zi = X_zi @ gammas + b[ids, 1]
+    y = rng.rnbinom_mu(n * K, 2.0, np.exp(eta_y))
+    y[rng.rbinom1(n * K, expit(eta_zi)).astype(bool)] = 0.0
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z[:, :1], X_zi=X_zi, Z_zi=Z_zi, y=y)
+
+
+def custom_negbin_data():
+    """vignettes/Custom_Models.Rmd:69-75 (fm1, fm2): expand.grid(f1 = 1:3, f2 = A:B, g = 1:30,
+    rep = 1:15) (first factor fastest), rnbinom(mu = mu, size = 0.5); y ~ f1 * f2, ~ 1 | g.
+    mixed_model() sorts the rows by the grouping factor (R/mixed_model.R:50: stable order)."""
+    from .r_rng import RScalarRng
+    rng = RScalarRng(101)
+    N = 3 * 2 * 30 * 15
+    idx = np.arange(N)
+    f1, f2, g = idx % 3 + 1, (idx // 3) % 2 + 1, (idx // 6) % 30
+    mu = 5.0 * (-4 + f1 + 4 * f2)
+    y = rng.rnbinom_mu(N, 0.5, mu)
+    X = np.column_stack([np.ones(N), f1 == 2, f1 == 3, f2 == 2, (f1 == 2) & (f2 == 2),
+                         (f1 == 3) & (f2 == 2)]).astype(float)
+    o = np.argsort(g, kind="stable")
+    return dict(id=g[o], X=X[o], Z=np.ones((N, 1)), y=y[o])
+
+
+def beta_data():
+    """vignettes/Custom_Models.Rmd:262-290 (gm): rbeta(n * K, mu * phi, phi * (1 - mu)), squeezed
+    into (0, 1)."""
+    from .r_rng import RScalarRng
+    rng = RScalarRng(1234)
+    n, K, t_max = 100, 8, 15
+    ids, time, sex, X, Z = _design(rng, n, K, t_max)
+    betas = np.array([-2.2, -0.25, 0.24, -0.05])
+    phi = 5.0
+    b = rng.rnorm(n, sd=np.sqrt(0.9))
+    mu = expit(X @ betas + b[ids])
+    y = rng.rbeta(n * K, mu * phi, phi * (1.0 - mu))
+    y = (y * (n * K - 1) + 0.5) / (n * K)
+    return dict(id=ids, time=time, sex=sex, X=X, Z=Z[:, :1], y=y)

@@ -109,3 +109,47 @@ def test_kat_hurdle_lognormal_q2_and_hurdle_negative_binomial():
         th = np.concatenate([betas, np.log(np.diag(D)) if k["diag_D"] else agq.chol_transf(D), phis, gammas])
         ll = -agq.logLik_mixed(th, data, fam, gh, diag_D=k["diag_D"])
         assert abs(ll - k["loglik"]) < k["tol"], (k["name"], ll)
+
+
+# ---- families of BASELINE configs C2-C5: poisson, negative binomial, zi.poisson, zi.nb, beta ------
+def test_r_scalar_generators_reproducible():
+    """Structural checks of the restated rpois / rgamma / rnbinom / rbeta (the real pin is the
+    published numbers below): moments, and independence of the table-reuse path of rpois."""
+    from oracle.r_rng import RScalarRng
+    r = RScalarRng(7)
+    x = r.rpois(4000, 3.5)
+    assert abs(x.mean() - 3.5) < 0.1 and abs(x.var() - 3.5) < 0.3
+    x = r.rpois(4000, 40.0)
+    assert abs(x.mean() - 40.0) < 0.4 and abs(x.var() - 40.0) < 3.0
+    g = np.array([r.rgamma1(0.5, 2.0) for _ in range(4000)])
+    assert abs(g.mean() - 1.0) < 0.08
+    g = np.array([r.rgamma1(4.0, 0.5) for _ in range(4000)])
+    assert abs(g.mean() - 2.0) < 0.06 and abs(g.var() - 1.0) < 0.12
+    b = r.rbeta(4000, 0.5, 4.5)
+    assert abs(b.mean() - 0.1) < 0.01
+    b = r.rbeta(4000, 2.0, 3.0)
+    assert abs(b.mean() - 0.4) < 0.01
+    e = np.array([r.exp_rand() for _ in range(4000)])
+    assert abs(e.mean() - 1.0) < 0.06
+
+
+def _family_kats():
+    from kat_families import FAMILY_KATS
+    return FAMILY_KATS
+
+
+def test_kat_family_loglik_at_published_estimates():
+    """logLik_mixed at the published estimates of poisson gm1 (D7), zi.poisson fm1 / fm2 and zi.nb gm1
+    (D8), negative binomial fm2 and beta gm (D9) prints the published log-likelihood."""
+    from kat_families import kat_data, kat_theta
+    from helpers import oracle_family
+    for k in _family_kats():
+        data = agq.Data(**kat_data(k))
+        fam = oracle_family(k["family"])
+        q = k["q_y"] + k["q_zi"]
+        betas, D, phis, gammas = kat_theta(k)
+        gh = agq.GHfun(np.zeros((data.n, q)), data, fam, betas, np.linalg.inv(D), phis, gammas, k["nAGQ"], q,
+                       mode_finder="newton")
+        th = np.concatenate([v for v in (betas, agq.chol_transf(D), phis, gammas) if v is not None])
+        ll = -agq.logLik_mixed(th, data, fam, gh)
+        assert abs(ll - k["loglik"]) < k["eval_tol"], (k["name"], ll)
