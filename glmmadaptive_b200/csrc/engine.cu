@@ -444,6 +444,14 @@ static int dev_upload(glmma_handle* h, const T** out, const T* src, size_t count
     return GLMMA_OK;
 }
 
+// Restores the caller's current CUDA device when an ABI call returns: the host process (R, or Python
+// with torch) must not find itself on another device after calling into the engine.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
 int glmma_version(void) { return GLMMA_VERSION; }
@@ -466,6 +474,7 @@ const char* glmma_last_error(const glmma_handle* h) { return h ? h->error.c_str(
 
 void glmma_destroy(glmma_handle* h) {
     if (!h) return;
+    DeviceGuard device_guard_;
     if (!h->parts.empty()) {
         for (auto& w : h->workers) w->shutdown();
         for (glmma_handle* p : h->parts) glmma_destroy(p);
@@ -482,6 +491,7 @@ void glmma_destroy(glmma_handle* h) {
 }
 
 int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
+    DeviceGuard device_guard_;
     if (!data || !out) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
     *out = nullptr;
     const int64_t N = data->n_obs;
@@ -842,6 +852,7 @@ static int multi_find_modes(glmma_handle* h, const double* betas, const double* 
 
 int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
                      const double* gammas, int warm, glmma_mode_stats* stats) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_find_modes(h, betas, invD, phis, gammas, warm, stats);
     unsigned long long st[4];
     int rc = find_modes_enqueue(h, betas, invD, phis, gammas, warm, st);
@@ -868,6 +879,7 @@ static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int respo
                           const double* beta, double* out);
 
 int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_get_modes(h, post_modes, chol_upper, log_dets);
     int rc = enter(h);
     if (rc) return rc;
@@ -889,6 +901,7 @@ int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, dou
 }
 
 int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_set_modes(h, post_modes, chol_upper);
     int rc = enter(h);
     if (rc) return rc;
@@ -905,6 +918,7 @@ int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* cho
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_modes = true;
+    h->have_pby = false;       // the stored posterior node weights belong to the previous grid
     return GLMMA_OK;
 }
 
@@ -960,6 +974,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
 
 int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, const double* phis,
                       const double* gammas, int want_score, double* d_result) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "glmma_eval_device needs a single-device handle");
     int rc = enter(h);
     if (rc) return rc;
@@ -969,6 +984,7 @@ int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, con
 
 int glmma_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                const double* gammas, int want_score, double* result) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, want_score, result, 0);
     int rc = enter(h);
     if (rc) return rc;
@@ -984,6 +1000,7 @@ int glmma_eval(glmma_handle* h, const double* betas, const double* D, const doub
 int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
                        const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
                        double* sphi_obs, double* S_i) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_eval_contrib(h, betas, D, phis, gammas, ll_i, zbar, zbar_zi, sphi_obs, S_i);
     int rc = enter(h);
     if (rc) return rc;
@@ -1024,6 +1041,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
 
 int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const double* phis,
                    const double* gammas, double* result) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, 1, result, 1);
     int rc = enter(h);
     if (rc) return rc;
@@ -1042,6 +1060,7 @@ int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const 
 
 int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
                    double* result) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_eval(h, betas, nullptr, phis, gammas, 1, result, 2);
     int rc = enter(h);
     if (rc) return rc;
@@ -1061,6 +1080,7 @@ int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, con
 
 int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
                    const double* beta, double* out) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return multi_glm_pass(h, design, glm_family, response, use_offset, first, beta, out);
     int rc = enter(h);
     if (rc) return rc;
@@ -1120,15 +1140,31 @@ static int multi_fail(glmma_handle* h, const glmma_handle* p, int rc) {
 }
 
 int glmma_create_multi(const glmma_data* data, const int* devices, int ndev, glmma_handle** out) {
+    DeviceGuard device_guard_;
     if (!data || !out || !devices || ndev < 1) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
     *out = nullptr;
     if (ndev == 1) return glmma_create(data, devices[0], out);
     const int64_t N = data->n_obs;
-    if (N <= 0 || !data->y || !data->X || !data->Z) return fail(nullptr, GLMMA_ERR_ARG, "y, X, Z and positive sizes are required");
-    // global CSR index
+    if (N <= 0 || data->p <= 0 || data->q_y <= 0 || !data->y || !data->X || !data->Z)
+        return fail(nullptr, GLMMA_ERR_ARG, "y, X, Z and positive sizes are required");
+    // scalar arguments are checked before any slice of the inputs is read
+    if (N >= (int64_t)1 << 31) return fail(nullptr, GLMMA_ERR_ARG, "n_obs must be below 2^31");
+    if (data->p > GLMMA_PMAX || data->p_zi > GLMMA_PZIMAX) return fail(nullptr, GLMMA_ERR_ARG, "too many fixed-effect columns");
+    if (data->nAGQ < 1 || data->nAGQ > GLMMA_NAGQ_MAX) return fail(nullptr, GLMMA_ERR_ARG, "nAGQ out of range");
+    if (data->family < 0 || data->family >= GLMMA_N_FAMILIES) return fail(nullptr, GLMMA_ERR_ARG, "unknown family");
+    if (data->y_cols != 1 && data->y_cols != 2) return fail(nullptr, GLMMA_ERR_ARG, "y_cols must be 1 or 2");
+    if ((data->q_zi > 0 && !data->Z_zi) || (data->p_zi > 0 && !data->X_zi))
+        return fail(nullptr, GLMMA_ERR_ARG, "X_zi / Z_zi missing");
+    if (!lookup_ops(data->family, data->link, data->q_y, data->q_zi))
+        return fail(nullptr, GLMMA_ERR_ARG, "family / link / random-effects dimensions not supported by the engine");
+    // global CSR index, validated before it is used to slice y / X / Z
     std::vector<int64_t> rp;
     if (data->row_ptr) {
         if (data->n_clusters <= 0) return fail(nullptr, GLMMA_ERR_ARG, "n_clusters must be positive");
+        if (data->row_ptr[0] != 0 || data->row_ptr[data->n_clusters] != N)
+            return fail(nullptr, GLMMA_ERR_ARG, "row_ptr must start at 0 and end at n_obs");
+        for (int64_t i = 0; i < data->n_clusters; ++i)
+            if (data->row_ptr[i + 1] <= data->row_ptr[i]) return fail(nullptr, GLMMA_ERR_ARG, "row_ptr must be strictly increasing");
         rp.assign(data->row_ptr, data->row_ptr + data->n_clusters + 1);
     } else if (data->id) {
         rp.push_back(0);
@@ -1278,6 +1314,7 @@ static int multi_set_modes(glmma_handle* h, const double* post_modes, const doub
         if (rc) return multi_fail(h, p, rc);
     }
     h->have_modes = true;
+    h->have_pby = false;
     return GLMMA_OK;
 }
 
@@ -1304,7 +1341,9 @@ static int multi_eval(glmma_handle* h, const double* betas, const double* D, con
         return GLMMA_OK;
     });
     if (rc) return rc;
-    for (int t = 0; t < rl; ++t) result[t] = 0.0;
+    // only the entries glmma.h promises for this call are touched (4 without the score): a caller may
+    // pass a 4-double buffer when want_score = 0, exactly as with a single-device handle
+    for (int t = 0; t < len; ++t) result[t] = 0.0;
     for (glmma_handle* p : h->parts)          // device order: deterministic
         for (int t = 0; t < len; ++t) result[t] += p->h_pinned[t];
     result[3] = 0.0;
@@ -1344,6 +1383,7 @@ static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int respo
 
 int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                     const double* gammas, int want_score, int iters, float* ms_per_eval, float* ms_main_kernel) {
+    DeviceGuard device_guard_;
     if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "glmma_time_eval needs a single-device handle");
     int rc = enter(h);
     if (rc) return rc;
@@ -1371,6 +1411,7 @@ int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const
 }
 
 int glmma_measure_fp64_peak(int device, double* tflops) {
+    DeviceGuard device_guard_;
     if (!tflops) return GLMMA_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {

@@ -99,7 +99,10 @@ class Engine:
             raise ValueError("id must have one entry per row of X")
         change = np.flatnonzero(labels[1:] != labels[:-1]) + 1
         row_ptr = np.ascontiguousarray(np.concatenate(([0], change, [len(labels)])), dtype=np.int64)
-        if len(labels) <= 2_000_000 and len(np.unique(labels)) != len(row_ptr) - 1:
+        # a label that heads two runs means the rows are not grouped: checked on the run heads only
+        # (n values, not N), for every size
+        heads = labels[row_ptr[:-1]]
+        if len(np.unique(heads)) != len(heads):
             raise ValueError("rows are not grouped by id: sort the data by the grouping factor first")
         N = X.shape[0]
         self.N, self.p, self.q_y = N, X.shape[1], Z.shape[1]

@@ -187,3 +187,30 @@ def test_mixed_model_reproduces_published_standard_errors():
     from test_fit_oracle import check_multcomp
     v = vignette_data.multcomp_binary_data()
     check_multcomp(gb.mixed_model(v["y"], v["X"], v["Z"], v["id"], "binomial", hessian=True))
+
+
+def _family_kats():
+    from kat_families import FAMILY_KATS
+    return FAMILY_KATS
+
+
+@pytest.mark.parametrize("name", [k["name"] for k in _family_kats()])
+def test_engine_reproduces_published_family_fits(name):
+    """Families of BASELINE configs C2-C5 against real R output (tests/kat_families.py): the engine's
+    log-likelihood at the published estimates prints the published value, and the engine's whole
+    mixed_model() fit lands on the published estimates (poisson, zi.poisson q = 1 / 2,
+    zi.negative.binomial, negative binomial, beta)."""
+    from kat_families import kat_data, kat_theta, check_family_fit
+    k = [r for r in _family_kats() if r["name"] == name][0]
+    d = kat_data(k)
+    betas, D, phis, gammas = kat_theta(k)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], k["family"], nAGQ=k["nAGQ"], X_zi=d.get("X_zi"),
+                    Z_zi=d.get("Z_zi"))
+    st = eng.find_modes(betas, np.linalg.inv(D), phis, gammas, warm=False)
+    assert st["n_not_converged"] == 0 and st["n_chol_failed"] == 0
+    got = eng.eval(betas, D, phis, gammas)
+    assert abs(got["loglik"] - k["loglik"]) < k["eval_tol"], (name, got["loglik"])
+    eng.close()
+    fit = gb.mixed_model(d["y"], d["X"], d["Z"], d["id"], k["family"], X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"),
+                         control=dict(nAGQ=k["nAGQ"]), hessian=False)
+    check_family_fit(k, fit, newton=True)

@@ -64,10 +64,29 @@ def check_eval(d, th, fam_name, link=None, rtol=RTOL):
     return got, ref
 
 
-@pytest.mark.parametrize("name", ["C1", "C2", "C3"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C5a", "C5b"])
 def test_eval_parity_core_families(name):
+    """Every BASELINE.json configuration's own shape: family, D, phis, nAGQ (11; 7 for the q = 3
+    zero-inflated model), censoring pattern -- at a size the oracle finishes in seconds."""
     d, th, fam_name = small_case(name)
     check_eval(d, th, fam_name)
+
+
+@pytest.mark.parametrize("name", ["C4", "C5a", "C5b"])
+def test_eval_parity_baseline_configs_complete_clusters(name):
+    """The same configurations with the benchmark's complete clusters of 8 observations (the register
+    variant's one-block-of-8 path) and the engine's own Newton modes on the oracle's grid."""
+    d, th, fam_name = small_case(name, n=48, ni=8, ragged=False, seed=5)
+    check_eval(d, th, fam_name)
+    fam = oracle_family(fam_name)
+    od, gh = oracle_grid(d, th, fam, mode_finder="newton")
+    eng = make_engine(d, th, fam_name)
+    st = eng.find_modes(th["betas"], np.linalg.inv(th["D"]), th.get("phis"), th.get("gammas"), warm=False)
+    assert st["n_not_converged"] == 0 and st["n_chol_failed"] == 0
+    modes, chol, logdet = eng.get_modes()
+    assert np.max(np.abs(modes - gh.post_modes)) < 1e-7
+    assert np.max(np.abs(logdet - gh.log_dets)) < 1e-7
+    eng.close()
 
 
 def test_eval_parity_weights_offset():
