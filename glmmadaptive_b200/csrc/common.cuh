@@ -12,6 +12,9 @@
 // per-warp / per-block partial sums of one evaluation:
 //   0 loglik, 1 sum_w, 2 n_nonfinite, 3 g_phi, 4.. S packed upper (d <= e, row-major)
 #define GLMMA_NACC (4 + GLMMA_NPACK)
+// fused mode: a block partial also carries X'zbar and X_zi'zbar_zi, column l in slot GLMMA_NACC + l
+#define GLMMA_FOLD_COLS 32
+#define GLMMA_PSTRIDE (GLMMA_NACC + GLMMA_FOLD_COLS)     // doubles per block partial (every mode)
 
 #define GLMMA_DBL_EPS 2.220446049250313e-16
 #define GLMMA_INV_DBL_EPS 4503599627370496.0

@@ -85,6 +85,15 @@ struct glmma_handle {
     int fast_threads[3][2];    // block shape of the register variant (chosen for resident warps per SM)
     int4* d_order[3];          // cluster lists of the tiles: {cluster, first row, n_i, 0}
     int64_t n_order[3];
+    // fused mode (kernels.cuh, EvalArgs): the register variant does the prep and score-reduce work itself
+    // and eval_kernel's last block finalises -- an evaluation is [ytab] + fast launches + eval_kernel
+    bool fused;
+    int xw;                    // staged design columns per observation (p + p_zi + offsets)
+    int32_t* d_defer_list;     // clusters no tile of the register variant takes (they still need prep)
+    int64_t n_defer_list;
+    unsigned* d_counter;       // blocks-done counter of the in-kernel finalisation
+    bool ytab_valid;           // d_ytab holds the table of ytab_phis
+    double ytab_phis;
     int score_grid;
     double* d_partials;        // eval block partials
     double* d_score_partials;  // score_grid * (p + p_zi)
@@ -257,54 +266,15 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_reduce_kernel(DevData d, 
     }
 }
 
-// result vector (include/glmma.h, glmma_eval) from the block partials, one block: warp w reduces
-// accumulator w (then score column w, w + 8, ...) -- lanes stride the blocks, a fixed shuffle tree
-// finishes, so the sum order is fixed (deterministic) and nothing is serialised behind block barriers
+// result vector from the block partials (kernels.cuh: finalize_block), one block -- the separate launch
+// of the non-fused path; the fused path finalises inside eval_kernel
 __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* eval_partials, int n_eval_blocks,
                                                                   const double* score_partials, int n_score_blocks,
                                                                   int p, int n_phis, int p_zi, int q, int want_score,
                                                                   double* result) {
-    __shared__ double acc[GLMMA_NACC];
-    __shared__ double col[GLMMA_PMAX + GLMMA_PZIMAX];
-    const int np = q * (q + 1) / 2;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = FINAL_THREADS / 32;
-    const int ncol = p + p_zi;
-    for (int a = w; a < 4 + np; a += nw) {
-        double s = 0.0;
-        for (int b = lane; b < n_eval_blocks; b += 32) s += eval_partials[(int64_t)b * GLMMA_NACC + a];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) acc[a] = s;
-    }
-    if (want_score) {
-        for (int l = w; l < ncol; l += nw) {
-            double s = 0.0;
-            for (int b = lane; b < n_score_blocks; b += 32) s += score_partials[(int64_t)b * ncol + l];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) col[l] = s;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
-    }
-    if (!want_score) return;
-    for (int l = threadIdx.x; l < ncol; l += FINAL_THREADS) {
-        if (l < p) result[4 + l] = col[l];
-        else result[4 + p + n_phis + (l - p)] = col[l];
-    }
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3];
-        double* S = result + 4 + p + n_phis + p_zi;
-        int t = 0;
-        for (int dd = 0; dd < q; ++dd)
-            for (int e = dd; e < q; ++e) {
-                S[dd + e * q] = acc[4 + t];
-                S[e + dd * q] = acc[4 + t];
-                ++t;
-            }
-    }
+    __shared__ double sh[GLMMA_NACC + GLMMA_PMAX + GLMMA_PZIMAX];
+    finalize_block(eval_partials, n_eval_blocks, score_partials, n_score_blocks, false, p, n_phis, p_zi, q, want_score,
+                   result, sh);
 }
 
 // ------------------------------------------------------------------------------
@@ -553,6 +523,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->have_modes = false; h->launches = 0; h->sticky = 0; h->d_ytab = nullptr;
     h->family_df = data->family_df;
     h->d_pby = nullptr; h->have_pby = false;
+    h->fused = false; h->xw = 0; h->d_defer_list = nullptr; h->n_defer_list = 0; h->d_counter = nullptr;
+    h->ytab_valid = false; h->ytab_phis = 0.0;
     for (int v = 0; v < 3; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
@@ -683,12 +655,15 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         const bool use8 = n_le8 > 0 && (n_le8 >= (int64_t)(0.1 * (double)n) || !(use12 || use16));
         h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0);
     }
+    // fused mode whenever the register variant runs and the design columns fit a warp's lanes
+    h->xw = d.p + d.p_zi + (d.offset ? 1 : 0) + (d.offset_zi ? 1 : 0);
+    h->fused = h->nj != 0 && d.p + d.p_zi <= GLMMA_FOLD_COLS && !std::getenv("GLMMA_NO_FUSED");
     if (h->nj) {
         for (int v = 0; v < 3; ++v) {
             if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
             for (int s = 0; s < 2; ++s) {
                 int bps = 0;
-                ce = ops->fast_config(s, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
+                ce = ops->fast_config(h->fused ? h->xw : 0, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
                 if (ce != cudaSuccess || bps < 1) {
                     cuda_fail(h, ce, "fast eval kernel configuration");
                     g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
@@ -707,10 +682,10 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         for (int v = 0; v < 3; ++v) if (h->nj & (1 << v)) top = kTile[v];
         {
             std::vector<int4> lists[3];
-            std::vector<int32_t> flags(n, 0);
+            std::vector<int32_t> flags(n, 0), too_big;
             for (int64_t i = 0; i < n; ++i) {
                 const int ni = row_ptr[i + 1] - row_ptr[i];
-                if (ni > top) { flags[i] = 1; continue; }
+                if (ni > top) { flags[i] = 1; too_big.push_back((int32_t)i); continue; }
                 for (int v = 0; v < 3; ++v)           // the smallest tile in use that holds the cluster
                     if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); break; }
             }
@@ -728,12 +703,30 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                 }
             }
             cudaMemcpyAsync(d.defer, flags.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream);
+            if (h->fused) {
+                // clusters beyond the largest tile keep the prep kernel (on their list only); Z'y1 of the
+                // linear-eta hoist is data, not theta: computed here once (find_modes' prep pass rewrites it)
+                h->n_defer_list = (int64_t)too_big.size();
+                if (!too_big.empty()) {
+                    const int32_t* tmp = nullptr;
+                    TRY(dev_upload(h, &tmp, too_big.data(), too_big.size()));
+                    h->d_defer_list = const_cast<int32_t*>(tmp);
+                }
+                std::vector<double> cs((size_t)n * GLMMA_NCSUM, 0.0);
+                for (int64_t i = 0; i < n; ++i)
+                    for (int64_t r = row_ptr[i]; r < row_ptr[i + 1]; ++r)
+                        for (int dd = 0; dd < d.q_y; ++dd)
+                            cs[(size_t)i * GLMMA_NCSUM + 3 + dd] = std::fma(y1[r], data->Z[r + (int64_t)dd * N], cs[(size_t)i * GLMMA_NCSUM + 3 + dd]);
+                cudaMemcpyAsync(d.csum, cs.data(), sizeof(double) * cs.size(), cudaMemcpyHostToDevice, h->stream);
+                TRY(dev_alloc(h, &h->d_counter, 1));
+                cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream);
+            }
             cudaStreamSynchronize(h->stream);      // lists / flags are block-local; errors surface at the final check
         }
     }
     max_grid += max_fast;
     h->score_grid = (int)std::min<int64_t>((N + SCORE_THREADS * 8 - 1) / (SCORE_THREADS * 8), (int64_t)prop.multiProcessorCount * 4);
-    TRY(dev_alloc(h, &h->d_partials, (size_t)max_grid * GLMMA_NACC));
+    TRY(dev_alloc(h, &h->d_partials, (size_t)max_grid * GLMMA_PSTRIDE));
     TRY(dev_alloc(h, &h->d_score_partials, (size_t)h->score_grid * (d.p + d.p_zi)));
     TRY(dev_alloc(h, &h->d_result, (size_t)glmma_result_len(h)));
     TRY(dev_alloc(h, &h->d_stats, 4));
@@ -810,6 +803,18 @@ static int fill_coef(glmma_handle* h, const double* betas, const double* gammas,
     return GLMMA_OK;
 }
 
+// table of the node-independent terms for y = 0 .. GLMMA_YTAB - 1 (count families): a function of the
+// family and phis only, so it is rebuilt only when phis changed (never for poisson / zi.poisson)
+static void ensure_ytab(glmma_handle* h, const FamPar& fp, const double* phis) {
+    if (!h->d_ytab || !h->ops->y_table) return;
+    const double key = (h->d.n_phis > 0 && phis) ? phis[0] : 0.0;
+    if (h->ytab_valid && key == h->ytab_phis) return;
+    h->ops->ytab(fp, h->d_ytab, h->stream);
+    h->launches++;
+    h->ytab_valid = true;
+    h->ytab_phis = key;
+}
+
 static int run_prep(glmma_handle* h, const double* betas, const double* phis, const double* gammas, FamPar* fp) {
     CoefPar c;
     int rc = fill_coef(h, betas, gammas, &c);
@@ -817,8 +822,10 @@ static int run_prep(glmma_handle* h, const double* betas, const double* phis, co
     if (!fill_fampar(h->family, h->d.n_phis, phis, fp, h->error, h->family_df)) return GLMMA_ERR_ARG;
     PrepArgs pa;
     pa.d = h->d; pa.fam = *fp; pa.want_score = 1; pa.ytab = h->d.csum ? h->d_ytab : nullptr;
+    pa.list = nullptr; pa.n_list = 0;
+    ensure_ytab(h, *fp, phis);
     h->ops->prep(pa, c, h->stream);
-    h->launches += (pa.ytab && h->ops->y_table) ? 2 : 1;      // ytab_kernel + prep_cluster_kernel
+    h->launches++;
     CU(h, cudaGetLastError());
     return GLMMA_OK;
 }
@@ -929,11 +936,30 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
     if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
     const int s = want_score ? 1 : 0;
+    // the per-observation contributions (dd_override) read the prep kernel's work arrays: plain path
+    const bool fused = h->fused && !dd_override;
     FamPar fp;
-    int rc = run_prep(h, betas, phis, gammas, &fp);
-    if (rc) return rc;
+    int rc;
     EvalArgs ea;
     std::memset(&ea, 0, sizeof(ea));
+    if (fused) {
+        rc = fill_coef(h, betas, gammas, &ea.coef);
+        if (rc) return rc;
+        if (!fill_fampar(h->family, h->d.n_phis, phis, &fp, h->error, h->family_df)) return GLMMA_ERR_ARG;
+        ensure_ytab(h, fp, phis);
+        if (h->n_defer_list > 0) {
+            PrepArgs pa;
+            pa.d = h->d; pa.fam = fp; pa.want_score = 1; pa.ytab = h->d_ytab;
+            pa.list = h->d_defer_list; pa.n_list = h->n_defer_list;
+            h->ops->prep(pa, ea.coef, h->stream);
+            h->launches++;
+        }
+        ea.fused = 1; ea.xw = h->xw; ea.zbar_out = 0; ea.ytab = h->ops->y_table ? h->d_ytab : nullptr;
+        ea.fin_counter = h->d_counter; ea.fin_partials = h->d_partials; ea.fin_want_score = s; ea.fin_result = d_out;
+    } else {
+        rc = run_prep(h, betas, phis, gammas, &fp);
+        if (rc) return rc;
+    }
     ea.em_mode = em_mode; ea.pby = h->d_pby;
     ea.d = dd_override ? *dd_override : h->d;
     ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.asum_doubles = h->asum_doubles;
@@ -948,19 +974,21 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
             if (!(h->nj & (1 << v))) continue;
             ea.order = h->d_order[v];
             ea.n_order = h->n_order[v];
-            ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
+            ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_PSTRIDE;
             h->ops->eval_fast(ea, s, kTile[v], h->fast_grid[v][s], h->fast_threads[v][s], h->fast_smem[v][s], h->stream);
             h->launches++;
             n_blocks += h->fast_grid[v][s];
         }
         ea.only_deferred = 1;
-        ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_NACC;
+        ea.partials = h->d_partials + (size_t)n_blocks * GLMMA_PSTRIDE;
     }
+    ea.fin_blocks = n_blocks + h->eval_grid[s];
     h->ops->eval(ea, s, h->eval_grid[s], h->eval_threads[s], h->eval_smem[s], h->stream);
     n_blocks += h->eval_grid[s];
     if (k1) CU(h, cudaEventRecord(k1, h->stream));
     h->launches++;
     CU(h, cudaGetLastError());
+    if (fused) return GLMMA_OK;            // eval_kernel's last block wrote the result vector
     if (s) {
         score_reduce_kernel<<<h->score_grid, SCORE_THREADS, 0, h->stream>>>(ea.d, h->d_score_partials);
         h->launches++;

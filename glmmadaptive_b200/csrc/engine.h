@@ -8,16 +8,17 @@ struct EvalArgs;
 struct ModeArgs;
 
 struct FamOps {
+    void (*ytab)(const FamPar&, double* tab, cudaStream_t);      // table of obs_const(y), count families
     void (*prep)(const PrepArgs&, const CoefPar&, cudaStream_t);
     cudaError_t (*eval_config)(int score, int jt, int nagq, int extra, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval)(const EvalArgs&, int score, int grid, int threads, size_t smem, cudaStream_t);
-    cudaError_t (*fast_config)(int score, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads);
+    cudaError_t (*fast_config)(int xw, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
     void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
     bool has_zi, has_phi, uses_y2;
-    bool y_table;      // prep launches ytab_kernel too (count families)
+    bool y_table;      // obs_const() is tabulated by ytab (count families)
 };
 
 // one lookup per family translation unit (nullptr: dimensions not compiled in)

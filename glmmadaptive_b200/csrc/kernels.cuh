@@ -39,6 +39,21 @@ struct EvalArgs {
     // eval_kernel.
     const int4* order;       // {cluster, first row, n_i, 0} per listed cluster: one 16-byte load
     int64_t n_order;
+    // Fused mode (engine.cu, enqueue_eval): the register variant forms X beta (+ offset), X_zi gamma and
+    // the node-independent terms itself from the staged design columns, and accumulates X'zbar /
+    // X_zi'zbar_zi per warp -- no prep_cluster / score_reduce launches, no xb / zbar round trips
+    // through HBM; the last block of eval_kernel (always the last launch of an evaluation) turns the
+    // block partials into the result vector -- no finalize launch.
+    int fused;
+    int xw;                  // staged design columns per observation: p + p_zi + [offset] + [offset_zi]
+    int zbar_out;            // fused mode: also write zbar / zbar_zi (per-observation contributions wanted)
+    const double* ytab;      // 2 x GLMMA_YTAB table of obs_const(y) (count families) or null
+    CoefPar coef;            // fixed effects (fused mode)
+    unsigned* fin_counter;   // eval_kernel: blocks-done counter; null = separate finalize launch
+    const double* fin_partials;   // first block partial of this evaluation (all launches)
+    int fin_blocks;          // block partials written by this evaluation's launches in total
+    int fin_want_score;
+    double* fin_result;      // result vector (include/glmma.h, glmma_eval)
 };
 
 struct PrepArgs {
@@ -46,6 +61,8 @@ struct PrepArgs {
     FamPar fam;
     int want_score;
     double* ytab;            // 2 x GLMMA_YTAB table of obs_const(y) (count families) or null
+    const int32_t* list;     // prep_cluster_kernel: only these clusters (null: all)
+    int64_t n_list;
 };
 
 struct ModeArgs {
@@ -70,6 +87,11 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) 
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc) : "memory");
 }
+// 16-byte variant (source and destination 16-byte aligned)
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
@@ -93,6 +115,62 @@ __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+
+// Result vector (include/glmma.h, glmma_eval) from the block partials of one evaluation, by ONE block of
+// any size: warp w reduces accumulator w (then w + nw, ...) -- lanes stride the blocks, a fixed shuffle
+// tree finishes, so the sum order is fixed (deterministic) and nothing is serialised behind block
+// barriers.  cols_in_ep: the score columns X'zbar, X_zi'zbar_zi travel in the block partials (fused
+// mode); otherwise they come from score_reduce_kernel's partials.  sh: GLMMA_NACC + GLMMA_PMAX +
+// GLMMA_PZIMAX doubles of shared memory.
+__device__ __forceinline__ void finalize_block(const double* ep, int n_eval_blocks, const double* sp, int n_score_blocks,
+                                               bool cols_in_ep, int p, int n_phis, int p_zi, int q, int want_score,
+                                               double* result, double* sh) {
+    double* acc = sh;
+    double* col = sh + GLMMA_NACC;
+    const int np = q * (q + 1) / 2;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ncol = p + p_zi;
+    for (int a = w; a < 4 + np; a += nw) {
+        double s = 0.0;
+        for (int b = lane; b < n_eval_blocks; b += 32) s += __ldcg(ep + (int64_t)b * GLMMA_PSTRIDE + a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) acc[a] = s;
+    }
+    if (want_score) {
+        for (int l = w; l < ncol; l += nw) {
+            double s = 0.0;
+            if (cols_in_ep) {
+                for (int b = lane; b < n_eval_blocks; b += 32) s += __ldcg(ep + (int64_t)b * GLMMA_PSTRIDE + GLMMA_NACC + l);
+            } else {
+                for (int b = lane; b < n_score_blocks; b += 32) s += sp[(int64_t)b * ncol + l];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) col[l] = s;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
+    }
+    if (!want_score) return;
+    for (int l = threadIdx.x; l < ncol; l += blockDim.x) {
+        if (l < p) result[4 + l] = col[l];
+        else result[4 + p + n_phis + (l - p)] = col[l];
+    }
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3];
+        double* S = result + 4 + p + n_phis + p_zi;
+        int t = 0;
+        for (int dd = 0; dd < q; ++dd)
+            for (int e = dd; e < q; ++e) {
+                S[dd + e * q] = acc[4 + t];
+                S[e + dd * q] = acc[4 + t];
+                ++t;
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------
@@ -348,6 +426,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
     double tot[GLMMA_NACC];
 #pragma unroll
     for (int a = 0; a < GLMMA_NACC; ++a) tot[a] = 0.0;
+    double gcol = 0.0;      // fused mode: lane l sums column l of X'zbar | X_zi'zbar_zi over this warp's clusters
 
     const int64_t nwarps = (int64_t)gridDim.x * wpb;
     // only_deferred: every warp owns blocks of 32 consecutive clusters, reads their flags with
@@ -703,6 +782,26 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
                     if (F::HAS_ZI) d.zbar_zi[r0 + j] *= inv;
                 }
             }
+            if (A.fused) {
+                // no score_reduce launch in fused mode: this cluster's part of X'zbar (X_zi'zbar_zi),
+                // column l summed over the warp and kept by lane l
+                __syncwarp();
+                for (int j0 = 0; j0 < ni; j0 += 32) {
+                    const int j = j0 + lane;
+                    const double zb = j < ni ? d.zbar[r0 + j] : 0.0;
+                    for (int l = 0; l < d.p; ++l) {
+                        const double v = warp_sum(j < ni ? d.X[r0 + j + (int64_t)l * d.N] * zb : 0.0);
+                        if (lane == l) gcol += v;
+                    }
+                    if (F::HAS_ZI) {
+                        const double zz = j < ni ? d.zbar_zi[r0 + j] : 0.0;
+                        for (int l = 0; l < d.p_zi; ++l) {
+                            const double v = warp_sum(j < ni ? d.X_zi[r0 + j + (int64_t)l * d.N] * zz : 0.0);
+                            if (lane == d.p + l) gcol += v;
+                        }
+                    }
+                }
+            }
         }
         __syncwarp();
       }
@@ -710,17 +809,34 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
 
     // block partials, fixed order (deterministic for a fixed launch shape)
     __syncthreads();
-    double* red = smem;    // reuse: wpb * NACC doubles
+    double* red = smem;    // reuse: wpb * PSTRIDE doubles
 #pragma unroll
     for (int a = 0; a < GLMMA_NACC; ++a) {
         const double v = warp_sum(tot[a]);
-        if (lane == 0) red[wib * GLMMA_NACC + a] = v;
+        if (lane == 0) red[wib * GLMMA_PSTRIDE + a] = v;
     }
+    red[wib * GLMMA_PSTRIDE + GLMMA_NACC + lane] = gcol;
     __syncthreads();
-    if (threadIdx.x < GLMMA_NACC) {
+    if (threadIdx.x < GLMMA_PSTRIDE) {
         double v = 0.0;
-        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
-        A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_PSTRIDE + threadIdx.x];
+        A.partials[(int64_t)blockIdx.x * GLMMA_PSTRIDE + threadIdx.x] = v;
+    }
+    // Finalisation by the last block to finish (this kernel is the last launch of an evaluation, so the
+    // partials of the earlier launches are complete): its fixed-order sum over ALL block partials is
+    // the result vector, whichever block happens to be last -- deterministic.
+    if (A.fin_counter != nullptr) {
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(A.fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            finalize_block(A.fin_partials, A.fin_blocks, nullptr, 0, true, d.p, d.n_phis, d.p_zi, Q, A.fin_want_score,
+                           A.fin_result, smem + (size_t)wpb * GLMMA_PSTRIDE);
+            if (threadIdx.x == 0) *A.fin_counter = 0u;
+        }
     }
 }
 
@@ -759,14 +875,24 @@ __device__ __forceinline__ void obs_const_tab(double y1, double y2, const FamPar
     F::obs_const(y1, y2, fam, cll, cphi);
 }
 
+// obs_const() out of line: the register variant calls it (fused mode) only for responses the y table
+// does not cover, and libm's lgamma inlined into that kernel would cost it registers everywhere
+template <class F>
+__device__ __noinline__ void obs_const_slow(double y1, double y2, FamPar fam, double* out) {
+    double cll, cphi;
+    F::obs_const(y1, y2, fam, cll, cphi);
+    out[0] = cll; out[1] = cphi;
+}
+
 template <class F>
 __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C) {
     const DevData& d = A.d;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t i = gtid >> 3;
+    const int64_t pos = gtid >> 3;
     const int lg = (int)(gtid & 7);
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
-    const bool live = i < d.n;
+    const bool live = pos < (A.list ? A.n_list : d.n);
+    const int64_t i = (live && A.list) ? (int64_t)A.list[pos] : pos;
     const int64_t r0 = live ? d.row_ptr[i] : 0, r1 = live ? d.row_ptr[i + 1] : 0;
     double s[GLMMA_NCSUM];
 #pragma unroll
@@ -833,7 +959,12 @@ struct FastLayout {
     static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + GLMMA_NCSUM + 1;
     static constexpr int PRE = ((NJ * W + NSC) + 1) & ~1;   // one prefetch buffer (records + scalars)
     static constexpr int NJR = NJ <= 8 ? 8 : 16;            // rows of the per-observation reduction scratch (power of two)
-    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJR * 32 + NTOT * 32 + 4;
+    // fused mode: per observation (c_ll, c_phi) -- copied asynchronously from the y table --, y1 * xb, pad
+    static constexpr int STASH = 4 * NJ;
+    // + one per-lane row for the node-independent log-likelihood terms (fused mode)
+    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJR * 32 + (NTOT + 1) * 32 + 4 + STASH;
+    // fused mode stages xw design columns (X, X_zi, offsets) per observation, double-buffered
+    __host__ __device__ static size_t warp_stride(int xw) { return (size_t)WARP_DOUBLES + (((size_t)2 * NJ * xw + 1) & ~(size_t)1); }
     // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed node indices (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
     // indices): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
@@ -841,8 +972,8 @@ struct FastLayout {
     __host__ __device__ static size_t node_doubles(int K) {
         return (((has_ntab(K) ? (size_t)K * (Q + 1) : 0) + (K + 1) / 2) + 1) & ~(size_t)1;
     }
-    __host__ static size_t smem_bytes(int warps, int K) {
-        return sizeof(double) * (L::head_doubles() + node_doubles(K) + (size_t)warps * WARP_DOUBLES);
+    __host__ static size_t smem_bytes(int warps, int K, int xw) {
+        return sizeof(double) * (L::head_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw));
     }
 };
 
@@ -868,13 +999,19 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     const bool has_ntab = Q < 3 || FL::has_ntab(K);
     double* ntab = smem + L::head_doubles();                 // K x (Q + 1): z_0.., log wGH (small grids)
     int* nidx = reinterpret_cast<int*>(ntab + (has_ntab ? (size_t)K * (Q + 1) : 0));   // K packed node indices
-    double* pre0 = smem + L::head_doubles() + FL::node_doubles(K) + wib * FL::WARP_DOUBLES;
+    const bool fused = A.fused != 0;
+    const int xw = fused ? A.xw : 0;
+    double* pre0 = smem + L::head_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw);
     double* tabF = pre0 + 2 * FL::PRE;
     double* tabL = tabF + NJ * FL::TF;
     double* acc_eta = tabL + NJ * FL::TL;
     double* acc_zi = acc_eta + FL::NJR * 32;
     double* totl = acc_eta + FL::NACCS * FL::NJR * 32;       // NTOT x 32 per-lane totals
-    double* tots = totl + FL::NTOT * 32;                     // loglik, sum_w, n_nonfinite (lane 0)
+    double* totc = totl + FL::NTOT * 32;                     // per-lane node-independent loglik terms (fused mode)
+    double* tots = totc + 32;                                // loglik, sum_w, n_nonfinite (lane 0)
+    double* stash = tots + 4;                                // fused mode: {c_ll, c_phi, y1 xb, -} per observation
+    double* xst0 = stash + FL::STASH;                        // fused mode: 2 x (xw columns x NJ rows)
+    double gcol = 0.0;                                       // fused mode: lane l sums column l of X'zbar | X_zi'zbar_zi
 
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
@@ -896,7 +1033,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (has_ntab) ntab[k * (Q + 1) + Q] = lw;
         nidx[k] = packed;
     }
-    for (int t = lane; t < FL::NTOT * 32 + 4; t += 32) totl[t] = 0.0;
+    for (int t = lane; t < (FL::NTOT + 1) * 32 + 4; t += 32) totl[t] = 0.0;
     __syncthreads();
     const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const int nrounds = (K + 31) >> 5;
@@ -906,15 +1043,25 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     // Asynchronous prefetch (cp.async, LDGSTS) of one cluster's observation columns and
     // per-cluster scalars into a shared-memory buffer: issued one cluster ahead, so the
     // global-memory latency is covered by the previous cluster's arithmetic.
-    auto prefetch = [&](int64_t ci, int64_t c_r0, int c_ni, double* buf) {
+    auto prefetch = [&](int64_t ci, int64_t c_r0, int c_ni, double* buf, double* xbuf) {
         if (c_ni <= NJ) {
             if (lane < c_ni) {
                 const int64_t row = c_r0 + lane;
                 double* r = buf + lane * W;
                 cp_async8(r + 0, d.y1 + row);
                 if (F::USES_Y2) cp_async8(r + 1, d.y2 + row);
-                cp_async8(r + 2, d.xb + row);
-                if (F::HAS_ZI) cp_async8(r + L::OFF_XG, d.xg + row);
+                if (!fused) {
+                    cp_async8(r + 2, d.xb + row);
+                    if (F::HAS_ZI) cp_async8(r + L::OFF_XG, d.xg + row);
+                } else {
+                    // design columns, column-major per cluster as in HBM: X | X_zi | offset | offset_zi
+                    double* xr = xbuf + lane;
+                    for (int l = 0; l < d.p; ++l) { cp_async8(xr, d.X + row + (int64_t)l * d.N); xr += NJ; }
+                    if (F::HAS_ZI)
+                        for (int l = 0; l < d.p_zi; ++l) { cp_async8(xr, d.X_zi + row + (int64_t)l * d.N); xr += NJ; }
+                    if (d.offset) { cp_async8(xr, d.offset + row); xr += NJ; }
+                    if (F::HAS_ZI && d.offset_zi) cp_async8(xr, d.offset_zi + row);
+                }
 #pragma unroll
                 for (int dd = 0; dd < QY; ++dd) cp_async8(r + L::OFF_Z + dd, d.Z + row + (int64_t)dd * d.N);
 #pragma unroll
@@ -942,12 +1089,13 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     int4 cur = make_int4(0, 0, 0, 0), nxt = make_int4(0, 0, 0, 0);
     if (p0 < n_pos) {
         cur = order[p0];
-        prefetch(cur.x, cur.y, cur.z, pre0);
+        prefetch(cur.x, cur.y, cur.z, pre0, xst0);
     }
     if (p0 + nwarps < n_pos) nxt = order[p0 + nwarps];
     int pbuf = 0;
     for (int64_t pos = p0; pos < n_pos; pos += nwarps) {
         double* rec = pre0 + pbuf * FL::PRE;
+        const double* xcur = xst0 + pbuf * NJ * xw;
         const double* sc = rec + NJ * W;
         // rotate the pipeline and start the next cluster's copies
         const int64_t i = cur.x;      // 64-bit: i * K, i * Q ... index arrays of up to n * K elements
@@ -957,7 +1105,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         const int64_t pnext = pos + nwarps, pnext2 = pos + 2 * nwarps;
         cp_async_wait_all();
         __syncwarp();
-        if (pnext < n_pos) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * FL::PRE);
+        if (pnext < n_pos) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * FL::PRE, xst0 + (pbuf ^ 1) * NJ * xw);
         if (pnext2 < n_pos) nxt = order[pnext2];
         pbuf ^= 1;
         if (nic > NJ) {
@@ -987,6 +1135,33 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (lane < nic) {
             double* r = rec + lane * W;
             if (!F::USES_Y2) r[1] = 0.0;
+            if (fused) {
+                // xb = X beta + offset, xg = X_zi gamma + offset_zi from the staged design columns
+                const double* xr = xcur + lane;
+                const int ncol = d.p + (F::HAS_ZI ? d.p_zi : 0);
+                double xb = d.offset ? xr[ncol * NJ] : 0.0;
+                for (int l = 0; l < d.p; ++l) xb = fma(xr[l * NJ], A.coef.betas[l], xb);
+                r[2] = xb;
+                if (F::HAS_ZI) {
+                    double xg = d.offset_zi ? xr[(ncol + (d.offset ? 1 : 0)) * NJ] : 0.0;
+                    for (int l = 0; l < d.p_zi; ++l) xg = fma(xr[(d.p + l) * NJ], A.coef.gammas[l], xg);
+                    r[L::OFF_XG] = xg;
+                }
+                // node-independent terms of log f and d log f / d phis: from the y table by an
+                // asynchronous copy (consumed after the rounds), else computed out of line
+                const double y1 = r[0];
+                double* st = stash + 4 * lane;
+                st[2] = y1 * xb;
+                bool tab = false;
+                if (F::Y_TABLE && A.ytab != nullptr) {
+                    const int iy = (int)y1;
+                    if (y1 >= 0.0 && y1 < (double)GLMMA_YTAB && (double)iy == y1) {
+                        cp_async16(st, A.ytab + 2 * iy);
+                        tab = true;
+                    }
+                }
+                if (!tab) obs_const_slow<F>(y1, r[1], A.fam, st);
+            }
             F::stage(r[0], r[1], A.fam);
             const double xmax = gx[0];
             if (F::NEED_EMU) {
@@ -1037,10 +1212,26 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 if (!(base - amp >= -667.0 && base + amp <= 667.0)) bad = true;
             }
         }
+        if (fused) cp_async_commit();
         bad = __any_sync(0xffffffffu, bad);
         __syncwarp();                              // coefficient stores -> table-building reads
         if (lane == 0) d.defer[i] = bad ? 1 : 0;
-        if (bad) continue;
+        if (bad) {
+            if (fused) {
+                // eval_kernel takes this cluster from the work arrays the prep kernel would have written
+                cp_async_wait_all();
+                if (lane < nic) {
+                    const int64_t row = r0c + lane;
+                    const double* r = rec + lane * W;
+                    d.xb[row] = r[2];
+                    if (F::HAS_ZI) d.xg[row] = r[L::OFF_XG];
+                    d.cll[row] = stash[4 * lane];
+                    if (F::HAS_PHI) d.cphi[row] = stash[4 * lane + 1];
+                }
+                __syncwarp();
+            }
+            continue;
+        }
         // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
         // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
         // test above
@@ -1103,7 +1294,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         }
 
         const double* cs = sc + SC_CS;
-        const double syxb = F::LIN_ETA ? cs[2] : 0.0;
+        const double syxb = (F::LIN_ETA && !fused) ? cs[2] : 0.0;     // fused: y1 xb joins the per-lane terms below
         double zty[QY];
 #pragma unroll
         for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? cs[3 + dd] : 0.0;
@@ -1317,13 +1508,33 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         const double w = d.weights ? sc[SC_W] : 1.0;
         double lsum, isum;
         fast_log_rcp<true>(sum_e, cx, lsum, isum);
-        const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD] + cs[0];
-        const bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
+        // fused mode: lane j holds observation j's node-independent terms (c_ll_j + y1_j xb_j, c_phi_j);
+        // they are added per lane, not per cluster (no reduction: the cluster's sum is only needed
+        // for the per-cluster contributions)
+        double cl = 0.0, cph = 0.0;
+        if (fused) {
+            cp_async_wait_all();
+            if (lane < nic) {
+                const double* st = stash + 4 * lane;
+                cl = F::LIN_ETA ? st[0] + st[2] : st[0];
+                cph = st[1];
+            }
+        }
+        const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD] + (fused ? 0.0 : cs[0]);
+        bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
+        if (fused && A.em_mode != 2) ok = __all_sync(0xffffffffu, ok && fabs(cl) < INFINITY);
         if (A.em_mode == 1 && !ok)
             for (int k = lane; k < K; k += 32) A.pby[i * K + k] = 0.0;
         if (lane == 0) {
             if (ok) { tots[0] += w * ll; tots[1] += w; } else tots[2] += 1.0;
-            if (d.ll_i) d.ll_i[i] = w * ll;
+            if (d.ll_i && !fused) d.ll_i[i] = w * ll;
+        }
+        if (fused) {
+            if (ok && A.em_mode != 2) totc[lane] = fma(w, cl, totc[lane]);
+            if (d.ll_i) {
+                const double s = warp_sum(cl);
+                if (lane == 0) d.ll_i[i] = w * (ll + s);
+            }
         }
         if (SCORE) {
             const double inv = ok ? w * isum : 0.0;
@@ -1335,7 +1546,8 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         if (j < nic) gphi = fma(rec[j * W + 1], acc_e[j], gphi);
                 }
                 double g = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
-                if (lane == 0 && ok) g = fma(w, cs[1], g);
+                if (fused) { if (ok) g = fma(w, cph, g); }
+                else if (lane == 0 && ok) g = fma(w, cs[1], g);
                 totl[lane] = g;
             }
 #pragma unroll
@@ -1381,11 +1593,34 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
+                double zb = 0.0, zz = 0.0;
                 if (lane < nic) {
                     const double sc = F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
                                                         : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
-                    d.zbar[r0c + lane] = ok ? w * sc : 0.0;
-                    if (F::HAS_ZI) d.zbar_zi[r0c + lane] = inv * s2;
+                    zb = ok ? w * sc : 0.0;
+                    if (F::HAS_ZI) zz = inv * s2;
+                    if (!fused || A.zbar_out) {
+                        d.zbar[r0c + lane] = zb;
+                        if (F::HAS_ZI) d.zbar_zi[r0c + lane] = zz;
+                    }
+                }
+                if (fused) {
+                    // X'zbar (and X_zi'zbar_zi): lane l owns column l; the posterior-mean scores of the
+                    // cluster's observations pass through the (now free) accumulator scratch
+                    __syncwarp();
+                    if (lane < NJ) {
+                        acc_eta[lane] = zb;
+                        if (F::HAS_ZI) acc_zi[lane] = zz;
+                    }
+                    __syncwarp();
+                    const int ncol = d.p + (F::HAS_ZI ? d.p_zi : 0);
+                    if (lane < ncol) {
+                        const double* xc = xcur + lane * NJ;
+                        const double* zs = (F::HAS_ZI && lane >= d.p) ? acc_zi : acc_eta;
+#pragma unroll
+                        for (int jj = 0; jj < NJ; ++jj)
+                            if (jj < nic) gcol = fma(xc[jj], zs[jj], gcol);
+                    }
                 }
             }
         }
@@ -1397,6 +1632,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     {
         // per-warp totals: [0] loglik [1] sum_w [2] n_nonfinite [3] g_phi [4..] S
         double v3 = warp_sum(totl[lane]);
+        const double vc = warp_sum(totc[lane]);
         double vs[NP];
 #pragma unroll
         for (int t = 0; t < NP; ++t) vs[t] = warp_sum(totl[(2 + t) * 32 + lane]);
@@ -1405,20 +1641,21 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             tots[3] = v3;      // tots has 4 slots: reuse the pad for g_phi
         }
         __syncthreads();
-        double* red = smem;    // wpb * NACC doubles (fastmath tables are no longer needed)
+        double* red = smem;    // wpb * PSTRIDE doubles (fastmath tables are no longer needed)
         if (lane == 0) {
-            red[wib * GLMMA_NACC + 0] = tots[0];
-            red[wib * GLMMA_NACC + 1] = tots[1];
-            red[wib * GLMMA_NACC + 2] = tots[2];
-            red[wib * GLMMA_NACC + 3] = v3;
+            red[wib * GLMMA_PSTRIDE + 0] = tots[0] + vc;
+            red[wib * GLMMA_PSTRIDE + 1] = tots[1];
+            red[wib * GLMMA_PSTRIDE + 2] = tots[2];
+            red[wib * GLMMA_PSTRIDE + 3] = v3;
 #pragma unroll
-            for (int t = 0; t < GLMMA_NPACK; ++t) red[wib * GLMMA_NACC + 4 + t] = t < NP ? vs[t] : 0.0;
+            for (int t = 0; t < GLMMA_NPACK; ++t) red[wib * GLMMA_PSTRIDE + 4 + t] = t < NP ? vs[t] : 0.0;
         }
+        red[wib * GLMMA_PSTRIDE + GLMMA_NACC + lane] = gcol;     // column `lane` of X'zbar | X_zi'zbar_zi (fused)
         __syncthreads();
-        if (threadIdx.x < GLMMA_NACC) {
+        if (threadIdx.x < GLMMA_PSTRIDE) {
             double v = 0.0;
-            for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_NACC + threadIdx.x];
-            A.partials[(int64_t)blockIdx.x * GLMMA_NACC + threadIdx.x] = v;
+            for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_PSTRIDE + threadIdx.x];
+            A.partials[(int64_t)blockIdx.x * GLMMA_PSTRIDE + threadIdx.x] = v;
         }
     }
 }

@@ -19,10 +19,13 @@ template <class F, int QY, int QZ>
 struct OpsImpl {
     using L = EvalLayout<F, QY, QZ>;
 
+    static void ytab(const FamPar& fam, double* tab, cudaStream_t s) {
+        if (F::Y_TABLE) ytab_kernel<F><<<GLMMA_YTAB / 256, 256, 0, s>>>(fam, tab);
+    }
     static void prep(const PrepArgs& a, const CoefPar& c, cudaStream_t s) {
-        if (F::Y_TABLE && a.ytab) ytab_kernel<F><<<GLMMA_YTAB / 256, 256, 0, s>>>(a.fam, a.ytab);
         if (a.d.csum) {
-            prep_cluster_kernel<F><<<(unsigned)((a.d.n * 8 + 255) / 256), 256, 0, s>>>(a, c);
+            const int64_t ncl = a.list ? a.n_list : a.d.n;
+            if (ncl > 0) prep_cluster_kernel<F><<<(unsigned)((ncl * 8 + 255) / 256), 256, 0, s>>>(a, c);
         } else {
             const int64_t blocks = (a.d.N + 255) / 256;
             prep_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(a, c);
@@ -67,13 +70,13 @@ struct OpsImpl {
     // large per-warp areas (zero-inflated, q = 3) keep more warps resident with fewer, larger blocks.
     // Picks the shape with the most resident warps per SM; ties go to the smaller block.
     template <int NJ>
-    static cudaError_t fast_config_nj(int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+    static cudaError_t fast_config_nj(int K, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
         for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t *= 2) {
-            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K);
+            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ>, t, smem);
@@ -82,10 +85,10 @@ struct OpsImpl {
         }
         return cudaSuccess;
     }
-    static cudaError_t fast_config(int /*score*/, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
-        return nj == 8 ? fast_config_nj<8>(K, blocks_per_sm, smem_bytes, threads)
-             : nj == 12 ? fast_config_nj<12>(K, blocks_per_sm, smem_bytes, threads)
-                        : fast_config_nj<16>(K, blocks_per_sm, smem_bytes, threads);
+    static cudaError_t fast_config(int xw, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+        return nj == 8 ? fast_config_nj<8>(K, xw, blocks_per_sm, smem_bytes, threads)
+             : nj == 12 ? fast_config_nj<12>(K, xw, blocks_per_sm, smem_bytes, threads)
+                        : fast_config_nj<16>(K, xw, blocks_per_sm, smem_bytes, threads);
     }
     static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, int threads, size_t smem, cudaStream_t s) {
         if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
@@ -107,7 +110,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE};
+        static const FamOps ops = {ytab, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE};
         return &ops;
     }
 };

@@ -449,25 +449,62 @@ def _fused_eval(thetas, engine, gh, diag_D):
     return val
 
 
-def logLik_mixed(thetas, engine, gh, diag_D=False, i_contributions=False, fused=True):
-    """R/Fit_Funs.R:1-42 (penalized = FALSE): the NEGATIVE marginal log-likelihood on the
-    fixed grid ``gh``; with ``i_contributions`` the per-cluster vector -w_i log p(y_i).
-    ``fused`` evaluates the score in the same pass and keeps it for a following
+class Penalty:
+    """Student's t penalty on the fixed effects, `penalized = TRUE` or a list(pen_mu, pen_sigma,
+    pen_df) in mixed_model() (R/mixed_model.R:196-208; R/mixed_fit.R:64-69): the log-likelihood gains
+    dmvt(betas, pen_mu, invSigma = diag(1 / pen_sigma^2), pen_df, log = TRUE, prop = TRUE)
+    (R/Fit_Funs.R:39-40, R/Functions.R:424-462) and the beta-score the term of R/Fit_Funs.R:169-173
+    (written there with betas, not betas - pen_mu).  p-sized host algebra: the engine is not involved."""
+
+    def __init__(self, ncx, pen_mu=0.0, pen_sigma=1.0, pen_df=3.0):
+        self.mu = np.resize(np.atleast_1d(np.asarray(pen_mu, float)), ncx)
+        self.inv_sigma = np.resize(1.0 / np.atleast_1d(np.asarray(pen_sigma, float)) ** 2, ncx)
+        self.df = float(pen_df)
+
+    @classmethod
+    def from_arg(cls, penalized, ncx):
+        if penalized is None or penalized is False:
+            return None
+        if penalized is True:
+            return cls(ncx)
+        if isinstance(penalized, cls):
+            return penalized
+        if isinstance(penalized, dict):
+            if not set(penalized) <= {"pen_mu", "pen_sigma", "pen_df"}:
+                raise ValueError("when 'penalized' is a dict it needs the components 'pen_mu', 'pen_sigma' and 'pen_df'")
+            return cls(ncx, **penalized)
+        raise ValueError("argument 'penalized' must be a logical or a dict")
+
+    def log_dens(self, betas):
+        d = np.asarray(betas, float) - self.mu
+        return -0.5 * (self.df + len(d)) * np.log(1.0 + np.sum(d * self.inv_sigma * d) / self.df)
+
+    def score(self, betas):
+        betas = np.asarray(betas, float)
+        v = betas * self.inv_sigma / self.df
+        return v * ((self.df + len(betas)) / (1.0 + betas @ v))
+
+
+def logLik_mixed(thetas, engine, gh, diag_D=False, i_contributions=False, fused=True, penalty=None):
+    """R/Fit_Funs.R:1-42: the NEGATIVE marginal log-likelihood on the fixed grid ``gh`` (minus the
+    log penalty when ``penalty`` is given); with ``i_contributions`` the per-cluster vector
+    -w_i log p(y_i).  ``fused`` evaluates the score in the same pass and keeps it for a following
     score_mixed() at the same thetas (optim calls fn then gr)."""
+    pen = 0.0 if penalty is None else penalty.log_dens(np.asarray(thetas, float)[:engine.p])
     if i_contributions:
         _ensure_grid(engine, gh)
         betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
-        return -engine.eval_contrib(betas, D, phis, gammas)["ll_i"]
+        return -engine.eval_contrib(betas, D, phis, gammas)["ll_i"] - pen
     if fused:
         res, _, _ = _fused_eval(thetas, engine, gh, diag_D)
-        return -res["loglik"]
+        return -res["loglik"] - pen
     _ensure_grid(engine, gh)
     betas, D, U, phis, gammas = split_thetas(thetas, engine, diag_D)
-    return -engine.eval(betas, D, phis, gammas, want_score=False)["loglik"]
+    return -engine.eval(betas, D, phis, gammas, want_score=False)["loglik"] - pen
 
 
-def score_mixed(thetas, engine, gh, diag_D=False, i_contributions=False):
-    """R/Fit_Funs.R:44-293 (penalized = FALSE): gradient of the NEGATIVE log-likelihood,
+def score_mixed(thetas, engine, gh, diag_D=False, i_contributions=False, penalty=None):
+    """R/Fit_Funs.R:44-293: gradient of the NEGATIVE log-likelihood (with the penalty term of :169-173),
     c(score.betas, score.D, score.phis, score.gammas).  With ``i_contributions`` the
     per-observation / per-cluster pieces (R/Fit_Funs.R:288-290)."""
     if i_contributions:
@@ -486,7 +523,10 @@ def score_mixed(thetas, engine, gh, diag_D=False, i_contributions=False):
             out["score_gammas"] = -engine_X(engine, zi=True) * c["zbar_zi"][:, None]
         return out
     res, D, U = _fused_eval(thetas, engine, gh, diag_D)
-    parts = [-res["g_beta"], score_D(res["S"], res["sum_w"], engine.n, D, U, diag_D)]
+    g_beta = -res["g_beta"]
+    if penalty is not None:
+        g_beta = g_beta + penalty.score(np.asarray(thetas, float)[:engine.p])
+    parts = [g_beta, score_D(res["S"], res["sum_w"], engine.n, D, U, diag_D)]
     if engine.n_phis:
         parts.append(-res["g_phi"])
     if engine.p_zi:

@@ -21,7 +21,7 @@ import time
 import numpy as np
 
 from ._lib import GlmmaError, ERR_NUMERIC
-from .engine import Engine, GHfun, chol_transf, logLik_mixed, score_mixed, split_thetas
+from .engine import Engine, GHfun, Penalty, chol_transf, logLik_mixed, score_mixed, split_thetas
 
 _EPS = np.finfo(float).eps
 
@@ -38,8 +38,11 @@ CONTROL = dict(iter_EM=30, iter_qN_outer=15, iter_qN=10, iter_qN_incr=10, optimi
 class _GlmFamily:
     """initialize / link / variance / deviance pieces of the four stats families used for starts."""
 
-    def __init__(self, name):
+    def __init__(self, name, link=None):
         self.name = name
+        # binomial(link = "probit" / "cloglog"): glm.fit is called with the model's own family object
+        # (R/mixed_model.R:176), so the starting values follow its link
+        self.blink = link if (name == "binomial" and link in ("probit", "cloglog")) else None
 
     def start(self, y, w):
         if self.name == "binomial":
@@ -47,10 +50,21 @@ class _GlmFamily:
         return y + 0.1 if self.name == "poisson" else y
 
     def link(self, mu):
+        if self.blink == "probit":
+            from scipy.special import ndtri
+            return ndtri(mu)
+        if self.blink == "cloglog":
+            return np.log(-np.log1p(-mu))
         return {"binomial": lambda m: np.log(m / (1 - m)), "poisson": np.log,
                 "Gamma": lambda m: 1 / m, "gaussian": lambda m: m}[self.name](mu)
 
     def inv(self, eta):
+        if self.blink == "probit":
+            from scipy.special import ndtr
+            th = 8.125890664701906            # -qnorm(.Machine$double.eps)
+            return ndtr(np.clip(eta, -th, th))
+        if self.blink == "cloglog":
+            return np.clip(-np.expm1(-np.exp(eta)), _EPS, 1.0 - _EPS)
         if self.name == "binomial":
             return 1 / (1 + np.exp(-np.clip(eta, -30.0, 30.0)))
         if self.name == "poisson":
@@ -58,6 +72,11 @@ class _GlmFamily:
         return 1 / eta if self.name == "Gamma" else eta
 
     def dmu(self, eta):
+        if self.blink == "probit":
+            return np.maximum(np.exp(-0.5 * eta * eta) / np.sqrt(2.0 * np.pi), _EPS)
+        if self.blink == "cloglog":
+            e = np.minimum(eta, 700.0)
+            return np.maximum(np.exp(e) * np.exp(-np.exp(e)), _EPS)
         if self.name == "binomial":
             e = np.exp(-np.abs(eta))
             return np.maximum(e / (1 + e) ** 2, _EPS)
@@ -81,11 +100,11 @@ class _GlmFamily:
         return float(2 * np.sum(w * r))
 
 
-def glm_fit(X, y, family, offset=None, epsilon=1e-8, maxit=25):
+def glm_fit(X, y, family, offset=None, epsilon=1e-8, maxit=25, link=None):
     """Iteratively reweighted least squares with glm.fit's starts and stopping rule."""
     X = np.asarray(X, float)
     y = np.asarray(y, float)
-    fam = _GlmFamily(family)
+    fam = _GlmFamily(family, link)
     w = np.ones(len(X))
     if family == "binomial" and y.ndim == 2:
         w = y.sum(axis=1)
@@ -112,13 +131,13 @@ def glm_fit(X, y, family, offset=None, epsilon=1e-8, maxit=25):
     return beta
 
 
-def starting_values(y, X, X_zi, family, nRE, n_phis, diag_D=False, offset=None, offset_zi=None):
+def starting_values(y, X, X_zi, family, nRE, n_phis, diag_D=False, offset=None, offset_zi=None, link=None):
     """R/mixed_model.R:157-194, 251-263: glm coefficients * sqrt(1.346) for the families the
     reference calls `known`, zeros otherwise; identity D; phis = 0; logistic fit of y == 0 for gammas."""
     fam = family
     starts = {"binomial": "binomial", "poisson": "poisson", "negative binomial": "poisson", "Gamma": "Gamma"}
     if fam in starts:
-        betas = glm_fit(X, y, starts[fam], offset) * np.sqrt(1.346)
+        betas = glm_fit(X, y, starts[fam], offset, link=link) * np.sqrt(1.346)
     else:
         betas = np.zeros(np.shape(X)[1])
     out = dict(betas=betas, D=np.ones(nRE) if diag_D else np.eye(nRE))
@@ -314,7 +333,7 @@ def _thetas(betas, D, phis, gammas, diag_D):
     return np.concatenate([np.atleast_1d(v) for v in (betas, Dv, phis, gammas) if v is not None])
 
 
-def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, trace=None):
+def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, trace=None, penalized=False):
     """R/mixed_fit.R:62-349 on a device-resident data set.  Returns the list mixed_fit() returns
     (coefficients, phis, D, gammas, post_modes, post_vars, logLik, Hessian, converged) plus timing
     and evaluation counters."""
@@ -329,6 +348,7 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
     gammas = None if initial_values.get("gammas") is None else np.array(initial_values["gammas"], float)
     nderiv = fd_vec if con["numeric_deriv"] == "fd" else cd_vec
     counts = dict(find_modes=0, estep=0, em_score=0, eval=0)
+    pen = Penalty.from_arg(penalized, eng.p)        # R/mixed_fit.R:64-69
     t_start = time.perf_counter()
 
     def new_grid(cold=False):
@@ -363,7 +383,7 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
             es = eng.em_estep(betas, D, phis, gammas)
             counts["estep"] += 1
             last.clear()
-            lls.append(es["loglik"])
+            lls.append(es["loglik"] + (0.0 if pen is None else pen.log_dens(betas)))      # R/mixed_fit.R:156-159
             if trace is not None:
                 trace.append(("EM", it, es["loglik"], betas.copy()))
             if it > 4 and lls[-1] > lls[-2]:
@@ -381,7 +401,8 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
             if phis is not None:
                 f = lambda v: em_sc("g_phi", betas, v, gammas)
                 phis = phis - np.linalg.solve(nearPD(nderiv(phis, f)), f(phis))
-            f = lambda v: em_sc("g_beta", v, phis, gammas)
+            f = (lambda v: em_sc("g_beta", v, phis, gammas)) if pen is None else \
+                (lambda v: em_sc("g_beta", v, phis, gammas) + pen.score(v))          # R/Fit_Funs.R:360-364
             betas = betas - np.linalg.solve(nearPD(nderiv(betas, f)), f(betas))
             if gammas is not None:
                 f = lambda v: em_sc("g_gamma", betas, phis, v)
@@ -409,7 +430,7 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
             counts["eval"] += 1
             try:
                 with np.errstate(over="ignore", invalid="ignore"):
-                    v = logLik_mixed(t, eng, gh, diag_D)
+                    v = logLik_mixed(t, eng, gh, diag_D, penalty=pen)
             except GlmmaError as e:
                 if e.code != ERR_NUMERIC:
                     raise
@@ -419,7 +440,8 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
         for it in range(1, con["iter_qN_outer"] + 1):
             n_outer = it
             gh = new_grid(cold=(gh is None))
-            tht, val, conv, _, _ = vmmin(tht, fn, lambda t: score_mixed(t, eng, gh, diag_D), iter_qN, con["tol3"], parscale)
+            tht, val, conv, _, _ = vmmin(tht, fn, lambda t: score_mixed(t, eng, gh, diag_D, penalty=pen), iter_qN,
+                                         con["tol3"], parscale)
             betas, D, _, phis, gammas = split_thetas(tht, eng, diag_D)
             betas = betas.copy()
             phis = None if phis is None else phis.copy()
@@ -428,6 +450,9 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
                 trace.append(("qN", it, -val, betas.copy()))
             if too_large():
                 raise FloatingPointError("A large coefficient value has been detected during the optimization")
+            if eng.spec.family in ("negative binomial", "zero-inflated negative binomial") and \
+                    np.exp(phis[0]) > con["max_phis_value"]:                          # R/mixed_fit.R:300-303
+                raise FloatingPointError("shape/size parameter of the negative binomial above max_phis_value")
             if conv == 0:
                 converged = True
                 break
@@ -437,10 +462,11 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
     tht = _thetas(betas, D, phis, gammas, diag_D)
     gh = new_grid(cold=(gh is None))
     out = dict(coefficients=betas, phis=phis, D=D, gammas=gammas, post_modes=gh.post_modes, gh=gh,
-               logLik=-logLik_mixed(tht, eng, gh, diag_D), converged=converged, converged_during_EM=during_EM,
+               logLik=-logLik_mixed(tht, eng, gh, diag_D, penalty=pen), converged=converged,
+               converged_during_EM=during_EM,
                thetas=tht, n_outer=n_outer, counts=counts)
     if hessian:
-        out["Hessian"] = cd_vec(tht, lambda t: score_mixed(t, eng, gh, diag_D))
+        out["Hessian"] = cd_vec(tht, lambda t: score_mixed(t, eng, gh, diag_D, penalty=pen))
         counts["eval"] += 2 * len(tht)
     out["seconds"] = dict(EM=t_em, quasi_newton=t_qn, total=time.perf_counter() - t_start)
     return out
@@ -448,22 +474,28 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
 
 def mixed_model(y, X, Z, id, family, link=None, X_zi=None, Z_zi=None, offset=None, offset_zi=None,
                 weights=None, initial_values=None, control=None, diag_D=False, device=0, hessian=True,
-                engine=None):
+                engine=None, penalized=False, df=None):
     """mixed_model() from design matrices.  Rows must be grouped by `id` (the reference sorts its
-    data frame by the grouping factor, R/mixed_model.R:50).  Returns mixed_fit()'s list."""
+    data frame by the grouping factor, R/mixed_model.R:50).  Returns mixed_fit()'s list.
+    ``penalized``: False, True (Student's t penalty on the fixed effects, mean 0, scale 1, 3 df) or a
+    dict(pen_mu, pen_sigma, pen_df) (R/mixed_model.R:196-208); ``df``: the degrees of freedom of the
+    family object for family = "students.t" (students.t(df), R/Fit_Funs.R:1006)."""
     con = dict(control or {})
     own = engine is None
     if own:
         engine = Engine(y, X, Z, id, family, link=link, nAGQ=con.get("nAGQ"), X_zi=X_zi, Z_zi=Z_zi,
-                        offset=offset, offset_zi=offset_zi, weights=weights, device=device)
+                        offset=offset, offset_zi=offset_zi, weights=weights, device=device, df=df)
     try:
-        if engine.p <= 8 and engine.p_zi <= 8 and hasattr(engine, "glm_pass"):
+        other_link = engine.spec.family == "binomial" and engine.spec.link != "logit"
+        if engine.p <= 8 and engine.p_zi <= 8 and hasattr(engine, "glm_pass") and not other_link:
             inits = starting_values_device(engine, diag_D)
         else:
-            inits = starting_values(y, X, X_zi, engine.spec.family, engine.q, engine.n_phis, diag_D, offset, offset_zi)
+            # binomial(probit / cloglog): glm.fit with the model's own link (R/mixed_model.R:176), on the host
+            inits = starting_values(y, X, X_zi, engine.spec.family, engine.q, engine.n_phis, diag_D, offset, offset_zi,
+                                    link=engine.spec.link)
         if initial_values:
             inits.update(initial_values)
-        fit = mixed_fit(engine, inits, con, diag_D, hessian)
+        fit = mixed_fit(engine, inits, con, diag_D, hessian, penalized=penalized)
         fit["post_vars"] = fit["gh"].post_vars if engine.n <= 100_000 else None
         fit["nAGQ"] = engine.nAGQ
     finally:

@@ -582,22 +582,47 @@ def _common(thetas, data, family, gh, diag_D):
                 log_wGH=log_wGH, n=n, K=K)
 
 
+class Penalty:
+    """Student's t penalty on the fixed effects: R/mixed_model.R:196-208 (pen_mu = 0, pen_sigma = 1,
+    pen_df = 3 for penalized = TRUE), R/mixed_fit.R:64-69 (pen_invSigma = diag(1 / pen_sigma^2)),
+    dmvt(log = TRUE, prop = TRUE) of R/Functions.R:424-462 and the score term of
+    R/Fit_Funs.R:169-173 / :360-364 (which uses betas, not betas - pen_mu: the reference's form)."""
+
+    def __init__(self, ncx, pen_mu=0.0, pen_sigma=1.0, pen_df=3.0):
+        self.mu = np.resize(np.atleast_1d(np.asarray(pen_mu, float)), ncx)          # rep(., length.out = ncx)
+        self.inv = np.resize(1.0 / np.atleast_1d(np.asarray(pen_sigma, float)) ** 2, ncx)
+        self.df = float(pen_df)
+
+    def log_dens(self, betas):
+        ss = np.asarray(betas, float) - self.mu
+        quad = np.sum(ss * self.inv * ss) / self.df
+        return -0.5 * (self.df + len(ss)) * np.log(1.0 + quad)
+
+    def score(self, betas):
+        betas = np.asarray(betas, float)
+        v = betas * self.inv / self.df
+        return v * (self.df + len(betas)) / (1.0 + betas @ v)
+
+
 def rowsum(a, data):
     return np.add.reduceat(a, data.row_ptr[:-1], axis=0)
 
 
-def logLik_mixed(thetas, data, family, gh, diag_D=False, i_contributions=False):
-    """R/Fit_Funs.R:1-42 (penalized = FALSE).  Returns the NEGATIVE log-likelihood."""
+def logLik_mixed(thetas, data, family, gh, diag_D=False, i_contributions=False, penalty=None):
+    """R/Fit_Funs.R:1-42.  Returns the NEGATIVE log-likelihood (minus the log penalty, :39-40)."""
     c = _common(thetas, data, family, gh, diag_D)
     log_p_y = logsumexp(c["log_p_yb"] + c["log_p_b"] + c["log_wGH"], axis=1) + gh.log_dets
     w = data.weights
-    if i_contributions:
-        return -(log_p_y if w is None else w * log_p_y)
-    return -np.nansum(log_p_y if w is None else w * log_p_y)
+    out = -(log_p_y if w is None else w * log_p_y) if i_contributions else \
+        -np.nansum(log_p_y if w is None else w * log_p_y)
+    if penalty is not None:
+        out = out - penalty.log_dens(c["betas"])
+    return out
 
 
-def score_mixed(thetas, data, family, gh, diag_D=False, i_contributions=False, return_parts=False):
-    """R/Fit_Funs.R:44-293 (penalized = FALSE).  Gradient of the NEGATIVE log-likelihood,
+def score_mixed(thetas, data, family, gh, diag_D=False, i_contributions=False, return_parts=False,
+                penalty=None):
+    """R/Fit_Funs.R:44-293.  Gradient of the NEGATIVE log-likelihood (plus the penalty term, :169-173),
     c(score.betas, score.D, score.phis, score.gammas)."""
     canonical, user_defined = family_flags(family)
     c = _common(thetas, data, family, gh, diag_D)
@@ -657,6 +682,9 @@ def score_mixed(thetas, data, family, gh, diag_D=False, i_contributions=False, r
             else:
                 z = (y[:, None] - mu_y) * deriv / var
             score_betas = -col_scores(X, z)
+
+    if penalty is not None:                   # R/Fit_Funs.R:169-173
+        score_betas = score_betas + penalty.score(c["betas"])
 
     score_phis = None
     if phis is not None:

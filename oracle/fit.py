@@ -223,8 +223,13 @@ def _col_scores(Xm, z, p_by, wGH, data):
     return sc
 
 
-def score_betas(betas, data, family, gh, phis, eta_zi, p_by):
-    """R/Fit_Funs.R:295-365 (penalized = FALSE)."""
+def score_betas(betas, data, family, gh, phis, eta_zi, p_by, penalty=None):
+    """R/Fit_Funs.R:295-365 (the penalty term :360-364 added by the wrapper below)."""
+    out = _score_betas(betas, data, family, gh, phis, eta_zi, p_by)
+    return out if penalty is None else out + penalty.score(betas)
+
+
+def _score_betas(betas, data, family, gh, phis, eta_zi, p_by):
     canonical, user_defined = agq.family_flags(family)
     eta_y = (data.X @ betas)[:, None] + gh.Ztb
     if data.offset is not None:
@@ -289,11 +294,15 @@ def _pack(betas, D, phis, gammas, diag_D, for_params=False):
 
 
 def mixed_fit(data, family, inits=None, control=None, diag_D=False, mode_finder="newton", hessian=True,
-              trace=None):
+              trace=None, penalized=False):
     """R/mixed_fit.R.  mode_finder: "bfgs" is the reference's optim() inside find_modes, "newton"
     the engine's algorithm; both reach the same modes to ~1e-5 / 1e-10."""
     con = dict(CONTROL_DEFAULTS)
     con.update(control or {})
+    # R/mixed_model.R:196-208, R/mixed_fit.R:64-69
+    if penalized is True:
+        penalized = dict(pen_mu=0.0, pen_sigma=1.0, pen_df=3.0)
+    pen = agq.Penalty(data.X.shape[1], **penalized) if penalized else None
     nRE = data.nRE
     nAGQ = con["nAGQ"] or (11 if nRE < 3 else 7)
     inits = initial_values(data, family, diag_D) if inits is None else inits
@@ -320,6 +329,8 @@ def mixed_fit(data, family, inits=None, control=None, diag_D=False, mode_finder=
                 post_modes = gh.post_modes
             Params.append(_pack(betas, D, phis, gammas, diag_D, for_params=True))
             p_by, post_b2, ll, eta_zi = e_step(data, family, gh, betas, D, phis, gammas)
+            if pen is not None:
+                ll = ll + pen.log_dens(betas)             # R/mixed_fit.R:156-159
             lgLik.append(ll)
             if trace is not None:
                 trace.append(("EM", it, ll, betas.copy()))
@@ -338,7 +349,7 @@ def mixed_fit(data, family, inits=None, control=None, diag_D=False, mode_finder=
                 f = lambda ph: score_phis(ph, data, family, gh, betas, eta_zi, p_by)
                 H = nearPD(numer_deriv_vec(phis, f))
                 phis = phis - np.linalg.solve(H, f(phis))
-            f = lambda bt: score_betas(bt, data, family, gh, phis, eta_zi, p_by)
+            f = lambda bt: score_betas(bt, data, family, gh, phis, eta_zi, p_by, pen)
             H = nearPD(numer_deriv_vec(betas, f))
             betas = betas - np.linalg.solve(H, f(betas))
             if gammas is not None:
@@ -366,8 +377,8 @@ def mixed_fit(data, family, inits=None, control=None, diag_D=False, mode_finder=
         for it in range(1, con["iter_qN_outer"] + 1):
             n_outer = it
             gh = ghfun(post_modes)
-            opt = agq.vmmin(tht, lambda t: agq.logLik_mixed(t, data, family, gh, diag_D),
-                            lambda t: agq.score_mixed(t, data, family, gh, diag_D),
+            opt = agq.vmmin(tht, lambda t: agq.logLik_mixed(t, data, family, gh, diag_D, penalty=pen),
+                            lambda t: agq.score_mixed(t, data, family, gh, diag_D, penalty=pen),
                             maxit=iter_qN, reltol=con["tol3"], parscale=parscale)
             tht = opt["par"]
             betas, D, phis, gammas = unpack(tht)
@@ -380,10 +391,10 @@ def mixed_fit(data, family, inits=None, control=None, diag_D=False, mode_finder=
             iter_qN += con["iter_qN_incr"]
     tht = _pack(betas, D, phis, gammas, diag_D)
     gh = ghfun(post_modes)
-    logLik = -agq.logLik_mixed(tht, data, family, gh, diag_D)
+    logLik = -agq.logLik_mixed(tht, data, family, gh, diag_D, penalty=pen)
     out = dict(coefficients=betas, D=D, phis=phis, gammas=gammas, post_modes=gh.post_modes,
                post_vars=gh.post_vars, logLik=float(logLik), converged=converged, thetas=tht,
                n_outer=n_outer)
     if hessian:
-        out["Hessian"] = agq.cd_vec(tht, lambda t: agq.score_mixed(t, data, family, gh, diag_D))
+        out["Hessian"] = agq.cd_vec(tht, lambda t: agq.score_mixed(t, data, family, gh, diag_D, penalty=pen))
     return out

@@ -138,3 +138,18 @@ def test_oracle_fit_reproduces_published_family_fits(name):
         out = ofit.mixed_fit(data, oracle_family(k["family"]), control=dict(nAGQ=k["nAGQ"]), hessian=False,
                              mode_finder=k.get("fit_mode_finder", "newton"))
     check_family_fit(k, out)
+
+
+def test_oracle_penalized_fit_reproduces_published_gm2():
+    """gm2 <- mixed_model(y ~ sex * time, random = ~ 1 | id, family = poisson(), penalized = TRUE):
+    cbind(fixef(gm1), fixef(gm2)) of docs/articles/GLMMadaptive.html:471-478 prints the penalised
+    estimates with seven decimals; the oracle's fit (reference-faithful BFGS mode finder, as gm1 in
+    tests/kat_families.py) lands on them."""
+    import warnings
+    v = vignette_data.poisson_data()
+    data = agq.Data(y=v["y"], X=v["X"], Z=v["Z"], id=v["id"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = ofit.mixed_fit(data, F.poisson(), hessian=False, mode_finder="bfgs", penalized=True)
+    assert out["converged"]
+    assert np.max(np.abs(out["coefficients"] - np.array([2.9433925, -0.8599374, 0.2404593, -0.0511505]))) < 5e-7
