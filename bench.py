@@ -167,44 +167,127 @@ def _head(od, k):
 
 
 def _oracle_worker(args):
-    d, th, n_sample = args
+    """One pool process: pinned to its own core, single-threaded numpy, its OWN slice of clusters."""
+    seed, n_sample, core = args
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    from glmmadaptive_b200 import synth
+    d, th = synth.make("C3", n=n_sample, ni=8, seed=seed)
     return oracle_eval_time(d, th, n_sample)
 
 
+R_TIMING_SCRIPT = os.path.join(ROOT, "oracle", "time_reference.R")
+
+
+def find_reference_tree():
+    """The unmodified reference sources, if they travelled to this machine (they do not travel to the
+    GPU box: /root/reference exists in the build container only)."""
+    for cand in (os.environ.get("GLMMA_REFERENCE_DIR"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "R", "Fit_Funs.R")):
+            return cand
+    return None
+
+
+def try_real_reference(n_sample):
+    """when Rscript (with matrixStats) AND the reference tree are present, time the
+    reference's own logLik_mixed + score_mixed (R/Fit_Funs.R, sourced unmodified by
+    oracle/time_reference.R) on the C3 workload.  Returns (seconds per evaluation on n_sample clusters,
+    description) or None."""
+    import shutil
+    import tempfile
+    rs, ref = shutil.which("Rscript"), find_reference_tree()
+    if rs is None or ref is None:
+        return None
+    try:
+        if subprocess.run([rs, "-e", "library(matrixStats)"], capture_output=True, timeout=120).returncode != 0:
+            return None
+        from glmmadaptive_b200 import synth
+        d, th = synth.make("C3", n=n_sample, ni=8, seed=3)
+        with tempfile.TemporaryDirectory() as tmp:
+            for k in ("y", "X", "Z"):
+                np.asarray(d[k], np.float64).ravel(order="F").tofile(os.path.join(tmp, k + ".bin"))
+            np.asarray(d["id"] + 1, np.int32).tofile(os.path.join(tmp, "id.bin"))
+            theta = np.concatenate([th["betas"], np.asarray(th["D"]).ravel(order="F"), th["phis"]])
+            theta.tofile(os.path.join(tmp, "theta.bin"))
+            r = subprocess.run([rs, R_TIMING_SCRIPT, ref, tmp, str(len(d["y"])), str(d["X"].shape[1]),
+                                str(d["Z"].shape[1]), str(th["nAGQ"])], capture_output=True, text=True, timeout=1800)
+            if r.returncode != 0:
+                return None
+            secs = float([ln for ln in r.stdout.splitlines() if ln.startswith("SECONDS_PER_EVAL")][-1].split()[1])
+        return secs, f"unmodified {ref}/R/*.R under {rs}: logLik_mixed + score_mixed on {n_sample} clusters, one core"
+    except Exception:
+        return None
+
+
 def run_reference(args):
-    """The reference's own CPU implementation of the path.  R is not installed in this image
-    (and the reference is pure R), so this times the oracle port of the R code, on all host
-    cores: the sample's clusters are split over a process pool."""
+    """The reference's own CPU implementation of the path on the host cores.
+
+    If Rscript and the reference tree are both on this machine the unmodified R code is timed
+    (kind "reference").  Otherwise -- this image has no R, and the reference sources do not travel to
+    the GPU box -- the numpy port of the R code is timed on ALL host cores (kind "port"): every pool
+    process is pinned to its own core, runs single-threaded numpy on its own slice of distinct clusters,
+    and a step takes as long as the slowest process.  The port is timed at three slice sizes (linearity
+    check: the figure is extrapolated linearly to 1e6 clusters) and the reported value is the MEDIAN over
+    the timed steps at the largest size, with the spread alongside."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from glmmadaptive_b200 import synth
     from concurrent.futures import ProcessPoolExecutor
-    cores = max(1, min(os.cpu_count() or 1, 16))
-    per_worker = 4000
-    d, th = synth.make("C3", n=per_worker, ni=8, seed=3)
     n_total = 1_000_000
-    times = []
+    real = try_real_reference(4000)
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+    except Exception:
+        avail = list(range(os.cpu_count() or 1))
+    cores = max(1, min(len(avail), 16))
+    sizes = [1000, 2000, 4000]
+    steps = max(args.steps, 5)
+    med = {}
+    spread = None
     with ProcessPoolExecutor(max_workers=cores) as ex:
-        for it in range(args.warmup + args.steps):
-            # each process times its own logLik_mixed + score_mixed pass (grid set-up excluded);
-            # the step takes as long as the slowest process
-            dt = max(ex.map(_oracle_worker, [(d, th, per_worker)] * cores))
-            if it >= args.warmup:
-                times.append(dt)
-    t_step = float(np.mean(times))
-    n_sample = per_worker * cores
+        for m in sizes:
+            k = steps if m == sizes[-1] else 3
+            times = []
+            for it in range(args.warmup + k):
+                jobs = [(1000 + w, m, avail[w]) for w in range(cores)]        # distinct clusters per process
+                dt = max(ex.map(_oracle_worker, jobs))
+                if it >= args.warmup:
+                    times.append(dt)
+            med[m] = float(np.median(times))
+            if m == sizes[-1]:
+                spread = [float(np.min(times)), float(np.max(times))]
+    m = sizes[-1]
+    n_sample = m * cores
+    t_step = med[m]
     value = 1.0 / (t_step * n_total / n_sample)
-    sample = (f"{n_sample} clusters x 8 obs per step ({per_worker} per process x {cores} processes), "
-              f"logLik_mixed + score_mixed of the numpy port; evals/s extrapolated linearly to 1e6 clusters")
+    kind = "port"
+    sample = (f"{n_sample} clusters x 8 obs per step ({m} distinct clusters per process x {cores} pinned, "
+              f"single-threaded processes), logLik_mixed + score_mixed of the numpy port; median of {steps} steps "
+              f"(min {spread[0]:.3f} s, max {spread[1]:.3f} s); evals/s extrapolated linearly to 1e6 clusters")
+    extra = {"seconds_per_step_by_slice": {str(k): v for k, v in med.items()},
+             "linearity": {"t(2000)/t(1000)": med[2000] / med[1000], "t(4000)/t(2000)": med[4000] / med[2000],
+                           "note": "2.0 = linear in the number of clusters"},
+             "spread_s": spread}
+    if real is not None:
+        secs, what = real
+        value_r = 1.0 / (secs * n_total / 4000)
+        extra["port_all_cores"] = {"value": value, "sample": sample}
+        value, kind, cores, sample = value_r, "reference", 1, what + "; extrapolated linearly to 1e6 clusters"
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+           "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic",
            "config": {"workload": "C3: negative.binomial, q=2, nAGQ=11 (K=121), 1e6 clusters x 8 obs"},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "R is not installed in the image; the reference (pure R) cannot run, its numpy port is timed"}
+           "note": "Rscript probed: " + ("found, unmodified reference timed" if real is not None else
+                                         ("not found" if __import__("shutil").which("Rscript") is None else
+                                          "found, but the reference tree or matrixStats is missing") +
+                                         "; the reference is pure R, so its numpy port is timed instead")}
     print(json.dumps(out), flush=True)
 
 
@@ -322,6 +405,36 @@ def run_ours(args):
     # ---- kernel-level timing of the dominant kernel (rank-local) and the roofline
     ms_eval, ms_kernel = eng.time_eval(betas, D, phis, gammas, True, iters=max(3, min(args.steps, 10)))
     barrier()
+
+    # ---- the single-process multi-GPU handle (glmma_create_multi: the shape an R session needs) checked
+    # where several GPUs are visible: rank 0 spreads a 3000-cluster sample over all of them behind ONE
+    # handle and compares its evaluation with a single-device engine on the same sample
+    multi_check = None
+    if rank == 0 and torch.cuda.device_count() > 1:
+        try:
+            ndev = torch.cuda.device_count()
+            dm, thm = synth.make(args.workload, n=3000, ni=args.ni, seed=17, ragged=True)
+            fm = dm.pop("family")
+            kw = dict(nAGQ=thm["nAGQ"], X_zi=dm.get("X_zi"), Z_zi=dm.get("Z_zi"))
+            one = gb.Engine(dm["y"], dm["X"], dm["Z"], dm["id"], fm, device=local_rank, **kw)
+            one.find_modes(thm["betas"], np.linalg.inv(thm["D"]), thm["phis"], thm["gammas"], warm=False)
+            m_, c_, _ = one.get_modes()
+            r1_ = one.eval_raw(thm["betas"], thm["D"], thm["phis"], thm["gammas"])
+            many = gb.Engine(dm["y"], dm["X"], dm["Z"], dm["id"], fm, device=list(range(ndev)), **kw)
+            many.set_modes(m_, c_)
+            rN = many.eval_raw(thm["betas"], thm["D"], thm["phis"], thm["gammas"])
+            stN = many.find_modes(thm["betas"], np.linalg.inv(thm["D"]), thm["phis"], thm["gammas"], warm=False)
+            mN, _, _ = many.get_modes()
+            err = float(np.max(np.abs(rN - r1_) / np.maximum(1.0, np.abs(r1_))))
+            multi_check = {"devices": ndev, "clusters": 3000, "max_rel_diff_vs_single_device": err,
+                           "modes_max_abs_diff": float(np.max(np.abs(mN - m_))), "ok": bool(err < 1e-13),
+                           "not_converged": int(stN["n_not_converged"]),
+                           "what": "glmma_create_multi handle over all visible GPUs in ONE process vs a single-device "
+                                   "engine: same grid (set_modes), glmma_eval result vector; then its own mode search"}
+            one.close(); many.close()
+        except Exception as exc:                      # never let the check break the benchmark line
+            multi_check = {"error": repr(exc)}
+    barrier()
     out = None
     if rank == 0:
         peak = measure_fp64_peak(local_rank)
@@ -367,6 +480,33 @@ def run_ours(args):
                     "hbm": {"achieved": byts / (ms_kernel * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": byts / (ms_kernel * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": byts,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+        cpu_fit = None
+        if world == 1 and not args.no_cpu_baseline and not args.no_fit:
+            # the CPU side of "mixed_model() s" -- the oracle's restatement of
+            # R/mixed_fit.R (default control: 30 EM iterations, BFGS, cd_vec Hessian) on a sample the
+            # port finishes in seconds, with the engine's fit of the SAME sample beside it
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from oracle import agq as _agq, fit as _ofit
+            from helpers import oracle_family as _of
+            n_f = 1000
+            df_, thf = synth.make(args.workload, n=n_f, ni=args.ni, seed=23)
+            ff = df_.pop("family")
+            t0 = time.perf_counter()
+            try:
+                rf = _ofit.mixed_fit(_agq.Data(y=df_["y"], X=df_["X"], Z=df_["Z"], id=df_["id"], X_zi=df_.get("X_zi"),
+                                               Z_zi=df_.get("Z_zi")), _of(ff), mode_finder="newton", hessian=True)
+                t_cpu = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                gf = gb.mixed_model(df_["y"], df_["X"], df_["Z"], df_["id"], ff, X_zi=df_.get("X_zi"), Z_zi=df_.get("Z_zi"),
+                                    device=local_rank)
+                t_gpu = time.perf_counter() - t0
+                cpu_fit = {"clusters": n_f, "cpu_port_seconds": t_cpu, "engine_seconds": t_gpu, "cores": 1,
+                           "kind": "port", "max_abs_diff_coefficients": float(np.max(np.abs(rf["coefficients"] - gf["coefficients"]))),
+                           "what": "whole mixed_model() fit (default control) of the same 1000-cluster sample: numpy "
+                                   "restatement of R/mixed_fit.R on one core vs the engine (incl. glmma_create); at "
+                                   "this size the engine is launch-latency bound, the CPU time grows linearly with n"}
+            except Exception as exc:
+                cpu_fit = {"error": repr(exc)}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_s = min(60000, n_total)           # ~6 s per pass on one core, two passes
@@ -386,9 +526,11 @@ def run_ours(args):
                           "cluster_evals_per_s": n_total * 1e3 / ms_step,
                           "point_evals_per_s": n_total * ni * eng.K * 1e3 / ms_step},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "what": "glmma_eval through the C ABI: host theta in (kernel parameters), result vector "
-                               "copied back and synchronised every step; the data set is uploaded once by "
-                               "glmma_create, as the R glue does",
+                       "what": ("glmma_eval through the C ABI: host theta in (kernel parameters), result vector "
+                                "copied back and synchronised every step" if world == 1 else
+                                "glmma_eval_device through the C ABI on every rank (host theta in), one all-reduce of "
+                                "the result vector, device-to-host copy and synchronisation every step") +
+                               "; the data set is uploaded once by glmma_create, as the R glue does",
                        "create_s": t_create, "upload_bytes": eng.input_bytes,
                        "cold_first_eval_s": t_create + t_modes_cold + 1.0 / e2e_value,
                        "cold_what": "from host arrays to the first result: glmma_create (host->device copy of the "
@@ -396,7 +538,7 @@ def run_ours(args):
                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                "find_modes": {"cold_clusters_per_s": n_total / t_modes_cold, "warm_clusters_per_s": n_total / t_modes_warm,
                               "mean_iterations_cold": st["mean_iterations"], "not_converged": st["n_not_converged"]},
-               "mixed_model": fit_info,
+               "mixed_model": fit_info, "mixed_model_cpu": cpu_fit, "multi_handle_check": multi_check,
                "ms_per_eval_local": ms_eval,
                "check": {"loglik": res["loglik"], "n_nonfinite": res["n_nonfinite"]}}
     eng.close()

@@ -84,6 +84,7 @@ struct DevData {
     double* ll_i;         // n (contrib only) or null
     double* S_i;          // n x q*q (contrib only) or null
     double* csum;         // n x GLMMA_NCSUM per-cluster scalars (cluster_sums_kernel)
+    double* clrec;        // n x (q + q(q+1)/2 + 1 + q_y + 1): packed {modes, R^-1, logdet, Z'y1, weight} (register variant)
     int32_t* defer;       // n : 1 = cluster left to the generic eval kernel by the register variant
 };
 

@@ -92,6 +92,12 @@ struct glmma_handle {
     int32_t* d_defer_list;     // clusters no tile of the register variant takes (they still need prep)
     int64_t n_defer_list;
     unsigned* d_counter;       // blocks-done counter of the in-kernel finalisation
+    double* d_roww;            // per-row cluster weight, 0 on rows of clusters the register variant does not take
+                               // (null: every row counts once) -- const_sums_kernel
+    double* d_cpart;           // const_sums_kernel block partials
+    int n_cpart;
+    std::vector<double> xty_w; // sum_i w_i X_i'y1_i over the register variant's clusters (linear-eta hoist)
+    double yoff_w;             // sum_i w_i y1_i'offset_i over the same clusters
     bool ytab_valid;           // d_ytab holds the table of ytab_phis
     double ytab_phis;
     int score_grid;
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* e
                                                                   const double* score_partials, int n_score_blocks,
                                                                   int p, int n_phis, int p_zi, int q, int want_score,
                                                                   double* result) {
-    __shared__ double sh[GLMMA_NACC + GLMMA_PMAX + GLMMA_PZIMAX];
+    __shared__ double sh[GLMMA_NACC + GLMMA_PMAX + GLMMA_PZIMAX + 2];
     finalize_block(eval_partials, n_eval_blocks, score_partials, n_score_blocks, false, p, n_phis, p_zi, q, want_score,
                    result, sh);
 }
@@ -524,6 +530,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->family_df = data->family_df;
     h->d_pby = nullptr; h->have_pby = false;
     h->fused = false; h->xw = 0; h->d_defer_list = nullptr; h->n_defer_list = 0; h->d_counter = nullptr;
+    h->d_roww = nullptr; h->d_cpart = nullptr; h->n_cpart = 0; h->yoff_w = 0.0;
     h->ytab_valid = false; h->ytab_phis = 0.0;
     for (int v = 0; v < 3; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
     for (auto& e : h->ev) e = nullptr;
@@ -644,7 +651,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     // ragged data run several tiles back to back, each on its own list of clusters.
     h->nj = 0;
     int max_fast = 0;
-    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && !std::getenv("GLMMA_NO_FAST")) {
+    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && !std::getenv("GLMMA_NO_FAST") &&
+        d.p + d.p_zi <= GLMMA_FOLD_COLS && d.p + d.p_zi + 2 + 2 + GLMMA_QMAX <= GLMMA_COLTAB_MAX) {
         int64_t n_le8 = 0, n_9_12 = 0, n_13_16 = 0;
         for (int v = 1; v <= 8; ++v) n_le8 += cnt[v];
         for (int v = 9; v <= 12; ++v) n_9_12 += cnt[v];
@@ -657,13 +665,13 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     }
     // fused mode whenever the register variant runs and the design columns fit a warp's lanes
     h->xw = d.p + d.p_zi + (d.offset ? 1 : 0) + (d.offset_zi ? 1 : 0);
-    h->fused = h->nj != 0 && d.p + d.p_zi <= GLMMA_FOLD_COLS && !std::getenv("GLMMA_NO_FUSED");
+    h->fused = h->nj != 0;          // the register variant is self-contained (kernels.cuh): no prep / score-reduce / finalize launches
     if (h->nj) {
         for (int v = 0; v < 3; ++v) {
             if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
             for (int s = 0; s < 2; ++s) {
                 int bps = 0;
-                ce = ops->fast_config(h->fused ? h->xw : 0, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
+                ce = ops->fast_config(h->xw, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
                 if (ce != cudaSuccess || bps < 1) {
                     cuda_fail(h, ce, "fast eval kernel configuration");
                     g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;
@@ -674,6 +682,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         }
         TRY(dev_alloc(h, &d.defer, n));
         TRY(dev_alloc(h, &d.csum, (size_t)n * GLMMA_NCSUM));
+        TRY(dev_alloc(h, &d.clrec, (size_t)n * (q + np + 1 + d.q_y + 1)));
         TRY(dev_alloc(h, &h->d_ytab, 2 * GLMMA_YTAB));
         // Size classes.  Each tile in use gets the list of the clusters it is the smallest fit for (the
         // identity when all clusters fit one tile) and the clusters beyond the largest tile are flagged
@@ -718,6 +727,38 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                         for (int dd = 0; dd < d.q_y; ++dd)
                             cs[(size_t)i * GLMMA_NCSUM + 3 + dd] = std::fma(y1[r], data->Z[r + (int64_t)dd * N], cs[(size_t)i * GLMMA_NCSUM + 3 + dd]);
                 cudaMemcpyAsync(d.csum, cs.data(), sizeof(double) * cs.size(), cudaMemcpyHostToDevice, h->stream);
+                // node-independent terms are summed once per evaluation over the rows of this variant's
+                // clusters (const_sums_kernel): per-row weights when clusters are weighted or excluded
+                std::vector<double> roww;
+                if (data->weights || !too_big.empty()) {
+                    roww.assign((size_t)N, 0.0);
+                    for (int64_t i = 0; i < n; ++i) {
+                        if (flags[i]) continue;
+                        const double wi = data->weights ? data->weights[i] : 1.0;
+                        for (int64_t r = row_ptr[i]; r < row_ptr[i + 1]; ++r) roww[r] = wi;
+                    }
+                    const double* tmp = nullptr;
+                    TRY(dev_upload(h, &tmp, roww.data(), roww.size()));
+                    h->d_roww = const_cast<double*>(tmp);
+                }
+                h->n_cpart = (int)std::min<int64_t>((N + GLMMA_CONST_THREADS * 4 - 1) / (GLMMA_CONST_THREADS * 4), (int64_t)prop.multiProcessorCount * 8);
+                TRY(dev_alloc(h, &h->d_cpart, (size_t)2 * h->n_cpart));
+                // linear-eta hoist: sum_i w_i sum_j y1_ij (x_ij' beta + offset_ij) = beta' (X'y1)_w + (y1'offset)_w
+                h->xty_w.assign(d.p, 0.0);
+                if (ops->lin_eta) {
+                    for (int l = 0; l < d.p; ++l) {
+                        const double* col = data->X + (size_t)l * N;
+                        double acc = 0.0;
+                        if (roww.empty()) for (int64_t r = 0; r < N; ++r) acc = std::fma(y1[r], col[r], acc);
+                        else for (int64_t r = 0; r < N; ++r) acc = std::fma(roww[r] * y1[r], col[r], acc);
+                        h->xty_w[l] = acc;
+                    }
+                    if (data->offset) {
+                        double acc = 0.0;
+                        for (int64_t r = 0; r < N; ++r) acc = std::fma((roww.empty() ? 1.0 : roww[r]) * y1[r], data->offset[r], acc);
+                        h->yoff_w = acc;
+                    }
+                }
                 TRY(dev_alloc(h, &h->d_counter, 1));
                 cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream);
             }
@@ -847,6 +888,12 @@ static int find_modes_enqueue(glmma_handle* h, const double* betas, const double
     const int G = mean_ni <= 12.0 ? 1 : (mean_ni <= 96.0 ? 8 : 32);
     h->ops->modes(ma, G, h->stream);
     h->launches++;
+    // the grid is DEFINED by (modes, chol): R^-1 and log_dets are re-derived from the stored factors by
+    // the same kernel glmma_set_modes uses, so that get_modes -> set_modes (the round trip the R glue
+    // makes when it re-injects a GH object) reproduces every later evaluation bit for bit
+    h->ops->rinv(h->d, h->stream);
+    h->launches++;
+    if (h->d.clrec) { h->ops->pack(h->d, h->stream); h->launches++; }
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(st_host, h->d_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     h->have_modes = true;
@@ -884,6 +931,7 @@ static int multi_eval_contrib(glmma_handle* h, const double* betas, const double
                               double* S_i);
 static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
                           const double* beta, double* out);
+static int multi_fail(glmma_handle* h, const glmma_handle* p, int rc);
 
 int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
     DeviceGuard device_guard_;
@@ -922,6 +970,7 @@ int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* cho
     CU(h, cudaMemcpyAsync(h->d.chol, chol_upper, sizeof(double) * n * np, cudaMemcpyHostToDevice, h->stream));
     h->ops->rinv(h->d, h->stream);
     h->launches++;
+    if (h->d.clrec) { h->ops->pack(h->d, h->stream); h->launches++; }
     CU(h, cudaGetLastError());
     CU(h, cudaStreamSynchronize(h->stream));
     h->have_modes = true;
@@ -936,8 +985,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
     if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
     const int s = want_score ? 1 : 0;
-    // the per-observation contributions (dd_override) read the prep kernel's work arrays: plain path
-    const bool fused = h->fused && !dd_override;
+    const bool fused = h->fused;
     FamPar fp;
     int rc;
     EvalArgs ea;
@@ -947,15 +995,24 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         if (rc) return rc;
         if (!fill_fampar(h->family, h->d.n_phis, phis, &fp, h->error, h->family_df)) return GLMMA_ERR_ARG;
         ensure_ytab(h, fp, phis);
-        if (h->n_defer_list > 0) {
+        // prep pass only over the clusters no tile takes -- or over all of them when the per-observation
+        // contributions are wanted (sphi_obs_kernel reads the work arrays)
+        if (h->n_defer_list > 0 || dd_override) {
             PrepArgs pa;
             pa.d = h->d; pa.fam = fp; pa.want_score = 1; pa.ytab = h->d_ytab;
-            pa.list = h->d_defer_list; pa.n_list = h->n_defer_list;
+            pa.list = dd_override ? nullptr : h->d_defer_list; pa.n_list = dd_override ? 0 : h->n_defer_list;
             h->ops->prep(pa, ea.coef, h->stream);
             h->launches++;
         }
-        ea.fused = 1; ea.xw = h->xw; ea.zbar_out = 0; ea.ytab = h->ops->y_table ? h->d_ytab : nullptr;
+        ea.fused = 1; ea.xw = h->xw; ea.zbar_out = dd_override ? 1 : 0; ea.ytab = h->ops->y_table ? h->d_ytab : nullptr;
         ea.fin_counter = h->d_counter; ea.fin_partials = h->d_partials; ea.fin_want_score = s; ea.fin_result = d_out;
+        // node-independent terms of the register variant's clusters, once per evaluation
+        h->ops->consts(h->d, fp, h->d_ytab, h->d_roww, h->d_cpart, h->n_cpart, h->stream);
+        h->launches++;
+        ea.fin_cpart = h->d_cpart; ea.fin_ncpart = h->n_cpart;
+        double llc = h->yoff_w;
+        for (int l = 0; l < h->d.p; ++l) llc = std::fma(betas[l], h->xty_w[l], llc);
+        ea.fin_ll_const = llc;
     } else {
         rc = run_prep(h, betas, phis, gammas, &fp);
         if (rc) return rc;
@@ -1151,6 +1208,51 @@ int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, in
             if (l < p && m < p) { out[1 + p + l + m * p] = tot[t]; out[1 + p + m + l * p] = tot[t]; }
             ++t;
         }
+    return GLMMA_OK;
+}
+
+// ---- predict()'s Metropolis step (R/methods.R:1013-1142) -----------------------------------
+
+int glmma_log_post_b(glmma_handle* h, const double* b, const double* betas, const double* invD,
+                     const double* phis, const double* gammas, double* out) {
+    DeviceGuard device_guard_;
+    if (h && !h->parts.empty()) {
+        if (!b || !out) return fail(h, GLMMA_ERR_ARG, "null argument");
+        const int64_t n = h->part_c0.back();
+        for (size_t k = 0; k < h->parts.size(); ++k) {
+            glmma_handle* p = h->parts[k];
+            const int64_t c0 = h->part_c0[k], m = p->d.n;
+            std::vector<double> tmp((size_t)m * h->q);
+            for (int dd = 0; dd < h->q; ++dd) std::memcpy(tmp.data() + (size_t)dd * m, b + (size_t)dd * n + c0, sizeof(double) * m);
+            int rc = glmma_log_post_b(p, tmp.data(), betas, invD, phis, gammas, out + c0);
+            if (rc) return multi_fail(h, p, rc);
+        }
+        return GLMMA_OK;
+    }
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!b || !out || !invD) return fail(h, GLMMA_ERR_ARG, "null argument");
+    FamPar fp;
+    rc = run_prep(h, betas, phis, gammas, &fp);
+    if (rc) return rc;
+    ModeArgs ma;
+    ma.d = h->d; ma.fam = fp; ma.fmtab = h->d_fmtab; fastmath_constants(ma.fmc); ma.warm = 0; ma.maxit = 0; ma.tol = 0.0; ma.stats = h->d_stats;
+    fill_prior(h, invD, true, &ma.prior);
+    const int64_t n = h->d.n;
+    double *d_b = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaMalloc(&d_b, sizeof(double) * n * h->q);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * n);
+    if (e != cudaSuccess) { cudaFree(d_b); return cuda_fail(h, e, "cudaMalloc (log_post_b)"); }
+    e = cudaMemcpyAsync(d_b, b, sizeof(double) * n * h->q, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        h->ops->logpost(ma, d_b, d_out, h->stream);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_b); cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(h, e, "log_post_b");
     return GLMMA_OK;
 }
 

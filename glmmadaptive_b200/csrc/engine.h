@@ -9,6 +9,9 @@ struct ModeArgs;
 
 struct FamOps {
     void (*ytab)(const FamPar&, double* tab, cudaStream_t);      // table of obs_const(y), count families
+    // node-independent terms of the register variant's clusters: block partials {sum w c_ll, sum w c_phi}
+    void (*consts)(const DevData&, const FamPar&, const double* ytab, const double* roww, double* partials, int blocks,
+                   cudaStream_t);
     void (*prep)(const PrepArgs&, const CoefPar&, cudaStream_t);
     cudaError_t (*eval_config)(int score, int jt, int nagq, int extra, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval)(const EvalArgs&, int score, int grid, int threads, size_t smem, cudaStream_t);
@@ -16,9 +19,12 @@ struct FamOps {
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
     void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
+    void (*logpost)(const ModeArgs&, const double* b, double* out, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
+    void (*pack)(const DevData&, cudaStream_t);       // packed per-cluster records of the register variant
     bool has_zi, has_phi, uses_y2;
     bool y_table;      // obs_const() is tabulated by ytab (count families)
+    bool lin_eta;      // the register variant hoists y1 * eta out of the point loop (families.cuh: LIN_ETA)
 };
 
 // one lookup per family translation unit (nullptr: dimensions not compiled in)

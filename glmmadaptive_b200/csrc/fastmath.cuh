@@ -60,6 +60,10 @@ struct MathCtx {
     const double* exptab;   // device: replicated table + (lane & 15);    host: 64 x 2^(j/64)
     double c[GLMMA_FM_NCONST];   // constants, order of fastmath_constants(); on the device they come
                                  // from the kernel parameters (constant bank), not from shared memory
+    // device: the log table's shared-window address split into its block-uniform base and this lane's
+    // byte offset (16 * (lane & 7)), so that a lookup is shift + one 3-input logic op (index bits | lane
+    // bits) + a load with a uniform base register
+    unsigned lt_base, lt_lane;
 };
 #define FMC_L6 0      // -1/6
 #define FMC_L5 1      // 1/5
@@ -79,6 +83,12 @@ GLMMA_HD MathCtx make_mathctx(const double* logtab, const double* exptab, const 
     MathCtx m;
     m.logtab = logtab; m.exptab = exptab;
     for (int i = 0; i < GLMMA_FM_NCONST; ++i) m.c[i] = c[i];
+#ifdef __CUDA_ARCH__
+    m.lt_lane = (threadIdx.x & 7u) * 16u;
+    m.lt_base = (unsigned)__cvta_generic_to_shared(logtab) - m.lt_lane;
+#else
+    m.lt_base = m.lt_lane = 0;
+#endif
     return m;
 }
 
@@ -185,8 +195,9 @@ GLMMA_HD void fast_log_rcp_vec(const double* t, const MathCtx& cx, double* L, do
         kd[i] = (double)ke[i];                      // k * 2^20: the shift is folded into the constant below
         z[i] = fm_make(hi - ke[i], fm_lo(t[i]));
 #ifdef __CUDA_ARCH__
-        const double2 tc = *reinterpret_cast<const double2*>(cx.logtab + FM_LOG_STRIDE * idx);
-        invc[i] = tc.x; logc[i] = tc.y;
+        (void)idx;
+        const unsigned off = (((unsigned)tmp >> 6) & 0x3F80u) | cx.lt_lane;       // 128 bytes per entry
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc[i]), "=d"(logc[i]) : "r"(cx.lt_base + off));
 #else
         invc[i] = cx.logtab[FM_LOG_STRIDE * idx]; logc[i] = cx.logtab[FM_LOG_STRIDE * idx + 1];
 #endif

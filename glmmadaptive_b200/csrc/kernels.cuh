@@ -54,6 +54,9 @@ struct EvalArgs {
     int fin_blocks;          // block partials written by this evaluation's launches in total
     int fin_want_score;
     double* fin_result;      // result vector (include/glmma.h, glmma_eval)
+    const double* fin_cpart; // const_sums_kernel block partials {sum w c_ll, sum w c_phi} (fused mode)
+    int fin_ncpart;
+    double fin_ll_const;     // beta' X'y1 + sum w y1 offset over the register variant's clusters (linear-eta hoist)
 };
 
 struct PrepArgs {
@@ -122,10 +125,11 @@ __device__ __forceinline__ double warp_max(double v) {
 // tree finishes, so the sum order is fixed (deterministic) and nothing is serialised behind block
 // barriers.  cols_in_ep: the score columns X'zbar, X_zi'zbar_zi travel in the block partials (fused
 // mode); otherwise they come from score_reduce_kernel's partials.  sh: GLMMA_NACC + GLMMA_PMAX +
-// GLMMA_PZIMAX doubles of shared memory.
+// GLMMA_PZIMAX + 2 doubles of shared memory.  The block must have at least two warps.
 __device__ __forceinline__ void finalize_block(const double* ep, int n_eval_blocks, const double* sp, int n_score_blocks,
                                                bool cols_in_ep, int p, int n_phis, int p_zi, int q, int want_score,
-                                               double* result, double* sh) {
+                                               double* result, double* sh, const double* cpart = nullptr, int ncpart = 0,
+                                               double ll_const = 0.0, bool ll_consts_on = true) {
     double* acc = sh;
     double* col = sh + GLMMA_NACC;
     const int np = q * (q + 1) / 2;
@@ -151,9 +155,20 @@ __device__ __forceinline__ void finalize_block(const double* ep, int n_eval_bloc
             if (lane == 0) col[l] = s;
         }
     }
+    // fused mode: node-independent terms of the register variant's clusters (const_sums_kernel partials:
+    // warps 0 / 1 sum the two columns in a fixed order) and the linear-eta constant
+    double* cadd = sh + GLMMA_NACC + GLMMA_PMAX + GLMMA_PZIMAX;
+    if (w < 2) {
+        double s = 0.0;
+        for (int b = lane; b < ncpart; b += 32) s += __ldcg(cpart + 2 * b + w);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) cadd[w] = s;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        result[0] = acc[0]; result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
+        result[0] = acc[0] + (ll_consts_on ? cadd[0] + ll_const : 0.0);
+        result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
     }
     if (!want_score) return;
     for (int l = threadIdx.x; l < ncol; l += blockDim.x) {
@@ -161,7 +176,7 @@ __device__ __forceinline__ void finalize_block(const double* ep, int n_eval_bloc
         else result[4 + p + n_phis + (l - p)] = col[l];
     }
     if (threadIdx.x == 0) {
-        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3];
+        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3] + cadd[1];
         double* S = result + 4 + p + n_phis + p_zi;
         int t = 0;
         for (int dd = 0; dd < q; ++dd)
@@ -826,15 +841,17 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
     // partials of the earlier launches are complete): its fixed-order sum over ALL block partials is
     // the result vector, whichever block happens to be last -- deterministic.
     if (A.fin_counter != nullptr) {
-        __shared__ int s_last;
+        // (no static shared memory in this kernel: its dynamic allocation is raised to the opt-in maximum)
+        int* s_last = reinterpret_cast<int*>(smem + (size_t)wpb * GLMMA_PSTRIDE);
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(A.fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+        if (threadIdx.x == 0) *s_last = (atomicAdd(A.fin_counter, 1u) == gridDim.x - 1) ? 1 : 0;
         __syncthreads();
-        if (s_last) {
+        if (*s_last) {
             __threadfence();
             finalize_block(A.fin_partials, A.fin_blocks, nullptr, 0, true, d.p, d.n_phis, d.p_zi, Q, A.fin_want_score,
-                           A.fin_result, smem + (size_t)wpb * GLMMA_PSTRIDE);
+                           A.fin_result, smem + (size_t)wpb * GLMMA_PSTRIDE + 2, A.fin_cpart, A.fin_ncpart, A.fin_ll_const,
+                           A.em_mode != 2);
             if (threadIdx.x == 0) *A.fin_counter = 0u;
         }
     }
@@ -935,8 +952,19 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 // CAREFUL = false, which is exact when no link clamp is active on the cluster's grid and
 // all separable factors are in range; clusters that fail that test (or are larger than
 // NJ) are flagged in d.defer and handled by eval_kernel.
-// Shared memory per block: [fastmath | gx, glw | node table (z.., lw per node) | node idx
-// | per-warp areas: rec, tabF, tabL, acc (also scratch), totals].
+//
+// The kernel is self-contained per evaluation ("fused"): it stages the cluster's design columns
+// (X, X_zi, offsets) next to its records, forms xb = X beta + offset and xg = X_zi gamma + offset_zi
+// itself and accumulates X'zbar and X_zi'zbar_zi per warp (lane l owns column l), so there is no prep
+// pass over the data, no xb / zbar round trip through HBM and no score-reduce launch.  The
+// node-independent terms of log f and d log f / d phis do not enter the posterior node weights; they
+// are added to the totals once per evaluation (const_sums_kernel over the rows of this variant's
+// clusters + beta' X'y1 for the linear-eta hoist; engine.cu) and only a cluster that drops out of the
+// sums (non-finite, or left to eval_kernel) takes its share back here, on a rare path.
+//
+// Shared memory per block: [fastmath | gx, glw | column table | node table (z.., lw per node) | node
+// idx | per-warp areas: 2 prefetch buffers (records, scalars, design columns), tabF, tabL, acc (also
+// scratch), wv, totals].
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
 #define GLMMA_K_FAST 512
@@ -944,6 +972,14 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 // Launch shape: 128 registers per thread at any block size from GLMMA_EVAL_THREADS (four blocks per
 // SM) to GLMMA_FAST_MAX_THREADS (one); the host picks the shape that keeps most warps resident.
 #define GLMMA_FAST_MAX_THREADS 512
+#define GLMMA_COLTAB_MAX 48        // staged columns: y1, y2, Z, Z_zi, X, X_zi, offsets
+
+// one staged column: where it starts in HBM, where row j of it goes in the prefetch buffer
+struct __align__(16) ColEnt {
+    const double* base;
+    int off;            // doubles from the start of the buffer
+    int stride;         // doubles between consecutive rows
+};
 
 template <class F, int QY, int QZ, int NJ>
 struct FastLayout {
@@ -951,20 +987,24 @@ struct FastLayout {
     static constexpr int Q = QY + QZ;
     static constexpr int W = L::W;
     static constexpr int NT = L::NTABL;
-    static constexpr int TF = Q * GLMMA_NAGQ_FAST;          // doubles of tabF per observation
-    static constexpr int TL = NT * GLMMA_NAGQ_FAST;
+    static constexpr int NG = GLMMA_NAGQ_FAST;
+    // separable tables: the NJ observations of one (dimension, node index) are contiguous, row pitch
+    // RP: even (16-byte pairs) with RP / 2 odd, so the 16-byte loads of a quarter warp, whose lanes
+    // walk consecutive node indices of the fastest dimension, fall on distinct bank groups
+    static constexpr int RP = NJ + 2;
+    static constexpr int TFD = Q * NG * RP;                 // doubles of tabF
+    static constexpr int TLD = NT * NG * RP;
     static constexpr int NACCS = F::HAS_ZI ? 2 : 1;
     static constexpr int NTOT = 2 + Q * (Q + 1) / 2;        // per-lane totals: g_phi, (pad), S packed
-    // per-cluster scalars prefetched with the records: modes, R^-1, logdet, csum, weight
-    static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + GLMMA_NCSUM + 1;
-    static constexpr int PRE = ((NJ * W + NSC) + 1) & ~1;   // one prefetch buffer (records + scalars)
+    // per-cluster scalars prefetched with the records, one packed record per cluster in HBM
+    // (pack_cluster_kernel): modes, R^-1, logdet, Z'y1, weight
+    static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + QY + 1;
+    static constexpr int XOFF = ((NJ * W + NSC) + 1) & ~1;  // design columns follow records + scalars
     static constexpr int NJR = NJ <= 8 ? 8 : 16;            // rows of the per-observation reduction scratch (power of two)
-    // fused mode: per observation (c_ll, c_phi) -- copied asynchronously from the y table --, y1 * xb, pad
-    static constexpr int STASH = 4 * NJ;
-    // + one per-lane row for the node-independent log-likelihood terms (fused mode)
-    static constexpr int WARP_DOUBLES = 2 * PRE + NJ * (TF + TL) + NACCS * NJR * 32 + (NTOT + 1) * 32 + 4 + STASH;
-    // fused mode stages xw design columns (X, X_zi, offsets) per observation, double-buffered
-    __host__ __device__ static size_t warp_stride(int xw) { return (size_t)WARP_DOUBLES + (((size_t)2 * NJ * xw + 1) & ~(size_t)1); }
+    static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
+    __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
+    static constexpr int FIXED = TFD + TLD + NACCS * NJR * 32 + NJ + NTOT * 32 + 4;
+    __host__ __device__ static size_t warp_stride(int xw) { return (size_t)(2 * pre(xw) + FIXED + 1) & ~(size_t)1; }
     // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed node indices (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
     // indices): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
@@ -972,10 +1012,21 @@ struct FastLayout {
     __host__ __device__ static size_t node_doubles(int K) {
         return (((has_ntab(K) ? (size_t)K * (Q + 1) : 0) + (K + 1) / 2) + 1) & ~(size_t)1;
     }
+    __host__ __device__ static size_t coltab_doubles() { return 2 * GLMMA_COLTAB_MAX; }
     __host__ static size_t smem_bytes(int warps, int K, int xw) {
-        return sizeof(double) * (L::head_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw));
+        return sizeof(double) * (L::head_doubles() + coltab_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw));
     }
 };
+
+// node-independent terms of one observation, out of line (rare paths of the register variant only:
+// a cluster that leaves the sums, per-cluster contributions): {c_ll + [LIN_ETA] y1 xb, c_phi}
+template <class F>
+__device__ __noinline__ double2 obs_consts_rare(double y1, double y2, double xb, FamPar fam, const double* ytab) {
+    double cll, cphi;
+    obs_const_tab<F>(y1, y2, fam, ytab, cll, cphi);
+    if (F::LIN_ETA) cll = fma(y1, xb, cll);
+    return make_double2(cll, cphi);
+}
 
 template <class F, int QY, int QZ, bool SCORE, int NJ>
 __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(EvalArgs A) {
@@ -985,6 +1036,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     constexpr int NP = L::NP;
     constexpr int W = L::W;
     constexpr int NG = GLMMA_NAGQ_FAST;
+    constexpr int RP = FL::RP;
     const DevData& d = A.d;
     extern __shared__ double smem[];
     double* fmtab = smem;
@@ -997,26 +1049,53 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     const int K = A.grid->K;
     // K > GLMMA_NTAB_MAX_K needs nagq^Q > 256 with nagq <= 16, i.e. Q >= 3: for Q < 3 the test folds away
     const bool has_ntab = Q < 3 || FL::has_ntab(K);
-    double* ntab = smem + L::head_doubles();                 // K x (Q + 1): z_0.., log wGH (small grids)
+    ColEnt* coltab = reinterpret_cast<ColEnt*>(smem + L::head_doubles());
+    double* ntab = smem + L::head_doubles() + FL::coltab_doubles();       // K x (Q + 1): z_0.., log wGH (small grids)
     int* nidx = reinterpret_cast<int*>(ntab + (has_ntab ? (size_t)K * (Q + 1) : 0));   // K packed node indices
-    const bool fused = A.fused != 0;
-    const int xw = fused ? A.xw : 0;
-    double* pre0 = smem + L::head_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw);
-    double* tabF = pre0 + 2 * FL::PRE;
-    double* tabL = tabF + NJ * FL::TF;
-    double* acc_eta = tabL + NJ * FL::TL;
+    const int xw = A.xw;
+    const int PRE = FL::pre(xw);
+    double* pre0 = smem + L::head_doubles() + FL::coltab_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw);
+    double* tabF = pre0 + 2 * PRE;
+    double* tabL = tabF + FL::TFD;
+    double* acc_eta = tabL + FL::TLD;
     double* acc_zi = acc_eta + FL::NJR * 32;
-    double* totl = acc_eta + FL::NACCS * FL::NJR * 32;       // NTOT x 32 per-lane totals
-    double* totc = totl + FL::NTOT * 32;                     // per-lane node-independent loglik terms (fused mode)
-    double* tots = totc + 32;                                // loglik, sum_w, n_nonfinite (lane 0)
-    double* stash = tots + 4;                                // fused mode: {c_ll, c_phi, y1 xb, -} per observation
-    double* xst0 = stash + FL::STASH;                        // fused mode: 2 x (xw columns x NJ rows)
-    double gcol = 0.0;                                       // fused mode: lane l sums column l of X'zbar | X_zi'zbar_zi
+    double* wv = acc_eta + FL::NACCS * FL::NJR * 32;         // staged second record field (y + phi, trials ...), contiguous
+    double* totl = wv + NJ;                                  // NTOT x 32 per-lane totals
+    double* tots = totl + FL::NTOT * 32;                     // loglik, sum_w, n_nonfinite (lane 0)
+    double gcol = 0.0;                                       // lane l sums column l of X'zbar | X_zi'zbar_zi
 
     load_fmtab(fmtab, A.fmtab);
     if (threadIdx.x < GLMMA_NAGQ_MAX) {
         gx[threadIdx.x] = A.grid->x[threadIdx.x];
         glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    }
+    // staged columns: record fields first (row stride W), then the design columns (column-major per
+    // cluster, as in HBM): X | X_zi | offset | offset_zi
+    const int ncol_rec = 1 + (F::USES_Y2 ? 1 : 0) + QY + QZ;
+    const int ncols = ncol_rec + xw;
+    if (threadIdx.x < ncols) {
+        const int c = threadIdx.x;
+        ColEnt e;
+        e.stride = W;
+        int f = c;
+        if (f == 0) { e.base = d.y1; e.off = 0; }
+        else if (F::USES_Y2 && f == 1) { e.base = d.y2; e.off = 1; }
+        else {
+            f -= 1 + (F::USES_Y2 ? 1 : 0);
+            if (f < QY) { e.base = d.Z + (int64_t)f * d.N; e.off = L::OFF_Z + f; }
+            else if (f < QY + QZ) { e.base = d.Z_zi + (int64_t)(f - QY) * d.N; e.off = L::OFF_Z + f; }
+            else {
+                f -= QY + QZ;
+                e.stride = 1;
+                e.off = FL::XOFF + f * NJ;
+                const int pz_ = F::HAS_ZI ? d.p_zi : 0;
+                if (f < d.p) e.base = d.X + (int64_t)f * d.N;
+                else if (f < d.p + pz_) e.base = d.X_zi + (int64_t)(f - d.p) * d.N;
+                else if (f == d.p + pz_ && d.offset) e.base = d.offset;
+                else e.base = d.offset_zi;
+            }
+        }
+        coltab[c] = e;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -1033,80 +1112,60 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (has_ntab) ntab[k * (Q + 1) + Q] = lw;
         nidx[k] = packed;
     }
-    for (int t = lane; t < (FL::NTOT + 1) * 32 + 4; t += 32) totl[t] = 0.0;
+    for (int t = lane; t < FL::NTOT * 32 + 4; t += 32) totl[t] = 0.0;
     __syncthreads();
     const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const int nrounds = (K + 31) >> 5;
     const int rc = ((K - 1) >> 1) >> 5;
-    constexpr int SC_M = 0, SC_RI = Q, SC_LD = Q + NP, SC_CS = Q + NP + 1, SC_W = Q + NP + 1 + GLMMA_NCSUM;
+    constexpr int SC_M = 0, SC_RI = Q, SC_LD = Q + NP, SC_ZTY = Q + NP + 1, SC_W = Q + NP + 1 + QY;
+    const int p_x = d.p, p_z = F::HAS_ZI ? d.p_zi : 0;
+    const bool has_off = d.offset != nullptr, has_offz = F::HAS_ZI && d.offset_zi != nullptr;
 
-    // Asynchronous prefetch (cp.async, LDGSTS) of one cluster's observation columns and
-    // per-cluster scalars into a shared-memory buffer: issued one cluster ahead, so the
-    // global-memory latency is covered by the previous cluster's arithmetic.
-    auto prefetch = [&](int64_t ci, int64_t c_r0, int c_ni, double* buf, double* xbuf) {
+    // Asynchronous prefetch (cp.async, LDGSTS) of one cluster's columns and per-cluster scalars into a
+    // shared-memory buffer, issued one cluster ahead so that the global-memory latency is covered by the
+    // previous cluster's arithmetic.  Lane (c, j) = (lane / NJ, lane % NJ) copies row j of columns
+    // c, c + CG, ...: a trip moves CG columns side by side.
+    const int pj = lane % NJ, pc = lane / NJ;
+    auto prefetch = [&](int ci, int c_r0, int c_ni, double* buf) {
         if (c_ni <= NJ) {
-            if (lane < c_ni) {
-                const int64_t row = c_r0 + lane;
-                double* r = buf + lane * W;
-                cp_async8(r + 0, d.y1 + row);
-                if (F::USES_Y2) cp_async8(r + 1, d.y2 + row);
-                if (!fused) {
-                    cp_async8(r + 2, d.xb + row);
-                    if (F::HAS_ZI) cp_async8(r + L::OFF_XG, d.xg + row);
-                } else {
-                    // design columns, column-major per cluster as in HBM: X | X_zi | offset | offset_zi
-                    double* xr = xbuf + lane;
-                    for (int l = 0; l < d.p; ++l) { cp_async8(xr, d.X + row + (int64_t)l * d.N); xr += NJ; }
-                    if (F::HAS_ZI)
-                        for (int l = 0; l < d.p_zi; ++l) { cp_async8(xr, d.X_zi + row + (int64_t)l * d.N); xr += NJ; }
-                    if (d.offset) { cp_async8(xr, d.offset + row); xr += NJ; }
-                    if (F::HAS_ZI && d.offset_zi) cp_async8(xr, d.offset_zi + row);
+            if (pj < c_ni && pc < FL::CG) {
+                for (int c = pc; c < ncols; c += FL::CG) {
+                    const ColEnt e = coltab[c];
+                    cp_async8(buf + e.off + pj * e.stride, e.base + c_r0 + pj);
                 }
-#pragma unroll
-                for (int dd = 0; dd < QY; ++dd) cp_async8(r + L::OFF_Z + dd, d.Z + row + (int64_t)dd * d.N);
-#pragma unroll
-                for (int dd = 0; dd < QZ; ++dd) cp_async8(r + L::OFF_Z + QY + dd, d.Z_zi + row + (int64_t)dd * d.N);
             }
-            double* sc = buf + NJ * W;
-            if (lane < FL::NSC) {
-                const double* src;
-                if (lane < SC_RI) src = d.modes + ci * Q + lane;
-                else if (lane < SC_LD) src = d.rinv + ci * NP + (lane - SC_RI);
-                else if (lane < SC_CS) src = d.logdet + ci;
-                else if (lane < SC_W) src = d.csum + ci * GLMMA_NCSUM + (lane - SC_CS);
-                else src = d.weights ? d.weights + ci : nullptr;
-                if (src) cp_async8(sc + lane, src);
-            }
+            if (lane < FL::NSC) cp_async8(buf + NJ * W + lane, d.clrec + ci * FL::NSC + lane);
         }
         cp_async_commit();
     };
 
-    const int64_t nwarps = (int64_t)gridDim.x * wpb;
-    const int64_t p0 = (int64_t)blockIdx.x * wpb + wib;
-    const int64_t n_pos = A.n_order;
+    // positions in the cluster list fit 32 bits (n < 2^31)
+    const int nwarps = (int)gridDim.x * wpb;
+    const int p0 = (int)blockIdx.x * wpb + wib;
+    const int n_pos = (int)A.n_order;
     const int4* __restrict__ order = A.order;
     // cluster id, first row and size of the current and the next cluster are kept in registers
     int4 cur = make_int4(0, 0, 0, 0), nxt = make_int4(0, 0, 0, 0);
     if (p0 < n_pos) {
         cur = order[p0];
-        prefetch(cur.x, cur.y, cur.z, pre0, xst0);
+        prefetch(cur.x, cur.y, cur.z, pre0);
     }
     if (p0 + nwarps < n_pos) nxt = order[p0 + nwarps];
     int pbuf = 0;
-    for (int64_t pos = p0; pos < n_pos; pos += nwarps) {
-        double* rec = pre0 + pbuf * FL::PRE;
-        const double* xcur = xst0 + pbuf * NJ * xw;
+    for (int pos = p0; pos < n_pos; pos += nwarps) {
+        double* rec = pre0 + pbuf * PRE;
+        const double* xcur = rec + FL::XOFF;
         const double* sc = rec + NJ * W;
         // rotate the pipeline and start the next cluster's copies
         const int64_t i = cur.x;      // 64-bit: i * K, i * Q ... index arrays of up to n * K elements
         const int64_t r0c = cur.y;
         const int nic = cur.z;
         cur = nxt;
-        const int64_t pnext = pos + nwarps, pnext2 = pos + 2 * nwarps;
+        // (pos + 2 nwarps may pass 2^31: compare the remaining distance instead)
         cp_async_wait_all();
         __syncwarp();
-        if (pnext < n_pos) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * FL::PRE, xst0 + (pbuf ^ 1) * NJ * xw);
-        if (pnext2 < n_pos) nxt = order[pnext2];
+        if (n_pos - pos > nwarps) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * PRE);
+        if (n_pos - pos > 2 * nwarps) nxt = order[pos + 2 * nwarps];
         pbuf ^= 1;
         if (nic > NJ) {
             if (lane == 0) d.defer[i] = 1;
@@ -1118,8 +1177,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         for (int dd = 0; dd < Q; ++dd) m[dd] = sc[SC_M + dd];
 #pragma unroll
         for (int t = 0; t < NP; ++t) ri[t] = GLMMA_SQRT2 * sc[SC_RI + t];
-        // Lane j < n_i owns observation j: stages its record, forms the coefficients of its
-        // separable factors  exp(eta_jk) = prod_e exp(c_je x_{a_e(k)} + [e == 0] base_j)
+        // Lane j < n_i owns observation j: forms xb (xg) from the staged design columns, stages its
+        // record, forms the coefficients of its separable factors
+        //   exp(eta_jk) = prod_e exp(c_je x_{a_e(k)} + [e == 0] base_j)
         // and tests the range of eta (and eta_zi) over the whole grid: every factor is monotone in
         // its node, so the extremes are base -+ sum_e |c_e| x_max.  Outside the fast range (a link
         // clamp could be active, or a factor / fast_log_rcp argument could leave its range) the
@@ -1135,34 +1195,19 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (lane < nic) {
             double* r = rec + lane * W;
             if (!F::USES_Y2) r[1] = 0.0;
-            if (fused) {
-                // xb = X beta + offset, xg = X_zi gamma + offset_zi from the staged design columns
+            {
                 const double* xr = xcur + lane;
-                const int ncol = d.p + (F::HAS_ZI ? d.p_zi : 0);
-                double xb = d.offset ? xr[ncol * NJ] : 0.0;
-                for (int l = 0; l < d.p; ++l) xb = fma(xr[l * NJ], A.coef.betas[l], xb);
+                double xb = has_off ? xr[(p_x + p_z) * NJ] : 0.0;
+                for (int l = 0; l < p_x; ++l) xb = fma(xr[l * NJ], A.coef.betas[l], xb);
                 r[2] = xb;
                 if (F::HAS_ZI) {
-                    double xg = d.offset_zi ? xr[(ncol + (d.offset ? 1 : 0)) * NJ] : 0.0;
-                    for (int l = 0; l < d.p_zi; ++l) xg = fma(xr[(d.p + l) * NJ], A.coef.gammas[l], xg);
+                    double xg = has_offz ? xr[(p_x + p_z + (has_off ? 1 : 0)) * NJ] : 0.0;
+                    for (int l = 0; l < p_z; ++l) xg = fma(xr[(p_x + l) * NJ], A.coef.gammas[l], xg);
                     r[L::OFF_XG] = xg;
                 }
-                // node-independent terms of log f and d log f / d phis: from the y table by an
-                // asynchronous copy (consumed after the rounds), else computed out of line
-                const double y1 = r[0];
-                double* st = stash + 4 * lane;
-                st[2] = y1 * xb;
-                bool tab = false;
-                if (F::Y_TABLE && A.ytab != nullptr) {
-                    const int iy = (int)y1;
-                    if (y1 >= 0.0 && y1 < (double)GLMMA_YTAB && (double)iy == y1) {
-                        cp_async16(st, A.ytab + 2 * iy);
-                        tab = true;
-                    }
-                }
-                if (!tab) obs_const_slow<F>(y1, r[1], A.fam, st);
             }
             F::stage(r[0], r[1], A.fam);
+            if (F::FAST_KIND == 1) wv[lane] = r[1];
             const double xmax = gx[0];
             if (F::NEED_EMU) {
                 double base = r[2], amp = 0.0;
@@ -1212,29 +1257,46 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 if (!(base - amp >= -667.0 && base + amp <= 667.0)) bad = true;
             }
         }
-        if (fused) cp_async_commit();
         bad = __any_sync(0xffffffffu, bad);
         __syncwarp();                              // coefficient stores -> table-building reads
+        const double w = sc[SC_W];
+        // A cluster that leaves the sums (left to eval_kernel here, or dropped as non-finite below) takes
+        // back its share of the node-independent terms, which const_sums_kernel / beta' X'y1 added for
+        // every cluster of this variant; with ll_i the same terms complete the cluster's contribution.
+        auto cluster_consts = [&](double& s_ll, double& s_phi) {
+            double2 cc = make_double2(0.0, 0.0);
+            if (lane < nic) {
+                const int64_t row = r0c + lane;
+                cc = obs_consts_rare<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, rec[lane * W + 2], A.fam, A.ytab);
+            }
+            s_ll = warp_sum(cc.x);
+            s_phi = warp_sum(cc.y);
+        };
         if (lane == 0) d.defer[i] = bad ? 1 : 0;
         if (bad) {
-            if (fused) {
-                // eval_kernel takes this cluster from the work arrays the prep kernel would have written
-                cp_async_wait_all();
-                if (lane < nic) {
-                    const int64_t row = r0c + lane;
-                    const double* r = rec + lane * W;
-                    d.xb[row] = r[2];
-                    if (F::HAS_ZI) d.xg[row] = r[L::OFF_XG];
-                    d.cll[row] = stash[4 * lane];
-                    if (F::HAS_PHI) d.cphi[row] = stash[4 * lane + 1];
-                }
-                __syncwarp();
+            // eval_kernel takes this cluster from the work arrays the prep kernel would have written
+            double s_ll, s_phi;
+            cluster_consts(s_ll, s_phi);
+            if (lane < nic) {
+                const int64_t row = r0c + lane;
+                const double* r = rec + lane * W;
+                double cll, cphi;
+                obs_const_tab<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, A.fam, A.ytab, cll, cphi);
+                d.xb[row] = r[2];
+                if (F::HAS_ZI) d.xg[row] = r[L::OFF_XG];
+                d.cll[row] = cll;
+                if (F::HAS_PHI) d.cphi[row] = cphi;
             }
+            if (lane == 0) {
+                if (A.em_mode != 2) tots[0] -= w * s_ll;
+                if (F::HAS_PHI) tots[3] -= w * s_phi;
+            }
+            __syncwarp();
             continue;
         }
         // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
         // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
-        // test above
+        // test above.  Entry (observation j, dimension e, node index a) goes to row e * NG + a, column j.
         {
             const unsigned inv_nagq = (65536u + (unsigned)nagq - 1u) / (unsigned)nagq;
             if (F::NEED_EMU) {
@@ -1249,7 +1311,8 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         const int na = t - p * nagq;
                         const double2 cb = coef[p];
                         x3[u] = fma(cb.x, gx[na], cb.y);
-                        off[u] = p * NG + na;
+                        const int pj_ = p / Q, pe_ = p - pj_ * Q;
+                        off[u] = (pe_ * NG + na) * RP + pj_;
                     }
                     fast_exp_vec<3>(x3, cx, o3);
 #pragma unroll
@@ -1270,7 +1333,8 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         const int na = t - p * nz;
                         const double2 cb = coef[NJ * Q + p];
                         x3[u] = fma(cb.x, QZ > 0 ? gx[na] : 0.0, cb.y);
-                        off[u] = p * NG + na;
+                        const int pj_ = p / NTc, pe_ = p - pj_ * NTc;
+                        off[u] = (pe_ * NG + na) * RP + pj_;
                     }
                     fast_exp_vec<3>(x3, cx, o3);
 #pragma unroll
@@ -1287,17 +1351,15 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 const int j = (int)(((unsigned)t * inv_nz) >> 16);
                 const int na = t - j * nz;
                 double l1p, pi;
-                fast_l1p_sigmoid<false>(tabL[j * FL::TL + na], cx, l1p, pi);
+                fast_l1p_sigmoid<false>(tabL[na * RP + j], cx, l1p, pi);
                 tabZ[j * NG + na] = make_double2(l1p, pi);
             }
             __syncwarp();
         }
 
-        const double* cs = sc + SC_CS;
-        const double syxb = (F::LIN_ETA && !fused) ? cs[2] : 0.0;     // fused: y1 xb joins the per-lane terms below
         double zty[QY];
 #pragma unroll
-        for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? cs[3 + dd] : 0.0;
+        for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? sc[SC_ZTY + dd] : 0.0;
 
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
@@ -1347,16 +1409,17 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 double a = fma(-0.5, quad, A.prior.logprior_const) + nt[Q];
                 const double* pf[Q];
 #pragma unroll
-                for (int e = 0; e < Q; ++e) pf[e] = tabF + e * NG + ((packed >> (8 * e)) & 0xff);
+                for (int e = 0; e < Q; ++e) pf[e] = tabF + (e * NG + ((packed >> (8 * e)) & 0xff)) * RP;
                 const double* pl[QZ > 0 ? QZ : 1];
 #pragma unroll
                 for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e)
-                    pl[e] = tabL + e * NG + (QZ > 0 ? ((packed >> (8 * (QY + e))) & 0xff) : 0);
+                    pl[e] = tabL + (e * NG + (QZ > 0 ? ((packed >> (8 * (QY + e))) & 0xff) : 0)) * RP;
                 const double2* pz = tabZ + (QZ > 0 ? ((packed >> (8 * QY)) & 0xff) : 0);
                 double vphi = 0.0;
                 double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
                 if (F::LIN_ETA) {
-                    a += syxb;
+                    // sum_j y1_j eta_jk = sum_j y1_j xb_j + (Z'y1) . b_k: the first term does not depend on
+                    // the node -- it is added to the log-likelihood once per evaluation (beta' X'y1)
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd) a = fma(zty[dd], b[dd], a);
                 }
@@ -1367,15 +1430,15 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         _Pragma("unroll") for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);     \
         double ez = 0.0, emu = 0.0, elam = 0.0;                                                        \
         if (F::NEED_EMU) {                                                                             \
-            emu = pf[0][(j) * FL::TF];                                                                 \
-            _Pragma("unroll") for (int e = 1; e < Q; ++e) emu *= pf[e][(j) * FL::TF];                   \
+            emu = pf[0][(j)];                                                                 \
+            _Pragma("unroll") for (int e = 1; e < Q; ++e) emu *= pf[e][(j)];                   \
         }                                                                                              \
         if (F::HAS_ZI) {                                                                               \
             ez = rj[L::OFF_XG];                                                                        \
             _Pragma("unroll") for (int dd = 0; dd < QZ; ++dd)                                           \
                 ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);                                      \
-            elam = pl[0][(j) * FL::TL];                                                                \
-            _Pragma("unroll") for (int e = 1; e < QZ; ++e) elam *= pl[e][(j) * FL::TL];                 \
+            elam = pl[0][(j)];                                                                \
+            _Pragma("unroll") for (int e = 1; e < QZ; ++e) elam *= pl[e][(j)];                 \
         }                                                                                              \
         double ld, se, sz, sp;                                                                         \
         if (ZT) {                                                                                      \
@@ -1399,27 +1462,39 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     auto chunk = [&](const int c4, auto full_tag) {
                         constexpr bool FULL = decltype(full_tag)::value;
                         double t4[4], L4[4], r4[4];
+                        // the chunk's factors: the tables keep the observations of one (dimension, node
+                        // index) contiguous, so two 16-byte loads per table serve four observations
+                        double fq[Q][4];
+#pragma unroll
+                        for (int e = 0; e < Q; ++e) {
+                            const double2 f01 = *reinterpret_cast<const double2*>(pf[e] + 4 * c4);
+                            const double2 f23 = *reinterpret_cast<const double2*>(pf[e] + 4 * c4 + 2);
+                            fq[e][0] = f01.x; fq[e][1] = f01.y; fq[e][2] = f23.x; fq[e][3] = f23.y;
+                        }
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
                             const int j = 4 * c4 + jj;
-                            double pr = pf[0][j * FL::TF];
+                            double pr = fq[0][jj];
 #pragma unroll
-                            for (int e = 1; e < Q - 1; ++e) pr *= pf[e][j * FL::TF];
+                            for (int e = 1; e < Q - 1; ++e) pr *= fq[e][jj];
                             if (F::FAST_KIND == 1)
-                                t4[jj] = Q > 1 ? fma(pr, pf[Q - 1][j * FL::TF], F::fast_addend(A.fam)) : pr + F::fast_addend(A.fam);
+                                t4[jj] = Q > 1 ? fma(pr, fq[Q - 1][jj], F::fast_addend(A.fam)) : pr + F::fast_addend(A.fam);
                             else
-                                t4[jj] = Q > 1 ? pr * pf[Q - 1][j * FL::TF] : pr;
+                                t4[jj] = Q > 1 ? pr * fq[Q - 1][jj] : pr;
                             // rows past the cluster's end hold stale table entries: keep the argument of
                             // the unchecked log in range (their results are discarded below)
                             if (!FULL && j >= nic) t4[jj] = 1.0;
                         }
                         if (F::FAST_KIND == 1) {
                             fast_log_rcp_vec<4>(t4, cx, L4, r4);
+                            const double2 w01 = *reinterpret_cast<const double2*>(wv + 4 * c4);
+                            const double2 w23 = *reinterpret_cast<const double2*>(wv + 4 * c4 + 2);
+                            const double w4[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
                                 const int j = 4 * c4 + jj;
                                 const bool on = FULL || j < nic;
-                                const double wj = on ? rec[j * W + 1] : 0.0;
+                                const double wj = on ? w4[jj] : 0.0;
                                 if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
                                 if (SCORE) {
                                     se_[j] = on ? r4[jj] : 0.0;
@@ -1474,8 +1549,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 #undef GLMMA_FAST_OBS
                 if (valid) amax = fmax(amax, a);
                 if (rr == 0 && attempt == 0) {
-                    shift = warp_max(valid ? a : -INFINITY);
-                    if (!(fabs(shift) < INFINITY)) shift = 0.0;
+                    // any value near the maximum will do as the shift: single precision (a NaN or an
+                    // infinite a gives shift 0; the retry below then takes the true maximum)
+                    float sf = valid ? (float)a : -INFINITY;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sf = fmaxf(sf, __shfl_xor_sync(0xffffffffu, sf, o));
+                    shift = fabsf(sf) < INFINITY ? (double)sf : 0.0;
                 }
                 double e = valid ? fast_exp(a - shift, cx) : 0.0;
                 if (A.em_mode) {             // EM phase: store (E-step) / replace (M-step) the node weights
@@ -1505,35 +1584,25 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
             shift = mx;
         }
-        const double w = d.weights ? sc[SC_W] : 1.0;
         double lsum, isum;
         fast_log_rcp<true>(sum_e, cx, lsum, isum);
-        // fused mode: lane j holds observation j's node-independent terms (c_ll_j + y1_j xb_j, c_phi_j);
-        // they are added per lane, not per cluster (no reduction: the cluster's sum is only needed
-        // for the per-cluster contributions)
-        double cl = 0.0, cph = 0.0;
-        if (fused) {
-            cp_async_wait_all();
-            if (lane < nic) {
-                const double* st = stash + 4 * lane;
-                cl = F::LIN_ETA ? st[0] + st[2] : st[0];
-                cph = st[1];
-            }
-        }
-        const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD] + (fused ? 0.0 : cs[0]);
-        bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
-        if (fused && A.em_mode != 2) ok = __all_sync(0xffffffffu, ok && fabs(cl) < INFINITY);
+        // node-independent terms are not part of ll here (added once per evaluation, see the header)
+        const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD];
+        const bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
         if (A.em_mode == 1 && !ok)
             for (int k = lane; k < K; k += 32) A.pby[i * K + k] = 0.0;
         if (lane == 0) {
             if (ok) { tots[0] += w * ll; tots[1] += w; } else tots[2] += 1.0;
-            if (d.ll_i && !fused) d.ll_i[i] = w * ll;
         }
-        if (fused) {
-            if (ok && A.em_mode != 2) totc[lane] = fma(w, cl, totc[lane]);
-            if (d.ll_i) {
-                const double s = warp_sum(cl);
-                if (lane == 0) d.ll_i[i] = w * (ll + s);
+        if (!ok || d.ll_i != nullptr) {
+            double s_ll, s_phi;
+            cluster_consts(s_ll, s_phi);
+            if (lane == 0) {
+                if (!ok) {
+                    if (A.em_mode != 2) tots[0] -= w * s_ll;
+                    if (F::HAS_PHI) tots[3] -= w * s_phi;
+                }
+                if (d.ll_i) d.ll_i[i] = w * (ll + s_ll);
             }
         }
         if (SCORE) {
@@ -1543,12 +1612,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     // second term of the phi-score, sum_k e_k sum_j rec1_j r_jk, from the carrier sums
 #pragma unroll
                     for (int j = 0; j < NJ; ++j)
-                        if (j < nic) gphi = fma(rec[j * W + 1], acc_e[j], gphi);
+                        if (j < nic) gphi = fma(wv[j], acc_e[j], gphi);
                 }
-                double g = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
-                if (fused) { if (ok) g = fma(w, cph, g); }
-                else if (lane == 0 && ok) g = fma(w, cs[1], g);
-                totl[lane] = g;
+                totl[lane] = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
             }
 #pragma unroll
             for (int t = 0; t < NP; ++t) totl[(2 + t) * 32 + lane] = fma(inv, S[t], totl[(2 + t) * 32 + lane]);
@@ -1595,32 +1661,29 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 }
                 double zb = 0.0, zz = 0.0;
                 if (lane < nic) {
-                    const double sc = F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
-                                                        : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
-                    zb = ok ? w * sc : 0.0;
+                    const double scv = F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
+                                                         : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                    zb = ok ? w * scv : 0.0;
                     if (F::HAS_ZI) zz = inv * s2;
-                    if (!fused || A.zbar_out) {
+                    if (A.zbar_out) {
                         d.zbar[r0c + lane] = zb;
                         if (F::HAS_ZI) d.zbar_zi[r0c + lane] = zz;
                     }
                 }
-                if (fused) {
-                    // X'zbar (and X_zi'zbar_zi): lane l owns column l; the posterior-mean scores of the
-                    // cluster's observations pass through the (now free) accumulator scratch
-                    __syncwarp();
-                    if (lane < NJ) {
-                        acc_eta[lane] = zb;
-                        if (F::HAS_ZI) acc_zi[lane] = zz;
-                    }
-                    __syncwarp();
-                    const int ncol = d.p + (F::HAS_ZI ? d.p_zi : 0);
-                    if (lane < ncol) {
-                        const double* xc = xcur + lane * NJ;
-                        const double* zs = (F::HAS_ZI && lane >= d.p) ? acc_zi : acc_eta;
+                // X'zbar (and X_zi'zbar_zi): lane l owns column l; the posterior-mean scores of the
+                // cluster's observations pass through the (now free) accumulator scratch
+                __syncwarp();
+                if (lane < NJ) {
+                    acc_eta[lane] = zb;
+                    if (F::HAS_ZI) acc_zi[lane] = zz;
+                }
+                __syncwarp();
+                if (lane < p_x + p_z) {
+                    const double* xc = xcur + lane * NJ;
+                    const double* zs = (F::HAS_ZI && lane >= p_x) ? acc_zi : acc_eta;
 #pragma unroll
-                        for (int jj = 0; jj < NJ; ++jj)
-                            if (jj < nic) gcol = fma(xc[jj], zs[jj], gcol);
-                    }
+                    for (int jj = 0; jj < NJ; ++jj)
+                        if (jj < nic) gcol = fma(xc[jj], zs[jj], gcol);
                 }
             }
         }
@@ -1631,32 +1694,58 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     __syncwarp();
     {
         // per-warp totals: [0] loglik [1] sum_w [2] n_nonfinite [3] g_phi [4..] S
-        double v3 = warp_sum(totl[lane]);
-        const double vc = warp_sum(totc[lane]);
+        const double v3 = warp_sum(totl[lane]);
         double vs[NP];
 #pragma unroll
         for (int t = 0; t < NP; ++t) vs[t] = warp_sum(totl[(2 + t) * 32 + lane]);
-        __syncwarp();
-        if (lane == 0) {
-            tots[3] = v3;      // tots has 4 slots: reuse the pad for g_phi
-        }
         __syncthreads();
         double* red = smem;    // wpb * PSTRIDE doubles (fastmath tables are no longer needed)
         if (lane == 0) {
-            red[wib * GLMMA_PSTRIDE + 0] = tots[0] + vc;
+            red[wib * GLMMA_PSTRIDE + 0] = tots[0];
             red[wib * GLMMA_PSTRIDE + 1] = tots[1];
             red[wib * GLMMA_PSTRIDE + 2] = tots[2];
-            red[wib * GLMMA_PSTRIDE + 3] = v3;
+            red[wib * GLMMA_PSTRIDE + 3] = v3 + tots[3];       // tots[3]: phi-score terms taken back on the rare paths
 #pragma unroll
             for (int t = 0; t < GLMMA_NPACK; ++t) red[wib * GLMMA_PSTRIDE + 4 + t] = t < NP ? vs[t] : 0.0;
         }
-        red[wib * GLMMA_PSTRIDE + GLMMA_NACC + lane] = gcol;     // column `lane` of X'zbar | X_zi'zbar_zi (fused)
+        red[wib * GLMMA_PSTRIDE + GLMMA_NACC + lane] = gcol;     // column `lane` of X'zbar | X_zi'zbar_zi
         __syncthreads();
         if (threadIdx.x < GLMMA_PSTRIDE) {
             double v = 0.0;
             for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_PSTRIDE + threadIdx.x];
             A.partials[(int64_t)blockIdx.x * GLMMA_PSTRIDE + threadIdx.x] = v;
         }
+    }
+}
+
+// Node-independent terms of one evaluation for the clusters of the register variant:
+//   partial[b] = { sum_rows w_row c_ll(row), sum_rows w_row c_phi(row) }
+// over the rows whose weight is non-zero (roww: the cluster weight, 0 for the rows of clusters that
+// belong to eval_kernel; null: every row with weight 1).  One memory-bound pass over y (8 or 16 bytes
+// per observation), fixed-order block sums; finalize_block adds the partials.
+#define GLMMA_CONST_THREADS 256
+template <class F>
+__global__ void __launch_bounds__(GLMMA_CONST_THREADS) const_sums_kernel(DevData d, FamPar fam, const double* ytab,
+                                                                         const double* roww, double* partials) {
+    __shared__ double sh[2][GLMMA_CONST_THREADS / 32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < d.N; row += (int64_t)gridDim.x * blockDim.x) {
+        const double w = roww ? roww[row] : 1.0;
+        if (w == 0.0) continue;
+        double cll, cphi;
+        obs_const_tab<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, fam, ytab, cll, cphi);
+        s0 = fma(w, cll, s0);
+        if (F::HAS_PHI) s1 = fma(w, cphi, s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wi] = s0; sh[1][wi] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double v = 0.0;
+        for (int t = 0; t < GLMMA_CONST_THREADS / 32; ++t) v += sh[threadIdx.x][t];
+        partials[2 * blockIdx.x + threadIdx.x] = v;
     }
 }
 
@@ -2006,6 +2095,64 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
         atomicAdd(&A.stats[2], (unsigned long long)iters);
         atomicMax(&A.stats[3], (unsigned long long)iters);
     }
+}
+
+// ------------------------------------------------------------------------------
+// log_post_b of predict()'s Metropolis step (R/methods.R:1020-1036, evaluated there per proposal
+// and per cluster by mapply): one proposal b_i per cluster, 8 lanes per cluster,
+//   out_i = sum_j log f(y_ij | eta_ij(b_i)) (na.rm) - b_i' invD b_i / 2.
+// b_in is n x q column-major (R's matrix of proposals, one row per cluster).
+// ------------------------------------------------------------------------------
+template <class F, int QY, int QZ>
+__global__ void __launch_bounds__(128) log_post_b_kernel(ModeArgs A, const double* b_in, double* out) {
+    constexpr int Q = QY + QZ;
+    constexpr int G = 8;
+    const DevData& d = A.d;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = gtid / G;
+    const int lg = (int)(gtid % G);
+    const int lane = threadIdx.x & 31;
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
+    __shared__ double fmtab[GLMMA_FM_DOUBLES];
+    load_fmtab(fmtab, A.fmtab);
+    __syncthreads();
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
+    const bool live = i < d.n;
+    const int64_t r0 = live ? d.row_ptr[i] : 0;
+    const int ni = live ? (int)(d.row_ptr[i + 1] - r0) : 0;
+    double x[Q], g[Q], f;
+#pragma unroll
+    for (int dd = 0; dd < Q; ++dd) x[dd] = live ? b_in[i + (int64_t)dd * d.n] : 0.0;
+    mode_objective<F, QY, QZ, G, false>(d, A.prior, A.fam, r0, ni, lg, gmask, cx, x, f, g);
+    // node-independent parts of log f (prep kernel), dropped with the observation's density when NaN
+    double c = 0.0;
+    for (int j = lg; j < ni; j += G) {
+        const double v = d.cll[r0 + j];
+        if (v == v) c += v;
+    }
+    c = group_sum<G>(c, gmask);
+    if (live && lg == 0) out[i] = c - f;
+}
+
+// ------------------------------------------------------------------------------
+// Per-cluster record of the register variant (FastLayout::NSC doubles per cluster: modes, R^-1,
+// logdet, Z'y1, weight), packed after every change of the grid so that the kernel's prefetch is one
+// contiguous copy per cluster instead of five gathers.
+// ------------------------------------------------------------------------------
+template <int QY, int QZ>
+__global__ void pack_cluster_kernel(DevData d) {
+    constexpr int Q = QY + QZ, NP = Q * (Q + 1) / 2, NSC = Q + NP + 1 + QY + 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.n) return;
+    double* r = d.clrec + i * NSC;
+#pragma unroll
+    for (int t = 0; t < Q; ++t) r[t] = d.modes[i * Q + t];
+#pragma unroll
+    for (int t = 0; t < NP; ++t) r[Q + t] = d.rinv[i * NP + t];
+    r[Q + NP] = d.logdet[i];
+#pragma unroll
+    for (int t = 0; t < QY; ++t) r[Q + NP + 1 + t] = d.csum[i * GLMMA_NCSUM + 3 + t];
+    r[Q + NP + 1 + QY] = d.weights ? d.weights[i] : 1.0;
 }
 
 // ------------------------------------------------------------------------------

@@ -22,6 +22,10 @@ struct OpsImpl {
     static void ytab(const FamPar& fam, double* tab, cudaStream_t s) {
         if (F::Y_TABLE) ytab_kernel<F><<<GLMMA_YTAB / 256, 256, 0, s>>>(fam, tab);
     }
+    static void consts(const DevData& d, const FamPar& fam, const double* tab, const double* roww, double* partials,
+                       int blocks, cudaStream_t s) {
+        const_sums_kernel<F><<<blocks, GLMMA_CONST_THREADS, 0, s>>>(d, fam, F::Y_TABLE ? tab : nullptr, roww, partials);
+    }
     static void prep(const PrepArgs& a, const CoefPar& c, cudaStream_t s) {
         if (a.d.csum) {
             const int64_t ncl = a.list ? a.n_list : a.d.n;
@@ -105,12 +109,20 @@ struct OpsImpl {
         else if (G == 8) modes_kernel<F, QY, QZ, 8><<<blocks, 128, 0, s>>>(a);
         else modes_kernel<F, QY, QZ, 32><<<blocks, 128, 0, s>>>(a);
     }
+    static void logpost(const ModeArgs& a, const double* b, double* out, cudaStream_t s) {
+        const unsigned blocks = (unsigned)((a.d.n * 8 + 127) / 128);
+        log_post_b_kernel<F, QY, QZ><<<blocks, 128, 0, s>>>(a, b, out);
+    }
+    static void pack(const DevData& d, cudaStream_t s) {
+        const unsigned blocks = (unsigned)((d.n + 127) / 128);
+        pack_cluster_kernel<QY, QZ><<<blocks, 128, 0, s>>>(d);
+    }
     static void rinv(const DevData& d, cudaStream_t s) {
         const unsigned blocks = (unsigned)((d.n + 127) / 128);
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {ytab, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, rinv, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE};
+        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA};
         return &ops;
     }
 };

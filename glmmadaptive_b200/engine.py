@@ -283,6 +283,15 @@ class Engine:
                                             int(beta is None), _dp(b), _dp(out)))
         return out
 
+    def log_post_b(self, b, betas, invD, phis=None, gammas=None):
+        """log_post_b of predict()'s Metropolis step (R/methods.R:1020-1036) for one random-effects
+        vector per cluster: b is n x q; returns the n values sum_j log f(y_ij | b_i) - b_i' invD b_i / 2."""
+        b = _f(np.asarray(b, float).reshape(self.n, self.q))
+        keep, ptrs = self._theta_ptrs(betas, invD, phis, gammas)
+        out = np.zeros(self.n)
+        self._check(self.lib.glmma_log_post_b(self._h, _dp(b), *ptrs, _dp(out)))
+        return out
+
     def time_eval(self, betas, D, phis=None, gammas=None, want_score=True, iters=10):
         keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
         a, b = C.c_float(), C.c_float()

@@ -131,6 +131,9 @@ class ShardedEngine:
         if self.reduce_on_host:
             r = self._reduce_host(self.local.eval_raw(betas, D, phis, gammas, want_score))
             return self.local.unpack(r, want_score)
+        if self.dist is None:
+            # one rank: the plain C-ABI call (glmma_eval: host theta in, host result vector out)
+            return self.local.unpack(self.local.eval_raw(betas, D, phis, gammas, want_score), want_score)
         buf = self.eval_enqueue(betas, D, phis, gammas, want_score)
         return self.local.unpack(buf.cpu().numpy(), want_score)
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLMMA_VERSION 140
+#define GLMMA_VERSION 200
 
 #if defined(__GNUC__)
 #define GLMMA_API __attribute__((visibility("default")))
@@ -241,6 +241,16 @@ GLMMA_API int glmma_em_score(glmma_handle* h, const double* betas, const double*
  * sharded fit all-reduce `out` before solving. */
 GLMMA_API int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset,
                    int first, const double* beta, double* out);
+
+/* log_post_b of predict(type = "subject_specific", se.fit = TRUE)'s Metropolis step
+ * (reference R/methods.R:1020-1036, called there through mapply once per cluster for the current and
+ * once for the proposed random effects of every Monte-Carlo draw, :1093-1112): for ONE vector b_i per
+ * cluster, b an n x q column-major matrix,
+ *   out[i] = sum_j log f(y_ij | X_ij betas + Z_ij b_i[1:q_y], phis, X_zi,ij gammas + Z_zi,ij b_i[-(1:q_y)])
+ *            - b_i' invD b_i / 2            (non-finite log-density terms dropped: na.rm = TRUE)
+ * at the given (betas, invD, phis, gammas) -- the parameter draw of that Monte-Carlo iteration. */
+GLMMA_API int glmma_log_post_b(glmma_handle* h, const double* b, const double* betas, const double* invD,
+                     const double* phis, const double* gammas, double* out);
 
 /* ---- measurement helpers (bench.py; not part of the reference seam) ----- */
 

@@ -24,7 +24,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.load().glmma_version() == 140
+    assert _lib.load().glmma_version() == 200
 
 
 def test_family_ids_match_reference_strings():

@@ -214,3 +214,21 @@ def test_engine_reproduces_published_family_fits(name):
     fit = gb.mixed_model(d["y"], d["X"], d["Z"], d["id"], k["family"], X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"),
                          control=dict(nAGQ=k["nAGQ"]), hessian=False)
     check_family_fit(k, fit, newton=True)
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "C4", "C5a"])
+def test_log_post_b_batch_vs_oracle(name):
+    """glmma_log_post_b: log_post_b of predict()'s Metropolis step (R/methods.R:1020-1036) for one
+    proposal per cluster, against the oracle's restatement of the closure (relative 1e-10)."""
+    d, th, fam_name = _case(name, 35)
+    fam = oracle_family(fam_name)
+    od = oracle_data(d)
+    rng = np.random.default_rng(3)
+    b = rng.normal(0, 0.6, size=(od.n, od.nRE))
+    invD = np.linalg.inv(th["D"])
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"))
+    got = eng.log_post_b(b, th["betas"], invD, th.get("phis"), th.get("gammas"))
+    ref = np.array([-agq.make_log_post(od, fam, i, th["betas"], invD, th.get("phis"), th.get("gammas"))[0](b[i])
+                    for i in range(od.n)])
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-10
+    eng.close()
