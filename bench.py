@@ -427,7 +427,7 @@ def run_ours(args):
             mN, _, _ = many.get_modes()
             err = float(np.max(np.abs(rN - r1_) / np.maximum(1.0, np.abs(r1_))))
             multi_check = {"devices": ndev, "clusters": 3000, "max_rel_diff_vs_single_device": err,
-                           "modes_max_abs_diff": float(np.max(np.abs(mN - m_))), "ok": bool(err < 1e-13),
+                           "modes_max_abs_diff": float(np.max(np.abs(mN - m_))), "ok": bool(err < 1e-11),
                            "not_converged": int(stN["n_not_converged"]),
                            "what": "glmma_create_multi handle over all visible GPUs in ONE process vs a single-device "
                                    "engine: same grid (set_modes), glmma_eval result vector; then its own mode search"}

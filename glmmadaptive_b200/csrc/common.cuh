@@ -16,6 +16,23 @@
 #define GLMMA_FOLD_COLS 32
 #define GLMMA_PSTRIDE (GLMMA_NACC + GLMMA_FOLD_COLS)     // doubles per block partial (every mode)
 
+// Cluster-sharded evaluation over several processes (one per GPU): the ranks' result vectors are
+// exchanged through peer memory by the finalising block itself (kernels.cuh: exchange_block).
+#define GLMMA_MAX_RANKS 16
+#define GLMMA_XSLOT 128        // doubles per (parity, rank) slot: the result vector, flag in the last one
+struct XchgPar {
+    double* peer[GLMMA_MAX_RANKS];   // every rank's exchange buffer as mapped into THIS process (peer[rank]: our own)
+    int rank, nranks;                // nranks <= 1: no exchange
+    unsigned long long seq;          // evaluation counter, identical on all ranks (they evaluate in lockstep)
+};
+
+// zero-copy delivery of the result vector into pinned host memory (kernels.cuh: deliver_host)
+struct HostOut {
+    double* vec;                          // device-side address of the pinned host vector (null: not used)
+    unsigned long long* flag;             // raised to `seq` after the vector is complete
+    unsigned long long seq;
+};
+
 #define GLMMA_DBL_EPS 2.220446049250313e-16
 #define GLMMA_INV_DBL_EPS 4503599627370496.0
 #define GLMMA_LOG_DBL_EPS (-36.04365338911715)   // log(.Machine$double.eps)

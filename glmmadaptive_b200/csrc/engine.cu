@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -96,6 +97,14 @@ struct glmma_handle {
                                // (null: every row counts once) -- const_sums_kernel
     double* d_cpart;           // const_sums_kernel block partials
     int n_cpart;
+    // peer-memory all-reduce over the ranks of a sharded job (glmma_comm_export / glmma_comm_connect)
+    double* d_xchg;            // 2 (parity) x nranks x GLMMA_XSLOT doubles, exported to the other ranks
+    XchgPar xchg;              // the ranks' buffers as mapped here; nranks <= 1: not connected
+    std::vector<void*> ipc_opened;
+    // zero-copy result delivery (kernels.cuh: deliver_host): pinned, device-mapped host memory
+    double* h_out;             // result vector + flag (last slot), host address
+    double* h_out_dev;         // the same memory as the device sees it
+    unsigned long long out_seq;
     std::vector<double> xty_w; // sum_i w_i X_i'y1_i over the register variant's clusters (linear-eta hoist)
     double yoff_w;             // sum_i w_i y1_i'offset_i over the same clusters
     bool ytab_valid;           // d_ytab holds the table of ytab_phis
@@ -277,10 +286,10 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_reduce_kernel(DevData d, 
 __global__ void __launch_bounds__(FINAL_THREADS) finalize_kernel(const double* eval_partials, int n_eval_blocks,
                                                                   const double* score_partials, int n_score_blocks,
                                                                   int p, int n_phis, int p_zi, int q, int want_score,
-                                                                  double* result) {
+                                                                  double* result, XchgPar xchg, HostOut hout) {
     __shared__ double sh[GLMMA_NACC + GLMMA_PMAX + GLMMA_PZIMAX + 2];
     finalize_block(eval_partials, n_eval_blocks, score_partials, n_score_blocks, false, p, n_phis, p_zi, q, want_score,
-                   result, sh);
+                   result, sh, nullptr, 0, 0.0, true, &xchg, &hout);
 }
 
 // ------------------------------------------------------------------------------
@@ -461,6 +470,9 @@ void glmma_destroy(glmma_handle* h) {
     if (h->h_stats) cudaFreeHost(h->h_stats);
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->d_xchg) cudaFree(h->d_xchg);
     for (void* p : h->allocs) cudaFree(p);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
@@ -531,6 +543,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->d_pby = nullptr; h->have_pby = false;
     h->fused = false; h->xw = 0; h->d_defer_list = nullptr; h->n_defer_list = 0; h->d_counter = nullptr;
     h->d_roww = nullptr; h->d_cpart = nullptr; h->n_cpart = 0; h->yoff_w = 0.0;
+    h->d_xchg = nullptr; std::memset(&h->xchg, 0, sizeof(h->xchg));
+    h->h_out = nullptr; h->h_out_dev = nullptr; h->out_seq = 0;
     h->ytab_valid = false; h->ytab_phis = 0.0;
     for (int v = 0; v < 3; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
     for (auto& e : h->ev) e = nullptr;
@@ -721,12 +735,18 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                     TRY(dev_upload(h, &tmp, too_big.data(), too_big.size()));
                     h->d_defer_list = const_cast<int32_t*>(tmp);
                 }
-                std::vector<double> cs((size_t)n * GLMMA_NCSUM, 0.0);
-                for (int64_t i = 0; i < n; ++i)
-                    for (int64_t r = row_ptr[i]; r < row_ptr[i + 1]; ++r)
-                        for (int dd = 0; dd < d.q_y; ++dd)
-                            cs[(size_t)i * GLMMA_NCSUM + 3 + dd] = std::fma(y1[r], data->Z[r + (int64_t)dd * N], cs[(size_t)i * GLMMA_NCSUM + 3 + dd]);
-                cudaMemcpyAsync(d.csum, cs.data(), sizeof(double) * cs.size(), cudaMemcpyHostToDevice, h->stream);
+                // Z'y1 of the linear-eta hoist is data, not theta: one pass of the prep kernel with zero
+                // coefficients fills it (the same kernel -- hence the same summation order -- that a mode
+                // search's prep pass uses, so an engine whose grid was injected evaluates bit-identically to
+                // one that searched for it; its theta-dependent outputs are rewritten before any use)
+                {
+                    PrepArgs pa;
+                    std::memset(&pa, 0, sizeof(pa));
+                    pa.d = h->d; pa.want_score = 0; pa.ytab = nullptr; pa.list = nullptr; pa.n_list = 0;
+                    CoefPar c0;
+                    std::memset(&c0, 0, sizeof(c0));
+                    ops->prep(pa, c0, h->stream);
+                }
                 // node-independent terms are summed once per evaluation over the rows of this variant's
                 // clusters (const_sums_kernel): per-row weights when clusters are weighted or excluded
                 std::vector<double> roww;
@@ -981,7 +1001,8 @@ int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* cho
 // enqueue one evaluation on the stream; the result vector ends up at d_out
 static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                         const double* gammas, int want_score, double* d_out, const DevData* dd_override,
-                        cudaEvent_t k0, cudaEvent_t k1, int em_mode = 0) {
+                        cudaEvent_t k0, cudaEvent_t k1, int em_mode = 0, bool to_host = false) {
+    // (the per-observation contributions -- dd_override -- stay local to the rank: no exchange)
     if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
     if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
     const int s = want_score ? 1 : 0;
@@ -1018,6 +1039,15 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         if (rc) return rc;
     }
     ea.em_mode = em_mode; ea.pby = h->d_pby;
+    if (h->xchg.nranks > 1 && !dd_override) {
+        ea.xchg = h->xchg;
+        ea.xchg.seq = ++h->xchg.seq;
+    }
+    if (to_host && h->h_out_dev) {
+        ea.hout.vec = h->h_out_dev;
+        ea.hout.flag = reinterpret_cast<unsigned long long*>(h->h_out_dev + GLMMA_XSLOT - 1);
+        ea.hout.seq = ++h->out_seq;
+    }
     ea.d = dd_override ? *dd_override : h->d;
     ea.fam = fp; ea.grid = h->d_grid; ea.fmtab = h->d_fmtab; fastmath_constants(ea.fmc); ea.partials = h->d_partials; ea.jt = h->jt; ea.asum_doubles = h->asum_doubles;
     rc = fill_prior(h, D, false, &ea.prior);
@@ -1051,9 +1081,44 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         h->launches++;
     }
     finalize_kernel<<<1, FINAL_THREADS, 0, h->stream>>>(h->d_partials, n_blocks, h->d_score_partials, h->score_grid,
-                                                         h->d.p, h->d.n_phis, h->d.p_zi, h->q, s, d_out);
+                                                         h->d.p, h->d.n_phis, h->d.p_zi, h->q, s, d_out, ea.xchg, ea.hout);
     h->launches++;
     CU(h, cudaGetLastError());
+    return GLMMA_OK;
+}
+
+// Enqueues one evaluation whose result vector the finalising block delivers into pinned host memory,
+// waits for it (spinning on the flag; the stream is polled so that a failed launch cannot hang the host)
+// and copies `len` doubles to `result`.
+static int eval_to_host(glmma_handle* h, const double* betas, const double* D, const double* phis, const double* gammas,
+                        int want_score, double* result, int len, int em_mode) {
+    if (!h->h_out) {
+        // mapped pinned memory; with unified addressing the host pointer is also the device pointer
+        cudaError_t e = cudaHostAlloc((void**)&h->h_out, sizeof(double) * GLMMA_XSLOT, cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->h_out_dev, h->h_out, 0);
+        if (e != cudaSuccess) { h->h_out = nullptr; h->h_out_dev = nullptr; cudaGetLastError(); }
+        else std::memset(h->h_out, 0, sizeof(double) * GLMMA_XSLOT);
+    }
+    int rc = enqueue_eval(h, betas, D, phis, gammas, want_score, h->d_result, nullptr, nullptr, nullptr, em_mode, true);
+    if (rc) return rc;
+    if (!h->h_out) {        // no mapped memory: the plain copy
+        CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * len, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        return GLMMA_OK;
+    }
+    volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(h->h_out + GLMMA_XSLOT - 1);
+    for (unsigned spins = 0; *flag != h->out_seq; ++spins) {
+        if ((spins & 0x3fffu) == 0x3fffu) {
+            const cudaError_t q = cudaStreamQuery(h->stream);
+            if (q == cudaSuccess) {                  // the stream drained: the flag is there, or the kernel never ran
+                if (*flag != h->out_seq) return fail(h, GLMMA_ERR_CUDA, "evaluation finished without delivering its result");
+                break;
+            }
+            if (q != cudaErrorNotReady) return cuda_fail(h, q, "eval");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int t = 0; t < len; ++t) result[t] = h->h_out[t];
     return GLMMA_OK;
 }
 
@@ -1074,12 +1139,7 @@ int glmma_eval(glmma_handle* h, const double* betas, const double* D, const doub
     int rc = enter(h);
     if (rc) return rc;
     if (!result) return fail(h, GLMMA_ERR_ARG, "result is null");
-    rc = enqueue_eval(h, betas, D, phis, gammas, want_score, h->d_result, nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    const int len = want_score ? glmma_result_len(h) : 4;
-    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * len, cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    return GLMMA_OK;
+    return eval_to_host(h, betas, D, phis, gammas, want_score, result, want_score ? glmma_result_len(h) : 4, 0);
 }
 
 int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, const double* phis,
@@ -1135,10 +1195,8 @@ int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const 
         rc = dev_alloc(h, &h->d_pby, (size_t)h->d.n * (size_t)h->K);
         if (rc) return rc;
     }
-    rc = enqueue_eval(h, betas, D, phis, gammas, 1, h->d_result, nullptr, nullptr, nullptr, 1);
+    rc = eval_to_host(h, betas, D, phis, gammas, 1, result, glmma_result_len(h), 1);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * glmma_result_len(h), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
     h->have_pby = true;
     return GLMMA_OK;
 }
@@ -1154,11 +1212,7 @@ int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, con
     // the prior only enters the node weights, which are frozen: any positive definite D will do
     double eye[GLMMA_QMAX * GLMMA_QMAX] = {0};
     for (int i = 0; i < h->q; ++i) eye[i * h->q + i] = 1.0;
-    rc = enqueue_eval(h, betas, eye, phis, gammas, 1, h->d_result, nullptr, nullptr, nullptr, 2);
-    if (rc) return rc;
-    CU(h, cudaMemcpyAsync(result, h->d_result, sizeof(double) * glmma_result_len(h), cudaMemcpyDeviceToHost, h->stream));
-    CU(h, cudaStreamSynchronize(h->stream));
-    return GLMMA_OK;
+    return eval_to_host(h, betas, eye, phis, gammas, 1, result, glmma_result_len(h), 2);
 }
 
 // ---- starting values of mixed_model() (R/mixed_model.R:157-194) --------------------------
@@ -1510,6 +1564,59 @@ static int multi_glm_pass(glmma_handle* h, int design, int glm_family, int respo
     }
     return GLMMA_OK;
 }
+
+// ---- cluster-sharded jobs, one process per GPU: peer-memory all-reduce inside the engine ----------
+
+int glmma_comm_export(glmma_handle* h, void* handle_bytes) {
+    DeviceGuard device_guard_;
+    if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "a multi-device handle reduces on the host; no communicator needed");
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!handle_bytes) return fail(h, GLMMA_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == GLMMA_COMM_HANDLE_BYTES, "GLMMA_COMM_HANDLE_BYTES");
+    if (!h->d_xchg) {
+        const size_t bytes = sizeof(double) * 2 * GLMMA_MAX_RANKS * GLMMA_XSLOT;
+        CU(h, cudaMalloc(&h->d_xchg, bytes));          // its own allocation: IPC handles name whole allocations
+        CU(h, cudaMemset(h->d_xchg, 0, bytes));
+    }
+    cudaIpcMemHandle_t ih;
+    CU(h, cudaIpcGetMemHandle(&ih, h->d_xchg));
+    std::memcpy(handle_bytes, &ih, sizeof(ih));
+    return GLMMA_OK;
+}
+
+int glmma_comm_connect(glmma_handle* h, int rank, int nranks, const void* all_handles) {
+    DeviceGuard device_guard_;
+    if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "a multi-device handle reduces on the host; no communicator needed");
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!all_handles || nranks < 1 || nranks > GLMMA_MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(h, GLMMA_ERR_ARG, "bad rank / nranks (at most 16 ranks)");
+    if (!h->d_xchg) return fail(h, GLMMA_ERR_STATE, "call glmma_comm_export first");
+    if (glmma_result_len(h) > GLMMA_XSLOT - 1) return fail(h, GLMMA_ERR_ARG, "result vector too long for the exchange slot");
+    if (h->xchg.nranks > 1) return fail(h, GLMMA_ERR_STATE, "already connected");
+    XchgPar x;
+    std::memset(&x, 0, sizeof(x));
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { x.peer[r] = h->d_xchg; continue; }
+        cudaIpcMemHandle_t ih;
+        std::memcpy(&ih, (const char*)all_handles + (size_t)r * GLMMA_COMM_HANDLE_BYTES, sizeof(ih));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+            h->ipc_opened.clear();
+            return cuda_fail(h, e, "cudaIpcOpenMemHandle (peer exchange buffer)");
+        }
+        h->ipc_opened.push_back(p);
+        x.peer[r] = (double*)p;
+    }
+    x.rank = rank; x.nranks = nranks; x.seq = 0;
+    h->xchg = x;
+    return GLMMA_OK;
+}
+
+int glmma_comm_size(const glmma_handle* h) { return !h ? 0 : (h->xchg.nranks > 1 ? h->xchg.nranks : 1); }
 
 int glmma_time_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                     const double* gammas, int want_score, int iters, float* ms_per_eval, float* ms_main_kernel) {

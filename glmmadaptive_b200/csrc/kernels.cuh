@@ -57,6 +57,8 @@ struct EvalArgs {
     const double* fin_cpart; // const_sums_kernel block partials {sum w c_ll, sum w c_phi} (fused mode)
     int fin_ncpart;
     double fin_ll_const;     // beta' X'y1 + sum w y1 offset over the register variant's clusters (linear-eta hoist)
+    XchgPar xchg;            // peer-memory all-reduce of the result vector over the ranks of a sharded job
+    HostOut hout;            // result vector delivered straight into pinned host memory (glmma_eval)
 };
 
 struct PrepArgs {
@@ -120,6 +122,57 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// Zero-copy delivery of the (reduced) result vector: the finalising block stores it into pinned,
+// device-mapped host memory and then raises a flag the host thread is spinning on -- glmma_eval returns
+// without a cudaMemcpy or a stream synchronisation (which cost more than the 100 bytes they move).
+__device__ __forceinline__ void deliver_host(const HostOut& ho, const double* result, int len) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < len; e += blockDim.x) ho.vec[e] = result[e];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(ho.flag) = ho.seq;
+}
+
+// All-reduce (sum) of the result vector over the ranks of a cluster-sharded job, done by the block that
+// finalised this rank's evaluation -- compute and collective in ONE kernel, over peer memory (NVLink /
+// NVSwitch P2P stores), no NCCL launch and no host round trip:
+//   1. the block stores its vector into slot [parity][rank] of EVERY rank's exchange buffer (its own
+//      included), fences at system scope and then raises the slot's flag to this evaluation's number;
+//   2. thread r spins on the flag of slot [parity][r] in OUR buffer until rank r's vector has arrived;
+//   3. every rank adds the vectors in rank order: the same sum on every rank, bit for bit.
+// Ranks evaluate in lockstep (the host loops are identical), so a slot of parity p is not rewritten
+// before all ranks have read evaluation seq - 2 from it.  A peer that never arrives (a crashed rank)
+// poisons the result with NaN after ~2 s instead of hanging the GPU.
+__device__ __forceinline__ void exchange_block(const XchgPar& x, double* result, int len) {
+    __syncthreads();                           // the block's own writes of `result`
+    const size_t par = (size_t)(x.seq & 1ull) * x.nranks;
+    const size_t mine = (par + x.rank) * GLMMA_XSLOT;
+    for (int t = threadIdx.x; t < len * x.nranks; t += blockDim.x) {
+        const int r = t / len, e = t - r * len;
+        x.peer[r][mine + e] = result[e];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < x.nranks)
+        *reinterpret_cast<volatile unsigned long long*>(x.peer[threadIdx.x] + mine + GLMMA_XSLOT - 1) = x.seq;
+    bool arrived = true;
+    double* own = x.peer[x.rank];
+    if ((int)threadIdx.x < x.nranks) {
+        const volatile unsigned long long* f =
+            reinterpret_cast<const volatile unsigned long long*>(own + (par + threadIdx.x) * GLMMA_XSLOT + GLMMA_XSLOT - 1);
+        const long long t0 = clock64();
+        while (*f != x.seq)
+            if (clock64() - t0 > (4ll << 30)) { arrived = false; break; }
+    }
+    arrived = __syncthreads_and(arrived);
+    __threadfence_system();
+    for (int e = threadIdx.x; e < len; e += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < x.nranks; ++r) s += __ldcv(own + (par + r) * GLMMA_XSLOT + e);
+        result[e] = arrived ? s : NAN;
+    }
+}
+
 // Result vector (include/glmma.h, glmma_eval) from the block partials of one evaluation, by ONE block of
 // any size: warp w reduces accumulator w (then w + nw, ...) -- lanes stride the blocks, a fixed shuffle
 // tree finishes, so the sum order is fixed (deterministic) and nothing is serialised behind block
@@ -129,7 +182,8 @@ __device__ __forceinline__ double warp_max(double v) {
 __device__ __forceinline__ void finalize_block(const double* ep, int n_eval_blocks, const double* sp, int n_score_blocks,
                                                bool cols_in_ep, int p, int n_phis, int p_zi, int q, int want_score,
                                                double* result, double* sh, const double* cpart = nullptr, int ncpart = 0,
-                                               double ll_const = 0.0, bool ll_consts_on = true) {
+                                               double ll_const = 0.0, bool ll_consts_on = true, const XchgPar* xchg = nullptr,
+                                               const HostOut* hout = nullptr) {
     double* acc = sh;
     double* col = sh + GLMMA_NACC;
     const int np = q * (q + 1) / 2;
@@ -170,22 +224,26 @@ __device__ __forceinline__ void finalize_block(const double* ep, int n_eval_bloc
         result[0] = acc[0] + (ll_consts_on ? cadd[0] + ll_const : 0.0);
         result[1] = acc[1]; result[2] = acc[2]; result[3] = 0.0;
     }
-    if (!want_score) return;
-    for (int l = threadIdx.x; l < ncol; l += blockDim.x) {
-        if (l < p) result[4 + l] = col[l];
-        else result[4 + p + n_phis + (l - p)] = col[l];
+    if (want_score) {
+        for (int l = threadIdx.x; l < ncol; l += blockDim.x) {
+            if (l < p) result[4 + l] = col[l];
+            else result[4 + p + n_phis + (l - p)] = col[l];
+        }
+        if (threadIdx.x == 0) {
+            for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3] + cadd[1];
+            double* S = result + 4 + p + n_phis + p_zi;
+            int t = 0;
+            for (int dd = 0; dd < q; ++dd)
+                for (int e = dd; e < q; ++e) {
+                    S[dd + e * q] = acc[4 + t];
+                    S[e + dd * q] = acc[4 + t];
+                    ++t;
+                }
+        }
     }
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < n_phis; ++t) result[4 + p + t] = acc[3] + cadd[1];
-        double* S = result + 4 + p + n_phis + p_zi;
-        int t = 0;
-        for (int dd = 0; dd < q; ++dd)
-            for (int e = dd; e < q; ++e) {
-                S[dd + e * q] = acc[4 + t];
-                S[e + dd * q] = acc[4 + t];
-                ++t;
-            }
-    }
+    const int len = want_score ? 4 + p + n_phis + p_zi + q * q : 4;
+    if (xchg != nullptr && xchg->nranks > 1) exchange_block(*xchg, result, len);
+    if (hout != nullptr && hout->vec != nullptr) deliver_host(*hout, result, len);
 }
 
 // ------------------------------------------------------------------------------
@@ -851,7 +909,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
             __threadfence();
             finalize_block(A.fin_partials, A.fin_blocks, nullptr, 0, true, d.p, d.n_phis, d.p_zi, Q, A.fin_want_score,
                            A.fin_result, smem + (size_t)wpb * GLMMA_PSTRIDE + 2, A.fin_cpart, A.fin_ncpart, A.fin_ll_const,
-                           A.em_mode != 2);
+                           A.em_mode != 2, &A.xchg, &A.hout);
             if (threadIdx.x == 0) *A.fin_counter = 0u;
         }
     }

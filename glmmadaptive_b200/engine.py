@@ -135,6 +135,7 @@ class Engine:
         if rc != 0:
             raise GlmmaError(rc, self.lib.glmma_last_error(None).decode())
         self._h = h
+        self._stage, self._res, self._res_p = None, None, None
         self.device = int(device)
         self.n_devices = int(self.lib.glmma_n_devices(h))
         self.n = int(self.lib.glmma_n_clusters(h))
@@ -172,21 +173,31 @@ class Engine:
 
     # -- GHfun pieces ---------------------------------------------------------
     def _theta_ptrs(self, betas, M, phis, gammas):
-        b = _f(np.atleast_1d(betas), "C")
-        if b.shape != (self.p,):
+        """theta into the engine's persistent staging buffer (betas | M column-major | phis | gammas) and
+        the four pointers into it: an optimiser calls this thousands of times, so nothing is allocated
+        and no ctypes object is created per call."""
+        st = self._stage
+        if st is None:
+            p, q, nph, pz = self.p, self.q, self.n_phis, self.p_zi
+            buf = np.zeros(p + q * q + nph + pz)
+            base = buf.ctypes.data
+            ptr = lambda off, n: C.cast(base + 8 * off, _lib.c_double_p) if n else None
+            st = self._stage = dict(buf=buf, b=buf[:p], M=buf[p:p + q * q].reshape(q, q, order="F"),
+                                    ph=buf[p + q * q:p + q * q + nph], g=buf[p + q * q + nph:],
+                                    ptrs=(ptr(0, p), ptr(p, q * q), ptr(p + q * q, nph), ptr(p + q * q + nph, pz)))
+        if np.size(betas) != self.p:
             raise ValueError("betas has the wrong length")
-        M = _f(np.asarray(M, float).reshape(self.q, self.q))
-        ph = None
+        st["b"][:] = betas
+        st["M"][...] = np.reshape(M, (self.q, self.q))
         if self.n_phis:
-            ph = _f(np.atleast_1d(phis), "C")
-            if ph.shape != (self.n_phis,):
+            if phis is None or np.size(phis) != self.n_phis:
                 raise ValueError("phis has the wrong length")
-        g = None
+            st["ph"][:] = phis
         if self.p_zi:
-            g = _f(np.atleast_1d(gammas), "C")
-            if g.shape != (self.p_zi,):
+            if gammas is None or np.size(gammas) != self.p_zi:
                 raise ValueError("gammas has the wrong length")
-        return (b, M, ph, g), (_dp(b), _dp(M), _dp(ph), _dp(g))
+            st["g"][:] = gammas
+        return st["buf"], st["ptrs"]
 
     def find_modes(self, betas, invD, phis=None, gammas=None, warm=True):
         keep, ptrs = self._theta_ptrs(betas, invD, phis, gammas)
@@ -225,9 +236,12 @@ class Engine:
     def eval_raw(self, betas, D, phis=None, gammas=None, want_score=True):
         """The raw result vector of glmma_eval (layout in include/glmma.h)."""
         keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
-        res = np.zeros(self.result_len)
-        self._check(self.lib.glmma_eval(self._h, *ptrs, int(bool(want_score)), _dp(res)))
-        return res
+        if self._res is None:
+            self._res = np.zeros(self.result_len)
+            self._res_p = _dp(self._res)
+        self._res[4:] = 0.0
+        self._check(self.lib.glmma_eval(self._h, *ptrs, 1 if want_score else 0, self._res_p))
+        return self._res.copy()
 
     def eval(self, betas, D, phis=None, gammas=None, want_score=True):
         return self.unpack(self.eval_raw(betas, D, phis, gammas, want_score), want_score)
@@ -282,6 +296,23 @@ class Engine:
                                             0 if response == "y" else 1, int(bool(use_offset)),
                                             int(beta is None), _dp(b), _dp(out)))
         return out
+
+    # -- sharded jobs, one process per GPU: all-reduce inside the engine (include/glmma.h) --------
+    def comm_export(self):
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.glmma_comm_export(self._h, buf))
+        return bytes(buf.raw)
+
+    def comm_connect(self, rank, nranks, handles):
+        """handles: the nranks exported byte strings in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self.lib.glmma_comm_connect(self._h, int(rank), int(nranks), buf))
+
+    @property
+    def comm_size(self):
+        return int(self.lib.glmma_comm_size(self._h))
 
     def log_post_b(self, b, betas, invD, phis=None, gammas=None):
         """log_post_b of predict()'s Metropolis step (R/methods.R:1020-1036) for one random-effects

@@ -59,12 +59,24 @@ class ShardedEngine:
 
     _SIZES = ("p", "q", "q_y", "q_zi", "p_zi", "n_phis", "npack", "nAGQ", "K", "result_len", "spec", "device")
 
-    def __init__(self, local, dist=None, group=None, reduce_on_host=False):
+    def __init__(self, local, dist=None, group=None, reduce_on_host=False, in_engine=True):
         self.local = local
         self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size(group) > 1) else None
         self.group = group
         self.reduce_on_host = reduce_on_host      # gloo (CPU tests): reduce host vectors
         self._buf = None
+        # All-reduce inside the engine (include/glmma.h, glmma_comm_*): the handles' exchange buffers are
+        # gathered once through the process group; from then on an evaluation's finalising block sums
+        # the ranks' vectors itself over peer memory -- no collective is launched per evaluation.
+        self.in_engine = False
+        if self.dist is not None and in_engine and not reduce_on_host and hasattr(local, "comm_export") \
+                and self.dist.get_world_size(group) <= 16:
+            world, rank = self.dist.get_world_size(group), self.dist.get_rank(group)
+            handles = [None] * world
+            self.dist.all_gather_object(handles, local.comm_export(), group=group)
+            local.comm_connect(rank, world, handles)
+            self.dist.barrier(group=group)
+            self.in_engine = True
         for k in self._SIZES:
             setattr(self, k, getattr(local, k))
         self.n_local = local.n
@@ -123,7 +135,7 @@ class ShardedEngine:
         the device tensor holding the reduced result vector."""
         buf = self._buffer()
         self.local.eval_device(betas, D, phis, gammas, want_score, buf.data_ptr())
-        if self.dist is not None:
+        if self.dist is not None and not self.in_engine:
             self.dist.all_reduce(buf, group=self.group)
         return buf
 
@@ -131,17 +143,20 @@ class ShardedEngine:
         if self.reduce_on_host:
             r = self._reduce_host(self.local.eval_raw(betas, D, phis, gammas, want_score))
             return self.local.unpack(r, want_score)
-        if self.dist is None:
-            # one rank: the plain C-ABI call (glmma_eval: host theta in, host result vector out)
+        if self.dist is None or self.in_engine:
+            # the plain C-ABI call (glmma_eval: host theta in, host result vector out); with the handles
+            # connected the vector it returns is already the sum over the ranks
             return self.local.unpack(self.local.eval_raw(betas, D, phis, gammas, want_score), want_score)
         buf = self.eval_enqueue(betas, D, phis, gammas, want_score)
         return self.local.unpack(buf.cpu().numpy(), want_score)
 
     def em_estep(self, betas, D, phis=None, gammas=None):
-        return self.local.unpack(self._reduce_host(self.local.em_estep_raw(betas, D, phis, gammas)), True)
+        r = self.local.em_estep_raw(betas, D, phis, gammas)
+        return self.local.unpack(r if self.in_engine else self._reduce_host(r), True)
 
     def em_score(self, betas, phis=None, gammas=None):
-        return self.local.unpack(self._reduce_host(self.local.em_score_raw(betas, phis, gammas)), True)
+        r = self.local.em_score_raw(betas, phis, gammas)
+        return self.local.unpack(r if self.in_engine else self._reduce_host(r), True)
 
     def glm_pass(self, *a, **k):
         return self._reduce_host(self.local.glm_pass(*a, **k))

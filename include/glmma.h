@@ -252,6 +252,24 @@ GLMMA_API int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int re
 GLMMA_API int glmma_log_post_b(glmma_handle* h, const double* b, const double* betas, const double* invD,
                      const double* phis, const double* gammas, double* out);
 
+/* ---- cluster-sharded jobs: one process per GPU, all-reduce inside the engine ----------------
+ * Clusters are conditionally independent, so the log-likelihood and every score component are sums over
+ * shards (reference R/Fit_Funs.R:33-37,105,194,231,244-247,271-278).  When each GPU of the box is driven
+ * by its own process (one handle per process on its shard of the clusters), connecting the handles makes
+ * glmma_eval, glmma_eval_device, glmma_em_estep and glmma_em_score return the sum over ALL ranks: the
+ * block that finalises a rank's evaluation stores its ~100-byte vector into every rank's exchange
+ * buffer through peer memory (NVLink), waits for the others' and adds them in rank order -- the same
+ * bits on every rank, no collective launch, no host round trip.  All ranks must then issue the same
+ * sequence of these calls (they do: every rank runs the same optimiser on the same reduced numbers).
+ *   1. every rank:  glmma_comm_export(h, bytes)           bytes: GLMMA_COMM_HANDLE_BYTES
+ *   2. the host program gathers the nranks handles (any transport: MPI, torch.distributed, files)
+ *   3. every rank:  glmma_comm_connect(h, rank, nranks, all_handles)     handles in rank order
+ * Mode searches, per-cluster contributions and glmma_glm_pass stay local to the rank. */
+#define GLMMA_COMM_HANDLE_BYTES 64
+GLMMA_API int glmma_comm_export(glmma_handle* h, void* handle_bytes);
+GLMMA_API int glmma_comm_connect(glmma_handle* h, int rank, int nranks, const void* all_handles);
+GLMMA_API int glmma_comm_size(const glmma_handle* h);      /* ranks summed by an evaluation (1: not connected) */
+
 /* ---- measurement helpers (bench.py; not part of the reference seam) ----- */
 
 /* Runs `iters` evaluations back to back on the handle's stream and returns the

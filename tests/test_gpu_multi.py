@@ -70,3 +70,67 @@ def test_multi_device_fit_equals_single_device_fit():
     assert f1["converged"] == f2["converged"]
     assert np.max(np.abs(f1["thetas"] - f2["thetas"])) < 1e-8
     assert abs(f1["logLik"] - f2["logLik"]) < 1e-10 * abs(f1["logLik"])
+
+
+# ---- one process per GPU: the all-reduce inside the engine (glmma_comm_export / glmma_comm_connect) ----
+def _comm_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch
+    import torch.distributed as dist
+    from glmmadaptive_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d, th = synth.make("C3", n=4001, ni=7, seed=9, ragged=True)
+    fam = d.pop("family")
+    arrays = {k: d.get(k) for k in ("y", "X", "Z")}
+    loc, _, _ = sharded.shard_arrays(arrays, d["id"], rank, world)
+    eng = gb.Engine(loc["y"], loc["X"], loc["Z"], loc["id"], fam, nAGQ=th["nAGQ"], device=rank)
+    sh = sharded.ShardedEngine(eng, dist)
+    assert sh.in_engine and eng.comm_size == world
+    betas, D, phis = th["betas"], th["D"], th["phis"]
+    sh.find_modes(betas, np.linalg.inv(D), phis, None, warm=False)
+    outs = []
+    for k in range(6):                      # several evaluations: both parities of the exchange slots
+        r = sh.eval(betas * (1.0 + 0.01 * k), D, phis, None)
+        outs.append(np.concatenate([[r["loglik"], r["sum_w"], r["n_nonfinite"]], r["g_beta"], r["g_phi"], r["S"].ravel()]))
+    es = sh.em_estep(betas, D, phis, None)
+    sc = sh.em_score(betas * 1.02, phis, None)
+    outs.append(np.concatenate([[es["loglik"], es["sum_w"], es["n_nonfinite"]], es["g_beta"], es["g_phi"], es["S"].ravel()]))
+    outs.append(np.concatenate([[0.0, sc["sum_w"], sc["n_nonfinite"]], sc["g_beta"], sc["g_phi"], sc["S"].ravel()]))
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.stack(outs))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_in_engine_allreduce_matches_unsharded(tmp_path):
+    """Two processes, one GPU each, handles connected through peer memory: every rank gets the same
+    bits, equal (1e-11 relative: the shards are summed in a different order, and the phi-score cancels) to the unsharded engine's evaluation of the whole data set."""
+    if _ndev() < 2:
+        pytest.skip("needs at least two GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_comm_worker, args=(world, 29561, str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(str(tmp_path / f"rank{r}.npy")) for r in range(world)]
+    assert np.array_equal(res[0], res[1])
+    d, th = synth.make("C3", n=4001, ni=7, seed=9, ragged=True)
+    fam = d.pop("family")
+    one = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam, nAGQ=th["nAGQ"], device=0)
+    betas, D, phis = th["betas"], th["D"], th["phis"]
+    one.find_modes(betas, np.linalg.inv(D), phis, None, warm=False)
+    for k in range(6):
+        r = one.eval(betas * (1.0 + 0.01 * k), D, phis, None)
+        ref = np.concatenate([[r["loglik"], r["sum_w"], r["n_nonfinite"]], r["g_beta"], r["g_phi"], r["S"].ravel()])
+        assert np.max(np.abs(res[0][k] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-11, k
+    es = one.em_estep(betas, D, phis, None)
+    ref = np.concatenate([[es["loglik"], es["sum_w"], es["n_nonfinite"]], es["g_beta"], es["g_phi"], es["S"].ravel()])
+    assert np.max(np.abs(res[0][6] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-11
+    sc = one.em_score(betas * 1.02, phis, None)
+    ref = np.concatenate([[0.0, sc["sum_w"], sc["n_nonfinite"]], sc["g_beta"], sc["g_phi"], sc["S"].ravel()])
+    assert np.max(np.abs(res[0][7] - ref) / np.maximum(1.0, np.abs(ref))) < 1e-11
+    one.close()
