@@ -73,6 +73,7 @@ SIGNATURES = {
     "glmma_comm_export": (C.c_int, [_H, C.c_void_p]),
     "glmma_comm_connect": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "glmma_comm_size": (C.c_int, [_H]),
+    "glmma_observed_information": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, c_double_p]),
     "glmma_log_post_b": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "glmma_time_eval": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),

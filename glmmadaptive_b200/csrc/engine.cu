@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <nvtx3/nvToolsExt.h>       // header-only NVTX 3: ranges cost nothing unless a profiler is attached
 #include "../../include/glmma.h"
 #include "kernels.cuh"
 #include "engine.h"
@@ -429,6 +430,12 @@ static int dev_upload(glmma_handle* h, const T** out, const T* src, size_t count
     return GLMMA_OK;
 }
 
+// NVTX range around an ABI call (mode search / evaluation / EM passes show up as named spans in Nsight)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Restores the caller's current CUDA device when an ABI call returns: the host process (R, or Python
 // with torch) must not find itself on another device after calling into the engine.
 struct DeviceGuard {
@@ -480,6 +487,7 @@ void glmma_destroy(glmma_handle* h) {
 
 int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_create");
     if (!data || !out) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
     *out = nullptr;
     const int64_t N = data->n_obs;
@@ -927,6 +935,7 @@ static int multi_find_modes(glmma_handle* h, const double* betas, const double* 
 int glmma_find_modes(glmma_handle* h, const double* betas, const double* invD, const double* phis,
                      const double* gammas, int warm, glmma_mode_stats* stats) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_find_modes");
     if (h && !h->parts.empty()) return multi_find_modes(h, betas, invD, phis, gammas, warm, stats);
     unsigned long long st[4];
     int rc = find_modes_enqueue(h, betas, invD, phis, gammas, warm, st);
@@ -955,6 +964,7 @@ static int multi_fail(glmma_handle* h, const glmma_handle* p, int rc);
 
 int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, double* log_dets) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_get_modes");
     if (h && !h->parts.empty()) return multi_get_modes(h, post_modes, chol_upper, log_dets);
     int rc = enter(h);
     if (rc) return rc;
@@ -977,6 +987,7 @@ int glmma_get_modes(glmma_handle* h, double* post_modes, double* chol_upper, dou
 
 int glmma_set_modes(glmma_handle* h, const double* post_modes, const double* chol_upper) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_set_modes");
     if (h && !h->parts.empty()) return multi_set_modes(h, post_modes, chol_upper);
     int rc = enter(h);
     if (rc) return rc;
@@ -1125,6 +1136,7 @@ static int eval_to_host(glmma_handle* h, const double* betas, const double* D, c
 int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, const double* phis,
                       const double* gammas, int want_score, double* d_result) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_eval_device");
     if (h && !h->parts.empty()) return fail(h, GLMMA_ERR_ARG, "glmma_eval_device needs a single-device handle");
     int rc = enter(h);
     if (rc) return rc;
@@ -1135,6 +1147,7 @@ int glmma_eval_device(glmma_handle* h, const double* betas, const double* D, con
 int glmma_eval(glmma_handle* h, const double* betas, const double* D, const double* phis,
                const double* gammas, int want_score, double* result) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_eval");
     if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, want_score, result, 0);
     int rc = enter(h);
     if (rc) return rc;
@@ -1146,6 +1159,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
                        const double* gammas, double* ll_i, double* zbar, double* zbar_zi,
                        double* sphi_obs, double* S_i) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_eval_contrib");
     if (h && !h->parts.empty()) return multi_eval_contrib(h, betas, D, phis, gammas, ll_i, zbar, zbar_zi, sphi_obs, S_i);
     int rc = enter(h);
     if (rc) return rc;
@@ -1187,6 +1201,7 @@ int glmma_eval_contrib(glmma_handle* h, const double* betas, const double* D, co
 int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const double* phis,
                    const double* gammas, double* result) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_em_estep");
     if (h && !h->parts.empty()) return multi_eval(h, betas, D, phis, gammas, 1, result, 1);
     int rc = enter(h);
     if (rc) return rc;
@@ -1204,6 +1219,7 @@ int glmma_em_estep(glmma_handle* h, const double* betas, const double* D, const 
 int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, const double* gammas,
                    double* result) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_em_score");
     if (h && !h->parts.empty()) return multi_eval(h, betas, nullptr, phis, gammas, 1, result, 2);
     int rc = enter(h);
     if (rc) return rc;
@@ -1220,6 +1236,7 @@ int glmma_em_score(glmma_handle* h, const double* betas, const double* phis, con
 int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset, int first,
                    const double* beta, double* out) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_glm_pass");
     if (h && !h->parts.empty()) return multi_glm_pass(h, design, glm_family, response, use_offset, first, beta, out);
     int rc = enter(h);
     if (rc) return rc;
@@ -1265,11 +1282,173 @@ int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, in
     return GLMMA_OK;
 }
 
+// ---- observed information (replaces cd_vec(score_mixed), R/mixed_fit.R:324-342) --------------------
+
+// small dense helpers, q <= GLMMA_QMAX, row-major q x q
+static void mm(const double* A, const double* B, int q, double* C) {
+    double T[GLMMA_QMAX * GLMMA_QMAX];
+    for (int r = 0; r < q; ++r)
+        for (int c = 0; c < q; ++c) {
+            double s = 0.0;
+            for (int t = 0; t < q; ++t) s += A[r * q + t] * B[t * q + c];
+            T[r * q + c] = s;
+        }
+    for (int i = 0; i < q * q; ++i) C[i] = T[i];
+}
+
+int glmma_observed_information(glmma_handle* h, const double* betas, const double* D, const double* phis,
+                               const double* gammas, int diag_D, double* H) {
+    NvtxRange nvtx_range_("glmma_observed_information");
+    DeviceGuard device_guard_;
+    if (!h || !H) return h ? fail(h, GLMMA_ERR_ARG, "null argument") : GLMMA_ERR_ARG;
+    const int q = h->q;
+    const int nD = diag_D ? q : q * (q + 1) / 2;
+    if (!h->parts.empty()) {
+        const int P = h->multi_p + nD + h->multi_nphis + h->multi_pzi;
+        std::vector<double> tmp((size_t)P * P);
+        for (int t = 0; t < P * P; ++t) H[t] = 0.0;
+        for (glmma_handle* p : h->parts) {          // device order: deterministic
+            int rc = glmma_observed_information(p, betas, D, phis, gammas, diag_D, tmp.data());
+            if (rc) return multi_fail(h, p, rc);
+            for (int t = 0; t < P * P; ++t) H[t] += tmp[t];
+        }
+        return GLMMA_OK;
+    }
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_modes) return fail(h, GLMMA_ERR_STATE, "no modes yet: call glmma_find_modes or glmma_set_modes first");
+    if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
+    const int p = h->d.p, pz = h->d.p_zi, nphi = h->d.n_phis;
+    const int P = p + nD + nphi + pz;
+    if (P > GLMMA_INFO_PMAX) return fail(h, GLMMA_ERR_ARG, "more than 12 parameters: use the finite-difference Hessian");
+    InfoArgs ia;
+    std::memset(&ia, 0, sizeof(ia));
+    rc = run_prep(h, betas, phis, gammas, &ia.fam);
+    if (rc) return rc;
+    ia.eps_eta = 1e-4; ia.eps_phi = 1e-4;
+    if (nphi) {
+        const double hi = phis[0] + ia.eps_phi, lo = phis[0] - ia.eps_phi;
+        if (!fill_fampar(h->family, nphi, &hi, &ia.fam_hi, h->error, h->family_df) ||
+            !fill_fampar(h->family, nphi, &lo, &ia.fam_lo, h->error, h->family_df)) return GLMMA_ERR_ARG;
+    } else { ia.fam_hi = ia.fam; ia.fam_lo = ia.fam; }
+    rc = fill_prior(h, D, false, &ia.prior);
+    if (rc) return rc;
+    // log N(b; 0, D) = -log|D| / 2 - b' D^-1 b / 2 as a function of the D parameters theta_D:
+    //   d/d theta_t       = -tr(D^-1 D_t) / 2 + b' (D^-1 D_t D^-1) b / 2
+    //   d2/d theta_t d_u  = -tr(-D^-1 D_u D^-1 D_t + D^-1 D_tu) / 2
+    //                       + b' (-D^-1 D_u D^-1 D_t D^-1 + D^-1 D_tu D^-1 - D^-1 D_t D^-1 D_u D^-1) b / 2
+    // with D_t, D_tu the derivatives of the parametrisation: log(diag(D)) (random = ~ . || g), or
+    // chol_transf(D) -- upper Cholesky factor U, D = U'U, diagonal logged, column-major over the upper
+    // triangle (R/Functions.R:140-147).
+    {
+        double Dm[GLMMA_QMAX * GLMMA_QMAX], Di[GLMMA_QMAX * GLMMA_QMAX], U[GLMMA_QMAX * GLMMA_QMAX] = {0};
+        for (int r = 0; r < q; ++r)
+            for (int c = 0; c < q; ++c) { Dm[r * q + c] = D[r + c * q]; Di[r * q + c] = ia.prior.Dinv[r * q + c]; }
+        // upper factor: D = U'U  (U = L' of the lower Cholesky factor)
+        for (int c = 0; c < q; ++c) {
+            double sdiag = Dm[c * q + c];
+            for (int t = 0; t < c; ++t) sdiag -= U[t * q + c] * U[t * q + c];
+            U[c * q + c] = std::sqrt(sdiag);
+            for (int r = c + 1; r < q; ++r) {
+                double v = Dm[c * q + r];
+                for (int t = 0; t < c; ++t) v -= U[t * q + c] * U[t * q + r];
+                U[c * q + r] = v / U[c * q + c];
+            }
+        }
+        std::vector<std::vector<double>> dU(nD, std::vector<double>(q * q, 0.0)), Dt(nD, std::vector<double>(q * q, 0.0));
+        std::vector<bool> is_diag(nD, false);
+        if (diag_D) {
+            for (int t = 0; t < q; ++t) { Dt[t][t * q + t] = Dm[t * q + t]; is_diag[t] = true; }
+        } else {
+            int t = 0;
+            for (int c = 0; c < q; ++c)
+                for (int r = 0; r <= c; ++r) {
+                    dU[t][r * q + c] = (r == c) ? U[c * q + c] : 1.0;
+                    is_diag[t] = (r == c);
+                    // D_t = dU' U + U' dU
+                    for (int a = 0; a < q; ++a)
+                        for (int b = 0; b < q; ++b) {
+                            double s = 0.0;
+                            for (int k = 0; k < q; ++k) s += dU[t][k * q + a] * U[k * q + b] + U[k * q + a] * dU[t][k * q + b];
+                            Dt[t][a * q + b] = s;
+                        }
+                    ++t;
+                }
+        }
+        ia.nD = nD;
+        double T1[GLMMA_QMAX * GLMMA_QMAX], T2[GLMMA_QMAX * GLMMA_QMAX], Gt[GLMMA_INFO_NDMAX][GLMMA_QMAX * GLMMA_QMAX];
+        for (int t = 0; t < nD; ++t) {
+            mm(Di, Dt[t].data(), q, T1);                 // D^-1 D_t
+            double tr = 0.0;
+            for (int a = 0; a < q; ++a) tr += T1[a * q + a];
+            ia.dc[t] = -0.5 * tr;
+            for (int i = 0; i < q * q; ++i) Gt[t][i] = T1[i];
+            mm(T1, Di, q, T2);                           // D^-1 D_t D^-1
+            for (int i = 0; i < q * q; ++i) ia.dM[t][i] = T2[i];
+        }
+        int tu = 0;
+        for (int t = 0; t < nD; ++t)
+            for (int u = t; u < nD; ++u) {
+                double Dtu[GLMMA_QMAX * GLMMA_QMAX] = {0};
+                if (diag_D) {
+                    if (t == u) Dtu[t * q + t] = Dm[t * q + t];
+                } else {
+                    for (int a = 0; a < q; ++a)
+                        for (int b = 0; b < q; ++b) {
+                            double s = 0.0;
+                            for (int k = 0; k < q; ++k) s += dU[t][k * q + a] * dU[u][k * q + b] + dU[u][k * q + a] * dU[t][k * q + b];
+                            Dtu[a * q + b] = s;
+                        }
+                    if (t == u && is_diag[t])            // d2U/dtheta_t^2 = dU_t for a logged diagonal entry
+                        for (int i = 0; i < q * q; ++i) Dtu[i] += Dt[t][i];
+                }
+                double GuGt[GLMMA_QMAX * GLMMA_QMAX], GtGu[GLMMA_QMAX * GLMMA_QMAX], Gtu[GLMMA_QMAX * GLMMA_QMAX];
+                mm(Gt[u], Gt[t], q, GuGt);               // D^-1 D_u D^-1 D_t
+                mm(Gt[t], Gt[u], q, GtGu);
+                mm(Di, Dtu, q, Gtu);                     // D^-1 D_tu
+                double tr = 0.0;
+                for (int a = 0; a < q; ++a) tr += -GuGt[a * q + a] + Gtu[a * q + a];
+                ia.dcc[tu] = -0.5 * tr;
+                double A1[GLMMA_QMAX * GLMMA_QMAX], A2[GLMMA_QMAX * GLMMA_QMAX], A3[GLMMA_QMAX * GLMMA_QMAX];
+                mm(GuGt, Di, q, A1);
+                mm(Gtu, Di, q, A2);
+                mm(GtGu, Di, q, A3);
+                for (int i = 0; i < q * q; ++i) ia.dMM[tu][i] = -A1[i] + A2[i] - A3[i];
+                ++tu;
+            }
+    }
+    ia.d = h->d; ia.grid = h->d_grid; ia.fmtab = h->d_fmtab; fastmath_constants(ia.fmc);
+    ia.ksm = h->K <= 344 ? h->K : 0;         // 4 warps x 344 doubles: stays under the default 48 KB of dynamic shared memory
+    const int grid = (int)std::min<int64_t>((h->d.n + 3) / 4, 148 * 8);
+    double* d_part = nullptr;
+    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * (size_t)grid * GLMMA_INFO_NPAIR);
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc (observed information)");
+    ia.partials = d_part;
+    h->ops->info(ia, grid, h->stream);
+    h->launches++;
+    std::vector<double> part((size_t)grid * GLMMA_INFO_NPAIR);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_part);
+    if (e != cudaSuccess) return cuda_fail(h, e, "info_kernel");
+    for (int r = 0; r < P; ++r)
+        for (int c = r; c < P; ++c) {
+            const int t = info_pair(r, c);
+            double s = 0.0;
+            for (int b = 0; b < grid; ++b) s += part[(size_t)b * GLMMA_INFO_NPAIR + t];    // fixed order
+            H[r + c * P] = -s;             // Hessian of the NEGATIVE log-likelihood
+            H[c + r * P] = -s;
+        }
+    return GLMMA_OK;
+}
+
 // ---- predict()'s Metropolis step (R/methods.R:1013-1142) -----------------------------------
 
 int glmma_log_post_b(glmma_handle* h, const double* b, const double* betas, const double* invD,
                      const double* phis, const double* gammas, double* out) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_log_post_b");
     if (h && !h->parts.empty()) {
         if (!b || !out) return fail(h, GLMMA_ERR_ARG, "null argument");
         const int64_t n = h->part_c0.back();
@@ -1325,6 +1504,7 @@ static int multi_fail(glmma_handle* h, const glmma_handle* p, int rc) {
 
 int glmma_create_multi(const glmma_data* data, const int* devices, int ndev, glmma_handle** out) {
     DeviceGuard device_guard_;
+    NvtxRange nvtx_range_("glmma_create_multi");
     if (!data || !out || !devices || ndev < 1) return fail(nullptr, GLMMA_ERR_ARG, "null argument");
     *out = nullptr;
     if (ndev == 1) return glmma_create(data, devices[0], out);

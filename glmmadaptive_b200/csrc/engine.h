@@ -6,6 +6,7 @@
 struct PrepArgs;
 struct EvalArgs;
 struct ModeArgs;
+struct InfoArgs;
 
 struct FamOps {
     void (*ytab)(const FamPar&, double* tab, cudaStream_t);      // table of obs_const(y), count families
@@ -19,6 +20,7 @@ struct FamOps {
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
     void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
+    void (*info)(const InfoArgs&, int grid, cudaStream_t);      // observed information, one pass
     void (*logpost)(const ModeArgs&, const double* b, double* out, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
     void (*pack)(const DevData&, cudaStream_t);       // packed per-cluster records of the register variant

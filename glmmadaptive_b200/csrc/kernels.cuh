@@ -1904,6 +1904,292 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
 }
 
 // ------------------------------------------------------------------------------
+// Observed information on the fixed grid: the Hessian of the NEGATIVE marginal log-likelihood the
+// reference obtains as cd_vec(score_mixed) (R/mixed_fit.R:324-342: 2 * nparams evaluations), here from
+// ONE pass over the data.  With a_ik(theta) the log of the k-th term of cluster i's quadrature sum and
+// pi_ik its posterior node weight,
+//     d^2 log p(y_i) / d theta d theta' = E_pi[ d^2 a ] + E_pi[ da da' ] - E_pi[da] E_pi[da]',
+// theta = (betas, D parameters, phis, gammas) in the reference's order (R/mixed_fit.R:240-247).
+//   da / d beta = X_i' s_eta(k),  da / d phis = sum_j s_phi,  da / d gamma = X_zi,i' s_zi(k)   (family scores)
+//   da / d D_t  = c_t + b_k' M_t b_k / 2      (log N(b_k; 0, D): c_t, M_t from the host, engine.cu)
+// The second derivatives of log f with respect to (eta, phis, eta_zi) are central differences of the
+// functors' ANALYTIC first derivatives at every point (relative error ~1e-8, two orders below the
+// truncation error of the reference's own cd_vec with eps = 1e-3), so no family needs hand-derived second
+// derivatives.  A warp owns a cluster, lanes own nodes; two passes over the nodes (log-sum-exp, then the
+// derivatives).  Run once per fit: clarity over speed (accumulators in local memory).
+// ------------------------------------------------------------------------------
+#define GLMMA_INFO_PMAX 12
+#define GLMMA_INFO_NPAIR (GLMMA_INFO_PMAX * (GLMMA_INFO_PMAX + 1) / 2)
+#define GLMMA_INFO_NDMAX (GLMMA_QMAX * (GLMMA_QMAX + 1) / 2)
+#define GLMMA_INFO_NDPAIR (GLMMA_INFO_NDMAX * (GLMMA_INFO_NDMAX + 1) / 2)
+#define GLMMA_INFO_JT 16
+struct InfoArgs {
+    DevData d;
+    PriorPar prior;
+    FamPar fam, fam_hi, fam_lo;      // phis, phis + eps_phi, phis - eps_phi
+    const GridPar* grid;
+    const double* fmtab;
+    double fmc[GLMMA_FM_NCONST];
+    int nD;                                               // number of D parameters (q, or q (q + 1) / 2)
+    double dc[GLMMA_INFO_NDMAX];                          // d log N / d D_t   = dc[t]  + b' dM[t]  b / 2
+    double dM[GLMMA_INFO_NDMAX][GLMMA_QMAX * GLMMA_QMAX];
+    double dcc[GLMMA_INFO_NDPAIR];                        // d^2 / d D_t d D_u = dcc[tu] + b' dMM[tu] b / 2   (t <= u, row-major)
+    double dMM[GLMMA_INFO_NDPAIR][GLMMA_QMAX * GLMMA_QMAX];
+    double eps_eta, eps_phi;
+    double* partials;                                     // gridDim.x x npair(P) block partial Hessians of log p(y)
+    int ksm;                                              // K when the K node terms of a cluster fit the warp's shared
+                                                          // memory (pass 2 then reads them instead of recomputing), else 0
+};
+
+__host__ __device__ __forceinline__ int info_pair(int r, int c) {      // r <= c, packed row-major over the upper triangle of P x P
+    return r * (2 * GLMMA_INFO_PMAX - r + 1) / 2 + (c - r);
+}
+
+template <class F, int QY, int QZ>
+__global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
+    using L = EvalLayout<F, QY, QZ>;
+    constexpr int Q = L::Q;
+    constexpr int NP = L::NP;
+    constexpr int JT = GLMMA_INFO_JT;
+    const DevData& d = A.d;
+    extern __shared__ double smem[];
+    double* fmtab = smem;
+    double* gx = smem + GLMMA_FM_DOUBLES;
+    double* glw = gx + GLMMA_NAGQ_MAX;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int p = d.p, pz = F::HAS_ZI ? d.p_zi : 0, nphi = F::HAS_PHI ? 1 : 0, nD = A.nD;
+    const int P = p + nD + nphi + pz;
+    const int oD = p, oPhi = p + nD, oG = p + nD + nphi;
+    const int xw = p + pz;
+    double* rec = smem + L::head_doubles() + wib * (size_t)(JT * L::W + JT * GLMMA_INFO_PMAX + ((A.ksm + 1) & ~1));
+    double* xt = rec + JT * L::W;                         // design rows of the staged tile: X | X_zi
+    double* aks = xt + JT * GLMMA_INFO_PMAX;              // the cluster's K node terms a_k (pass 1 -> pass 2)
+    const int nagq = A.grid->nagq, K = A.grid->K;
+    const unsigned rcp_nagq = nagq_rcp(nagq);
+    load_fmtab(fmtab, A.fmtab);
+    if (threadIdx.x < GLMMA_NAGQ_MAX) {
+        gx[threadIdx.x] = A.grid->x[threadIdx.x];
+        glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    }
+    __syncthreads();
+    const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
+    const double lw_const = A.grid->lw_const;
+    const int nrounds = (K + 31) >> 5;
+    const double ie = 0.5 / A.eps_eta, ip = 0.5 / A.eps_phi;
+
+    double tot[GLMMA_INFO_NPAIR];                         // this lane's share of the block total
+    for (int t = 0; t < GLMMA_INFO_NPAIR; ++t) tot[t] = 0.0;
+
+    auto point_at = [&](const double* rj, double eta, double ez, const FamPar& fam, double& ld, double& se, double& sz, double& sp) {
+        const double emu = F::NEED_EMU ? fast_exp(eta, cx) : 0.0;
+        const double elam = F::HAS_ZI ? fast_exp(fmin(fmax(ez, -690.0), 690.0), cx) : 0.0;
+        F::template point<true, true>(rj[0], rj[1], eta, ez, emu, elam, fam, cx, ld, se, sz, sp);
+    };
+    auto stage = [&](int64_t r0, int cnt) {
+        __syncwarp();
+        stage_tile<F, QY, QZ>(d, r0, cnt, lane, rec);
+        for (int t = lane; t < cnt * xw; t += 32) {
+            const int j = t / xw, l = t - j * xw;
+            xt[j * GLMMA_INFO_PMAX + l] = l < p ? d.X[r0 + j + (int64_t)l * d.N] : d.X_zi[r0 + j + (int64_t)(l - p) * d.N];
+        }
+        __syncwarp();
+    };
+
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t i = (int64_t)blockIdx.x * wpb + wib; i < d.n; i += nwarps) {
+        const int64_t r0 = d.row_ptr[i];
+        const int ni = (int)(d.row_ptr[i + 1] - r0);
+        const double w = d.weights ? d.weights[i] : 1.0;
+        double m[Q], ri[NP];
+#pragma unroll
+        for (int dd = 0; dd < Q; ++dd) m[dd] = d.modes[i * Q + dd];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) ri[t] = d.rinv[i * NP + t];
+        // pass 1: log-sum-exp of the node terms (node-independent parts cancel in the weights)
+        double mx = -INFINITY, se_sum = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int r = 0; r < nrounds; ++r) {
+                const int k = (r << 5) + lane;
+                const bool valid = k < K;
+                double b[Q];
+                int idx[Q];
+                double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+                for (int j0 = 0; j0 < ni; j0 += JT) {
+                    const int cnt = min(JT, ni - j0);
+                    stage(r0 + j0, cnt);
+                    for (int j = 0; j < cnt; ++j) {
+                        const double* rj = rec + j * L::W;
+                        double eta = rj[2], ez = F::HAS_ZI ? rj[L::OFF_XG] : 0.0;
+#pragma unroll
+                        for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
+#pragma unroll
+                        for (int dd = 0; dd < QZ; ++dd) ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);
+                        double ld, se, sz, sp;
+                        point_at(rj, eta, ez, A.fam, ld, se, sz, sp);
+                        a += ld;
+                    }
+                }
+                if (pass == 0) { if (valid) mx = fmax(mx, a); }
+                else if (valid) { se_sum += exp(a - mx); if (A.ksm) aks[k] = a; }
+            }
+            if (pass == 0) { mx = warp_max(mx); if (!(fabs(mx) < INFINITY)) mx = 0.0; }
+        }
+        se_sum = warp_sum(se_sum);
+        const double lse = mx + log(se_sum);
+        const bool ok = fabs(lse) < INFINITY;
+
+        // pass 2: derivatives
+        double Aacc[GLMMA_INFO_NPAIR], gbar[GLMMA_INFO_PMAX];
+        for (int t = 0; t < GLMMA_INFO_NPAIR; ++t) Aacc[t] = 0.0;
+        for (int t = 0; t < GLMMA_INFO_PMAX; ++t) gbar[t] = 0.0;
+        for (int r = 0; r < nrounds && ok; ++r) {
+            const int k = (r << 5) + lane;
+            const bool valid = k < K;
+            double b[Q];
+            int idx[Q];
+            double a = node_setup<Q>(valid ? k : K - 1, nagq, rcp_nagq, gx, glw, lw_const, m, ri, A.prior, b, idx);
+            // node weight first: from pass 1's terms, or by its own loop over the observations
+            if (A.ksm) a = valid ? aks[k] : 0.0;
+            else for (int j0 = 0; j0 < ni; j0 += JT) {
+                const int cnt = min(JT, ni - j0);
+                stage(r0 + j0, cnt);
+                for (int j = 0; j < cnt; ++j) {
+                    const double* rj = rec + j * L::W;
+                    double eta = rj[2], ez = F::HAS_ZI ? rj[L::OFF_XG] : 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
+#pragma unroll
+                    for (int dd = 0; dd < QZ; ++dd) ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);
+                    double ld, se, sz, sp;
+                    point_at(rj, eta, ez, A.fam, ld, se, sz, sp);
+                    a += ld;
+                }
+            }
+            const double pik = valid ? exp(a - lse) : 0.0;
+            double g[GLMMA_INFO_PMAX];
+            for (int t = 0; t < GLMMA_INFO_PMAX; ++t) g[t] = 0.0;
+            for (int j0 = 0; j0 < ni; j0 += JT) {
+                const int cnt = min(JT, ni - j0);
+                stage(r0 + j0, cnt);
+                for (int j = 0; j < cnt; ++j) {
+                    const double* rj = rec + j * L::W;
+                    const double* xj = xt + j * GLMMA_INFO_PMAX;
+                    double eta = rj[2], ez = F::HAS_ZI ? rj[L::OFF_XG] : 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
+#pragma unroll
+                    for (int dd = 0; dd < QZ; ++dd) ez = fma(rj[L::OFF_Z + QY + dd], b[QY + dd], ez);
+                    double ld, se, sz, sp, t0, se1, sz1, sp1, se2, sz2, sp2;
+                    point_at(rj, eta, ez, A.fam, ld, se, sz, sp);
+                    point_at(rj, eta + A.eps_eta, ez, A.fam, t0, se1, sz1, sp1);
+                    point_at(rj, eta - A.eps_eta, ez, A.fam, t0, se2, sz2, sp2);
+                    const double hee = (se1 - se2) * ie, hep = (sp1 - sp2) * ie, hez = (sz1 - sz2) * ie;
+                    double hpp = 0.0, hzp = 0.0, hzz = 0.0;
+                    if (F::HAS_PHI) {
+                        point_at(rj, eta, ez, A.fam_hi, t0, se1, sz1, sp1);
+                        point_at(rj, eta, ez, A.fam_lo, t0, se2, sz2, sp2);
+                        hpp = (sp1 - sp2) * ip;
+                        hzp = (sz1 - sz2) * ip;
+                    }
+                    if (F::HAS_ZI) {
+                        point_at(rj, eta, ez + A.eps_eta, A.fam, t0, se1, sz1, sp1);
+                        point_at(rj, eta, ez - A.eps_eta, A.fam, t0, se2, sz2, sp2);
+                        hzz = (sz1 - sz2) * ie;
+                    }
+                    // first derivatives of a_k and pi_k-weighted second derivatives
+                    for (int l = 0; l < p; ++l) {
+                        g[l] = fma(xj[l], se, g[l]);
+                        const double wx = pik * hee * xj[l];
+                        for (int c = l; c < p; ++c) Aacc[info_pair(l, c)] = fma(wx, xj[c], Aacc[info_pair(l, c)]);
+                        if (F::HAS_PHI) Aacc[info_pair(l, oPhi)] = fma(pik * hep, xj[l], Aacc[info_pair(l, oPhi)]);
+                        if (F::HAS_ZI) {
+                            const double wz = pik * hez * xj[l];
+                            for (int c = 0; c < pz; ++c) Aacc[info_pair(l, oG + c)] = fma(wz, xj[p + c], Aacc[info_pair(l, oG + c)]);
+                        }
+                    }
+                    if (F::HAS_PHI) {
+                        g[oPhi] += sp;
+                        Aacc[info_pair(oPhi, oPhi)] = fma(pik, hpp, Aacc[info_pair(oPhi, oPhi)]);
+                    }
+                    if (F::HAS_ZI) {
+                        for (int l = 0; l < pz; ++l) {
+                            g[oG + l] = fma(xj[p + l], sz, g[oG + l]);
+                            const double wz = pik * hzz * xj[p + l];
+                            for (int c = l; c < pz; ++c) Aacc[info_pair(oG + l, oG + c)] = fma(wz, xj[p + c], Aacc[info_pair(oG + l, oG + c)]);
+                            if (F::HAS_PHI) Aacc[info_pair(oPhi, oG + l)] = fma(pik * hzp, xj[p + l], Aacc[info_pair(oPhi, oG + l)]);
+                        }
+                    }
+                }
+            }
+            // prior part: D parameters
+            for (int t = 0; t < nD; ++t) {
+                double qf = 0.0;
+#pragma unroll
+                for (int a_ = 0; a_ < Q; ++a_)
+#pragma unroll
+                    for (int c_ = 0; c_ < Q; ++c_) qf = fma(b[a_] * A.dM[t][a_ * Q + c_], b[c_], qf);
+                g[oD + t] = fma(0.5, qf, A.dc[t]);
+            }
+            {
+                int tu = 0;
+                for (int t = 0; t < nD; ++t)
+                    for (int u = t; u < nD; ++u) {
+                        double qf = 0.0;
+#pragma unroll
+                        for (int a_ = 0; a_ < Q; ++a_)
+#pragma unroll
+                            for (int c_ = 0; c_ < Q; ++c_) qf = fma(b[a_] * A.dMM[tu][a_ * Q + c_], b[c_], qf);
+                        Aacc[info_pair(oD + t, oD + u)] = fma(pik, fma(0.5, qf, A.dcc[tu]), Aacc[info_pair(oD + t, oD + u)]);
+                        ++tu;
+                    }
+            }
+            // E[da da'] and E[da]
+            for (int r_ = 0; r_ < P; ++r_) {
+                gbar[r_] = fma(pik, g[r_], gbar[r_]);
+                const double pg = pik * g[r_];
+                for (int c_ = r_; c_ < P; ++c_) Aacc[info_pair(r_, c_)] = fma(pg, g[c_], Aacc[info_pair(r_, c_)]);
+            }
+        }
+        // node-independent part of d^2 log f / d phis^2 (obs_const's c_phi differenced in phis)
+        double cpp = 0.0;
+        if (F::HAS_PHI && ok) {
+            for (int j = lane; j < ni; j += 32) {
+                double c0, c1, c2;
+                const double y1 = d.y1[r0 + j], y2 = F::USES_Y2 ? d.y2[r0 + j] : 0.0;
+                F::obs_const(y1, y2, A.fam_hi, c0, c1);
+                F::obs_const(y1, y2, A.fam_lo, c0, c2);
+                cpp += (c1 - c2) * ip;
+            }
+            cpp = warp_sum(cpp);
+        }
+        // cluster total over the lanes (nodes), then w_i (A - gbar gbar'); lane t keeps pairs t, t + 32, ...
+        for (int r_ = 0; r_ < P; ++r_) gbar[r_] = warp_sum(gbar[r_]);
+        for (int r_ = 0; r_ < P; ++r_)
+            for (int c_ = r_; c_ < P; ++c_) {
+                const int t = info_pair(r_, c_);
+                double v = warp_sum(Aacc[t]) - gbar[r_] * gbar[c_];
+                if (F::HAS_PHI && r_ == oPhi && c_ == oPhi) v += cpp;
+                if (ok && ((r_ * P + c_) & 31) == lane) tot[t] = fma(w, v, tot[t]);
+            }
+        __syncwarp();
+    }
+    // block partials: every pair lives on exactly one lane of each warp
+    __syncthreads();
+    double* red = smem;        // wpb x NPAIR
+    for (int r_ = 0; r_ < P; ++r_)
+        for (int c_ = r_; c_ < P; ++c_) {
+            const int t = info_pair(r_, c_);
+            if (((r_ * P + c_) & 31) == lane) red[wib * GLMMA_INFO_NPAIR + t] = tot[t];
+        }
+    __syncthreads();
+    for (int t = threadIdx.x; t < GLMMA_INFO_NPAIR; t += blockDim.x) {
+        double v = 0.0;
+        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_INFO_NPAIR + t];
+        A.partials[(int64_t)blockIdx.x * GLMMA_INFO_NPAIR + t] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------
 // find_modes: per-cluster damped Newton on the reference's objective
 //   g(b) = -sum_j log f(y_ij | b) + b' invD b / 2          (R/Functions.R:5-20)
 // with its analytic gradient (R/Functions.R:21-65); the Newton matrix and the

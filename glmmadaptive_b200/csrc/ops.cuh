@@ -109,6 +109,11 @@ struct OpsImpl {
         else if (G == 8) modes_kernel<F, QY, QZ, 8><<<blocks, 128, 0, s>>>(a);
         else modes_kernel<F, QY, QZ, 32><<<blocks, 128, 0, s>>>(a);
     }
+    static void info(const InfoArgs& a, int grid, cudaStream_t s) {
+        using LL = EvalLayout<F, QY, QZ>;
+        const size_t smem = sizeof(double) * (LL::head_doubles() + 4 * (size_t)(GLMMA_INFO_JT * LL::W + GLMMA_INFO_JT * GLMMA_INFO_PMAX + ((a.ksm + 1) & ~1)));
+        info_kernel<F, QY, QZ><<<grid, 128, smem, s>>>(a);
+    }
     static void logpost(const ModeArgs& a, const double* b, double* out, cudaStream_t s) {
         const unsigned blocks = (unsigned)((a.d.n * 8 + 127) / 128);
         log_post_b_kernel<F, QY, QZ><<<blocks, 128, 0, s>>>(a, b, out);
@@ -122,7 +127,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA};
+        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, info, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA};
         return &ops;
     }
 };

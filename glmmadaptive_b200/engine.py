@@ -314,6 +314,17 @@ class Engine:
     def comm_size(self):
         return int(self.lib.glmma_comm_size(self._h))
 
+    def observed_information(self, betas, D, phis=None, gammas=None, diag_D=False):
+        """Hessian of the NEGATIVE log-likelihood on the current grid w.r.t. c(betas, D-params, phis,
+        gammas) from one device pass (glmma_observed_information); what the reference computes as
+        cd_vec(score_mixed), R/mixed_fit.R:324-342."""
+        nD = self.q if diag_D else self.npack
+        P = self.p + nD + self.n_phis + self.p_zi
+        keep, ptrs = self._theta_ptrs(betas, D, phis, gammas)
+        H = np.zeros((P, P), order="F")
+        self._check(self.lib.glmma_observed_information(self._h, *ptrs, int(bool(diag_D)), _dp(H)))
+        return np.ascontiguousarray(H)
+
     def log_post_b(self, b, betas, invD, phis=None, gammas=None):
         """log_post_b of predict()'s Metropolis step (R/methods.R:1020-1036) for one random-effects
         vector per cluster: b is n x q; returns the n values sum_j log f(y_ij | b_i) - b_i' invD b_i / 2."""
@@ -523,6 +534,14 @@ class Penalty:
         betas = np.asarray(betas, float)
         v = betas * self.inv_sigma / self.df
         return v * ((self.df + len(betas)) / (1.0 + betas @ v))
+
+    def hessian(self, betas):
+        """Jacobian of score() (symmetric): the penalty's block of the observed information."""
+        betas = np.asarray(betas, float)
+        v = betas * self.inv_sigma / self.df
+        den = 1.0 + betas @ v
+        f = (self.df + len(betas)) / den
+        return f * np.diag(self.inv_sigma / self.df) - (2.0 * f / den) * np.outer(v, v)
 
 
 def logLik_mixed(thetas, engine, gh, diag_D=False, i_contributions=False, fused=True, penalty=None):

@@ -466,8 +466,24 @@ def mixed_fit(engine, initial_values, control=None, diag_D=False, hessian=True, 
                converged_during_EM=during_EM,
                thetas=tht, n_outer=n_outer, counts=counts)
     if hessian:
-        out["Hessian"] = cd_vec(tht, lambda t: score_mixed(t, eng, gh, diag_D, penalty=pen))
-        counts["eval"] += 2 * len(tht)
+        # Observed information.  The reference differentiates score_mixed numerically (cd_vec,
+        # R/mixed_fit.R:324-342: 2 * nparams evaluations); the engine forms the same matrix in one pass
+        # (glmma_observed_information), which control["hessian"] = "cd_vec" turns off.
+        H = None
+        if con.get("hessian", "analytic") == "analytic" and hasattr(eng, "observed_information"):
+            try:
+                H = eng.observed_information(betas, D, phis, gammas, diag_D)
+                if pen is not None:
+                    H[:eng.p, :eng.p] += pen.hessian(betas)
+                counts["observed_information"] = 1
+            except GlmmaError as e:
+                if e.code not in (1,):          # GLMMA_ERR_ARG: more parameters than the one-pass kernel takes
+                    raise
+                H = None
+        if H is None:
+            H = cd_vec(tht, lambda t: score_mixed(t, eng, gh, diag_D, penalty=pen))
+            counts["eval"] += 2 * len(tht)
+        out["Hessian"] = H
     out["seconds"] = dict(EM=t_em, quasi_newton=t_qn, total=time.perf_counter() - t_start)
     return out
 

@@ -158,6 +158,10 @@ class ShardedEngine:
         r = self.local.em_score_raw(betas, phis, gammas)
         return self.local.unpack(r if self.in_engine else self._reduce_host(r), True)
 
+    def observed_information(self, *a, **k):
+        H = self.local.observed_information(*a, **k)
+        return self._reduce_host(H.reshape(-1)).reshape(H.shape)
+
     def glm_pass(self, *a, **k):
         return self._reduce_host(self.local.glm_pass(*a, **k))
 

@@ -242,6 +242,18 @@ GLMMA_API int glmma_em_score(glmma_handle* h, const double* betas, const double*
 GLMMA_API int glmma_glm_pass(glmma_handle* h, int design, int glm_family, int response, int use_offset,
                    int first, const double* beta, double* out);
 
+/* Observed information: the Hessian of the NEGATIVE marginal log-likelihood on the current grid with
+ * respect to theta = c(betas, D parameters, phis, gammas) (reference order, R/mixed_fit.R:240-247;
+ * D parameters: log(diag(D)) when diag_D, else chol_transf(D)), nparams x nparams column-major.  The
+ * reference differentiates score_mixed numerically for it (cd_vec, R/mixed_fit.R:324-342: 2 * nparams
+ * evaluations, relative truncation error ~1e-6); this is one pass over the data with the exact
+ * structure E[d2a] + Cov(da) per cluster and the families' analytic scores differenced point-wise
+ * (kernels.cuh: info_kernel), agreeing with cd_vec(score_mixed) to its truncation error.  Supports up to
+ * 12 parameters (GLMMA_ERR_ARG beyond: fall back to finite differences of glmma_eval).  The penalty
+ * term of penalized = TRUE (R/Fit_Funs.R:169-173) is the caller's (p x p host algebra). */
+GLMMA_API int glmma_observed_information(glmma_handle* h, const double* betas, const double* D,
+                               const double* phis, const double* gammas, int diag_D, double* H);
+
 /* log_post_b of predict(type = "subject_specific", se.fit = TRUE)'s Metropolis step
  * (reference R/methods.R:1020-1036, called there through mapply once per cluster for the current and
  * once for the proposed random effects of every Monte-Carlo draw, :1093-1112): for ONE vector b_i per

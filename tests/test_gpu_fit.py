@@ -232,3 +232,33 @@ def test_log_post_b_batch_vs_oracle(name):
                     for i in range(od.n)])
     assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-10
     eng.close()
+
+
+@pytest.mark.parametrize("name,diag", [("C1", False), ("C2", False), ("C3", False), ("C3", True), ("C4", False),
+                                        ("C5a", False), ("C5b", False)])
+def test_observed_information_vs_cd_vec_of_the_score(name, diag):
+    """glmma_observed_information (one pass: E[d2a] + Cov(da) per cluster) against what the reference
+    computes, cd_vec of score_mixed on the same grid (R/mixed_fit.R:324-342) -- through the engine's score
+    and through the oracle's -- to 1e-5 of the largest entry (cd_vec's own truncation error is ~1e-6)."""
+    from glmmadaptive_b200.fit import cd_vec
+    d, th, fam_name = _case(name, 50)
+    if name == "C3" and not diag:
+        d["weights"] = np.random.default_rng(4).uniform(0.5, 2.0, 50)
+    fam = oracle_family(fam_name)
+    if diag:
+        th = dict(th); th["D"] = np.diag(np.diag(th["D"]))
+    od, gh = oracle_grid(d, th, fam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], X_zi=d.get("X_zi"),
+                    Z_zi=d.get("Z_zi"), weights=d.get("weights"))
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    tv = thetas_vec(th, diag_D=diag)
+    H = eng.observed_information(th["betas"], th["D"], th.get("phis"), th.get("gammas"), diag_D=diag)
+    assert np.allclose(H, H.T)
+    ref = cd_vec(tv, lambda t: gb.score_mixed(t, eng, None, diag))
+    ref_o = agq.cd_vec(tv, lambda t: agq.score_mixed(t, od, fam, gh, diag_D=diag))
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(ref - ref_o)) < 1e-7 * scale
+    # entry-wise against the scale of its row and column (blocks differ by orders of magnitude)
+    sd = np.sqrt(np.abs(np.diag(ref)))
+    assert np.max(np.abs(H - ref) / np.outer(sd, sd)) < 2e-5, np.max(np.abs(H - ref) / np.outer(sd, sd))
+    eng.close()
