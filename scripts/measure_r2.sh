@@ -1,0 +1,17 @@
+# round-2 measurement set (one B200): other BASELINE configurations at 1e6 clusters, cluster-size sweep of
+# the config-3 model, ragged clusters, family sweep; launch list + ncu --set full of the dominant kernel.
+mkdir -p gpurun_out
+: > gpurun_out/r2_configs_1gpu_1e6.jsonl
+python bench.py --steps 20 --warmup 3 2>/dev/null | tail -1 >> gpurun_out/r2_configs_1gpu_1e6.jsonl
+for w in C2 C4 C5a C5b C1; do
+  python bench.py --workload $w --clusters 1000000 --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 >> gpurun_out/r2_configs_1gpu_1e6.jsonl
+done
+: > gpurun_out/r2_cluster_sizes_C3.jsonl
+for ni in 8 12 16 17 24 32 64; do
+  python bench.py --ni $ni --clusters $((4000000 / ni)) --steps 10 --warmup 3 --no-cpu-baseline --no-fit 2>/dev/null | tail -1 >> gpurun_out/r2_cluster_sizes_C3.jsonl
+done
+python bench.py --ragged --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/r2_ragged_C3.jsonl
+python scripts/family_sweep.py 200000 > gpurun_out/r2_family_sweep.txt 2>&1
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fit > gpurun_out/plain3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_dev.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fit > gpurun_out/ncu3.log 2>&1
+python bench.py --steps 3 --warmup 3 --clusters 200000 --no-cpu-baseline --no-fit > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:eval_fast -s 3 -c 1 -f -o gpurun_out/prof_dev python bench.py --steps 3 --warmup 3 --clusters 200000 --no-cpu-baseline --no-fit > gpurun_out/ncu2.log 2>&1
+tail -2 gpurun_out/r2_family_sweep.txt
