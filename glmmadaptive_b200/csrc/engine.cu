@@ -693,7 +693,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
             if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
             for (int s = 0; s < 2; ++s) {
                 int bps = 0;
-                ce = ops->fast_config(h->xw, kTile[v], h->K, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
+                ce = ops->fast_config(h->xw, kTile[v], h->K, h->nagq, &bps, &h->fast_smem[v][s], &h->fast_threads[v][s]);
                 if (ce != cudaSuccess || bps < 1) {
                     cuda_fail(h, ce, "fast eval kernel configuration");
                     g_create_error = h->error; glmma_destroy(h); return GLMMA_ERR_CUDA;

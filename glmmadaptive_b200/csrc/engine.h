@@ -16,7 +16,7 @@ struct FamOps {
     void (*prep)(const PrepArgs&, const CoefPar&, cudaStream_t);
     cudaError_t (*eval_config)(int score, int jt, int nagq, int extra, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval)(const EvalArgs&, int score, int grid, int threads, size_t smem, cudaStream_t);
-    cudaError_t (*fast_config)(int xw, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads);
+    cudaError_t (*fast_config)(int xw, int nj, int K, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads);
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
     void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);

@@ -88,6 +88,8 @@ struct FamBase {
     //              phi-score is sp_scale() * (L + rec1 r), whose second term needs no per-point work
     //              (it is sum_j rec1_j * [posterior sum of r_j], formed once per cluster);
     //           2  exp(eta) only: log f = -emu (+ y eta), carrier emu.
+    //           3  censored.normal: Gaussian part hoisted to one quadratic form per node, censored
+    //              observations from compact records (kernels.cuh).
     //           fast_score(mean(carrier), y1, rec1) maps the posterior mean of the carrier to the
     //           posterior mean of the eta-score.
     static constexpr bool LIN_ETA = false;
@@ -614,6 +616,9 @@ struct FamGamma : FamBase {
 // a[2] = 1/sigma ------------------------------------------------------------------
 struct FamCensoredNormal : FamBase {
     static constexpr int GENERIC_UNROLL = 2;
+    // Register variant: the Gaussian part of the cluster (its uncensored observations) is one quadratic
+    // form per node, only the censored observations are evaluated per point (kernels.cuh, FAST_KIND 3)
+    static constexpr int FAST_KIND = 3;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
     static constexpr bool NEED_EMU = false;

@@ -1050,9 +1050,16 @@ struct FastLayout {
     // RP: even (16-byte pairs) with RP / 2 odd, so the 16-byte loads of a quarter warp, whose lanes
     // walk consecutive node indices of the fastest dimension, fall on distinct bank groups
     static constexpr int RP = NJ + 2;
-    static constexpr int TFD = Q * NG * RP;                 // doubles of tabF
-    static constexpr int TLD = NT * NG * RP;
-    static constexpr int NACCS = F::HAS_ZI ? 2 : 1;
+    // table rows: (dimension e, node index a) -> row e * nagq + a, i.e. only the nagq rows per dimension
+    // that the grid has (nagq = 7 at q = 3 keeps 21 + 7 rows instead of 48 + 16: shared memory per warp
+    // is what bounds the resident warps of the zero-inflated q = 3 kernels and of the 16-observation tile)
+    // FAST_KIND 3 (Gaussian part hoisted, families.cuh): compact records of the cluster's censored
+    // observations {A, C_0.., y, sign} take the place of the (unused) separable table
+    static constexpr bool GQ = F::FAST_KIND == 3;
+    static constexpr int CRW = (QY + 3 + 1) & ~1;
+    __host__ __device__ static int tfd(int nagq) { return F::NEED_EMU ? Q * nagq * RP : (GQ ? NJ * CRW : 0); }   // doubles of tabF
+    __host__ __device__ static int tld(int nagq) { return NT * (QZ > 0 ? nagq : 1) * RP; }   // doubles of tabL
+    static constexpr int NACCS = (F::HAS_ZI || GQ) ? 2 : 1;
     static constexpr int NTOT = 2 + Q * (Q + 1) / 2;        // per-lane totals: g_phi, (pad), S packed
     // per-cluster scalars prefetched with the records, one packed record per cluster in HBM
     // (pack_cluster_kernel): modes, R^-1, logdet, Z'y1, weight
@@ -1061,18 +1068,19 @@ struct FastLayout {
     static constexpr int NJR = NJ <= 8 ? 8 : 16;            // rows of the per-observation reduction scratch (power of two)
     static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
     __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
-    static constexpr int FIXED = TFD + TLD + NACCS * NJR * 32 + NJ + NTOT * 32 + 4;
-    __host__ __device__ static size_t warp_stride(int xw) { return (size_t)(2 * pre(xw) + FIXED + 1) & ~(size_t)1; }
-    // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed node indices (K ints).  For
+    static constexpr int FIXED0 = (NACCS * NJR * 32 + NJ + NTOT * 32 + 4 + 1) & ~1;   // scratch, wv, per-lane totals, warp totals
+    __host__ __device__ static int fixed(int nagq) { return FIXED0 + tfd(nagq) + tld(nagq); }
+    __host__ __device__ static size_t warp_stride(int xw, int nagq) { return (size_t)(2 * pre(xw) + fixed(nagq) + 1) & ~(size_t)1; }
+    // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed table rows (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
-    // indices): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
+    // rows): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
     __host__ __device__ static bool has_ntab(int K) { return K <= GLMMA_NTAB_MAX_K; }
     __host__ __device__ static size_t node_doubles(int K) {
         return (((has_ntab(K) ? (size_t)K * (Q + 1) : 0) + (K + 1) / 2) + 1) & ~(size_t)1;
     }
     __host__ __device__ static size_t coltab_doubles() { return 2 * GLMMA_COLTAB_MAX; }
-    __host__ static size_t smem_bytes(int warps, int K, int xw) {
-        return sizeof(double) * (L::head_doubles() + coltab_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw));
+    __host__ static size_t smem_bytes(int warps, int K, int xw, int nagq) {
+        return sizeof(double) * (L::head_doubles() + coltab_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw, nagq));
     }
 };
 
@@ -1112,10 +1120,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     int* nidx = reinterpret_cast<int*>(ntab + (has_ntab ? (size_t)K * (Q + 1) : 0));   // K packed node indices
     const int xw = A.xw;
     const int PRE = FL::pre(xw);
-    double* pre0 = smem + L::head_doubles() + FL::coltab_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw);
-    double* tabF = pre0 + 2 * PRE;
-    double* tabL = tabF + FL::TFD;
-    double* acc_eta = tabL + FL::TLD;
+    double* pre0 = smem + L::head_doubles() + FL::coltab_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw, nagq);
+    // fixed-size areas sit between the prefetch buffers and the tables, at constant offsets below tabF (the
+    // table sizes depend on nagq: keeping them last leaves one anchor register for everything but tabL)
+    double* tabF = pre0 + 2 * PRE + FL::FIXED0;
+    double* tabL = tabF + FL::tfd(nagq);
+    double* acc_eta = tabF - FL::FIXED0;
     double* acc_zi = acc_eta + FL::NJR * 32;
     double* wv = acc_eta + FL::NACCS * FL::NJR * 32;         // staged second record field (y + phi, trials ...), contiguous
     double* totl = wv + NJ;                                  // NTOT x 32 per-lane totals
@@ -1163,7 +1173,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         for (int e = 0; e < Q; ++e) {
             const int a = kk % nagq;
             kk /= nagq;
-            packed |= a << (8 * e);
+            packed |= (e * nagq + a) << (8 * e);       // table row of (dimension e, node index a)
             if (has_ntab) ntab[k * (Q + 1) + e] = gx[a];
             lw += glw[a];
         }
@@ -1354,7 +1364,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         }
         // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
         // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
-        // test above.  Entry (observation j, dimension e, node index a) goes to row e * NG + a, column j.
+        // test above.  Entry (observation j, dimension e, node index a) goes to row e * nagq + a, column j.
         {
             const unsigned inv_nagq = (65536u + (unsigned)nagq - 1u) / (unsigned)nagq;
             if (F::NEED_EMU) {
@@ -1370,7 +1380,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         const double2 cb = coef[p];
                         x3[u] = fma(cb.x, gx[na], cb.y);
                         const int pj_ = p / Q, pe_ = p - pj_ * Q;
-                        off[u] = (pe_ * NG + na) * RP + pj_;
+                        off[u] = (pe_ * nagq + na) * RP + pj_;
                     }
                     fast_exp_vec<3>(x3, cx, o3);
 #pragma unroll
@@ -1392,7 +1402,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         const double2 cb = coef[NJ * Q + p];
                         x3[u] = fma(cb.x, QZ > 0 ? gx[na] : 0.0, cb.y);
                         const int pj_ = p / NTc, pe_ = p - pj_ * NTc;
-                        off[u] = (pe_ * NG + na) * RP + pj_;
+                        off[u] = (pe_ * nz + na) * RP + pj_;
                     }
                     fast_exp_vec<3>(x3, cx, o3);
 #pragma unroll
@@ -1419,15 +1429,70 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 #pragma unroll
         for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? sc[SC_ZTY + dd] : 0.0;
 
+        // FAST_KIND 3 (censored.normal): an uncensored observation contributes -t^2 / 2 with t linear in
+        // the node, so the sum over the cluster's uncensored observations is ONE quadratic form in
+        // delta_k = b_k - mode per node, sum_j (res_j - z_j' delta)^2 = U0 + delta' (U1 + U2 delta) with
+        // res_j the residual at the mode: no per-point work at all for them -- their eta-scores are linear
+        // in delta (posterior mean of delta) and their phi-scores are the same quadratic form.  Only the
+        // censored observations are walked per node, from compact records (x_jk = A_j + C_j' delta_k).
+        constexpr bool GQ = FL::GQ;
+        constexpr int NPY = QY * (QY + 1) / 2;
+        double* crec = tabF;
+        double gq_u0 = 0.0, gq_u1[QY], gq_u2[NPY];
+        int gq_nc = 0;
+        if (GQ) {
+            const bool live = lane < nic;
+            const double* r = rec + lane * W;
+            double resm = 0.0, zv[QY];
+            bool cens = false;
+#pragma unroll
+            for (int dd = 0; dd < QY; ++dd) zv[dd] = live ? r[L::OFF_Z + dd] : 0.0;
+            if (live) {
+                resm = r[0] - r[2];
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) resm = fma(-zv[dd], m[dd], resm);
+                cens = r[1] != 0.0;
+            }
+            const unsigned cm = __ballot_sync(0xffffffffu, live && cens);
+            gq_nc = __popc(cm);
+            const bool unc = live && !cens;
+            gq_u0 = warp_sum(unc ? resm * resm : 0.0);
+            int t = 0;
+#pragma unroll
+            for (int dd = 0; dd < QY; ++dd) {
+                gq_u1[dd] = -2.0 * warp_sum(unc ? resm * zv[dd] : 0.0);
+#pragma unroll
+                for (int ee = dd; ee < QY; ++ee) { gq_u2[t] = (ee == dd ? 1.0 : 2.0) * warp_sum(unc ? zv[dd] * zv[ee] : 0.0); ++t; }
+            }
+            if (live && cens) {
+                const int slot = __popc(cm & ((1u << lane) - 1u));
+                const double sg = r[1] == 1.0 ? 1.0 : -1.0;          // x = sg (y - eta) / sigma: left +, right -
+                const double s = sg * A.fam.a[2];
+                double* cr = crec + slot * FL::CRW;
+                cr[0] = s * resm;
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) cr[1 + dd] = -s * zv[dd];
+                cr[1 + QY] = r[0];
+                cr[2 + QY] = sg;
+            }
+            __syncwarp();
+        }
+
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
         double acc_e[NJ], acc_z[F::HAS_ZI ? NJ : 1];
+        double gq_bb[QY];             // FAST_KIND 3: sum_k e_k delta_k
         for (int attempt = 0; attempt < 2; ++attempt) {
             sum_e = 0.0; gphi = 0.0;
 #pragma unroll
             for (int t = 0; t < NP; ++t) S[t] = 0.0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) { acc_e[j] = 0.0; if (F::HAS_ZI) acc_z[j] = 0.0; }
+            if (GQ) {
+                for (int c = 0; c < gq_nc; ++c) acc_eta[c * 32 + lane] = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < QY; ++dd) gq_bb[dd] = 0.0;
+            }
             for (int rr = 0; rr < nrounds; ++rr) {
                 const int r = (rr == 0) ? rc : (rr <= rc ? rr - 1 : rr);
                 const int k = (r << 5) + lane;
@@ -1443,17 +1508,18 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     nt[Q] = A.grid->lw_const;
 #pragma unroll
                     for (int e = 0; e < Q; ++e) {
-                        const int ae = (packed >> (8 * e)) & 0xff;
+                        const int ae = ((packed >> (8 * e)) & 0xff) - e * nagq;
                         nt[e] = gx[ae];
                         nt[Q] += glw[ae];
                     }
                 }
-                double b[Q];
+                double b[Q], dl[GQ ? Q : 1];
 #pragma unroll
                 for (int dd = 0; dd < Q; ++dd) {
-                    double s = m[dd];
+                    double s = GQ ? 0.0 : m[dd];
 #pragma unroll
                     for (int e = dd; e < Q; ++e) s = fma(ri[Tri<Q>::rm(dd, e)], nt[e], s);
+                    if (GQ) { dl[dd] = s; s += m[dd]; }
                     b[dd] = s;
                 }
                 double quad = 0.0;
@@ -1467,12 +1533,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 double a = fma(-0.5, quad, A.prior.logprior_const) + nt[Q];
                 const double* pf[Q];
 #pragma unroll
-                for (int e = 0; e < Q; ++e) pf[e] = tabF + (e * NG + ((packed >> (8 * e)) & 0xff)) * RP;
+                for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
                 const double* pl[QZ > 0 ? QZ : 1];
 #pragma unroll
                 for (int e = 0; e < (QZ > 0 ? QZ : 1); ++e)
-                    pl[e] = tabL + (e * NG + (QZ > 0 ? ((packed >> (8 * (QY + e))) & 0xff) : 0)) * RP;
-                const double2* pz = tabZ + (QZ > 0 ? ((packed >> (8 * QY)) & 0xff) : 0);
+                    pl[e] = tabL + (QZ > 0 ? (int)((packed >> (8 * (QY + e))) & 0xff) - QY * nagq : 0) * RP;
+                const double2* pz = tabZ + (QZ > 0 ? (int)((packed >> (8 * QY)) & 0xff) - QY * nagq : 0);
                 double vphi = 0.0;
                 double se_[NJ], sz_[F::HAS_ZI ? NJ : 1];
                 if (F::LIN_ETA) {
@@ -1512,7 +1578,46 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             if (F::HAS_PHI) vphi += sp;                                                                \
         }                                                                                              \
     }
-                if (F::FAST_KIND != 0) {
+                if (GQ) {
+                    const double isig = A.fam.a[2], isig2 = isig * isig;
+                    double qk = gq_u0;
+                    {
+                        int t = 0;
+#pragma unroll
+                        for (int dd = 0; dd < QY; ++dd) {
+                            double s = gq_u1[dd];
+#pragma unroll
+                            for (int ee = dd; ee < QY; ++ee) { s = fma(gq_u2[t], dl[ee], s); ++t; }
+                            qk = fma(dl[dd], s, qk);
+                        }
+                    }
+                    a = fma(-0.5 * isig2, qk, a);
+                    vphi = isig2 * qk;
+#pragma unroll 1
+                    for (int c = 0; c < gq_nc; ++c) {
+                        const double* cr = crec + c * FL::CRW;
+                        double x = cr[0];
+#pragma unroll
+                        for (int dd = 0; dd < QY; ++dd) x = fma(cr[1 + dd], dl[dd], x);
+                        double ldc, lam, dn, B;
+                        fast_gauss_tail(x, cx, ldc, lam, dn, B);
+                        double cv = lam, spv = -x * lam;
+                        if (B < GLMMA_SQRT_DBL_EPS) {
+                            // the reference's sqrt(eps) floors (R/Fit_Funs.R:1395, 1413, 1421): rare
+                            const double Bf = GLMMA_SQRT_DBL_EPS;
+                            if (cr[2 + QY] > 0.0) {
+                                spv = -x * dn / Bf;
+                            } else {
+                                const double eta = fma(x, A.fam.a[0], cr[1 + QY]);
+                                cv = (A.fam.a[0] * dn - eta * (Bf - B)) / Bf * isig;
+                                spv = (B - Bf - x * dn) / Bf;
+                            }
+                        }
+                        a += ldc;
+                        vphi += spv;
+                        acc_zi[c * 32 + lane] = cv;
+                    }
+                } else if (F::FAST_KIND != 0) {
                     // stage-wise chunks of four observations (interleaved chains): separable
                     // product, (log t, 1/t) for the chunk, accumulation.  Two alternating
                     // accumulators keep the sum over observations off the critical path.
@@ -1629,10 +1734,17 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         for (int ee = dd; ee < Q; ++ee) { S[t] = fma(eb, b[ee], S[t]); ++t; }
                     }
                     if (F::HAS_PHI) gphi = fma(e, vphi, gphi);
+                    if (GQ) {
+#pragma unroll 1
+                        for (int c = 0; c < gq_nc; ++c) acc_eta[c * 32 + lane] = fma(e, acc_zi[c * 32 + lane], acc_eta[c * 32 + lane]);
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j) {
-                        acc_e[j] = fma(e, se_[j], acc_e[j]);
-                        if (F::HAS_ZI) acc_z[j] = fma(e, sz_[j], acc_z[j]);
+                        for (int dd = 0; dd < QY; ++dd) gq_bb[dd] = fma(e, dl[dd], gq_bb[dd]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            acc_e[j] = fma(e, se_[j], acc_e[j]);
+                            if (F::HAS_ZI) acc_z[j] = fma(e, sz_[j], acc_z[j]);
+                        }
                     }
                 }
             }
@@ -1694,10 +1806,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
             // per-observation sums over the 32 lanes: through shared memory; lane l sums the
             // (l / NJR)-th slice of columns of observation l % NJR, slices combined by shuffles
+            if (!GQ) {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                acc_eta[j * 32 + lane] = acc_e[j];
-                if (F::HAS_ZI) acc_zi[j * 32 + lane] = acc_z[j];
+                for (int j = 0; j < NJ; ++j) {
+                    acc_eta[j * 32 + lane] = acc_e[j];
+                    if (F::HAS_ZI) acc_zi[j * 32 + lane] = acc_z[j];
+                }
             }
             __syncwarp();
             {
@@ -1718,8 +1832,28 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
                 double zb = 0.0, zz = 0.0;
+                double scv_gq = 0.0;
+                if (GQ) {
+                    // censored observation in compact slot c: score = -sign / sigma * mean(carrier_c), the row sum
+                    // held by lane c; uncensored: (res - z' mean(delta)) / sigma^2
+                    const bool live = lane < nic;
+                    const double* r = rec + lane * W;
+                    const bool cens = live && r[1] != 0.0;
+                    const unsigned cm = __ballot_sync(0xffffffffu, cens);
+                    const int slot = __popc(cm & ((1u << lane) - 1u));
+                    const double sl = __shfl_sync(0xffffffffu, s1, cens ? slot : 0);
+                    double resd = live ? r[0] - r[2] : 0.0;
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd) {
+                        const double bbar = warp_sum(gq_bb[dd]) * isum;
+                        if (live) resd = fma(-r[L::OFF_Z + dd], m[dd] + bbar, resd);
+                    }
+                    const double isig = A.fam.a[2];
+                    scv_gq = cens ? (r[1] == 1.0 ? -isig : isig) * (sl * isum) : isig * isig * resd;
+                }
                 if (lane < nic) {
-                    const double scv = F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
+                    const double scv = GQ ? scv_gq
+                                     : F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
                                                          : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
                     zb = ok ? w * scv : 0.0;
                     if (F::HAS_ZI) zz = inv * s2;

@@ -74,13 +74,13 @@ struct OpsImpl {
     // large per-warp areas (zero-inflated, q = 3) keep more warps resident with fewer, larger blocks.
     // Picks the shape with the most resident warps per SM; ties go to the smaller block.
     template <int NJ>
-    static cudaError_t fast_config_nj(int K, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+    static cudaError_t fast_config_nj(int K, int nagq, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
         for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t *= 2) {
-            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw);
+            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw, nagq);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ>, t, smem);
@@ -89,10 +89,10 @@ struct OpsImpl {
         }
         return cudaSuccess;
     }
-    static cudaError_t fast_config(int xw, int nj, int K, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
-        return nj == 8 ? fast_config_nj<8>(K, xw, blocks_per_sm, smem_bytes, threads)
-             : nj == 12 ? fast_config_nj<12>(K, xw, blocks_per_sm, smem_bytes, threads)
-                        : fast_config_nj<16>(K, xw, blocks_per_sm, smem_bytes, threads);
+    static cudaError_t fast_config(int xw, int nj, int K, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
+        return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
+             : nj == 12 ? fast_config_nj<12>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
+                        : fast_config_nj<16>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
     }
     static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, int threads, size_t smem, cudaStream_t s) {
         if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
