@@ -59,6 +59,13 @@ __device__ __forceinline__ void zero_part(double ez, double elam, const MathCtx&
 // register variant tabulates them per (observation, zero-part node index) -- eta_zi depends on the
 // node only through the zero-part random effect, so with q_zi <= 1 there are n_i * nAGQ distinct
 // values per cluster instead of n_i * nAGQ^q)
+// YC (register variant, zero part hoisted -- kernels.cuh, "ZP" mode): the kernel has sorted the cluster's
+// observations into positive and zero responses and adds the zero-part terms that every observation
+// shares, -log(1 + exp(eta_zi)) in log f and -plogis(eta_zi) in the eta_zi-score, once per NODE from a
+// per-cluster table.  point<., false, true, YC> then returns ld and sz WITHOUT those two terms, for an
+// observation known to be positive (YC = 1) or zero (YC = 2); zl1p / zpi are not read.  The hurdle
+// families have nothing left to evaluate for a zero response (ld = eta_zi, sz = 1: ZERO_FREE), so the
+// kernel never calls them with YC = 2.
 #define GLMMA_POINT_ARGS double eta, double ez, double emu, double elam, const FamPar& fp, const MathCtx& cx, \
                          double& ld, double& se, double& sz, double& sp, double zl1p = 0.0, double zpi = 0.0
 
@@ -105,6 +112,8 @@ struct FamBase {
     // generic kernel: observations evaluated per trip of its point loop (independent chains for the FP64
     // pipe); 2 for the functors whose careful form is long (beta, censored normal, probit / cloglog)
     static constexpr int GENERIC_UNROLL = 4;
+    static constexpr bool ZERO_FREE = false;     // hurdle families: a zero response involves the zero part only
+    __device__ static __forceinline__ bool is_pos(double y1) { return y1 > 0.0; }
     __device__ static __forceinline__ double fast_addend(const FamPar&) { return 0.0; }
     __device__ static __forceinline__ double fast_score(double c, double, double, const FamPar&) { return c; }
     __device__ static __forceinline__ void stage(double&, double&, const FamPar&) {}
@@ -126,7 +135,7 @@ struct FamBinomialLogit : FamBase {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, lt, L;
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
@@ -172,7 +181,7 @@ struct FamBinomialOther : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
         FamBinomialLogit::obs_const(y, N, fp, cll, cphi);
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         sz = 0.0; sp = 0.0;
         if (!CAREFUL) {
@@ -225,7 +234,7 @@ struct FamPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = -lgamma(y + 1.0); cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu;
         link_log<CAREFUL>(eta, emu, mu, lmu);
@@ -259,7 +268,7 @@ struct FamNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         nb_const(y, fp, cll, cphi);
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double yp_, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu, L, r;
@@ -305,12 +314,13 @@ struct FamZiPoisson : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         double mu, lmu, pi, l1p;
         link_log<CAREFUL>(eta, emu, mu, lmu);
-        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);   // log(1 + lambda), plogis(eta_zi)
-        if (y > 0.0) {
+        if (YC != 0) { l1p = 0.0; pi = 0.0; }
+        else if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);   // log(1 + lambda), plogis(eta_zi)
+        if (YC == 1 || (YC == 0 && y > 0.0)) {
             ld = (CAREFUL ? fma(y, lmu, -mu) : -mu) - l1p;     // fast variant: + y eta at node level
             if (SCORE) { se = y - mu; sz = -pi; }
         } else {
@@ -337,14 +347,15 @@ struct FamZiNegBin : FamBase {
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu, L, r, pi, l1p;
         link_log<CAREFUL>(eta, emu, mu, lmu);
         fast_log_rcp<CAREFUL>(mu + phi, cx, L, r);
-        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
-        if (y > 0.0) {
+        if (YC != 0) { l1p = 0.0; pi = 0.0; }
+        else if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+        if (YC == 1 || (YC == 0 && y > 0.0)) {
             const double yp = y + phi;
             ld = (CAREFUL ? fma(y, lmu, -yp * L) : -yp * L) - l1p;     // fast variant: + y eta at node level
             if (SCORE) {
@@ -381,12 +392,13 @@ struct FamZiBinomial : FamBase {
         cll = (y == 0.0 || y == N) ? 0.0 : lgamma(N + 1.0) - lgamma(y + 1.0) - lgamma(N - y + 1.0);
         cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         double mu, lt, L, pi, l1p;
         link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
-        if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
-        if (y > 0.0) {
+        if (YC != 0) { l1p = 0.0; pi = 0.0; }
+        else if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+        if (YC == 1 || (YC == 0 && y > 0.0)) {
             ld = (CAREFUL ? fma(y, lt, -N * L) : -N * L) - l1p;        // fast variant: + y eta at node level
             if (SCORE) { se = fma(-N, mu, y); sz = -pi; }
         } else {
@@ -396,7 +408,8 @@ struct FamZiBinomial : FamBase {
             ld = lu - l1p;
             if (SCORE) {
                 se = -N * mu * F * ru;
-                sz = pi * (1.0 - F) * ru;
+                // lambda / (lambda + F) - pi = pi (1 - F) / (lambda + F); hoisted: the first term alone
+                sz = YC != 0 ? elam * ru : pi * (1.0 - F) * ru;
             }
         }
         sp = 0.0;
@@ -404,11 +417,12 @@ struct FamZiBinomial : FamBase {
 };
 
 // zero part shared by the hurdle families (e.g. R/Fit_Funs.R:652-655, 670-676)
-template <bool CAREFUL, bool ZT = false>
+template <bool CAREFUL, bool ZT = false, int YC = 0>
 __device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCtx& cx, bool pos, double& lz, double& sz,
                                             double zl1p = 0.0, double zpi = 0.0) {
     double pi, l1p;
-    if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
+    if (YC != 0) { l1p = 0.0; pi = 0.0; }
+    else if (ZT) { l1p = zl1p; pi = zpi; } else zero_part<CAREFUL>(ez, elam, cx, l1p, pi);
     // positive: log(1 - pi) = -log(1 + e^ez); zero: log pi = ez - log(1 + e^ez)
     lz = pos ? -l1p : ez - l1p;
     sz = pos ? -pi : 1.0 - pi;
@@ -416,16 +430,17 @@ __device__ __forceinline__ void hurdle_zero(double ez, double elam, const MathCt
 
 // ----- hurdle.poisson() -- R/Fit_Funs.R:642-688 --------------------------------
 struct FamHurdlePoisson : FamBase {
+    static constexpr bool ZERO_FREE = true;
     static constexpr bool Y_TABLE = true;
     static constexpr bool HAS_ZI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar&, double& cll, double& cphi) {
         cll = (y > 0.0) ? -lgamma(y + 1.0) : 0.0; cphi = 0.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
-        const bool pos = y > 0.0;
+        const bool pos = YC == 0 ? y > 0.0 : YC == 1;
         double lz;
-        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
+        hurdle_zero<CAREFUL, ZT, YC>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double mu, lmu;
@@ -448,17 +463,18 @@ struct FamHurdlePoisson : FamBase {
 
 // ----- hurdle.negative.binomial() -- R/Fit_Funs.R:690-764 ----------------------
 struct FamHurdleNegBin : FamBase {
+    static constexpr bool ZERO_FREE = true;
     static constexpr bool Y_TABLE = true;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     __device__ static __forceinline__ void obs_const(double y, double, const FamPar& fp, double& cll, double& cphi) {
         if (y > 0.0) nb_const(y, fp, cll, cphi); else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
-        const bool pos = y > 0.0;
+        const bool pos = YC == 0 ? y > 0.0 : YC == 1;
         double lz;
-        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
+        hurdle_zero<CAREFUL, ZT, YC>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double phi = fp.a[0];
@@ -491,6 +507,7 @@ struct FamHurdleNegBin : FamBase {
 // ----- hurdle.lognormal() -- R/Fit_Funs.R:829-885; a[0] = sigma, a[1] = log sigma,
 // a[2] = 1/sigma^2 ---------------------------------------------------------------
 struct FamHurdleLogNormal : FamBase {
+    static constexpr bool ZERO_FREE = true;
     static constexpr bool HAS_ZI = true;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
@@ -499,11 +516,11 @@ struct FamHurdleLogNormal : FamBase {
         if (y > 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double ly, GLMMA_POINT_ARGS) {
-        const bool pos = y > 0.0;
+        const bool pos = YC == 0 ? y > 0.0 : YC == 1;
         double lz;
-        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
+        hurdle_zero<CAREFUL, ZT, YC>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             const double d = ly - eta;
@@ -554,7 +571,7 @@ struct FamBeta : FamBase {
         cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y;
         cphi = fp.a[0] * fp.a[2];
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
         beta_point<SCORE, CAREFUL>(ly, l1y, eta, emu, fp, cx, ld, se, sp);
         sz = 0.0;
@@ -564,6 +581,8 @@ struct FamBeta : FamBase {
 // ----- hurdle.beta.fam() -- R/Fit_Funs.R:932-1004 (scores evaluated at the true mu;
 // the reference's attr(mu_y) <- eta slip, SURVEY appendix G, is not replicated) ---
 struct FamHurdleBeta : FamBase {
+    static constexpr bool ZERO_FREE = true;
+    __device__ static __forceinline__ bool is_pos(double ly) { return ly > -INFINITY; }
     static constexpr int GENERIC_UNROLL = 2;
     static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
     static constexpr double EMU_HI = 1e13;
@@ -576,11 +595,11 @@ struct FamHurdleBeta : FamBase {
         if (ly > -INFINITY) { cll = fp.a[1] - ly + (fp.a[0] - 1.0) * l1y; cphi = fp.a[0] * fp.a[2]; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double ly, double l1y, GLMMA_POINT_ARGS) {
-        const bool pos = ly > -INFINITY;
+        const bool pos = YC == 0 ? ly > -INFINITY : YC == 1;
         double lz;
-        hurdle_zero<CAREFUL, ZT>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
+        hurdle_zero<CAREFUL, ZT, YC>(ez, elam, cx, pos, lz, sz, zl1p, zpi);
         ld = lz; se = 0.0; sp = 0.0;
         if (pos) {
             double l2;
@@ -600,7 +619,7 @@ struct FamGamma : FamBase {
         cll = (phi - 1.0) * ly - fp.a[2] + phi * fp.a[1];
         cphi = phi * (ly + fp.a[1] + 1.0 - fp.a[3]);
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lmu;
@@ -626,7 +645,7 @@ struct FamCensoredNormal : FamBase {
         if (ind == 0.0) { cll = -fp.a[1] - 0.5 * GLMMA_LOG_2PI; cphi = -1.0; }
         else { cll = 0.0; cphi = 0.0; }
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double ind, GLMMA_POINT_ARGS) {
         const double sigma = fp.a[0], isig = fp.a[2];
         if (!CAREFUL) {
@@ -699,7 +718,7 @@ struct FamStudentsT : FamBase {
     __device__ static __forceinline__ void obs_const(double, double, const FamPar& fp, double& cll, double& cphi) {
         cll = fp.a[1]; cphi = -1.0;
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double, GLMMA_POINT_ARGS) {
         const double d = y - eta;
         const double t = d * fp.a[2];
@@ -750,7 +769,7 @@ struct FamBetaBinomial : FamBase {
         cll = lch + fp.a[1] - lgamma(N + fp.a[0]);
         cphi = fp.a[0] * (fp.a[2] - glmma_digamma(N + fp.a[0]));
     }
-    template <bool SCORE, bool CAREFUL, bool ZT = false>
+    template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
         double mu, lt, L;

@@ -1069,7 +1069,15 @@ struct FastLayout {
     static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
     __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
     static constexpr int FIXED0 = (NACCS * NJR * 32 + NJ + NTOT * 32 + 4 + 1) & ~1;   // scratch, wv, per-lane totals, warp totals
-    __host__ __device__ static int fixed(int nagq) { return FIXED0 + tfd(nagq) + tld(nagq); }
+    // "ZP" mode (zero part hoisted, kernel header): per-lane marginal node weights of the zero-part
+    // dimension (nz x 32) and the per-node sum of log(1 + exp(eta_zi)) over the cluster (nz), after tabL
+    static constexpr bool ZP = F::HAS_ZI && QZ <= 1 && F::FAST_KIND == 0;
+    // ... and plogis(eta_zi) per (observation slot, zero-part node index), pitch nz, for the epilogue (the zero-part
+    // table itself lives in the accumulator scratch, which serves as the zero responses' score stash during the rounds)
+    __host__ __device__ static int zpd(int nagq) {
+        return ZP ? (QZ > 0 ? nagq : 1) * 32 + GLMMA_NAGQ_FAST + ((NJ * (QZ > 0 ? nagq : 1) + 1) & ~1) : 0;
+    }
+    __host__ __device__ static int fixed(int nagq) { return FIXED0 + tfd(nagq) + tld(nagq) + zpd(nagq); }
     __host__ __device__ static size_t warp_stride(int xw, int nagq) { return (size_t)(2 * pre(xw) + fixed(nagq) + 1) & ~(size_t)1; }
     // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed table rows (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
@@ -1125,6 +1133,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     // table sizes depend on nagq: keeping them last leaves one anchor register for everything but tabL)
     double* tabF = pre0 + 2 * PRE + FL::FIXED0;
     double* tabL = tabF + FL::tfd(nagq);
+    double* zp_m = tabL + FL::tld(nagq);                     // ZP mode: nz x 32 marginal weights, then nz sums of log(1 + lambda)
+    double* zp_lz = zp_m + (QZ > 0 ? nagq : 1) * 32;
+    double* zp_pi = zp_lz + GLMMA_NAGQ_FAST;                 // n_i x nz values of plogis(eta_zi), by slot
     double* acc_eta = tabF - FL::FIXED0;
     double* acc_zi = acc_eta + FL::NJR * 32;
     double* wv = acc_eta + FL::NACCS * FL::NJR * 32;         // staged second record field (y + phi, trials ...), contiguous
@@ -1259,6 +1270,21 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         constexpr bool ZT = F::HAS_ZI && QZ <= 1;
         double2* tabZ = reinterpret_cast<double2*>(acc_eta + 2 * (NJ * Q + NJ * NTc));
         static_assert(!ZT || 2 * (NJ * Q + NJ * NTc) + 2 * NJ * NG <= FL::NACCS * FL::NJR * 32, "zero-part table does not fit");
+        static_assert(!FL::ZP || NJ * 64 <= FL::NACCS * FL::NJR * 32, "score stash of the zero responses does not fit");
+        // ZP mode: the cluster's observations are sorted into positive responses (slots 0 .. npos - 1) and
+        // zero responses (npos .. n_i - 1); records, coefficient and table columns are laid out by slot, so
+        // the round loop knows an observation's class from its position
+        constexpr bool ZP = FL::ZP;
+        int slot = lane, npos = nic;
+        if (ZP) {
+            const bool live = lane < nic;
+            const bool posv = live && F::is_pos(rec[lane * W]);
+            const unsigned pm = __ballot_sync(0xffffffffu, posv), zm = __ballot_sync(0xffffffffu, live && !posv);
+            const unsigned lt = (1u << lane) - 1u;
+            npos = __popc(pm);
+            slot = posv ? __popc(pm & lt) : npos + __popc(zm & lt);
+        }
+        double hz0 = 0.0, hz1 = 0.0;      // hurdle families: sum of eta_zi = hz0 + hz1 b_zi over the zero responses
         bool bad = false;
         if (lane < nic) {
             double* r = rec + lane * W;
@@ -1275,7 +1301,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 }
             }
             F::stage(r[0], r[1], A.fam);
-            if (F::FAST_KIND == 1) wv[lane] = r[1];
+            if (F::FAST_KIND == 1) wv[slot] = r[1];
             const double xmax = gx[0];
             if (F::NEED_EMU) {
                 double base = r[2], amp = 0.0;
@@ -1287,7 +1313,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd)
                         if (dd <= e) c = fma(r[L::OFF_Z + dd], ri[Tri<Q>::rm(dd, e)], c);
-                    coef[lane * Q + e] = make_double2(c, e == 0 ? base : 0.0);
+                    coef[slot * Q + e] = make_double2(c, e == 0 ? base : 0.0);
                     const double ae = fabs(c) * xmax;
                     if (!(ae + (e == 0 ? fabs(base) : 0.0) <= 230.0)) bad = true;
                     amp += ae;
@@ -1317,7 +1343,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 #pragma unroll
                     for (int dd = 0; dd < QZ; ++dd)
                         if (dd <= e) c = fma(r[L::OFF_Z + QY + dd], ri[Tri<Q>::rm(QY + dd, QY + e)], c);
-                    coef[NJ * Q + lane * NTc + e] = make_double2(c, e == 0 ? base : 0.0);
+                    coef[NJ * Q + slot * NTc + e] = make_double2(c, e == 0 ? base : 0.0);
                     const double ae = fabs(c) * xmax;
                     if (!(ae + (e == 0 ? fabs(base) : 0.0) <= 230.0)) bad = true;
                     amp += ae;
@@ -1331,11 +1357,11 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         // A cluster that leaves the sums (left to eval_kernel here, or dropped as non-finite below) takes
         // back its share of the node-independent terms, which const_sums_kernel / beta' X'y1 added for
         // every cluster of this variant; with ll_i the same terms complete the cluster's contribution.
-        auto cluster_consts = [&](double& s_ll, double& s_phi) {
+        auto cluster_consts = [&](int ridx, double& s_ll, double& s_phi) {
             double2 cc = make_double2(0.0, 0.0);
             if (lane < nic) {
                 const int64_t row = r0c + lane;
-                cc = obs_consts_rare<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, rec[lane * W + 2], A.fam, A.ytab);
+                cc = obs_consts_rare<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, rec[ridx * W + 2], A.fam, A.ytab);
             }
             s_ll = warp_sum(cc.x);
             s_phi = warp_sum(cc.y);
@@ -1344,7 +1370,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (bad) {
             // eval_kernel takes this cluster from the work arrays the prep kernel would have written
             double s_ll, s_phi;
-            cluster_consts(s_ll, s_phi);
+            cluster_consts(lane, s_ll, s_phi);
             if (lane < nic) {
                 const int64_t row = r0c + lane;
                 const double* r = rec + lane * W;
@@ -1361,6 +1387,24 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
             __syncwarp();
             continue;
+        }
+        if (ZP) {
+            double tmp[W];
+            if (lane < nic) {
+#pragma unroll
+                for (int t = 0; t < W; ++t) tmp[t] = rec[lane * W + t];
+            }
+            if (F::ZERO_FREE) {
+                const bool zr = lane < nic && slot >= npos;
+                hz0 = warp_sum(zr ? tmp[L::OFF_XG] : 0.0);
+                if (QZ > 0) hz1 = warp_sum(zr ? tmp[L::OFF_Z + QY] : 0.0);
+            }
+            __syncwarp();
+            if (lane < nic) {
+#pragma unroll
+                for (int t = 0; t < W; ++t) rec[slot * W + t] = tmp[t];
+            }
+            __syncwarp();
         }
         // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
         // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
@@ -1421,8 +1465,17 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 double l1p, pi;
                 fast_l1p_sigmoid<false>(tabL[na * RP + j], cx, l1p, pi);
                 tabZ[j * NG + na] = make_double2(l1p, pi);
+                if (ZP) zp_pi[j * nz + na] = pi;
             }
             __syncwarp();
+            if (ZP) {
+                if (lane < nz) {
+                    double sl = 0.0;
+                    for (int j = 0; j < nic; ++j) sl += tabZ[j * NG + lane].x;
+                    zp_lz[lane] = sl;
+                }
+                __syncwarp();
+            }
         }
 
         double zty[QY];
@@ -1488,6 +1541,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             for (int t = 0; t < NP; ++t) S[t] = 0.0;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) { acc_e[j] = 0.0; if (F::HAS_ZI) acc_z[j] = 0.0; }
+            if (ZP && SCORE) {
+                for (int a_ = 0; a_ < (QZ > 0 ? nagq : 1); ++a_) zp_m[a_ * 32 + lane] = 0.0;
+            }
             if (GQ) {
                 for (int c = 0; c < gq_nc; ++c) acc_eta[c * 32 + lane] = 0.0;
 #pragma unroll
@@ -1546,6 +1602,11 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     // the node -- it is added to the log-likelihood once per evaluation (beta' X'y1)
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd) a = fma(zty[dd], b[dd], a);
+                }
+                const int zp_az = (ZP && QZ > 0) ? (int)((packed >> (8 * QY)) & 0xff) - QY * nagq : 0;
+                if (ZP) {
+                    a -= zp_lz[zp_az];
+                    if (F::ZERO_FREE) a += QZ > 0 ? fma(hz1, b[QY < Q ? QY : 0], hz0) : hz0;
                 }
 #define GLMMA_FAST_OBS(j)                                                                              \
     {                                                                                                  \
@@ -1692,6 +1753,76 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         }
                     }
                     a += a1;
+                } else if (ZP) {
+                    // class known from the slot; the zero part's shared terms were added at node level
+                    auto obs = [&](auto j_tag, auto yc_tag) {
+                        constexpr int j = decltype(j_tag)::value;
+                        constexpr int YC = decltype(yc_tag)::value;
+                        const double* rj = rec + j * W;
+                        double eta = rj[2];
+#pragma unroll
+                        for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
+                        double emu = 0.0, elam = 0.0;
+                        if (F::NEED_EMU) {
+                            emu = pf[0][j];
+#pragma unroll
+                            for (int e = 1; e < Q; ++e) emu *= pf[e][j];
+                        }
+                        if (YC == 2) {
+                            elam = pl[0][j];
+#pragma unroll
+                            for (int e = 1; e < QZ; ++e) elam *= pl[e][j];
+                        }
+                        double ld, se, sz, sp;
+                        F::template point<SCORE, false, true, YC>(rj[0], rj[1], eta, 0.0, emu, elam, A.fam, cx, ld, se, sz, sp);
+                        a += ld;
+                        if (SCORE) {
+                            se_[j] = se;
+                            if (YC == 2) sz_[j] = sz;
+                            if (F::HAS_PHI) vphi += sp;
+                        }
+                    };
+                    auto obs_j = [&](auto j_tag) {
+                        constexpr int j = decltype(j_tag)::value;
+                        se_[j] = 0.0;
+                        if (j < npos) obs(j_tag, std::integral_constant<int, 1>{});
+                    };
+                    // zero responses (zero-inflated families): ONE copy of the long body, walked by a rolled loop;
+                    // the two score terms wait in shared memory (the accumulator scratch, idle during the rounds)
+                    // until the node weight is known
+                    if (!F::ZERO_FREE) {
+#pragma unroll 1
+                        for (int j = npos; j < nic; ++j) {
+                            const double* rj = rec + j * W;
+                            double emu = 0.0, elam;
+                            if (F::NEED_EMU) {
+                                emu = pf[0][j];
+#pragma unroll
+                                for (int e = 1; e < Q; ++e) emu *= pf[e][j];
+                            }
+                            elam = pl[0][j];
+                            double ld, se, sz, sp;
+                            F::template point<SCORE, false, true, 2>(rj[0], rj[1], 0.0, 0.0, emu, elam, A.fam, cx, ld, se, sz, sp);
+                            a += ld;
+                            if (SCORE) {
+                                acc_eta[(j - npos) * 64 + lane] = se;
+                                acc_eta[(j - npos) * 64 + 32 + lane] = sz;
+                                if (F::HAS_PHI) vphi += sp;
+                            }
+                        }
+                    }
+                    obs_j(std::integral_constant<int, 0>{}); obs_j(std::integral_constant<int, 1>{});
+                    obs_j(std::integral_constant<int, 2>{}); obs_j(std::integral_constant<int, 3>{});
+                    obs_j(std::integral_constant<int, 4>{}); obs_j(std::integral_constant<int, 5>{});
+                    obs_j(std::integral_constant<int, 6>{}); obs_j(std::integral_constant<int, 7>{});
+                    if (NJ > 8) {
+                        obs_j(std::integral_constant<int, (NJ > 8 ? 8 : 0)>{}); obs_j(std::integral_constant<int, (NJ > 8 ? 9 : 0)>{});
+                        obs_j(std::integral_constant<int, (NJ > 8 ? 10 : 0)>{}); obs_j(std::integral_constant<int, (NJ > 8 ? 11 : 0)>{});
+                    }
+                    if (NJ > 12) {
+                        obs_j(std::integral_constant<int, (NJ > 12 ? 12 : 0)>{}); obs_j(std::integral_constant<int, (NJ > 12 ? 13 : 0)>{});
+                        obs_j(std::integral_constant<int, (NJ > 12 ? 14 : 0)>{}); obs_j(std::integral_constant<int, (NJ > 12 ? 15 : 0)>{});
+                    }
                 } else {
 #pragma unroll
                 for (int c4 = 0; c4 < NJ / 4; ++c4) {
@@ -1739,6 +1870,19 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                         for (int c = 0; c < gq_nc; ++c) acc_eta[c * 32 + lane] = fma(e, acc_zi[c * 32 + lane], acc_eta[c * 32 + lane]);
 #pragma unroll
                         for (int dd = 0; dd < QY; ++dd) gq_bb[dd] = fma(e, dl[dd], gq_bb[dd]);
+                    } else if (ZP) {
+                        zp_m[zp_az * 32 + lane] += e;
+#pragma unroll
+                        for (int j = 0; j < NJ; ++j) {
+                            if (F::ZERO_FREE) {
+                                acc_e[j] = fma(e, se_[j], acc_e[j]);
+                            } else if (j < npos) {
+                                acc_e[j] = fma(e, se_[j], acc_e[j]);
+                            } else if (j < nic) {
+                                acc_e[j] = fma(e, acc_eta[(j - npos) * 64 + lane], acc_e[j]);
+                                acc_z[j] = fma(e, acc_eta[(j - npos) * 64 + 32 + lane], acc_z[j]);
+                            }
+                        }
                     } else {
 #pragma unroll
                         for (int j = 0; j < NJ; ++j) {
@@ -1766,7 +1910,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         }
         if (!ok || d.ll_i != nullptr) {
             double s_ll, s_phi;
-            cluster_consts(s_ll, s_phi);
+            cluster_consts(slot, s_ll, s_phi);
             if (lane == 0) {
                 if (!ok) {
                     if (A.em_mode != 2) tots[0] -= w * s_ll;
@@ -1806,6 +1950,23 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
             // per-observation sums over the 32 lanes: through shared memory; lane l sums the
             // (l / NJR)-th slice of columns of observation l % NJR, slices combined by shuffles
+            // ZP mode: posterior mean of plogis(eta_zi) per observation from the marginal node weights of the
+            // zero-part dimension (before the accumulator stores below overwrite the zero-part table)
+            double zp_epi = 0.0;
+            if (ZP) {
+                const int nz = QZ > 0 ? nagq : 1;
+                double ma = 0.0;
+                if (lane < nz) {
+#pragma unroll 8
+                    for (int c = 0; c < 32; ++c) ma += zp_m[lane * 32 + ((c + lane) & 31)];
+                }
+                for (int a_ = 0; a_ < nz; ++a_) {
+                    const double mv = __shfl_sync(0xffffffffu, ma, a_);
+                    if (lane < nic) zp_epi = fma(zp_pi[slot * nz + a_], mv, zp_epi);
+                }
+                zp_epi *= isum;
+                __syncwarp();
+            }
             if (!GQ) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
@@ -1840,8 +2001,8 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     const double* r = rec + lane * W;
                     const bool cens = live && r[1] != 0.0;
                     const unsigned cm = __ballot_sync(0xffffffffu, cens);
-                    const int slot = __popc(cm & ((1u << lane) - 1u));
-                    const double sl = __shfl_sync(0xffffffffu, s1, cens ? slot : 0);
+                    const int cslot = __popc(cm & ((1u << lane) - 1u));
+                    const double sl = __shfl_sync(0xffffffffu, s1, cens ? cslot : 0);
                     double resd = live ? r[0] - r[2] : 0.0;
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd) {
@@ -1851,12 +2012,19 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     const double isig = A.fam.a[2];
                     scv_gq = cens ? (r[1] == 1.0 ? -isig : isig) * (sl * isum) : isig * isig * resd;
                 }
+                if (ZP) {
+                    // row sums are held by slot: fetch this observation's
+                    s1 = __shfl_sync(0xffffffffu, s1, slot);
+                    s2 = __shfl_sync(0xffffffffu, s2, slot);
+                }
                 if (lane < nic) {
                     const double scv = GQ ? scv_gq
-                                     : F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam)
-                                                         : F::finish_se(s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                                     : F::FAST_KIND != 0 ? F::fast_score(s1 * isum, rec[slot * W], rec[slot * W + 1], A.fam)
+                                                         : F::finish_se(s1 * isum, rec[slot * W], rec[slot * W + 1], A.fam);
                     zb = ok ? w * scv : 0.0;
                     if (F::HAS_ZI) zz = inv * s2;
+                    // ZP: the hoisted -plogis(eta_zi) (and the hurdle families' +1 for a zero response)
+                    if (ZP && ok) zz += w * ((F::ZERO_FREE && slot >= npos ? 1.0 : 0.0) - zp_epi);
                     if (A.zbar_out) {
                         d.zbar[r0c + lane] = zb;
                         if (F::HAS_ZI) d.zbar_zi[r0c + lane] = zz;

@@ -79,7 +79,7 @@ struct OpsImpl {
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
-        for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t *= 2) {
+        for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t += 32) {
             const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw, nagq);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;

@@ -16,3 +16,4 @@ for l in open("gpurun_out/quick.jsonl"):
     if l.startswith("{"):
         j = json.loads(l); print(j["config"]["workload"][:60], "| %.1f evals/s  %.3f ms" % (j["value"], j["ms_per_step"]))
 PY
+python scripts/family_sweep.py 200000 2>&1 | tail -18
