@@ -1353,7 +1353,24 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         }
         bad = __any_sync(0xffffffffu, bad);
         __syncwarp();                              // coefficient stores -> table-building reads
+        // The round loop reads mode and sqrt(2) R^-1 (and Z'y1) from the cluster's record in shared memory
+        // instead of holding them in registers across the rounds: a few broadcast loads per trip buy
+        // Q + NP (+ QY) double registers in a kernel that sits at its 128-register ceiling
+        if (lane == 0) {
+            double* scw = rec + NJ * W;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) scw[SC_RI + t] = ri[t];
+        }
+        const volatile double* scv = sc;
+        // (measured: pays for the larger tiles, q = 3 and the zero-inflated families; the q <= 2, 8-observation
+        // kernels fit their registers and are 1.5 % faster with the values held there)
+        constexpr bool NODE_SMEM = NJ > 8 || Q >= 3 || F::HAS_ZI;
+        auto nd_m = [&](int dd) { return NODE_SMEM ? scv[SC_M + dd] : m[dd]; };
+        auto nd_ri = [&](int t) { return NODE_SMEM ? scv[SC_RI + t] : ri[t]; };
         const double w = sc[SC_W];
+        double zty[QY];
+#pragma unroll
+        for (int dd = 0; dd < QY; ++dd) zty[dd] = (F::LIN_ETA && !NODE_SMEM) ? sc[SC_ZTY + dd] : 0.0;
         // A cluster that leaves the sums (left to eval_kernel here, or dropped as non-finite below) takes
         // back its share of the node-independent terms, which const_sums_kernel / beta' X'y1 added for
         // every cluster of this variant; with ll_i the same terms complete the cluster's contribution.
@@ -1478,9 +1495,6 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
         }
 
-        double zty[QY];
-#pragma unroll
-        for (int dd = 0; dd < QY; ++dd) zty[dd] = F::LIN_ETA ? sc[SC_ZTY + dd] : 0.0;
 
         // FAST_KIND 3 (censored.normal): an uncensored observation contributes -t^2 / 2 with t linear in
         // the node, so the sum over the cluster's uncensored observations is ONE quadratic form in
@@ -1572,10 +1586,10 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 double b[Q], dl[GQ ? Q : 1];
 #pragma unroll
                 for (int dd = 0; dd < Q; ++dd) {
-                    double s = GQ ? 0.0 : m[dd];
+                    double s = GQ ? 0.0 : nd_m(dd);
 #pragma unroll
-                    for (int e = dd; e < Q; ++e) s = fma(ri[Tri<Q>::rm(dd, e)], nt[e], s);
-                    if (GQ) { dl[dd] = s; s += m[dd]; }
+                    for (int e = dd; e < Q; ++e) s = fma(nd_ri(Tri<Q>::rm(dd, e)), nt[e], s);
+                    if (GQ) { dl[dd] = s; s += nd_m(dd); }
                     b[dd] = s;
                 }
                 double quad = 0.0;
@@ -1601,7 +1615,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     // sum_j y1_j eta_jk = sum_j y1_j xb_j + (Z'y1) . b_k: the first term does not depend on
                     // the node -- it is added to the log-likelihood once per evaluation (beta' X'y1)
 #pragma unroll
-                    for (int dd = 0; dd < QY; ++dd) a = fma(zty[dd], b[dd], a);
+                    for (int dd = 0; dd < QY; ++dd) a = fma(NODE_SMEM ? scv[SC_ZTY + dd] : zty[dd], b[dd], a);
                 }
                 const int zp_az = (ZP && QZ > 0) ? (int)((packed >> (8 * QY)) & 0xff) - QY * nagq : 0;
                 if (ZP) {
@@ -2007,7 +2021,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd) {
                         const double bbar = warp_sum(gq_bb[dd]) * isum;
-                        if (live) resd = fma(-r[L::OFF_Z + dd], m[dd] + bbar, resd);
+                        if (live) resd = fma(-r[L::OFF_Z + dd], nd_m(dd) + bbar, resd);
                     }
                     const double isig = A.fam.a[2];
                     scv_gq = cens ? (r[1] == 1.0 ? -isig : isig) * (sl * isum) : isig * isig * resd;
