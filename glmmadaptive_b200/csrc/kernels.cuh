@@ -1025,6 +1025,9 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 // scratch), wv, totals].
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
+#ifndef GLMMA_NODE_PERM
+#define GLMMA_NODE_PERM 1
+#endif
 #define GLMMA_K_FAST 512
 #define GLMMA_NTAB_MAX_K 256
 // Launch shape: 128 registers per thread at any block size from GLMMA_EVAL_THREADS (four blocks per
@@ -1177,8 +1180,21 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         coltab[c] = e;
     }
     __syncthreads();
+    // Node order.  A quarter warp's 16-byte loads of table rows are conflict-free when its eight lanes read
+    // the same row or rows whose indices differ mod 8 (row pitch RP with RP / 2 odd).  In the natural order
+    // (index of dimension 0 fastest) eight consecutive nodes wrap around nAGQ (11: rows 8, 9, 10, 0, 1 ...) and
+    // collide (ncu, C3: 2.25 excess wavefronts per table load).  So the nodes are walked in two sections:
+    // first those with a_0 < 8 * (nAGQ / 8), a_0 fastest -- every aligned group of eight lanes has a_0 =
+    // 8 g .. 8 g + 7 and the other indices equal --, then the remaining nAGQ % 8 values of a_0, again a_0
+    // fastest: a group repeats a few rows (broadcast) that differ mod 8.  nAGQ < 8: the natural order.
+    const int nfull = nagq & ~7, nrem = nagq - nfull, nhi = K / nagq;
+    auto node_id = [&](int k) {          // position in the walk -> natural node index a_0 + nAGQ (a_1 + nAGQ a_2)
+        if (k < nfull * nhi) return (k % nfull) + nagq * (k / nfull);
+        const int k2 = k - nfull * nhi;
+        return nfull + (k2 % nrem) + nagq * (k2 / nrem);
+    };
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        int kk = k, packed = 0;
+        int kk = GLMMA_NODE_PERM ? node_id(k) : k, packed = 0;
         double lw = A.grid->lw_const;
 #pragma unroll
         for (int e = 0; e < Q; ++e) {
@@ -1195,7 +1211,11 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     __syncthreads();
     const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
     const int nrounds = (K + 31) >> 5;
-    const int rc = ((K - 1) >> 1) >> 5;
+    int rc;                                     // the round holding the central node
+    {
+        const int c = (K - 1) >> 1, a0c = c % nagq, hic = c / nagq;
+        rc = (GLMMA_NODE_PERM ? (a0c < nfull ? hic * nfull + a0c : nfull * nhi + hic * nrem + (a0c - nfull)) : c) >> 5;
+    }
     constexpr int SC_M = 0, SC_RI = Q, SC_LD = Q + NP, SC_ZTY = Q + NP + 1, SC_W = Q + NP + 1 + QY;
     const int p_x = d.p, p_z = F::HAS_ZI ? d.p_zi : 0;
     const bool has_off = d.offset != nullptr, has_offz = F::HAS_ZI && d.offset_zi != nullptr;
@@ -1238,6 +1258,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         // rotate the pipeline and start the next cluster's copies
         const int64_t i = cur.x;      // 64-bit: i * K, i * Q ... index arrays of up to n * K elements
         const int64_t r0c = cur.y;
+        // (ncu, C3: 3.4 % of the stall samples sit on the first write to the dead fourth register of the 16-byte
+        // `order` load while that load is in flight; keeping the register live instead -- nic = cur.z + cur.w --
+        // cost 4 % through register pressure, so the stall stays)
         const int nic = cur.z;
         cur = nxt;
         // (pos + 2 nwarps may pass 2^31: compare the remaining distance instead)
@@ -1423,11 +1446,13 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
             __syncwarp();
         }
-        // tables: item t <-> (pair p = t / nagq, node index a = t % nagq), lanes stride the items;
-        // three independent exp chains per lane and trip (fast_exp_vec), arguments in range by the
-        // test above.  Entry (observation j, dimension e, node index a) goes to row e * nagq + a, column j.
+        // tables: lanes stride the items, three independent exp chains per lane and trip (fast_exp_vec),
+        // arguments in range by the test above.  Entry (observation j, dimension e, node index a) goes to
+        // row e * nagq + a, column j.
         {
             const unsigned inv_nagq = (65536u + (unsigned)nagq - 1u) / (unsigned)nagq;
+            // (a row-major walk -- consecutive lanes on consecutive columns of a row, conflict-free stores -- was
+            // measured 2 % slower: its coefficient loads collide instead)
             if (F::NEED_EMU) {
                 const int items = nic * Q * nagq;
                 for (int t0 = lane; t0 < items; t0 += 96) {
@@ -1866,8 +1891,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 }
                 double e = valid ? fast_exp(a - shift, cx) : 0.0;
                 if (A.em_mode) {             // EM phase: store (E-step) / replace (M-step) the node weights
-                    if (A.em_mode == 2) e = valid ? A.pby[i * K + k] : 0.0;
-                    else if (valid) A.pby[i * K + k] = e;
+                    // (p_by is kept in the natural node order: eval_kernel may own this cluster in another pass)
+                    int kn = 0, mul = 1;
+#pragma unroll
+                    for (int ee = 0; ee < Q; ++ee) { kn += (int)(((packed >> (8 * ee)) & 0xff) - ee * nagq) * mul; mul *= nagq; }
+                    if (A.em_mode == 2) e = valid ? A.pby[i * K + kn] : 0.0;
+                    else if (valid) A.pby[i * K + kn] = e;
                 }
                 sum_e += e;
                 if (SCORE) {
