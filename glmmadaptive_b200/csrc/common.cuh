@@ -4,7 +4,7 @@
 #include <stdint.h>
 #include <math.h>
 
-#define GLMMA_QMAX 3          // max random-effect dimension q = q_y + q_zi compiled in
+#define GLMMA_QMAX 4          // max random-effect dimension q = q_y + q_zi compiled in
 #define GLMMA_NAGQ_MAX 32     // max nodes per dimension
 #define GLMMA_PMAX 64         // max ncol(X)
 #define GLMMA_PZIMAX 32       // max ncol(X_zi)

@@ -673,7 +673,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     // ragged data run several tiles back to back, each on its own list of clusters.
     h->nj = 0;
     int max_fast = 0;
-    if (h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && !std::getenv("GLMMA_NO_FAST") &&
+    if (q <= 3 && h->nagq <= GLMMA_NAGQ_FAST && h->K <= GLMMA_K_FAST && !std::getenv("GLMMA_NO_FAST") &&
         d.p + d.p_zi <= GLMMA_FOLD_COLS && d.p + d.p_zi + 2 + 2 + GLMMA_QMAX <= GLMMA_COLTAB_MAX) {
         int64_t n_le8 = 0, n_9_12 = 0, n_13_16 = 0;
         for (int v = 1; v <= 8; ++v) n_le8 += cnt[v];
@@ -1320,7 +1320,7 @@ int glmma_observed_information(glmma_handle* h, const double* betas, const doubl
     if (!D) return fail(h, GLMMA_ERR_ARG, "D is null");
     const int p = h->d.p, pz = h->d.p_zi, nphi = h->d.n_phis;
     const int P = p + nD + nphi + pz;
-    if (P > GLMMA_INFO_PMAX) return fail(h, GLMMA_ERR_ARG, "more than 12 parameters: use the finite-difference Hessian");
+    if (P > GLMMA_INFO_PMAX) return fail(h, GLMMA_ERR_ARG, "more than GLMMA_INFO_PMAX parameters: use the finite-difference Hessian");
     InfoArgs ia;
     std::memset(&ia, 0, sizeof(ia));
     rc = run_prep(h, betas, phis, gammas, &ia.fam);

@@ -2263,7 +2263,7 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
 // derivatives.  A warp owns a cluster, lanes own nodes; two passes over the nodes (log-sum-exp, then the
 // derivatives).  Run once per fit: clarity over speed (accumulators in local memory).
 // ------------------------------------------------------------------------------
-#define GLMMA_INFO_PMAX 12
+#define GLMMA_INFO_PMAX 24
 #define GLMMA_INFO_NPAIR (GLMMA_INFO_PMAX * (GLMMA_INFO_PMAX + 1) / 2)
 #define GLMMA_INFO_NDMAX (GLMMA_QMAX * (GLMMA_QMAX + 1) / 2)
 #define GLMMA_INFO_NDPAIR (GLMMA_INFO_NDMAX * (GLMMA_INFO_NDMAX + 1) / 2)

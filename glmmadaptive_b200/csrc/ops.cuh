@@ -2,6 +2,7 @@
 // dispatch from runtime dimensions to the compiled instantiation.  Each
 // fam_*.cu translation unit includes this file and exports one lookup function.
 #pragma once
+#include <cstdlib>
 #include "kernels.cuh"
 #include "engine.h"
 
@@ -72,30 +73,40 @@ struct OpsImpl {
     // outputs -- the loglik-only instantiations would add a quarter to build time and binary size.
     // Block shape of the register variant: the fastmath tables (24 KB) are per block, so families with
     // large per-warp areas (zero-inflated, q = 3) keep more warps resident with fewer, larger blocks.
-    // Picks the shape with the most resident warps per SM; ties go to the smaller block.
+    // Picks the shape with the most resident warps per SM; ties go to the larger block.
+    // q = 4: nAGQ^4 nodes exceed the register variant's grids for every nAGQ > 4 -- not instantiated
+    static constexpr bool HAS_FAST = QY + QZ <= 3;
     template <int NJ>
     static cudaError_t fast_config_nj(int K, int nagq, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
+        // tuning knob (measurements only): GLMMA_FAST_THREADS=<threads per block> pins the block shape
+        const char* pin = std::getenv("GLMMA_FAST_THREADS");
+        const int pinned = pin ? std::atoi(pin) : 0;
         for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t += 32) {
+            if (pinned && t != pinned) continue;
             const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw, nagq);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ>, t, smem);
             if (e != cudaSuccess) return e;
-            if (bps * t > best) { best = bps * t; *blocks_per_sm = bps; *smem_bytes = smem; *threads = t; }
+            // ties go to the LARGER block: one 16-warp block per SM measured 3 % faster than four 4-warp blocks
+            // at C3 (one copy of the per-block tables, one start-up)
+            if (bps > 0 && bps * t >= best) { best = bps * t; *blocks_per_sm = bps; *smem_bytes = smem; *threads = t; }
         }
         return cudaSuccess;
     }
     static cudaError_t fast_config(int xw, int nj, int K, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
-        return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
+        if constexpr (!HAS_FAST) { *blocks_per_sm = 0; *smem_bytes = 0; *threads = 0; return cudaSuccess; }
+        else return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
              : nj == 12 ? fast_config_nj<12>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
                         : fast_config_nj<16>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
     }
     static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, int threads, size_t smem, cudaStream_t s) {
-        if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
+        if constexpr (!HAS_FAST) return;
+        else if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
         else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, threads, smem, s>>>(a);
         else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
     }
@@ -139,12 +150,15 @@ static const FamOps* dispatch_ops(int qy, int qz) {
         if (qy == 1) return OpsImpl<F, 1, 0>::get();
         if (qy == 2) return OpsImpl<F, 2, 0>::get();
         if (qy == 3) return OpsImpl<F, 3, 0>::get();
+        if (qy == 4) return OpsImpl<F, 4, 0>::get();
         return nullptr;
     }
     if (F::HAS_ZI) {
         if (qy == 1 && qz == 1) return OpsImpl<F, 1, F::HAS_ZI ? 1 : 0>::get();
         if (qy == 2 && qz == 1) return OpsImpl<F, 2, F::HAS_ZI ? 1 : 0>::get();
         if (qy == 1 && qz == 2) return OpsImpl<F, 1, F::HAS_ZI ? 2 : 0>::get();
+        if (qy == 3 && qz == 1) return OpsImpl<F, 3, F::HAS_ZI ? 1 : 0>::get();
+        if (qy == 2 && qz == 2) return OpsImpl<F, 2, F::HAS_ZI ? 2 : 0>::get();
     }
     return nullptr;
 }
