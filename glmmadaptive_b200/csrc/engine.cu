@@ -1418,7 +1418,7 @@ int glmma_observed_information(glmma_handle* h, const double* betas, const doubl
             }
     }
     ia.d = h->d; ia.grid = h->d_grid; ia.fmtab = h->d_fmtab; fastmath_constants(ia.fmc);
-    ia.ksm = h->K <= 344 ? h->K : 0;         // 4 warps x 344 doubles: stays under the default 48 KB of dynamic shared memory
+    ia.ksm = h->K <= 1024 ? h->K : 0;        // 4 warps x K doubles of the kernel's (opt-in) dynamic shared memory
     const int grid = (int)std::min<int64_t>((h->d.n + 3) / 4, 148 * 8);
     double* d_part = nullptr;
     cudaError_t e = cudaMalloc(&d_part, sizeof(double) * (size_t)grid * GLMMA_INFO_NPAIR);

@@ -123,6 +123,7 @@ struct OpsImpl {
     static void info(const InfoArgs& a, int grid, cudaStream_t s) {
         using LL = EvalLayout<F, QY, QZ>;
         const size_t smem = sizeof(double) * (LL::head_doubles() + 4 * (size_t)(GLMMA_INFO_JT * LL::W + GLMMA_INFO_JT * GLMMA_INFO_PMAX + ((a.ksm + 1) & ~1)));
+        cudaFuncSetAttribute(info_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         info_kernel<F, QY, QZ><<<grid, 128, smem, s>>>(a);
     }
     static void logpost(const ModeArgs& a, const double* b, double* out, cudaStream_t s) {
