@@ -38,7 +38,11 @@ def test_multi_device_handle_matches_single_device(name):
     for a, b in zip(one.get_modes(), many.get_modes()):
         assert np.array_equal(a, b)
     r1, r2 = one.eval_raw(betas, D, phis, gammas), many.eval_raw(betas, D, phis, gammas)
-    assert np.max(np.abs(r1 - r2) / np.maximum(np.abs(r1), 1.0)) < 1e-13
+    # different shards sum in a different order: 1e-13 of the LARGEST component bounds the rounding of every sum (the
+    # phi-score is the small difference of two sums of the size of the log-likelihood: node-independent terms added
+    # once per evaluation against the per-node terms), 1e-11 relative what is left after that cancellation
+    assert np.max(np.abs(r1 - r2)) < 1e-13 * np.max(np.abs(r1))
+    assert np.max(np.abs(r1 - r2) / np.maximum(np.abs(r1), 1.0)) < 1e-11
     e1, e2 = one.em_estep(betas, D, phis, gammas), many.em_estep(betas, D, phis, gammas)
     assert abs(e1["loglik"] - e2["loglik"]) < 1e-13 * abs(e1["loglik"])
     b2 = betas + 0.03
@@ -55,7 +59,7 @@ def test_multi_device_handle_matches_single_device(name):
     # set_modes round trip on the multi handle
     modes, chol, _ = one.get_modes()
     many.set_modes(modes, chol)
-    assert np.max(np.abs(many.eval_raw(betas, D, phis, gammas) - r1) / np.maximum(np.abs(r1), 1.0)) < 1e-13
+    assert np.max(np.abs(many.eval_raw(betas, D, phis, gammas) - r1)) < 1e-13 * np.max(np.abs(r1))
     one.close(); many.close()
 
 
