@@ -207,3 +207,71 @@ def test_two_engines_with_different_tiles_on_one_device():
     for e, r in zip(engines, refs):          # the earlier handles still launch after the later ones were created
         assert np.array_equal(e.eval_raw(betas, D), r)
         e.close()
+
+
+@pytest.mark.parametrize("fam_name,q_zi", [("censored.normal", 0), ("zi.poisson", 0), ("zi.poisson", 1),
+                                           ("zi.negative.binomial", 1), ("zi.binomial", 0), ("hurdle.poisson", 1),
+                                           ("hurdle.negative.binomial", 0), ("hurdle.lognormal", 1),
+                                           ("hurdle.beta.fam", 0)])
+def test_hoisted_paths_at_their_class_extremes(fam_name, q_zi):
+    """The register variant sorts a cluster's observations into classes (censored / uncensored; positive / zero
+    response) and hoists the class-wide terms to the node: clusters that consist of ONE class only (all censored,
+    none censored, all zeros, no zeros), single observations, and all three tiles, with weights and offsets in
+    both linear predictors."""
+    rng = np.random.default_rng(31 + q_zi + len(fam_name))
+    sizes = np.concatenate([rng.integers(1, 9, 36), rng.integers(9, 13, 12), rng.integers(13, 17, 12)])
+    rng.shuffle(sizes)
+    n = len(sizes)
+    betas, D2 = np.array([0.2, 0.4, -0.3]), np.array([[0.4, 0.08], [0.08, 0.25]])
+    zi = fam_name != "censored.normal"
+    d, N = _mk(rng, sizes, 2, fam_name, zi=zi)
+    ids = d["id"]
+    q = 2 + q_zi
+    D = D2 if q == 2 else np.array([[0.4, 0.08, -0.05], [0.08, 0.25, 0.03], [-0.05, 0.03, 0.3]])
+    if q_zi:
+        d["Z_zi"] = np.ones((N, 1))
+    d["offset"] = rng.normal(0, 0.2, N)
+    if zi:
+        d["offset_zi"] = rng.normal(0, 0.3, N)
+    d["weights"] = rng.uniform(0.5, 1.5, n)
+    eta = d["X"] @ betas + d["offset"]
+    th = dict(betas=betas, D=D, nAGQ=7 if q == 3 else 9)
+    cls = rng.integers(0, 3, n)[ids]            # per cluster: 0 mixed, 1 all of the first class, 2 all of the second
+    if fam_name == "censored.normal":
+        v = eta + 0.7 * rng.standard_normal(N)
+        ind = rng.integers(0, 3, N).astype(float)
+        ind[cls == 1] = 0.0                                        # no observation censored
+        ind[cls == 2] = rng.integers(1, 3, int((cls == 2).sum()))  # every observation censored
+        d["y"] = np.column_stack([v, ind])
+        th["phis"] = np.array([np.log(0.7)])
+    else:
+        zero = rng.random(N) < 0.35
+        zero[cls == 1] = False
+        zero[cls == 2] = True
+        mu = np.exp(np.clip(eta, -3, 3))
+        if fam_name in ("zi.poisson", "zi.negative.binomial"):
+            y = rng.poisson(mu).astype(float)
+            y[cls == 1] += 1.0
+        elif fam_name in ("hurdle.poisson", "hurdle.negative.binomial"):
+            y = (1 + rng.poisson(mu)).astype(float)
+        elif fam_name == "zi.binomial":
+            trials = rng.integers(1, 6, N)
+            s = np.maximum(rng.binomial(trials, 1 / (1 + np.exp(-eta))), np.where(cls == 1, 1, 0))
+            s[zero] = 0
+            y = np.column_stack([s, trials - s]).astype(float)
+        elif fam_name == "hurdle.lognormal":
+            y = np.exp(eta + 0.5 * rng.standard_normal(N))
+        else:
+            m = 1 / (1 + np.exp(-eta))
+            y = np.clip(rng.beta(m * 5, (1 - m) * 5), 1e-4, 1 - 1e-4)
+        if y.ndim == 1:
+            y[zero] = 0.0
+        d["y"] = y
+        th["gammas"] = np.array([-0.8, 0.5])
+        if fam_name in ("zi.negative.binomial", "hurdle.negative.binomial"):
+            th["phis"] = np.array([0.5])
+        elif fam_name == "hurdle.lognormal":
+            th["phis"] = np.array([-0.3])
+        elif fam_name == "hurdle.beta.fam":
+            th["phis"] = np.array([1.5])
+    _check(d, th, fam_name)
