@@ -24,7 +24,8 @@
 #define FINAL_THREADS 256
 
 static thread_local std::string g_create_error;
-static const int kTile[3] = {8, 12, 16};       // observation tiles of the register variant
+#define GLMMA_NTILES 4
+static const int kTile[GLMMA_NTILES] = {8, 12, 16, 32};       // observation tiles of the register variant (32: two-pass form)
 
 // One host thread per device of a multi-device handle: the per-evaluation enqueue work (six kernel
 // launches and a copy per device) runs in parallel instead of serialising on the caller's thread.
@@ -82,11 +83,11 @@ struct glmma_handle {
     int eval_threads[2];       // block shape of the generic kernel
     int asum_doubles;          // per-warp node sums of the generic kernel's tile-outer path (0: no cluster needs it)
     int nj;                    // register-variant tiles in use: bit v = tile kTile[v] (8, 12, 16); 0 = generic kernel only
-    int fast_grid[3][2];       // [tile][loglik only / with score]
-    size_t fast_smem[3][2];
-    int fast_threads[3][2];    // block shape of the register variant (chosen for resident warps per SM)
-    int4* d_order[3];          // cluster lists of the tiles: {cluster, first row, n_i, 0}
-    int64_t n_order[3];
+    int fast_grid[GLMMA_NTILES][2];       // [tile][loglik only / with score]
+    size_t fast_smem[GLMMA_NTILES][2];
+    int fast_threads[GLMMA_NTILES][2];    // block shape of the register variant (chosen for resident warps per SM)
+    int4* d_order[GLMMA_NTILES];          // cluster lists of the tiles: {cluster, first row, n_i, 0}
+    int64_t n_order[GLMMA_NTILES];
     // fused mode (kernels.cuh, EvalArgs): the register variant does the prep and score-reduce work itself
     // and eval_kernel's last block finalises -- an evaluation is [ytab] + fast launches + eval_kernel
     bool fused;
@@ -554,7 +555,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
     h->d_xchg = nullptr; std::memset(&h->xchg, 0, sizeof(h->xchg));
     h->h_out = nullptr; h->h_out_dev = nullptr; h->out_seq = 0;
     h->ytab_valid = false; h->ytab_phis = 0.0;
-    for (int v = 0; v < 3; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
+    for (int v = 0; v < GLMMA_NTILES; ++v) { h->d_order[v] = nullptr; h->n_order[v] = 0; }
     for (auto& e : h->ev) e = nullptr;
     std::memset(&h->d, 0, sizeof(h->d));
     DevData& d = h->d;
@@ -683,13 +684,16 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         const bool use12 = n_9_12 > 0 && n_9_12 >= (int64_t)(0.05 * (double)n);
         const bool use16 = (n_13_16 > 0 && n_13_16 >= few) || (!use12 && n_9_12 > 0 && n_9_12 >= few);
         const bool use8 = n_le8 > 0 && (n_le8 >= (int64_t)(0.1 * (double)n) || !(use12 || use16));
-        h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0);
+        int64_t n_17_32 = 0;
+        for (int v = 17; v <= 32; ++v) n_17_32 += cnt[v];
+        const bool use32 = ops->tile32 && n_17_32 > 0 && n_17_32 >= few && !std::getenv("GLMMA_NO_TILE32");
+        h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0) | (use32 ? 8 : 0);
     }
     // fused mode whenever the register variant runs and the design columns fit a warp's lanes
     h->xw = d.p + d.p_zi + (d.offset ? 1 : 0) + (d.offset_zi ? 1 : 0);
     h->fused = h->nj != 0;          // the register variant is self-contained (kernels.cuh): no prep / score-reduce / finalize launches
     if (h->nj) {
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < GLMMA_NTILES; ++v) {
             if (!(h->nj & (1 << v))) { h->fast_grid[v][0] = h->fast_grid[v][1] = 0; continue; }
             for (int s = 0; s < 2; ++s) {
                 int bps = 0;
@@ -710,17 +714,17 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         // identity when all clusters fit one tile) and the clusters beyond the largest tile are flagged
         // for eval_kernel once and for all (no launch of the register variant ever visits them).
         int top = 0;
-        for (int v = 0; v < 3; ++v) if (h->nj & (1 << v)) top = kTile[v];
+        for (int v = 0; v < GLMMA_NTILES; ++v) if (h->nj & (1 << v)) top = kTile[v];
         {
-            std::vector<int4> lists[3];
+            std::vector<int4> lists[GLMMA_NTILES];
             std::vector<int32_t> flags(n, 0), too_big;
             for (int64_t i = 0; i < n; ++i) {
                 const int ni = row_ptr[i + 1] - row_ptr[i];
                 if (ni > top) { flags[i] = 1; too_big.push_back((int32_t)i); continue; }
-                for (int v = 0; v < 3; ++v)           // the smallest tile in use that holds the cluster
+                for (int v = 0; v < GLMMA_NTILES; ++v)           // the smallest tile in use that holds the cluster
                     if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); break; }
             }
-            for (int v = 0; v < 3; ++v) {
+            for (int v = 0; v < GLMMA_NTILES; ++v) {
                 if (!(h->nj & (1 << v))) continue;
                 h->n_order[v] = (int64_t)lists[v].size();
                 const int4* tmp = nullptr;
@@ -1068,7 +1072,7 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
     ea.only_deferred = 0;
     if (h->nj) {
         // register variant, smaller tile first; each launch flags what it leaves to the next one
-        for (int v = 0; v < 3; ++v) {
+        for (int v = 0; v < GLMMA_NTILES; ++v) {
             if (!(h->nj & (1 << v))) continue;
             ea.order = h->d_order[v];
             ea.n_order = h->n_order[v];

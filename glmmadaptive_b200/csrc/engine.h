@@ -27,6 +27,7 @@ struct FamOps {
     bool has_zi, has_phi, uses_y2;
     bool y_table;      // obs_const() is tabulated by ytab (count families)
     bool lin_eta;      // the register variant hoists y1 * eta out of the point loop (families.cuh: LIN_ETA)
+    bool tile32;       // the register variant has its two-pass form for clusters of 17 .. 32 observations
 };
 
 // one lookup per family translation unit (nullptr: dimensions not compiled in)

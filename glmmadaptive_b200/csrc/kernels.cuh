@@ -1068,8 +1068,13 @@ struct FastLayout {
     // (pack_cluster_kernel): modes, R^-1, logdet, Z'y1, weight
     static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + QY + 1;
     static constexpr int XOFF = ((NJ * W + NSC) + 1) & ~1;  // design columns follow records + scalars
-    static constexpr int NJR = NJ <= 8 ? 8 : 16;            // rows of the per-observation reduction scratch (power of two)
+    // NJ = 32: two-pass form (kernel header) -- observations reduced in chunks of eight, node terms of the cluster
+    // (a_k then e_k, and the phi-score's node sums) kept per warp after the tables
+    static constexpr bool TP = NJ == 32;
+    static constexpr int NJR = (NJ <= 8 || TP) ? 8 : 16;    // rows of the per-observation reduction scratch (power of two)
+    __host__ __device__ static int tpd(int K) { return TP ? 2 * ((K + 1) & ~1) : 0; }
     static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
+    static_assert(NJ <= 32, "a lane stages one observation");
     __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
     static constexpr int FIXED0 = (NACCS * NJR * 32 + NJ + NTOT * 32 + 4 + 1) & ~1;   // scratch, wv, per-lane totals, warp totals
     // "ZP" mode (zero part hoisted, kernel header): per-lane marginal node weights of the zero-part
@@ -1081,7 +1086,7 @@ struct FastLayout {
         return ZP ? (QZ > 0 ? nagq : 1) * 32 + GLMMA_NAGQ_FAST + ((NJ * (QZ > 0 ? nagq : 1) + 1) & ~1) : 0;
     }
     __host__ __device__ static int fixed(int nagq) { return FIXED0 + tfd(nagq) + tld(nagq) + zpd(nagq); }
-    __host__ __device__ static size_t warp_stride(int xw, int nagq) { return (size_t)(2 * pre(xw) + fixed(nagq) + 1) & ~(size_t)1; }
+    __host__ __device__ static size_t warp_stride(int xw, int nagq, int K) { return (size_t)(2 * pre(xw) + fixed(nagq) + tpd(K) + 1) & ~(size_t)1; }
     // node table: z_0.., log wGH per node (K x (Q + 1) doubles) + packed table rows (K ints).  For
     // large grids the double part is dropped (the round loop then reads gx / glw through the packed
     // rows): at K = 343 it is 11 KB of the block's shared memory and costs one resident block per SM.
@@ -1091,7 +1096,7 @@ struct FastLayout {
     }
     __host__ __device__ static size_t coltab_doubles() { return 2 * GLMMA_COLTAB_MAX; }
     __host__ static size_t smem_bytes(int warps, int K, int xw, int nagq) {
-        return sizeof(double) * (L::head_doubles() + coltab_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw, nagq));
+        return sizeof(double) * (L::head_doubles() + coltab_doubles() + node_doubles(K) + (size_t)warps * warp_stride(xw, nagq, K));
     }
 };
 
@@ -1131,7 +1136,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     int* nidx = reinterpret_cast<int*>(ntab + (has_ntab ? (size_t)K * (Q + 1) : 0));   // K packed node indices
     const int xw = A.xw;
     const int PRE = FL::pre(xw);
-    double* pre0 = smem + L::head_doubles() + FL::coltab_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw, nagq);
+    double* pre0 = smem + L::head_doubles() + FL::coltab_doubles() + FL::node_doubles(K) + wib * FL::warp_stride(xw, nagq, K);
     // fixed-size areas sit between the prefetch buffers and the tables, at constant offsets below tabF (the
     // table sizes depend on nagq: keeping them last leaves one anchor register for everything but tabL)
     double* tabF = pre0 + 2 * PRE + FL::FIXED0;
@@ -1574,6 +1579,203 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         double S[NP];
         double acc_e[NJ], acc_z[F::HAS_ZI ? NJ : 1];
         double gq_bb[QY];             // FAST_KIND 3: sum_k e_k delta_k
+        constexpr bool TP = FL::TP;
+        double tp_s1 = 0.0;              // two-pass form: this lane's observation's sum_k e_k carrier_jk
+        if constexpr (TP) {
+            // ---- Two-pass form for clusters of 17 .. 32 observations (FAST_KIND 1 / 2 families).  The one-pass
+            // form keeps an observation's score carrier in a register until the node weight is known: 2 x NJ
+            // double registers, impossible beyond 16 observations.  Here pass A walks all observations for the
+            // node terms only (log t, no reciprocal: a_k and the phi-score's sum_j log t_jk, kept per warp in
+            // shared memory), the weights e_k = exp(a_k - max) follow exactly, and pass B walks the observations
+            // again in chunks of eight for the carriers only (1 / t, no logarithm) with the weights known, so the
+            // chunk's eight sums are plain register accumulators.  19 FP64 instructions per point against 17 in
+            // one pass; the generic kernel, which this replaces for these sizes, needs about 30.
+            static_assert(F::FAST_KIND == 1 || F::FAST_KIND == 2, "two-pass form: carrier families only");
+            double* tp_a = zp_m;                          // K node terms, then the weights
+            double* tp_v = tp_a + ((K + 1) & ~1);         // K sums of log t over the observations
+            auto node = [&](int kc, double* b, const double** pf) {
+                const int packed = nidx[kc];
+                double nt[Q + 1];
+                if (has_ntab) {
+#pragma unroll
+                    for (int e = 0; e <= Q; ++e) nt[e] = ntab[kc * (Q + 1) + e];
+                } else {
+                    nt[Q] = A.grid->lw_const;
+#pragma unroll
+                    for (int e = 0; e < Q; ++e) {
+                        const int ae = ((packed >> (8 * e)) & 0xff) - e * nagq;
+                        nt[e] = gx[ae];
+                        nt[Q] += glw[ae];
+                    }
+                }
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) {
+                    double sdd = scv[SC_M + dd];
+#pragma unroll
+                    for (int e = dd; e < Q; ++e) sdd = fma(scv[SC_RI + Tri<Q>::rm(dd, e)], nt[e], sdd);
+                    b[dd] = sdd;
+                }
+#pragma unroll
+                for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
+                return nt[Q];
+            };
+            // the chunk's four table products (+ addend); rows past the cluster's end read stale columns
+            auto prod4 = [&](const double** pf, int c4, double* t4) {
+                double fq[Q][4];
+#pragma unroll
+                for (int e = 0; e < Q; ++e) {
+                    const double2 f01 = *reinterpret_cast<const double2*>(pf[e] + 4 * c4);
+                    const double2 f23 = *reinterpret_cast<const double2*>(pf[e] + 4 * c4 + 2);
+                    fq[e][0] = f01.x; fq[e][1] = f01.y; fq[e][2] = f23.x; fq[e][3] = f23.y;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    double pr = fq[0][jj];
+#pragma unroll
+                    for (int e = 1; e < Q - 1; ++e) pr *= fq[e][jj];
+                    if (F::FAST_KIND == 1)
+                        t4[jj] = Q > 1 ? fma(pr, fq[Q - 1][jj], F::fast_addend(A.fam)) : pr + F::fast_addend(A.fam);
+                    else
+                        t4[jj] = Q > 1 ? pr * fq[Q - 1][jj] : pr;
+                    if (4 * c4 + jj >= nic) t4[jj] = 1.0;
+                }
+            };
+            // ---- pass A
+            for (int r = 0; r < nrounds; ++r) {
+                const int k = (r << 5) + lane;
+                const bool valid = k < K;
+                const int kc = valid ? k : K - 1;
+                double b[Q];
+                const double* pf[Q];
+                const double lw = node(kc, b, pf);
+                double quad = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) {
+                    double sdd = 0.0;
+#pragma unroll
+                    for (int e = 0; e < Q; ++e) sdd = fma(A.prior.Dinv[dd * Q + e], b[e], sdd);
+                    quad = fma(b[dd], sdd, quad);
+                }
+                double a = fma(-0.5, quad, A.prior.logprior_const) + lw, a1 = 0.0, vphi = 0.0;
+                if (F::LIN_ETA) {
+#pragma unroll
+                    for (int dd = 0; dd < QY; ++dd) a = fma(scv[SC_ZTY + dd], b[dd], a);
+                }
+#pragma unroll 2
+                for (int c4 = 0; c4 < NJ / 4; ++c4) {
+                    if (4 * c4 >= nic) break;
+                    double t4[4];
+                    prod4(pf, c4, t4);
+                    if (F::FAST_KIND == 1) {
+                        double L4[4], r4[4];
+                        fast_log_rcp_vec<4>(t4, cx, L4, r4);             // the reciprocal half is dead code here
+                        const double2 w01 = *reinterpret_cast<const double2*>(wv + 4 * c4);
+                        const double2 w23 = *reinterpret_cast<const double2*>(wv + 4 * c4 + 2);
+                        const double w4[4] = {w01.x, w01.y, w23.x, w23.y};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const bool on = 4 * c4 + jj < nic;
+                            const double wj = on ? w4[jj] : 0.0;
+                            if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
+                            if (F::HAS_PHI) vphi += on ? L4[jj] : 0.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const double ej = 4 * c4 + jj < nic ? t4[jj] : 0.0;
+                            if (jj & 1) a1 -= ej; else a -= ej;
+                        }
+                    }
+                }
+                if (valid) { tp_a[k] = a + a1; tp_v[k] = vphi; }
+            }
+            __syncwarp();
+            // ---- weights: exact maximum, no retry
+            {
+                double mx = -INFINITY;
+                for (int k = lane; k < K; k += 32) mx = fmax(mx, tp_a[k]);
+                mx = warp_max(mx);
+                shift = fabs(mx) < INFINITY ? mx : 0.0;
+            }
+            sum_e = 0.0; gphi = 0.0;
+#pragma unroll
+            for (int t = 0; t < NP; ++t) S[t] = 0.0;
+            for (int r = 0; r < nrounds; ++r) {
+                const int k = (r << 5) + lane;
+                const bool valid = k < K;
+                const int kc = valid ? k : K - 1;
+                double b[Q];
+                const double* pf[Q];
+                node(kc, b, pf);
+                double e = valid ? fast_exp(tp_a[kc] - shift, cx) : 0.0;
+                if (A.em_mode) {
+                    const int packed = nidx[kc];
+                    int kn = 0, mul = 1;
+#pragma unroll
+                    for (int ee = 0; ee < Q; ++ee) { kn += (int)(((packed >> (8 * ee)) & 0xff) - ee * nagq) * mul; mul *= nagq; }
+                    if (A.em_mode == 2) e = valid ? A.pby[i * K + kn] : 0.0;
+                    else if (valid) A.pby[i * K + kn] = e;
+                }
+                if (valid) tp_a[k] = e;
+                sum_e += e;
+                int t = 0;
+#pragma unroll
+                for (int dd = 0; dd < Q; ++dd) {
+                    const double eb = e * b[dd];
+#pragma unroll
+                    for (int ee = dd; ee < Q; ++ee) { S[t] = fma(eb, b[ee], S[t]); ++t; }
+                }
+                if (F::HAS_PHI) gphi = fma(e, valid ? tp_v[kc] : 0.0, gphi);
+            }
+            sum_e = warp_sum(sum_e);
+            __syncwarp();
+            // ---- pass B: chunks of eight observations, carriers only
+            for (int c8 = 0; c8 < NJ / 8; ++c8) {
+                if (8 * c8 >= nic) break;
+                double acc8[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc8[jj] = 0.0;
+                for (int r = 0; r < nrounds; ++r) {
+                    const int k = (r << 5) + lane;
+                    const bool valid = k < K;
+                    const int kc = valid ? k : K - 1;
+                    const int packed = nidx[kc];
+                    const double* pf[Q];
+#pragma unroll
+                    for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
+                    const double e = valid ? tp_a[kc] : 0.0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c4 = 2 * c8 + h;
+                        double t4[4];
+                        prod4(pf, c4, t4);
+                        if (F::FAST_KIND == 1) {
+                            double L4[4], r4[4];
+                            fast_log_rcp_vec<4>(t4, cx, L4, r4);         // the logarithm half is dead code here
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? r4[jj] : 0.0, acc8[4 * h + jj]);
+                        } else {
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? t4[jj] : 0.0, acc8[4 * h + jj]);
+                        }
+                    }
+                }
+                // the chunk's eight sums over the 32 lanes (as the one-pass epilogue does for a tile of eight)
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) acc_eta[jj * 32 + lane] = acc8[jj];
+                __syncwarp();
+                {
+                    const int j = lane & 7, sl = lane >> 3;
+                    double s1 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s1 += acc_eta[j * 32 + sl * 8 + ((c + j) & 7)];
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    if ((lane >> 3) == c8) tp_s1 = s1;          // lane l owns observation l = 8 c8 + (l & 7)
+                }
+                __syncwarp();
+            }
+        } else {
         for (int attempt = 0; attempt < 2; ++attempt) {
             sum_e = 0.0; gphi = 0.0;
 #pragma unroll
@@ -1941,6 +2143,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             if (attempt == 1 || !(fabs(mx) < INFINITY) || mx == shift) break;
             shift = mx;
         }
+        }
         double lsum, isum;
         fast_log_rcp<true>(sum_e, cx, lsum, isum);
         // node-independent terms are not part of ll here (added once per evaluation, see the header)
@@ -1967,9 +2170,13 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             if (F::HAS_PHI) {
                 if (F::FAST_KIND == 1) {
                     // second term of the phi-score, sum_k e_k sum_j rec1_j r_jk, from the carrier sums
+                    if (TP) {
+                        if (lane < nic) gphi = fma(wv[lane], tp_s1, gphi);     // the complete sum of observation `lane`
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < NJ; ++j)
-                        if (j < nic) gphi = fma(wv[j], acc_e[j], gphi);
+                        for (int j = 0; j < NJ; ++j)
+                            if (j < nic) gphi = fma(wv[j], acc_e[j], gphi);
+                    }
                 }
                 totl[lane] = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
             }
@@ -2010,7 +2217,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 zp_epi *= isum;
                 __syncwarp();
             }
-            if (!GQ) {
+            if (!GQ && !TP) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     acc_eta[j * 32 + lane] = acc_e[j];
@@ -2035,6 +2242,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
+                if (TP) s1 = tp_s1;                    // two-pass form: reduced chunk by chunk above
                 double zb = 0.0, zz = 0.0;
                 double scv_gq = 0.0;
                 if (GQ) {

@@ -76,6 +76,8 @@ struct OpsImpl {
     // Picks the shape with the most resident warps per SM; ties go to the larger block.
     // q = 4: nAGQ^4 nodes exceed the register variant's grids for every nAGQ > 4 -- not instantiated
     static constexpr bool HAS_FAST = QY + QZ <= 3;
+    // tile of 32 observations: the register variant's two-pass form, carrier families only (kernels.cuh)
+    static constexpr bool HAS_TILE32 = HAS_FAST && (F::FAST_KIND == 1 || F::FAST_KIND == 2);
     template <int NJ>
     static cudaError_t fast_config_nj(int K, int nagq, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
@@ -100,15 +102,22 @@ struct OpsImpl {
     }
     static cudaError_t fast_config(int xw, int nj, int K, int nagq, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
         if constexpr (!HAS_FAST) { *blocks_per_sm = 0; *smem_bytes = 0; *threads = 0; return cudaSuccess; }
-        else return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
-             : nj == 12 ? fast_config_nj<12>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
-                        : fast_config_nj<16>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
+        else {
+            if (nj == 32) {
+                if constexpr (HAS_TILE32) return fast_config_nj<32>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
+                else { *blocks_per_sm = 0; *smem_bytes = 0; *threads = 0; return cudaSuccess; }
+            }
+            return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
+                 : nj == 12 ? fast_config_nj<12>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
+                            : fast_config_nj<16>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
+        }
     }
     static void eval_fast(const EvalArgs& a, int /*score*/, int nj, int grid, int threads, size_t smem, cudaStream_t s) {
         if constexpr (!HAS_FAST) return;
         else if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
         else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, threads, smem, s>>>(a);
-        else eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
+        else if (nj == 16) eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
+        else if constexpr (HAS_TILE32) eval_fast_kernel<F, QY, QZ, true, 32><<<grid, threads, smem, s>>>(a);
     }
     static void sphi(const EvalArgs& a, int grid, int threads, size_t smem, cudaStream_t s) {
         sphi_obs_kernel<F, QY, QZ><<<grid, threads, smem, s>>>(a);
@@ -139,7 +148,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, info, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA};
+        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, info, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA, HAS_TILE32};
         return &ops;
     }
 };

@@ -275,3 +275,56 @@ def test_hoisted_paths_at_their_class_extremes(fam_name, q_zi):
         elif fam_name == "hurdle.beta.fam":
             th["phis"] = np.array([1.5])
     _check(d, th, fam_name)
+
+
+@pytest.mark.parametrize("fam_name,q_y", [("negative.binomial", 2), ("poisson", 3), ("binomial", 1), ("poisson", 2)])
+def test_two_pass_tile_of_the_register_variant(fam_name, q_y):
+    """Clusters of 17 .. 32 observations only: the register variant's two-pass form (tile 32, carrier families)
+    is the only kernel that runs.  Fused evaluation, E-step / frozen-weight M-step and the per-cluster /
+    per-observation contributions against the oracle, with weights and an offset."""
+    from oracle import fit as ofit
+    rng = np.random.default_rng(50 + q_y + len(fam_name))
+    sizes = rng.integers(17, 33, 40)
+    sizes[:3] = (17, 32, 25)
+    betas = np.array([0.2, 0.4, -0.3])
+    D = {1: np.array([[0.5]]), 2: np.array([[0.4, 0.08], [0.08, 0.25]]),
+         3: np.array([[0.4, 0.08, -0.05], [0.08, 0.25, 0.03], [-0.05, 0.03, 0.2]])}[q_y]
+    ids = np.repeat(np.arange(len(sizes)), sizes)
+    N = len(ids)
+    x = rng.random(N)
+    g = rng.integers(0, 2, len(sizes)).astype(float)[ids]
+    d = dict(id=ids, X=np.column_stack([np.ones(N), x, g]), Z=np.column_stack([np.ones(N), x, x * x - 0.3])[:, :q_y])
+    d["offset"] = rng.normal(0, 0.2, N)
+    d["weights"] = rng.uniform(0.5, 1.5, len(sizes))
+    eta = d["X"] @ betas + d["offset"]
+    th = dict(betas=betas, D=D, nAGQ=7 if q_y == 3 else 11)
+    if fam_name == "negative.binomial":
+        d["y"] = rng.negative_binomial(2.0, 2.0 / (2.0 + np.exp(eta))).astype(float)
+        th["phis"] = np.array([np.log(2.0)])
+    elif fam_name == "poisson":
+        d["y"] = rng.poisson(np.exp(eta)).astype(float)
+    else:
+        d["y"] = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(float)
+    _check(d, th, fam_name)
+    fam = oracle_family(fam_name)
+    od, gh = oracle_grid(d, th, fam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=th["nAGQ"], offset=d["offset"], weights=d["weights"])
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    phis = th.get("phis")
+    p_by, post_b2, ll, eta_zi = ofit.e_step(od, fam, gh, betas, D, phis, None)
+    es = eng.em_estep(betas, D, phis, None)
+    assert relerr(es["loglik"], ll) < RTOL
+    b2 = betas + np.array([0.05, -0.03, 0.02])
+    ph2 = None if phis is None else phis + 0.07
+    sc = eng.em_score(b2, ph2, None)
+    ref_b = ofit.score_betas(b2, od, fam, gh, ph2, eta_zi, p_by)
+    assert np.max(np.abs(-sc["g_beta"] - ref_b)) < 10 * RTOL * max(1.0, np.max(np.abs(ref_b)))
+    # per-cluster / per-observation contributions (i_contributions = TRUE)
+    tvf = thetas_vec(th)
+    ll_i = gb.logLik_mixed(tvf, eng, None, i_contributions=True)
+    assert relerr(ll_i, agq.logLik_mixed(tvf, od, fam, gh, i_contributions=True)) < RTOL
+    cr = agq.score_mixed(tvf, od, fam, gh, i_contributions=True)
+    cg = gb.score_mixed(tvf, eng, None, i_contributions=True)
+    w_obs = d["weights"][d["id"]]
+    assert np.max(np.abs(cg["score_betas"] - cr["score_betas"] * w_obs[:, None])) < 1e-9
+    eng.close()
