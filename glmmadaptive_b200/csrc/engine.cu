@@ -7,6 +7,7 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <queue>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -684,9 +685,9 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         const bool use12 = n_9_12 > 0 && n_9_12 >= (int64_t)(0.05 * (double)n);
         const bool use16 = (n_13_16 > 0 && n_13_16 >= few) || (!use12 && n_9_12 > 0 && n_9_12 >= few);
         const bool use8 = n_le8 > 0 && (n_le8 >= (int64_t)(0.1 * (double)n) || !(use12 || use16));
-        int64_t n_17_32 = 0;
-        for (int v = 17; v <= 32; ++v) n_17_32 += cnt[v];
-        const bool use32 = ops->tile32 && n_17_32 > 0 && n_17_32 >= few && !std::getenv("GLMMA_NO_TILE32");
+        int64_t n_17_up = 0;
+        for (int v = 17; v <= GLMMA_JT_CAP + 1; ++v) n_17_up += cnt[v];        // (the last bin holds everything beyond)
+        const bool use32 = ops->tile32 && n_17_up > 0 && n_17_up >= few && !std::getenv("GLMMA_NO_TILE32");
         h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0) | (use32 ? 8 : 0);
     }
     // fused mode whenever the register variant runs and the design columns fit a warp's lanes
@@ -718,11 +719,54 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         {
             std::vector<int4> lists[GLMMA_NTILES];
             std::vector<int32_t> flags(n, 0), too_big;
+            const bool tp = (h->nj & 8) != 0;        // two-pass tile in use: it also takes the clusters beyond 32 rows
+            std::vector<int32_t> tp_clusters;
             for (int64_t i = 0; i < n; ++i) {
                 const int ni = row_ptr[i + 1] - row_ptr[i];
-                if (ni > top) { flags[i] = 1; too_big.push_back((int32_t)i); continue; }
-                for (int v = 0; v < GLMMA_NTILES; ++v)           // the smallest tile in use that holds the cluster
-                    if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); break; }
+                if (ni > top && !tp) { flags[i] = 1; too_big.push_back((int32_t)i); continue; }
+                bool placed = false;
+                for (int v = 0; v < GLMMA_NTILES - 1 && !placed; ++v)           // the smallest one-pass tile in use that holds the cluster
+                    if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); placed = true; }
+                if (!placed) tp_clusters.push_back((int32_t)i);
+            }
+            if (tp) {
+                // Two-pass tile (kernels.cuh): a cluster is a sequence of records -- its tiles of 32 rows for pass A
+                // (flags 1, +2 first tile, +4 last tile), then the same tiles for pass B (8); 15 = all in one record
+                // for at most 32 rows -- that ONE warp must walk in order.  The kernel gives position p of the list to
+                // warp p mod nwarps, so the records are laid out as per-warp queues (clusters dealt to the least
+                // loaded warp, longest first), padded with empty records to a common length.
+                const int v = GLMMA_NTILES - 1;
+                const int fwpb = h->fast_threads[v][1] / 32;
+                const int64_t want = ((int64_t)tp_clusters.size() + fwpb - 1) / fwpb;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][1]));
+                h->fast_grid[v][0] = h->fast_grid[v][1] = grid;
+                const int64_t nwarps = (int64_t)grid * fwpb;
+                std::vector<int32_t> byrows(tp_clusters);
+                std::stable_sort(byrows.begin(), byrows.end(), [&](int32_t a, int32_t b) {
+                    return row_ptr[a + 1] - row_ptr[a] > row_ptr[b + 1] - row_ptr[b]; });
+                std::vector<std::vector<int4>> queue((size_t)nwarps);
+                typedef std::pair<int64_t, int64_t> Load;       // (rows queued, warp)
+                std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+                for (int64_t wq = 0; wq < nwarps; ++wq) heap.push(Load(0, wq));
+                for (int32_t ci : byrows) {
+                    const int r0 = row_ptr[ci], ni = row_ptr[ci + 1] - r0;
+                    Load ld = heap.top(); heap.pop();
+                    std::vector<int4>& qv = queue[(size_t)ld.second];
+                    if (ni <= 32) qv.push_back(make_int4(ci, r0, ni, 15));
+                    else {
+                        const int T = (ni + 31) / 32;
+                        for (int t = 0; t < T; ++t)
+                            qv.push_back(make_int4(ci, r0 + 32 * t, std::min(32, ni - 32 * t), 1 | (t == 0 ? 2 : 0) | (t == T - 1 ? 4 : 0)));
+                        for (int t = 0; t < T; ++t) qv.push_back(make_int4(ci, r0 + 32 * t, std::min(32, ni - 32 * t), 8));
+                    }
+                    ld.first += ni;
+                    heap.push(ld);
+                }
+                size_t qlen = 0;
+                for (const auto& qv : queue) qlen = std::max(qlen, qv.size());
+                lists[v].assign(qlen * (size_t)nwarps, make_int4(0, 0, 0, 0));
+                for (int64_t wq = 0; wq < nwarps; ++wq)
+                    for (size_t m = 0; m < queue[(size_t)wq].size(); ++m) lists[v][m * (size_t)nwarps + (size_t)wq] = queue[(size_t)wq][m];
             }
             for (int v = 0; v < GLMMA_NTILES; ++v) {
                 if (!(h->nj & (1 << v))) continue;
@@ -731,7 +775,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                 if (lists[v].empty()) lists[v].push_back(make_int4(0, 0, 0, 0));
                 TRY(dev_upload(h, &tmp, lists[v].data(), lists[v].size()));
                 h->d_order[v] = const_cast<int4*>(tmp);
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < 2 && v != GLMMA_NTILES - 1; ++s) {       // (the two-pass tile's grid is fixed above: its list is laid out for it)
                     const int fwpb = h->fast_threads[v][s] / 32;
                     const int64_t want = (h->n_order[v] + fwpb - 1) / fwpb;
                     h->fast_grid[v][s] = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][s]));

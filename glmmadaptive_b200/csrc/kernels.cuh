@@ -1072,7 +1072,7 @@ struct FastLayout {
     // (a_k then e_k, and the phi-score's node sums) kept per warp after the tables
     static constexpr bool TP = NJ == 32;
     static constexpr int NJR = (NJ <= 8 || TP) ? 8 : 16;    // rows of the per-observation reduction scratch (power of two)
-    __host__ __device__ static int tpd(int K) { return TP ? 2 * ((K + 1) & ~1) : 0; }
+    __host__ __device__ static int tpd(int K) { return TP ? 2 * ((K + 1) & ~1) + 8 : 0; }   // + the cluster's state between its records
     static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
     static_assert(NJ <= 32, "a lane stages one observation");
     __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
@@ -1267,6 +1267,10 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         // `order` load while that load is in flight; keeping the register live instead -- nic = cur.z + cur.w --
         // cost 4 % through register pressure, so the stall stays)
         const int nic = cur.z;
+        // two-pass tile: what this record asks for -- 1 pass A over its rows, 2 first tile of the cluster, 4 last
+        // tile (the weights follow), 8 pass B over its rows; 15: a cluster of at most 32 observations in one record;
+        // 0: padding of a warp's queue
+        const int rflags = FL::TP ? cur.w : 0;
         cur = nxt;
         // (pos + 2 nwarps may pass 2^31: compare the remaining distance instead)
         cp_async_wait_all();
@@ -1274,6 +1278,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         if (n_pos - pos > nwarps) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * PRE);
         if (n_pos - pos > 2 * nwarps) nxt = order[pos + 2 * nwarps];
         pbuf ^= 1;
+        if (FL::TP && rflags == 0) continue;
         if (nic > NJ) {
             if (lane == 0) d.defer[i] = 1;
             continue;
@@ -1411,8 +1416,24 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             s_ll = warp_sum(cc.x);
             s_phi = warp_sum(cc.y);
         };
-        if (lane == 0) d.defer[i] = bad ? 1 : 0;
-        if (bad) {
+        // two-pass tile: a cluster may span several records (tiles of 32 rows, pass A records then pass B records,
+        // all in this warp's queue); it is left to eval_kernel as a whole when ANY of its tiles fails the range
+        // test.  The state travels in shared memory: tp_st[0] shift, [1] 1 / sum_e, [2] w / sum_e or 0, [3] dead,
+        // [4] ok, [5] log-likelihood of the cluster
+        double* tp_st = zp_m + 2 * ((K + 1) & ~1);
+        bool tp_dead = false;
+        if (FL::TP) {
+            tp_dead = (rflags & 2) ? false : tp_st[3] != 0.0;
+            if ((rflags & 1) && bad) tp_dead = true;
+            __syncwarp();
+            if (lane == 0) {
+                tp_st[3] = tp_dead ? 1.0 : 0.0;
+                if (rflags & 4) d.defer[i] = tp_dead ? 1 : 0;
+            }
+            __syncwarp();
+            if (tp_dead && !(rflags & 8)) continue;       // its pass B records write the work arrays of their rows
+        } else if (lane == 0) d.defer[i] = bad ? 1 : 0;
+        if (FL::TP ? tp_dead : bad) {
             // eval_kernel takes this cluster from the work arrays the prep kernel would have written
             double s_ll, s_phi;
             cluster_consts(lane, s_ll, s_phi);
@@ -1580,16 +1601,18 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         double acc_e[NJ], acc_z[F::HAS_ZI ? NJ : 1];
         double gq_bb[QY];             // FAST_KIND 3: sum_k e_k delta_k
         constexpr bool TP = FL::TP;
-        double tp_s1 = 0.0;              // two-pass form: this lane's observation's sum_k e_k carrier_jk
         if constexpr (TP) {
-            // ---- Two-pass form for clusters of 17 .. 32 observations (FAST_KIND 1 / 2 families).  The one-pass
-            // form keeps an observation's score carrier in a register until the node weight is known: 2 x NJ
-            // double registers, impossible beyond 16 observations.  Here pass A walks all observations for the
-            // node terms only (log t, no reciprocal: a_k and the phi-score's sum_j log t_jk, kept per warp in
-            // shared memory), the weights e_k = exp(a_k - max) follow exactly, and pass B walks the observations
-            // again in chunks of eight for the carriers only (1 / t, no logarithm) with the weights known, so the
-            // chunk's eight sums are plain register accumulators.  19 FP64 instructions per point against 17 in
-            // one pass; the generic kernel, which this replaces for these sizes, needs about 30.
+            // ---- Two-pass form (FAST_KIND 1 / 2 families) for clusters of more than 16 observations.  The
+            // one-pass form keeps an observation's score carrier in a register until the node weight is known:
+            // 2 x NJ double registers, impossible beyond 16 observations.  Here pass A walks the observations
+            // for the node terms only (log t, no reciprocal: a_k and the phi-score's sum_j log t_jk, kept per warp
+            // in shared memory), the weights e_k = exp(a_k - max) follow exactly, and pass B walks the
+            // observations again in chunks of eight for the carriers only (1 / t, no logarithm) with the weights
+            // known, so a chunk's eight sums are plain register accumulators.  19 FP64 instructions per point
+            // against 17 in one pass; the generic kernel, which this replaces, needs about 30.  A cluster of more
+            // than 32 observations is a sequence of records in ONE warp's queue -- its tiles of 32 rows for pass
+            // A, then the same tiles for pass B (staged and tabulated twice: Q nAGQ exponentials per observation
+            // against nAGQ^Q points) -- with the node terms accumulating across the pass A records.
             static_assert(F::FAST_KIND == 1 || F::FAST_KIND == 2, "two-pass form: carrier families only");
             double* tp_a = zp_m;                          // K node terms, then the weights
             double* tp_v = tp_a + ((K + 1) & ~1);         // K sums of log t over the observations
@@ -1619,7 +1642,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
                 return nt[Q];
             };
-            // the chunk's four table products (+ addend); rows past the cluster's end read stale columns
+            // the chunk's four table products (+ addend); rows past the tile's end read stale columns
             auto prod4 = [&](const double** pf, int c4, double* t4) {
                 double fq[Q][4];
 #pragma unroll
@@ -1640,141 +1663,227 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     if (4 * c4 + jj >= nic) t4[jj] = 1.0;
                 }
             };
-            // ---- pass A
-            for (int r = 0; r < nrounds; ++r) {
-                const int k = (r << 5) + lane;
-                const bool valid = k < K;
-                const int kc = valid ? k : K - 1;
-                double b[Q];
-                const double* pf[Q];
-                const double lw = node(kc, b, pf);
-                double quad = 0.0;
-#pragma unroll
-                for (int dd = 0; dd < Q; ++dd) {
-                    double sdd = 0.0;
-#pragma unroll
-                    for (int e = 0; e < Q; ++e) sdd = fma(A.prior.Dinv[dd * Q + e], b[e], sdd);
-                    quad = fma(b[dd], sdd, quad);
-                }
-                double a = fma(-0.5, quad, A.prior.logprior_const) + lw, a1 = 0.0, vphi = 0.0;
-                if (F::LIN_ETA) {
-#pragma unroll
-                    for (int dd = 0; dd < QY; ++dd) a = fma(scv[SC_ZTY + dd], b[dd], a);
-                }
-#pragma unroll 2
-                for (int c4 = 0; c4 < NJ / 4; ++c4) {
-                    if (4 * c4 >= nic) break;
-                    double t4[4];
-                    prod4(pf, c4, t4);
-                    if (F::FAST_KIND == 1) {
-                        double L4[4], r4[4];
-                        fast_log_rcp_vec<4>(t4, cx, L4, r4);             // the reciprocal half is dead code here
-                        const double2 w01 = *reinterpret_cast<const double2*>(wv + 4 * c4);
-                        const double2 w23 = *reinterpret_cast<const double2*>(wv + 4 * c4 + 2);
-                        const double w4[4] = {w01.x, w01.y, w23.x, w23.y};
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const bool on = 4 * c4 + jj < nic;
-                            const double wj = on ? w4[jj] : 0.0;
-                            if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
-                            if (F::HAS_PHI) vphi += on ? L4[jj] : 0.0;
-                        }
-                    } else {
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const double ej = 4 * c4 + jj < nic ? t4[jj] : 0.0;
-                            if (jj & 1) a1 -= ej; else a -= ej;
-                        }
-                    }
-                }
-                if (valid) { tp_a[k] = a + a1; tp_v[k] = vphi; }
-            }
-            __syncwarp();
-            // ---- weights: exact maximum, no retry
-            {
-                double mx = -INFINITY;
-                for (int k = lane; k < K; k += 32) mx = fmax(mx, tp_a[k]);
-                mx = warp_max(mx);
-                shift = fabs(mx) < INFINITY ? mx : 0.0;
-            }
-            sum_e = 0.0; gphi = 0.0;
-#pragma unroll
-            for (int t = 0; t < NP; ++t) S[t] = 0.0;
-            for (int r = 0; r < nrounds; ++r) {
-                const int k = (r << 5) + lane;
-                const bool valid = k < K;
-                const int kc = valid ? k : K - 1;
-                double b[Q];
-                const double* pf[Q];
-                node(kc, b, pf);
-                double e = valid ? fast_exp(tp_a[kc] - shift, cx) : 0.0;
-                if (A.em_mode) {
-                    const int packed = nidx[kc];
-                    int kn = 0, mul = 1;
-#pragma unroll
-                    for (int ee = 0; ee < Q; ++ee) { kn += (int)(((packed >> (8 * ee)) & 0xff) - ee * nagq) * mul; mul *= nagq; }
-                    if (A.em_mode == 2) e = valid ? A.pby[i * K + kn] : 0.0;
-                    else if (valid) A.pby[i * K + kn] = e;
-                }
-                if (valid) tp_a[k] = e;
-                sum_e += e;
-                int t = 0;
-#pragma unroll
-                for (int dd = 0; dd < Q; ++dd) {
-                    const double eb = e * b[dd];
-#pragma unroll
-                    for (int ee = dd; ee < Q; ++ee) { S[t] = fma(eb, b[ee], S[t]); ++t; }
-                }
-                if (F::HAS_PHI) gphi = fma(e, valid ? tp_v[kc] : 0.0, gphi);
-            }
-            sum_e = warp_sum(sum_e);
-            __syncwarp();
-            // ---- pass B: chunks of eight observations, carriers only
-            for (int c8 = 0; c8 < NJ / 8; ++c8) {
-                if (8 * c8 >= nic) break;
-                double acc8[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) acc8[jj] = 0.0;
+            // ---- pass A over this record's rows
+            if (rflags & 1) {
+                const bool first = (rflags & 2) != 0;
                 for (int r = 0; r < nrounds; ++r) {
                     const int k = (r << 5) + lane;
                     const bool valid = k < K;
                     const int kc = valid ? k : K - 1;
-                    const int packed = nidx[kc];
+                    double b[Q];
                     const double* pf[Q];
+                    const double lw = node(kc, b, pf);
+                    double a, a1 = 0.0, vphi;
+                    if (first) {
+                        // b_k' D^-1 b_k, log weights and the linear-eta hoist enter once per cluster
+                        double quad = 0.0;
 #pragma unroll
-                    for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
-                    const double e = valid ? tp_a[kc] : 0.0;
+                        for (int dd = 0; dd < Q; ++dd) {
+                            double sdd = 0.0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int c4 = 2 * c8 + h;
+                            for (int e = 0; e < Q; ++e) sdd = fma(A.prior.Dinv[dd * Q + e], b[e], sdd);
+                            quad = fma(b[dd], sdd, quad);
+                        }
+                        a = fma(-0.5, quad, A.prior.logprior_const) + lw;
+                        if (F::LIN_ETA) {
+#pragma unroll
+                            for (int dd = 0; dd < QY; ++dd) a = fma(scv[SC_ZTY + dd], b[dd], a);
+                        }
+                        vphi = 0.0;
+                    } else {
+                        a = tp_a[kc];
+                        vphi = tp_v[kc];
+                    }
+#pragma unroll 2
+                    for (int c4 = 0; c4 < NJ / 4; ++c4) {
+                        if (4 * c4 >= nic) break;
                         double t4[4];
                         prod4(pf, c4, t4);
                         if (F::FAST_KIND == 1) {
                             double L4[4], r4[4];
-                            fast_log_rcp_vec<4>(t4, cx, L4, r4);         // the logarithm half is dead code here
+                            fast_log_rcp_vec<4>(t4, cx, L4, r4);             // the reciprocal half is dead code here
+                            const double2 w01 = *reinterpret_cast<const double2*>(wv + 4 * c4);
+                            const double2 w23 = *reinterpret_cast<const double2*>(wv + 4 * c4 + 2);
+                            const double w4[4] = {w01.x, w01.y, w23.x, w23.y};
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? r4[jj] : 0.0, acc8[4 * h + jj]);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const bool on = 4 * c4 + jj < nic;
+                                const double wj = on ? w4[jj] : 0.0;
+                                if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
+                                if (F::HAS_PHI) vphi += on ? L4[jj] : 0.0;
+                            }
                         } else {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? t4[jj] : 0.0, acc8[4 * h + jj]);
+                            for (int jj = 0; jj < 4; ++jj) {
+                                const double ej = 4 * c4 + jj < nic ? t4[jj] : 0.0;
+                                if (jj & 1) a1 -= ej; else a -= ej;
+                            }
                         }
                     }
-                }
-                // the chunk's eight sums over the 32 lanes (as the one-pass epilogue does for a tile of eight)
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) acc_eta[jj * 32 + lane] = acc8[jj];
-                __syncwarp();
-                {
-                    const int j = lane & 7, sl = lane >> 3;
-                    double s1 = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) s1 += acc_eta[j * 32 + sl * 8 + ((c + j) & 7)];
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-                    if ((lane >> 3) == c8) tp_s1 = s1;          // lane l owns observation l = 8 c8 + (l & 7)
+                    if (valid) { tp_a[k] = a + a1; tp_v[k] = vphi; }
                 }
                 __syncwarp();
             }
+            // ---- after the cluster's last tile: weights (exact maximum, no retry), cluster totals
+            if (rflags & 4) {
+                {
+                    double mx = -INFINITY;
+                    for (int k = lane; k < K; k += 32) mx = fmax(mx, tp_a[k]);
+                    mx = warp_max(mx);
+                    shift = fabs(mx) < INFINITY ? mx : 0.0;
+                }
+                sum_e = 0.0; gphi = 0.0;
+#pragma unroll
+                for (int t = 0; t < NP; ++t) S[t] = 0.0;
+                for (int r = 0; r < nrounds; ++r) {
+                    const int k = (r << 5) + lane;
+                    const bool valid = k < K;
+                    const int kc = valid ? k : K - 1;
+                    double b[Q];
+                    const double* pf[Q];
+                    node(kc, b, pf);
+                    double e = valid ? fast_exp(tp_a[kc] - shift, cx) : 0.0;
+                    if (A.em_mode) {
+                        const int packed = nidx[kc];
+                        int kn = 0, mul = 1;
+#pragma unroll
+                        for (int ee = 0; ee < Q; ++ee) { kn += (int)(((packed >> (8 * ee)) & 0xff) - ee * nagq) * mul; mul *= nagq; }
+                        if (A.em_mode == 2) e = valid ? A.pby[i * K + kn] : 0.0;
+                        else if (valid) A.pby[i * K + kn] = e;
+                    }
+                    if (valid) tp_a[k] = e;
+                    sum_e += e;
+                    int t = 0;
+#pragma unroll
+                    for (int dd = 0; dd < Q; ++dd) {
+                        const double eb = e * b[dd];
+#pragma unroll
+                        for (int ee = dd; ee < Q; ++ee) { S[t] = fma(eb, b[ee], S[t]); ++t; }
+                    }
+                    if (F::HAS_PHI) gphi = fma(e, valid ? tp_v[kc] : 0.0, gphi);
+                }
+                sum_e = warp_sum(sum_e);
+                double lsum, isum;
+                fast_log_rcp<true>(sum_e, cx, lsum, isum);
+                const double ll = A.em_mode == 2 ? 0.0 : shift + lsum + sc[SC_LD];
+                const bool ok = A.em_mode == 2 ? (sum_e > 0.0 && sum_e < INFINITY) : fabs(ll) < INFINITY;
+                if (A.em_mode == 1 && !ok)
+                    for (int k = lane; k < K; k += 32) A.pby[i * K + k] = 0.0;
+                const double inv = ok ? w * isum : 0.0;
+                if (lane == 0) {
+                    if (ok) { tots[0] += w * ll; tots[1] += w; } else tots[2] += 1.0;
+                    if (d.ll_i) d.ll_i[i] = w * ll;          // the pass B records add their rows' node-independent terms
+                    tp_st[1] = isum; tp_st[2] = inv; tp_st[4] = ok ? 1.0 : 0.0;
+                }
+                if (SCORE) {
+                    if (F::HAS_PHI) totl[lane] = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
+#pragma unroll
+                    for (int t = 0; t < NP; ++t) totl[(2 + t) * 32 + lane] = fma(inv, S[t], totl[(2 + t) * 32 + lane]);
+                    if (d.S_i) {
+                        double Sr[NP];
+#pragma unroll
+                        for (int t = 0; t < NP; ++t) Sr[t] = inv * warp_sum(S[t]);
+                        if (lane == 0) {
+                            int t = 0;
+#pragma unroll
+                            for (int dd = 0; dd < Q; ++dd)
+#pragma unroll
+                                for (int ee = dd; ee < Q; ++ee) {
+                                    d.S_i[i * Q * Q + dd * Q + ee] = Sr[t];
+                                    d.S_i[i * Q * Q + ee * Q + dd] = Sr[t];
+                                    ++t;
+                                }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- pass B over this record's rows: chunks of eight observations, carriers only
+            if (rflags & 8) {
+                const double isum = tp_st[1], inv = tp_st[2];
+                const bool ok = tp_st[4] != 0.0;
+                if (!ok || d.ll_i != nullptr) {
+                    // node-independent terms of this record's rows: taken back when the cluster dropped out of the
+                    // sums, added to the cluster's contribution when those are wanted
+                    double s_ll, s_phi;
+                    cluster_consts(lane, s_ll, s_phi);
+                    if (lane == 0) {
+                        if (!ok) {
+                            if (A.em_mode != 2) tots[0] -= w * s_ll;
+                            if (F::HAS_PHI) tots[3] -= w * s_phi;
+                        }
+                        if (d.ll_i) d.ll_i[i] += w * s_ll;
+                    }
+                }
+                double tp_s1 = 0.0;              // this lane's observation's sum_k e_k carrier_jk
+                if (SCORE) {
+                    for (int c8 = 0; c8 < NJ / 8; ++c8) {
+                        if (8 * c8 >= nic) break;
+                        double acc8[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) acc8[jj] = 0.0;
+                        for (int r = 0; r < nrounds; ++r) {
+                            const int k = (r << 5) + lane;
+                            const bool valid = k < K;
+                            const int kc = valid ? k : K - 1;
+                            const int packed = nidx[kc];
+                            const double* pf[Q];
+#pragma unroll
+                            for (int e = 0; e < Q; ++e) pf[e] = tabF + ((packed >> (8 * e)) & 0xff) * RP;
+                            const double e = valid ? tp_a[kc] : 0.0;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int c4 = 2 * c8 + h;
+                                double t4[4];
+                                prod4(pf, c4, t4);
+                                if (F::FAST_KIND == 1) {
+                                    double L4[4], r4[4];
+                                    fast_log_rcp_vec<4>(t4, cx, L4, r4);         // the logarithm half is dead code here
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? r4[jj] : 0.0, acc8[4 * h + jj]);
+                                } else {
+#pragma unroll
+                                    for (int jj = 0; jj < 4; ++jj) acc8[4 * h + jj] = fma(e, 4 * c4 + jj < nic ? t4[jj] : 0.0, acc8[4 * h + jj]);
+                                }
+                            }
+                        }
+                        // the chunk's eight sums over the 32 lanes (as the one-pass epilogue does for a tile of eight)
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) acc_eta[jj * 32 + lane] = acc8[jj];
+                        __syncwarp();
+                        {
+                            const int j = lane & 7, sl = lane >> 3;
+                            double s1 = 0.0;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) s1 += acc_eta[j * 32 + sl * 8 + ((c + j) & 7)];
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                            if ((lane >> 3) == c8) tp_s1 = s1;          // lane l owns observation l = 8 c8 + (l & 7)
+                        }
+                        __syncwarp();
+                    }
+                    // second term of the phi-score of these rows: sum_j rec1_j sum_k e_k r_jk
+                    if (F::HAS_PHI && F::FAST_KIND == 1 && lane < nic)
+                        totl[lane] = fma(inv * F::sp_scale(A.fam), wv[lane] * tp_s1, totl[lane]);
+                    double zb = 0.0;
+                    if (lane < nic) {
+                        const double scv1 = F::fast_score(tp_s1 * isum, rec[lane * W], rec[lane * W + 1], A.fam);
+                        zb = ok ? w * scv1 : 0.0;
+                        if (A.zbar_out) d.zbar[r0c + lane] = zb;
+                    }
+                    __syncwarp();
+                    acc_eta[lane] = zb;
+                    __syncwarp();
+                    if (lane < p_x) {
+                        const double* xc = xcur + lane * NJ;
+#pragma unroll 8
+                        for (int jj = 0; jj < NJ; ++jj)
+                            if (jj < nic) gcol = fma(xc[jj], acc_eta[jj], gcol);
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
         } else {
         for (int attempt = 0; attempt < 2; ++attempt) {
             sum_e = 0.0; gphi = 0.0;
@@ -2170,13 +2279,9 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             if (F::HAS_PHI) {
                 if (F::FAST_KIND == 1) {
                     // second term of the phi-score, sum_k e_k sum_j rec1_j r_jk, from the carrier sums
-                    if (TP) {
-                        if (lane < nic) gphi = fma(wv[lane], tp_s1, gphi);     // the complete sum of observation `lane`
-                    } else {
 #pragma unroll
-                        for (int j = 0; j < NJ; ++j)
-                            if (j < nic) gphi = fma(wv[j], acc_e[j], gphi);
-                    }
+                    for (int j = 0; j < NJ; ++j)
+                        if (j < nic) gphi = fma(wv[j], acc_e[j], gphi);
                 }
                 totl[lane] = fma(inv * F::sp_scale(A.fam), gphi, totl[lane]);
             }
@@ -2217,7 +2322,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 zp_epi *= isum;
                 __syncwarp();
             }
-            if (!GQ && !TP) {
+            if (!GQ) {
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     acc_eta[j * 32 + lane] = acc_e[j];
@@ -2242,7 +2347,6 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     if (F::HAS_ZI) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
-                if (TP) s1 = tp_s1;                    // two-pass form: reduced chunk by chunk above
                 double zb = 0.0, zz = 0.0;
                 double scv_gq = 0.0;
                 if (GQ) {

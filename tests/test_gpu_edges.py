@@ -277,15 +277,18 @@ def test_hoisted_paths_at_their_class_extremes(fam_name, q_zi):
     _check(d, th, fam_name)
 
 
-@pytest.mark.parametrize("fam_name,q_y", [("negative.binomial", 2), ("poisson", 3), ("binomial", 1), ("poisson", 2)])
-def test_two_pass_tile_of_the_register_variant(fam_name, q_y):
-    """Clusters of 17 .. 32 observations only: the register variant's two-pass form (tile 32, carrier families)
-    is the only kernel that runs.  Fused evaluation, E-step / frozen-weight M-step and the per-cluster /
-    per-observation contributions against the oracle, with weights and an offset."""
+@pytest.mark.parametrize("fam_name,q_y,big", [("negative.binomial", 2, False), ("poisson", 3, False), ("binomial", 1, False),
+                                              ("poisson", 2, False), ("negative.binomial", 2, True), ("binomial", 2, True),
+                                              ("poisson", 1, True)])
+def test_two_pass_tile_of_the_register_variant(fam_name, q_y, big):
+    """Clusters of 17 .. 32 observations only (big: 33 .. 150, i.e. several records -- tiles of 32 rows for pass A,
+    then for pass B -- in one warp's queue): the register variant's two-pass form (tile 32, carrier families) is the
+    only kernel that runs.  Fused evaluation, E-step / frozen-weight M-step and the per-cluster / per-observation
+    contributions against the oracle, with weights and an offset."""
     from oracle import fit as ofit
-    rng = np.random.default_rng(50 + q_y + len(fam_name))
-    sizes = rng.integers(17, 33, 40)
-    sizes[:3] = (17, 32, 25)
+    rng = np.random.default_rng(50 + q_y + len(fam_name) + (7 if big else 0))
+    sizes = rng.integers(33, 151, 24) if big else rng.integers(17, 33, 40)
+    sizes[:3] = (33, 64, 97) if big else (17, 32, 25)
     betas = np.array([0.2, 0.4, -0.3])
     D = {1: np.array([[0.5]]), 2: np.array([[0.4, 0.08], [0.08, 0.25]]),
          3: np.array([[0.4, 0.08, -0.05], [0.08, 0.25, 0.03], [-0.05, 0.03, 0.2]])}[q_y]
