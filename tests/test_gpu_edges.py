@@ -331,3 +331,39 @@ def test_two_pass_tile_of_the_register_variant(fam_name, q_y, big):
     w_obs = d["weights"][d["id"]]
     assert np.max(np.abs(cg["score_betas"] - cr["score_betas"] * w_obs[:, None])) < 1e-9
     eng.close()
+
+
+@pytest.mark.parametrize("fam_name,p,p_zi", [("negative.binomial", 14, 0), ("zi.poisson", 12, 7), ("censored.normal", 20, 0),
+                                             ("poisson", 27, 0)])
+def test_many_fixed_effect_columns(fam_name, p, p_zi):
+    """Wide design matrices: the register variant stages p + p_zi design columns per cluster and folds X'zbar into
+    the block partials (up to 32 columns); sizes 1 .. 40 so that every tile and the large-cluster paths see them."""
+    rng = np.random.default_rng(70 + p + p_zi)
+    sizes = np.concatenate([rng.integers(1, 9, 30), rng.integers(9, 17, 20), rng.integers(17, 41, 8)])
+    rng.shuffle(sizes)
+    ids = np.repeat(np.arange(len(sizes)), sizes)
+    N = len(ids)
+    X = np.column_stack([np.ones(N), rng.normal(0, 0.5, (N, p - 1))])
+    Z = np.column_stack([np.ones(N), X[:, 1]])
+    betas = np.concatenate([[0.2], rng.normal(0, 0.15, p - 1)])
+    D = np.array([[0.4, 0.08], [0.08, 0.25]])
+    d = dict(id=ids, X=X, Z=Z)
+    eta = X @ betas
+    th = dict(betas=betas, D=D, nAGQ=9)
+    if fam_name == "negative.binomial":
+        d["y"] = rng.negative_binomial(2.0, 2.0 / (2.0 + np.exp(eta))).astype(float)
+        th["phis"] = np.array([np.log(2.0)])
+    elif fam_name == "poisson":
+        d["y"] = rng.poisson(np.exp(eta)).astype(float)
+    elif fam_name == "zi.poisson":
+        d["X_zi"] = np.column_stack([np.ones(N), rng.normal(0, 0.5, (N, p_zi - 1))])
+        y = rng.poisson(np.exp(eta)).astype(float)
+        y[rng.random(N) < 0.3] = 0.0
+        d["y"] = y
+        th["gammas"] = np.concatenate([[-1.0], rng.normal(0, 0.2, p_zi - 1)])
+    else:
+        v = eta + 0.7 * rng.standard_normal(N)
+        hi, lo = np.quantile(v, 0.8), np.quantile(v, 0.1)
+        d["y"] = np.column_stack([np.clip(v, lo, hi), np.where(v > hi, 2.0, np.where(v < lo, 1.0, 0.0))])
+        th["phis"] = np.array([np.log(0.7)])
+    _check(d, th, fam_name)
