@@ -244,7 +244,7 @@ static const FamOps* lookup_ops(int family, int link, int qy, int qz) {
         case GLMMA_GAMMA: return glmma_ops_gamma(qy, qz);
         case GLMMA_CENSORED_NORMAL: return glmma_ops_censored_normal(qy, qz);
         case GLMMA_STUDENTS_T: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_IDENTITY) ? glmma_ops_students_t(qy, qz) : nullptr;
-        case GLMMA_BETA_BINOMIAL: return (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_LOGIT) ? glmma_ops_beta_binomial(qy, qz) : nullptr;
+        case GLMMA_BETA_BINOMIAL: return glmma_ops_beta_binomial(link, qy, qz);
 #endif
     }
     return nullptr;

@@ -45,4 +45,4 @@ const FamOps* glmma_ops_hurdle_beta(int qy, int qz);
 const FamOps* glmma_ops_gamma(int qy, int qz);
 const FamOps* glmma_ops_censored_normal(int qy, int qz);
 const FamOps* glmma_ops_students_t(int qy, int qz);
-const FamOps* glmma_ops_beta_binomial(int qy, int qz);
+const FamOps* glmma_ops_beta_binomial(int link, int qy, int qz);

@@ -1,3 +1,8 @@
-// Instantiations of the AGQ kernels for one family functor (see families.cuh).
+// Instantiations of the AGQ kernels for beta.binomial() (logit, cloglog) (see families.cuh).
 #include "ops.cuh"
-const FamOps* glmma_ops_beta_binomial(int qy, int qz) { return dispatch_ops<FamBetaBinomial>(qy, qz); }
+#include "../../include/glmma.h"
+const FamOps* glmma_ops_beta_binomial(int link, int qy, int qz) {
+    if (link == GLMMA_LINK_DEFAULT || link == GLMMA_LINK_LOGIT) return dispatch_ops<FamBetaBinomialL<1>>(qy, qz);
+    if (link == GLMMA_LINK_CLOGLOG) return dispatch_ops<FamBetaBinomialL<5>>(qy, qz);
+    return nullptr;
+}

@@ -741,27 +741,36 @@ struct FamStudentsT : FamBase {
 // derivatives  sum_{i < y} 1 / (A + i), i.e. one fast_log_rcp per unit of y (Bernoulli data: one per
 // point); counts above GLMMA_BB_SUM_MAX (or non-integer responses) take lgamma / digamma. -----------
 #define GLMMA_BB_SUM_MAX 24
+// (the lgamma / digamma path is out of line: inlined at every point of every unrolled observation it made this
+// family's translation unit the longest to compile and the largest in the library)
+static __device__ __noinline__ void bb_rising_libm(double x, double cnt, double* out) {
+    out[0] = lgamma(x + cnt) - lgamma(x);
+    out[1] = glmma_digamma(x + cnt) - glmma_digamma(x);
+}
 __device__ __forceinline__ void bb_rising(double x, double cnt, const MathCtx& cx, double& dlg, double& dpsi) {
     // lgamma(x + cnt) - lgamma(x) and digamma(x + cnt) - digamma(x), cnt >= 0
     const int n = (int)cnt;
-    if ((double)n == cnt && n <= GLMMA_BB_SUM_MAX && x >= 1e-290) {
+    if ((double)n == cnt && n <= GLMMA_BB_SUM_MAX && x >= 1e-290 && x <= 1e290) {
         dlg = 0.0; dpsi = 0.0;
         for (int i = 0; i < n; ++i) {
             double L, r;
-            fast_log_rcp<true>(x + (double)i, cx, L, r);
+            fast_log_rcp<false>(x + (double)i, cx, L, r);       // in range by the test above: no library fallback inlined
             dlg += L; dpsi += r;
         }
     } else {
-        dlg = lgamma(x + cnt) - lgamma(x);
-        dpsi = glmma_digamma(x + cnt) - glmma_digamma(x);
+        double o[2];
+        bb_rising_libm(x, cnt, o);
+        dlg = o[0]; dpsi = o[1];
     }
 }
-struct FamBetaBinomial : FamBase {
+template <int LINK>   // 1 logit, 5 cloglog (enum glmma_link)
+struct FamBetaBinomialL : FamBase {
     static constexpr int GENERIC_UNROLL = 2;
-    static constexpr double EMU_LO = 1e-13;      // logit link: |eta| <= 30 - margin
-    static constexpr double EMU_HI = 1e13;
-    static constexpr double LOG_EMU_LO = -29.93;
-    static constexpr double LOG_EMU_HI = 29.93;
+    // logit link: |eta| <= 30 - margin; cloglog: eps <= mu <= 1 - eps  <=>  1e-15 <= exp(eta) <= 35 (as binomial)
+    static constexpr double EMU_LO = LINK == 5 ? 1e-15 : 1e-13;
+    static constexpr double EMU_HI = LINK == 5 ? 35.0 : 1e13;
+    static constexpr double LOG_EMU_LO = LINK == 5 ? -34.5 : -29.93;
+    static constexpr double LOG_EMU_HI = LINK == 5 ? 3.55 : 29.93;
     static constexpr bool HAS_PHI = true;
     static constexpr bool USES_Y2 = true;
     __device__ static __forceinline__ void obs_const(double y, double N, const FamPar& fp, double& cll, double& cphi) {
@@ -772,17 +781,32 @@ struct FamBetaBinomial : FamBase {
     template <bool SCORE, bool CAREFUL, bool ZT = false, int YC = 0>
     __device__ static __forceinline__ void point(double y, double N, GLMMA_POINT_ARGS) {
         const double phi = fp.a[0];
-        double mu, lt, L;
-        link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
-        const double A = phi * mu, B = phi - A;
+        double mu, dmu;
+        if (LINK == 5) {
+            // make.link("cloglog")$linkinv with its clamps; mu.eta is the reference's own expression
+            // -(1 - mu) log(1 - mu) on the ROUNDED 1 - mu (R/Fit_Funs.R:1288-1290), so that both sides are ill
+            // conditioned in the same way where mu is tiny
+            if (CAREFUL) mu = fmax(fmin(-expm1(-exp(eta)), 1.0 - GLMMA_DBL_EPS), GLMMA_DBL_EPS);
+            else mu = fast_one_minus_expneg(emu, cx);
+            const double q = 1.0 - mu;
+            double Lq, rq;
+            if (CAREFUL) { Lq = log(q); rq = 0.0; } else fast_log_rcp<false>(q, cx, Lq, rq);
+            dmu = -q * Lq;
+        } else {
+            double lt, L;
+            link_logit<CAREFUL>(eta, emu, cx, mu, lt, L);
+            dmu = mu - mu * mu;
+        }
+        const double A = phi * mu, B = LINK == 5 ? phi * (1.0 - mu) : phi - A;
         double lgA, psA, lgB, psB;
         bb_rising(A, y, cx, lgA, psA);
         bb_rising(B, N - y, cx, lgB, psB);
         ld = lgA + lgB;
         if (SCORE) {
-            se = phi * (psA - psB) * (mu - mu * mu);
+            se = phi * (psA - psB) * dmu;
             sp = phi * (mu * psA + (1.0 - mu) * psB);
         } else { se = 0.0; sp = 0.0; }
         sz = 0.0;
     }
 };
+typedef FamBetaBinomialL<1> FamBetaBinomial;

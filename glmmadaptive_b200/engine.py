@@ -63,6 +63,9 @@ def family_spec(name, link=None):
     if fam == "binomial":
         if link not in ("logit", "probit", "cloglog"):
             raise ValueError(f"binomial link {link!r} is not accelerated")
+    elif fam == "beta binomial":
+        if link not in ("logit", "cloglog"):
+            raise ValueError(f"beta.binomial link {link!r} is not accelerated")
     elif link != dlink:
         raise ValueError(f"{fam}: only the {dlink} link is accelerated")
     return FamilySpec(fam, link, n_phis, zi)

@@ -60,7 +60,7 @@ enum glmma_family {
     GLMMA_GAMMA = 11,            /* Gamma.fam()                  R/Fit_Funs.R:1323-1358 */
     GLMMA_CENSORED_NORMAL = 12,  /* censored.normal()            R/Fit_Funs.R:1360-1435 */
     GLMMA_STUDENTS_T = 13,       /* students.t(df)               R/Fit_Funs.R:1006-1041 */
-    GLMMA_BETA_BINOMIAL = 14,    /* beta.binomial() (logit)      R/Fit_Funs.R:1245-1321 */
+    GLMMA_BETA_BINOMIAL = 14,    /* beta.binomial() (logit, cloglog) R/Fit_Funs.R:1245-1321 */
     GLMMA_N_FAMILIES = 15
 };
 

@@ -845,14 +845,20 @@ class students_t(Family):
 
 
 class beta_binomial(Family):
-    """R/Fit_Funs.R:1245-1321 (logit link)."""
+    """R/Fit_Funs.R:1245-1321; link "logit" (default) or "cloglog" (the two the reference's score_eta_fun
+    switches on, R/Fit_Funs.R:1288-1290)."""
     family = "beta binomial"
     link = "logit"
     has_phis = True
     n_phis = 1
 
+    def __init__(self, link="logit"):
+        if link not in ("logit", "cloglog"):
+            raise ValueError("beta.binomial: link must be logit or cloglog")
+        self.link = link
+
     def linkinv(self, eta):
-        return logit_linkinv(eta)
+        return logit_linkinv(eta) if self.link == "logit" else cloglog_linkinv(eta)
 
     def _size_y(self, y, like):
         y = np.asarray(y, float)
@@ -875,7 +881,9 @@ class beta_binomial(Family):
         phi_mu, phi_1mu = phi * mu, phi * (1 - mu)
         comp1 = (sp.digamma(x + phi_mu) - sp.digamma(size - x + phi_1mu)) * phi
         comp2 = (sp.digamma(phi_mu) - sp.digamma(phi_1mu)) * phi
-        return (comp1 - comp2) * (mu - mu * mu)
+        # mu.eta <- switch(.link, "logit" = mu - mu * mu, "cloglog" = - (1 - mu) * log(1 - mu))
+        mu_eta = (mu - mu * mu) if self.link == "logit" else -(1 - mu) * np.log(1 - mu)
+        return (comp1 - comp2) * mu_eta
 
     def score_phis_fun(self, y, mu, phis, eta_zi=None):
         phi = np.exp(phis[0])

@@ -103,6 +103,8 @@ CASES = [
     ("students.t", None, 2, 0, [-0.4]),
     ("beta.binomial", None, 1, 0, [1.1]),
     ("beta.binomial2", None, 2, 0, [1.1]),
+    ("beta.binomial", "cloglog", 2, 0, [1.1]),
+    ("beta.binomial2", "cloglog", 1, 0, [0.6]),
 ]
 
 

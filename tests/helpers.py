@@ -24,7 +24,7 @@ def oracle_data(d):
 
 def oracle_family(name, link=None):
     cls = ORACLE_FAMILIES[name]
-    return cls(link) if (name == "binomial" and link) else cls()
+    return cls(link) if (name in ("binomial", "beta.binomial") and link) else cls()
 
 
 def pack_chol(chol_list):

@@ -145,6 +145,13 @@ def ld_beta_binomial(y, eta, ph, ez):
     return _lchoose(s + fl, s) + _lbeta(s + a, fl + b) - _lbeta(a, b)
 
 
+def ld_beta_binomial_cloglog(y, eta, ph, ez):
+    s, fl = y
+    phi, mu = mp.exp(ph), 1 - mp.exp(-mp.exp(eta))
+    a, b = phi * mu, phi * (1 - mu)
+    return _lchoose(s + fl, s) + _lbeta(s + a, fl + b) - _lbeta(a, b)
+
+
 TWO_COL = [(0.0, 5.0), (2.0, 3.0), (5.0, 0.0), (1.0, 0.0), (0.0, 1.0), (7.0, 13.0)]
 COUNTS = [0.0, 1.0, 2.0, 7.0, 30.0, 250.0]
 UNIT = [0.003, 0.2, 0.5, 0.77, 0.995]
@@ -169,6 +176,7 @@ CASES = [
     ("censored.normal", F.censored_normal, ld_censored_normal, CENS, [-1.5, -0.1, 0.6, 2.0], [-0.7, 0.0, 0.5], [None]),
     ("students.t", lambda: F.students_t(4.0), ld_students_t(4), [-3.0, 0.1, 2.2, 15.0], [-1.5, 0.0, 0.6, 2.0], [-0.7, 0.0, 0.5], [None]),
     ("beta.binomial", F.beta_binomial, ld_beta_binomial, TWO_COL, [-3.0, -0.3, 0.0, 1.7], [-1.0, 0.0, 1.5, 3.0], [None]),
+    ("beta.binomial-cloglog", lambda: F.beta_binomial("cloglog"), ld_beta_binomial_cloglog, TWO_COL, [-2.0, -0.3, 0.0, 0.9], [-1.0, 0.0, 1.5, 3.0], [None]),
 ]
 
 
@@ -200,7 +208,7 @@ def test_family_against_mpmath(case):
         ya, ym = _y_array(y), _y_mp(y)
         if name in ("binomial-logit", "binomial-probit", "binomial-cloglog") and ya[0].sum() == 1:
             ya_call = ya[:, 0]                      # the 0/1 vector form of a binary outcome
-        elif name in ("zi.binomial", "beta.binomial") and ya[0].sum() == 1:
+        elif name in ("zi.binomial", "beta.binomial", "beta.binomial-cloglog") and ya[0].sum() == 1:
             ya_call = ya[:, 0]
         else:
             ya_call = ya
