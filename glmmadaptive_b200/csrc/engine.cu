@@ -961,7 +961,8 @@ static int find_modes_enqueue(glmma_handle* h, const double* betas, const double
     fill_prior(h, invD, true, &ma.prior);
     CU(h, cudaMemsetAsync(h->d_stats, 0, 4 * sizeof(unsigned long long), h->stream));
     const double mean_ni = (double)h->d.N / (double)h->d.n;
-    const int G = mean_ni <= 12.0 ? 1 : (mean_ni <= 96.0 ? 8 : 32);
+    int G = mean_ni <= 12.0 ? 1 : (mean_ni <= 96.0 ? 8 : 32);
+    if (const char* g_env = std::getenv("GLMMA_MODES_G")) { const int g = std::atoi(g_env); if (g == 1 || g == 8 || g == 32) G = g; }
     h->ops->modes(ma, G, h->stream);
     h->launches++;
     // the grid is DEFINED by (modes, chol): R^-1 and log_dets are re-derived from the stored factors by

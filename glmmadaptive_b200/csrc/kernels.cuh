@@ -2962,7 +2962,7 @@ __device__ __forceinline__ bool chol_lower(const double* H, double lam, double* 
 }
 
 template <class F, int QY, int QZ, int G>
-__global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
+__global__ void __launch_bounds__(128) modes_kernel(const __grid_constant__ ModeArgs A) {     // (references into the parameter space: no local copy)
     constexpr int Q = QY + QZ;
     constexpr int NP = Q * (Q + 1) / 2;
     const DevData& d = A.d;
@@ -3105,7 +3105,7 @@ __global__ void __launch_bounds__(128) modes_kernel(ModeArgs A) {
 // b_in is n x q column-major (R's matrix of proposals, one row per cluster).
 // ------------------------------------------------------------------------------
 template <class F, int QY, int QZ>
-__global__ void __launch_bounds__(128) log_post_b_kernel(ModeArgs A, const double* b_in, double* out) {
+__global__ void __launch_bounds__(128) log_post_b_kernel(const __grid_constant__ ModeArgs A, const double* b_in, double* out) {
     constexpr int Q = QY + QZ;
     constexpr int G = 8;
     const DevData& d = A.d;
