@@ -205,3 +205,56 @@ def test_kat_hurdle_fits_published_loglik():
         ll = -gb.logLik_mixed(tv, eng, gh, diag_D=k["diag_D"])
         assert abs(ll - k["loglik"]) < k["tol"], (k["name"], ll)
         eng.close()
+
+
+@pytest.mark.parametrize("fam,link,q_y,q_zi,phis", [
+    ("censored.normal", None, 2, 0, [-0.3]), ("binomial", "probit", 2, 0, None), ("binomial", "cloglog", 1, 0, None),
+    ("beta.fam", None, 2, 0, [1.5]), ("Gamma.fam", None, 2, 0, [1.0]), ("students.t", None, 1, 0, [-0.4]),
+    ("beta.binomial", "cloglog", 2, 0, [1.1]), ("zi.negative.binomial", None, 2, 1, [0.5]),
+    ("hurdle.lognormal", None, 1, 1, [-0.3]), ("hurdle.poisson", None, 2, 0, None)], ids=lambda v: str(v))
+def test_families_on_clusters_beyond_the_register_variant(fam, link, q_y, q_zi, phis):
+    """Clusters of 17 .. 45 observations of the families without a two-pass form: the generic kernel (staged tile
+    and tile-outer form) with the careful functors -- which take their table-based branches wherever no link clamp
+    is active -- against the oracle."""
+    rng = np.random.default_rng(900 + sum(map(ord, fam)) + q_y)
+    fam_name = fam
+    zi = fam_name.startswith("zi.") or fam_name.startswith("hurdle.")
+    sizes = rng.integers(17, 46, 16)
+    ids = np.repeat(np.arange(len(sizes)), sizes)
+    N = len(ids)
+    x = rng.random(N)
+    g = rng.integers(0, 2, len(sizes)).astype(float)[ids]
+    d = dict(id=ids, X=np.column_stack([np.ones(N), x, g]), Z=np.column_stack([np.ones(N), x])[:, :q_y])
+    if zi:
+        d["X_zi"] = np.column_stack([np.ones(N), g])
+        if q_zi:
+            d["Z_zi"] = np.ones((N, 1))
+    q = q_y + q_zi
+    A = rng.standard_normal((q, q)) * 0.3
+    D = A @ A.T + 0.3 * np.eye(q)
+    betas = np.array([-0.2, 0.6, -0.3]) if fam in ("beta.fam", "binomial", "beta.binomial") else np.array([0.3, 0.5, -0.4])
+    b = rng.standard_normal((len(sizes), q)) @ np.linalg.cholesky(D).T
+    eta = d["X"] @ betas + np.sum(d["Z"] * b[ids, :q_y], axis=1)
+    d["y"] = response(fam, rng, N, eta)
+    th = dict(betas=betas, D=D, phis=None if phis is None else np.array(phis),
+              gammas=np.array([-0.8, 0.4]) if zi else None, nAGQ=7 if q >= 3 else 9, df=4.0 if fam == "students.t" else None)
+    ofam = oracle_family(fam_name, link)
+    od, gh = oracle_grid(d, th, ofam)
+    eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, link=link, nAGQ=th["nAGQ"],
+                    X_zi=d.get("X_zi"), Z_zi=d.get("Z_zi"), df=th.get("df"))
+    eng.set_modes(gh.post_modes, pack_chol(gh.chol_hessians))
+    tv = thetas_vec(th)
+    ref = agq.suff_stats(tv, od, ofam, gh)
+    got = eng.eval(th["betas"], th["D"], th["phis"], th["gammas"])
+    assert got["n_nonfinite"] == ref["n_nonfinite"] == 0
+    assert relerr(got["loglik"], ref["loglik"]) < RTOL
+    for key in ("g_beta", "g_phi", "g_gamma"):
+        if key in ref:
+            sc = max(1.0, np.max(np.abs(ref[key])))
+            assert np.max(np.abs(got[key] - ref[key])) < 10 * RTOL * sc, key
+    assert relerr(got["S"], ref["S"]) < RTOL
+    st = eng.find_modes(th["betas"], np.linalg.inv(D), th["phis"], th["gammas"], warm=False)
+    assert st["n_chol_failed"] == 0
+    modes, chol, logdet = eng.get_modes()
+    assert np.max(np.abs(modes - gh.post_modes)) < 1e-7
+    eng.close()
