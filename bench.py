@@ -426,8 +426,12 @@ def run_ours(args):
             stN = many.find_modes(thm["betas"], np.linalg.inv(thm["D"]), thm["phis"], thm["gammas"], warm=False)
             mN, _, _ = many.get_modes()
             err = float(np.max(np.abs(rN - r1_) / np.maximum(1.0, np.abs(r1_))))
+            # different shards sum in a different order: the rounding of every sum is bounded by 1e-13 of the LARGEST
+            # component (the phi-score is the cancelled difference of two sums of the size of the log-likelihood)
+            err_scaled = float(np.max(np.abs(rN - r1_)) / np.max(np.abs(r1_)))
             multi_check = {"devices": ndev, "clusters": 3000, "max_rel_diff_vs_single_device": err,
-                           "modes_max_abs_diff": float(np.max(np.abs(mN - m_))), "ok": bool(err < 1e-11),
+                           "max_diff_over_largest_component": err_scaled,
+                           "modes_max_abs_diff": float(np.max(np.abs(mN - m_))), "ok": bool(err_scaled < 1e-13 and err < 1e-9),
                            "not_converged": int(stN["n_not_converged"]),
                            "what": "glmma_create_multi handle over all visible GPUs in ONE process vs a single-device "
                                    "engine: same grid (set_modes), glmma_eval result vector; then its own mode search"}
