@@ -25,8 +25,12 @@
 #define FINAL_THREADS 256
 
 static thread_local std::string g_create_error;
-#define GLMMA_NTILES 4
-static const int kTile[GLMMA_NTILES] = {8, 12, 16, 32};       // observation tiles of the register variant (32: two-pass form)
+#define GLMMA_NTILES 5
+#define GLMMA_TILE32 3
+#define GLMMA_TILEPAIR 4
+// observation tiles of the register variant (32: two-pass form; 17: the code of the pair tile, two random-intercept
+// clusters of at most 8 observations each in one 16-row tile)
+static const int kTile[GLMMA_NTILES] = {8, 12, 16, 32, 17};
 
 // One host thread per device of a multi-device handle: the per-evaluation enqueue work (six kernel
 // launches and a copy per device) runs in parallel instead of serialising on the caller's thread.
@@ -688,7 +692,10 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         int64_t n_17_up = 0;
         for (int v = 17; v <= GLMMA_JT_CAP + 1; ++v) n_17_up += cnt[v];        // (the last bin holds everything beyond)
         const bool use32 = ops->tile32 && n_17_up > 0 && n_17_up >= few && !std::getenv("GLMMA_NO_TILE32");
-        h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0) | (use32 ? 8 : 0);
+        // pair tile: random intercepts, nAGQ <= 16 nodes, and enough small clusters to pair up
+        const bool usePair = ops->pair && q == 1 && h->K <= 16 && n_le8 >= (int64_t)(0.1 * (double)n) && n_le8 >= 2 &&
+                             !std::getenv("GLMMA_NO_PAIR");
+        h->nj = (use8 ? 1 : 0) | (use12 ? 2 : 0) | (use16 ? 4 : 0) | (use32 ? 8 : 0) | (usePair ? 16 : 0);
     }
     // fused mode whenever the register variant runs and the design columns fit a warp's lanes
     h->xw = d.p + d.p_zi + (d.offset ? 1 : 0) + (d.offset_zi ? 1 : 0);
@@ -715,17 +722,25 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
         // identity when all clusters fit one tile) and the clusters beyond the largest tile are flagged
         // for eval_kernel once and for all (no launch of the register variant ever visits them).
         int top = 0;
-        for (int v = 0; v < GLMMA_NTILES; ++v) if (h->nj & (1 << v)) top = kTile[v];
+        for (int v = 0; v <= GLMMA_TILE32; ++v) if (h->nj & (1 << v)) top = kTile[v];
         {
             std::vector<int4> lists[GLMMA_NTILES];
             std::vector<int32_t> flags(n, 0), too_big;
             const bool tp = (h->nj & 8) != 0;        // two-pass tile in use: it also takes the clusters beyond 32 rows
             std::vector<int32_t> tp_clusters;
+            const bool pairs = (h->nj & (1 << GLMMA_TILEPAIR)) != 0;
             for (int64_t i = 0; i < n; ++i) {
                 const int ni = row_ptr[i + 1] - row_ptr[i];
+                if (pairs && ni <= 8 && i + 1 < n && row_ptr[i + 2] - row_ptr[i + 1] <= 8) {
+                    // clusters i and i + 1 share a warp: {i, first row, n_A + n_B, n_A}
+                    const int nb = row_ptr[i + 2] - row_ptr[i + 1];
+                    lists[GLMMA_TILEPAIR].push_back(make_int4((int)i, row_ptr[i], ni + nb, ni));
+                    ++i;
+                    continue;
+                }
                 if (ni > top && !tp) { flags[i] = 1; too_big.push_back((int32_t)i); continue; }
                 bool placed = false;
-                for (int v = 0; v < GLMMA_NTILES - 1 && !placed; ++v)           // the smallest one-pass tile in use that holds the cluster
+                for (int v = 0; v < GLMMA_TILE32 && !placed; ++v)           // the smallest one-pass tile in use that holds the cluster
                     if ((h->nj & (1 << v)) && ni <= kTile[v]) { lists[v].push_back(make_int4((int)i, row_ptr[i], ni, 0)); placed = true; }
                 if (!placed) tp_clusters.push_back((int32_t)i);
             }
@@ -735,7 +750,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                 // for at most 32 rows -- that ONE warp must walk in order.  The kernel gives position p of the list to
                 // warp p mod nwarps, so the records are laid out as per-warp queues (clusters dealt to the least
                 // loaded warp, longest first), padded with empty records to a common length.
-                const int v = GLMMA_NTILES - 1;
+                const int v = GLMMA_TILE32;
                 const int fwpb = h->fast_threads[v][1] / 32;
                 const int64_t want = ((int64_t)tp_clusters.size() + fwpb - 1) / fwpb;
                 const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][1]));
@@ -775,7 +790,7 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                 if (lists[v].empty()) lists[v].push_back(make_int4(0, 0, 0, 0));
                 TRY(dev_upload(h, &tmp, lists[v].data(), lists[v].size()));
                 h->d_order[v] = const_cast<int4*>(tmp);
-                for (int s = 0; s < 2 && v != GLMMA_NTILES - 1; ++s) {       // (the two-pass tile's grid is fixed above: its list is laid out for it)
+                for (int s = 0; s < 2 && v != GLMMA_TILE32; ++s) {       // (the two-pass tile's grid is fixed above: its list is laid out for it)
                     const int fwpb = h->fast_threads[v][s] / 32;
                     const int64_t want = (h->n_order[v] + fwpb - 1) / fwpb;
                     h->fast_grid[v][s] = (int)std::max<int64_t>(1, std::min<int64_t>(want, h->fast_grid[v][s]));

@@ -28,6 +28,7 @@ struct FamOps {
     bool y_table;      // obs_const() is tabulated by ytab (count families)
     bool lin_eta;      // the register variant hoists y1 * eta out of the point loop (families.cuh: LIN_ETA)
     bool tile32;       // the register variant has its two-pass form for clusters of 17 .. 32 observations
+    bool pair;         // the register variant has its pair tile (two random-intercept clusters per warp)
 };
 
 // one lookup per family translation unit (nullptr: dimensions not compiled in)

@@ -1042,7 +1042,7 @@ struct __align__(16) ColEnt {
     int stride;         // doubles between consecutive rows
 };
 
-template <class F, int QY, int QZ, int NJ>
+template <class F, int QY, int QZ, int NJ, bool PAIR = false>
 struct FastLayout {
     using L = EvalLayout<F, QY, QZ>;
     static constexpr int Q = QY + QZ;
@@ -1067,7 +1067,9 @@ struct FastLayout {
     // per-cluster scalars prefetched with the records, one packed record per cluster in HBM
     // (pack_cluster_kernel): modes, R^-1, logdet, Z'y1, weight
     static constexpr int NSC = Q + Q * (Q + 1) / 2 + 1 + QY + 1;
-    static constexpr int XOFF = ((NJ * W + NSC) + 1) & ~1;  // design columns follow records + scalars
+    // PAIR (random intercepts, kernel header): two adjacent clusters share a warp; both packed records are staged
+    static constexpr int NSCP = PAIR ? 2 * NSC : NSC;
+    static constexpr int XOFF = ((NJ * W + NSCP) + 1) & ~1;  // design columns follow records + scalars
     // NJ = 32: two-pass form (kernel header) -- observations reduced in chunks of eight, node terms of the cluster
     // (a_k then e_k, and the phi-score's node sums) kept per warp after the tables
     static constexpr bool TP = NJ == 32;
@@ -1110,9 +1112,9 @@ __device__ __noinline__ double2 obs_consts_rare(double y1, double y2, double xb,
     return make_double2(cll, cphi);
 }
 
-template <class F, int QY, int QZ, bool SCORE, int NJ>
+template <class F, int QY, int QZ, bool SCORE, int NJ, bool PAIR = false>
 __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(EvalArgs A) {
-    using FL = FastLayout<F, QY, QZ, NJ>;
+    using FL = FastLayout<F, QY, QZ, NJ, PAIR>;
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
     constexpr int NP = L::NP;
@@ -1238,7 +1240,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                     cp_async8(buf + e.off + pj * e.stride, e.base + c_r0 + pj);
                 }
             }
-            if (lane < FL::NSC) cp_async8(buf + NJ * W + lane, d.clrec + ci * FL::NSC + lane);
+            if (lane < FL::NSCP) cp_async8(buf + NJ * W + lane, d.clrec + ci * FL::NSC + lane);
         }
         cp_async_commit();
     };
@@ -1271,6 +1273,8 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         // tile (the weights follow), 8 pass B over its rows; 15: a cluster of at most 32 observations in one record;
         // 0: padding of a warp's queue
         const int rflags = FL::TP ? cur.w : 0;
+        // pair tile: clusters i (rows 0 .. nA - 1 of the staged tile) and i + 1 (the rest)
+        const int nA = PAIR ? cur.w : nic;
         cur = nxt;
         // (pos + 2 nwarps may pass 2^31: compare the remaining distance instead)
         cp_async_wait_all();
@@ -1285,10 +1289,12 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         }
         // modes and sqrt(2) R^-1 (the factor of b_k = mode + sqrt(2) R^-1 z_k is folded in once)
         double m[Q], ri[NP];
+        // (pair tile: an observation lane takes the record of ITS cluster)
+        const double* sco = sc + ((PAIR && lane >= nA) ? FL::NSC : 0);
 #pragma unroll
-        for (int dd = 0; dd < Q; ++dd) m[dd] = sc[SC_M + dd];
+        for (int dd = 0; dd < Q; ++dd) m[dd] = sco[SC_M + dd];
 #pragma unroll
-        for (int t = 0; t < NP; ++t) ri[t] = GLMMA_SQRT2 * sc[SC_RI + t];
+        for (int t = 0; t < NP; ++t) ri[t] = GLMMA_SQRT2 * sco[SC_RI + t];
         // Lane j < n_i owns observation j: forms xb (xg) from the staged design columns, stages its
         // record, forms the coefficients of its separable factors
         //   exp(eta_jk) = prod_e exp(c_je x_{a_e(k)} + [e == 0] base_j)
@@ -1389,7 +1395,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         // The round loop reads mode and sqrt(2) R^-1 (and Z'y1) from the cluster's record in shared memory
         // instead of holding them in registers across the rounds: a few broadcast loads per trip buy
         // Q + NP (+ QY) double registers in a kernel that sits at its 128-register ceiling
-        if (lane == 0) {
+        if (!PAIR && lane == 0) {
             double* scw = rec + NJ * W;
 #pragma unroll
             for (int t = 0; t < NP; ++t) scw[SC_RI + t] = ri[t];
@@ -1432,8 +1438,33 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             }
             __syncwarp();
             if (tp_dead && !(rflags & 8)) continue;       // its pass B records write the work arrays of their rows
+        } else if (PAIR) {
+            // (a failed range test in either cluster leaves both to eval_kernel)
+            if (lane == 0) { d.defer[i] = bad ? 1 : 0; d.defer[i + 1] = bad ? 1 : 0; }
+            if (bad) {
+                double2 cc = make_double2(0.0, 0.0);
+                double wrow = 0.0;
+                if (lane < nic) {
+                    const int64_t row = r0c + lane;
+                    const double* r = rec + lane * W;
+                    wrow = sco[SC_W];
+                    cc = obs_consts_rare<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, r[2], A.fam, A.ytab);
+                    double cll, cphi;
+                    obs_const_tab<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, A.fam, A.ytab, cll, cphi);
+                    d.xb[row] = r[2];
+                    d.cll[row] = cll;
+                    if (F::HAS_PHI) d.cphi[row] = cphi;
+                }
+                const double s_ll = warp_sum(wrow * cc.x), s_phi = warp_sum(wrow * cc.y);
+                if (lane == 0) {
+                    if (A.em_mode != 2) tots[0] -= s_ll;
+                    if (F::HAS_PHI) tots[3] -= s_phi;
+                }
+                __syncwarp();
+                continue;
+            }
         } else if (lane == 0) d.defer[i] = bad ? 1 : 0;
-        if (FL::TP ? tp_dead : bad) {
+        if (!PAIR && (FL::TP ? tp_dead : bad)) {
             // eval_kernel takes this cluster from the work arrays the prep kernel would have written
             double s_ll, s_phi;
             cluster_consts(lane, s_ll, s_phi);
@@ -1596,6 +1627,165 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             __syncwarp();
         }
 
+        if constexpr (PAIR) {
+            // ---- Pair tile (random intercepts: q = 1, K = nAGQ <= 16 nodes).  One cluster would use nAGQ of the
+            // warp's 32 lanes for a single round; here lanes 0 .. 15 are the nodes of cluster i and lanes 16 .. 31
+            // those of cluster i + 1.  The two clusters' rows are adjacent in memory, so they are staged, formed
+            // and tabulated as ONE tile of n_A + n_B <= 16 observations (each observation lane with its own
+            // cluster's mode and scale); a node lane then walks only its cluster's columns.  All reductions over
+            // nodes stay inside a half warp (xor shuffles below 16), the exact maximum replaces the retry (one
+            // round), and lanes 0 / 16 speak for their clusters in the totals.
+            static_assert(Q == 1 && NJ == 16 && (F::FAST_KIND == 1 || F::FAST_KIND == 2), "pair tile: q = 1, carrier families");
+            const int h = lane >> 4, kq = lane & 15;
+            const bool valid = kq < K;
+            const int kc = valid ? kq : K - 1;
+            const double* sch = sc + h * FL::NSC;
+            const double w_h = sch[SC_W];
+            const int base = h ? nA : 0, cnt = h ? nic - nA : nA;
+            const int64_t i_h = i + h;
+            const int row_k = nidx[kc] & 0xff;                  // table row = node index (one dimension)
+            const double b = fma(GLMMA_SQRT2 * sch[SC_RI], ntab[kc * 2], sch[SC_M]);
+            double a = fma(-0.5 * A.prior.Dinv[0] * b, b, A.prior.logprior_const) + ntab[kc * 2 + 1];
+            if (F::LIN_ETA) a = fma(sch[SC_ZTY], b, a);
+            const double* pf0 = tabF + row_k * RP + base;       // this cluster's columns of the node's row
+            const double* wvh = wv + base;
+            double a1 = 0.0, vphi = 0.0, se8[8];
+            const int cmax = max(nA, nic - nA);
+#pragma unroll
+            for (int c4 = 0; c4 < 2; ++c4) {
+                if (4 * c4 >= cmax) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) se8[4 * c4 + jj] = 0.0;
+                    continue;
+                }
+                double t4[4];
+                bool on[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * c4 + jj;
+                    on[jj] = j < cnt;
+                    const double f = pf0[on[jj] ? j : 0];
+                    t4[jj] = F::FAST_KIND == 1 ? f + F::fast_addend(A.fam) : f;
+                }
+                if (F::FAST_KIND == 1) {
+                    double L4[4], r4[4];
+                    fast_log_rcp_vec<4>(t4, cx, L4, r4);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const double wj = on[jj] ? wvh[4 * c4 + jj] : 0.0;
+                        if (jj & 1) a1 = fma(-wj, L4[jj], a1); else a = fma(-wj, L4[jj], a);
+                        se8[4 * c4 + jj] = on[jj] ? r4[jj] : 0.0;
+                        if (F::HAS_PHI) vphi += on[jj] ? L4[jj] : 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const double ej = on[jj] ? t4[jj] : 0.0;
+                        if (jj & 1) a1 -= ej; else a -= ej;
+                        se8[4 * c4 + jj] = ej;
+                    }
+                }
+            }
+            a += a1;
+            double mx = valid ? a : -INFINITY;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            const double shift_h = fabs(mx) < INFINITY ? mx : 0.0;
+            double e = valid ? fast_exp(a - shift_h, cx) : 0.0;
+            if (A.em_mode) {
+                if (A.em_mode == 2) e = valid ? A.pby[i_h * K + row_k] : 0.0;
+                else if (valid) A.pby[i_h * K + row_k] = e;
+            }
+            double sum_h = e;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sum_h += __shfl_xor_sync(0xffffffffu, sum_h, o);
+            double lsum, isum;
+            fast_log_rcp<true>(sum_h, cx, lsum, isum);
+            const double ll = A.em_mode == 2 ? 0.0 : shift_h + lsum + sch[SC_LD];
+            const bool ok = A.em_mode == 2 ? (sum_h > 0.0 && sum_h < INFINITY) : fabs(ll) < INFINITY;
+            if (A.em_mode == 1 && !ok && valid) A.pby[i_h * K + row_k] = 0.0;
+            const double inv = ok ? w_h * isum : 0.0;
+            {
+                // lanes 0 and 16 carry their cluster's terms; lane 0 adds both to the warp's totals
+                double t0 = (kq == 0 && ok) ? w_h * ll : 0.0, t1 = (kq == 0 && ok) ? w_h : 0.0, t2 = (kq == 0 && !ok) ? 1.0 : 0.0;
+                t0 += __shfl_down_sync(0xffffffffu, t0, 16);
+                t1 += __shfl_down_sync(0xffffffffu, t1, 16);
+                t2 += __shfl_down_sync(0xffffffffu, t2, 16);
+                if (lane == 0) { tots[0] += t0; tots[1] += t1; tots[2] += t2; }
+            }
+            const bool okA = __shfl_sync(0xffffffffu, (int)ok, 0) != 0, okB = __shfl_sync(0xffffffffu, (int)ok, 16) != 0;
+            if (!okA || !okB || d.ll_i != nullptr) {
+                double2 cc = make_double2(0.0, 0.0);
+                if (lane < nic) {
+                    const int64_t row = r0c + lane;
+                    cc = obs_consts_rare<F>(d.y1[row], F::USES_Y2 ? d.y2[row] : 0.0, rec[lane * W + 2], A.fam, A.ytab);
+                }
+                const bool inA = lane < nA;
+                const double llA = warp_sum(inA ? cc.x : 0.0), llB = warp_sum(inA ? 0.0 : cc.x);
+                const double phA = warp_sum(inA ? cc.y : 0.0), phB = warp_sum(inA ? 0.0 : cc.y);
+                const double wA = __shfl_sync(0xffffffffu, w_h, 0), wB = __shfl_sync(0xffffffffu, w_h, 16);
+                const double lA = __shfl_sync(0xffffffffu, ll, 0), lB = __shfl_sync(0xffffffffu, ll, 16);
+                if (lane == 0) {
+                    if (!okA) { if (A.em_mode != 2) tots[0] -= wA * llA; if (F::HAS_PHI) tots[3] -= wA * phA; }
+                    if (!okB) { if (A.em_mode != 2) tots[0] -= wB * llB; if (F::HAS_PHI) tots[3] -= wB * phB; }
+                    if (d.ll_i) { d.ll_i[i] = wA * (lA + llA); d.ll_i[i + 1] = wB * (lB + llB); }
+                }
+            }
+            if (SCORE) {
+                const double ebb = e * b * b;
+                totl[2 * 32 + lane] = fma(inv, ebb, totl[2 * 32 + lane]);
+                if (F::HAS_PHI) {
+                    double gp = e * vphi;
+                    if (F::FAST_KIND == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < cnt) gp = fma(wvh[j] * e, se8[j], gp);
+                    }
+                    totl[lane] = fma(inv * F::sp_scale(A.fam), gp, totl[lane]);
+                }
+                if (d.S_i) {
+                    double sr = ebb;
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, o);
+                    if (kq == 0) d.S_i[i_h] = inv * sr;
+                }
+                // per-observation sums over the 16 node lanes of the observation's cluster
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc_eta[j * 32 + lane] = e * se8[j];
+                __syncwarp();
+                double s1 = 0.0;
+                {
+                    const int rw = lane & 7, sl = (lane >> 3) & 1;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s1 += acc_eta[rw * 32 + 16 * h + 8 * sl + ((c + rw) & 7)];
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+                }
+                // observation lane `lane` (row `lane` of the tile): its cluster, its position there
+                const int cl = (lane < nic && lane >= nA) ? 1 : 0;
+                const int src = lane < nic ? 16 * cl + (lane - (cl ? nA : 0)) : 0;
+                const double s1o = __shfl_sync(0xffffffffu, s1, src);
+                const double isum_o = __shfl_sync(0xffffffffu, isum, 16 * cl);
+                const double w_o = __shfl_sync(0xffffffffu, w_h, 16 * cl);
+                const bool ok_o = __shfl_sync(0xffffffffu, (int)ok, 16 * cl) != 0;
+                double zb = 0.0;
+                if (lane < nic) {
+                    const double scv1 = F::fast_score(s1o * isum_o, rec[lane * W], rec[lane * W + 1], A.fam);
+                    zb = ok_o ? w_o * scv1 : 0.0;
+                    if (A.zbar_out) d.zbar[r0c + lane] = zb;
+                }
+                __syncwarp();
+                if (lane < NJ) acc_eta[lane] = zb;
+                __syncwarp();
+                if (lane < p_x) {
+                    const double* xc = xcur + lane * NJ;
+#pragma unroll
+                    for (int jj = 0; jj < NJ; ++jj)
+                        if (jj < nic) gcol = fma(xc[jj], acc_eta[jj], gcol);
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         double shift = 0.0, sum_e = 0.0, gphi = 0.0, amax = -INFINITY;
         double S[NP];
         double acc_e[NJ], acc_z[F::HAS_ZI ? NJ : 1];

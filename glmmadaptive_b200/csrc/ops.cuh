@@ -78,9 +78,11 @@ struct OpsImpl {
     static constexpr bool HAS_FAST = QY + QZ <= 3;
     // tile of 32 observations: the register variant's two-pass form, carrier families only (kernels.cuh)
     static constexpr bool HAS_TILE32 = HAS_FAST && (F::FAST_KIND == 1 || F::FAST_KIND == 2);
-    template <int NJ>
+    // pair tile (nj code 17): two random-intercept clusters per warp, carrier families only (kernels.cuh)
+    static constexpr bool HAS_PAIR = QY == 1 && QZ == 0 && (F::FAST_KIND == 1 || F::FAST_KIND == 2);
+    template <int NJ, bool PAIR = false>
     static cudaError_t fast_config_nj(int K, int nagq, int xw, int* blocks_per_sm, size_t* smem_bytes, int* threads) {
-        cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
+        cudaError_t e = cudaFuncSetAttribute(eval_fast_kernel<F, QY, QZ, true, NJ, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
         if (e != cudaSuccess) return e;
         int best = 0;
         *blocks_per_sm = 0;
@@ -89,10 +91,10 @@ struct OpsImpl {
         const int pinned = pin ? std::atoi(pin) : 0;
         for (int t = GLMMA_EVAL_THREADS; t <= GLMMA_FAST_MAX_THREADS; t += 32) {
             if (pinned && t != pinned) continue;
-            const size_t smem = FastLayout<F, QY, QZ, NJ>::smem_bytes(t / 32, K, xw, nagq);
+            const size_t smem = FastLayout<F, QY, QZ, NJ, PAIR>::smem_bytes(t / 32, K, xw, nagq);
             if (smem > (size_t)glmma_optin_smem()) break;
             int bps = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ>, t, smem);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, eval_fast_kernel<F, QY, QZ, true, NJ, PAIR>, t, smem);
             if (e != cudaSuccess) return e;
             // ties go to the LARGER block: one 16-warp block per SM measured 3 % faster than four 4-warp blocks
             // at C3 (one copy of the per-block tables, one start-up)
@@ -107,6 +109,10 @@ struct OpsImpl {
                 if constexpr (HAS_TILE32) return fast_config_nj<32>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
                 else { *blocks_per_sm = 0; *smem_bytes = 0; *threads = 0; return cudaSuccess; }
             }
+            if (nj == 17) {
+                if constexpr (HAS_PAIR) return fast_config_nj<16, true>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
+                else { *blocks_per_sm = 0; *smem_bytes = 0; *threads = 0; return cudaSuccess; }
+            }
             return nj == 8 ? fast_config_nj<8>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
                  : nj == 12 ? fast_config_nj<12>(K, nagq, xw, blocks_per_sm, smem_bytes, threads)
                             : fast_config_nj<16>(K, nagq, xw, blocks_per_sm, smem_bytes, threads);
@@ -117,6 +123,7 @@ struct OpsImpl {
         else if (nj == 8) eval_fast_kernel<F, QY, QZ, true, 8><<<grid, threads, smem, s>>>(a);
         else if (nj == 12) eval_fast_kernel<F, QY, QZ, true, 12><<<grid, threads, smem, s>>>(a);
         else if (nj == 16) eval_fast_kernel<F, QY, QZ, true, 16><<<grid, threads, smem, s>>>(a);
+        else if (nj == 17) { if constexpr (HAS_PAIR) eval_fast_kernel<F, QY, QZ, true, 16, true><<<grid, threads, smem, s>>>(a); }
         else if constexpr (HAS_TILE32) eval_fast_kernel<F, QY, QZ, true, 32><<<grid, threads, smem, s>>>(a);
     }
     static void sphi(const EvalArgs& a, int grid, int threads, size_t smem, cudaStream_t s) {
@@ -148,7 +155,7 @@ struct OpsImpl {
         rinv_kernel<QY + QZ><<<blocks, 128, 0, s>>>(d);
     }
     static const FamOps* get() {
-        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, info, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA, HAS_TILE32};
+        static const FamOps ops = {ytab, consts, prep, eval_config, eval, fast_config, eval_fast, sphi, modes, info, logpost, rinv, pack, F::HAS_ZI, F::HAS_PHI, F::USES_Y2, F::Y_TABLE, F::LIN_ETA, HAS_TILE32, HAS_PAIR};
         return &ops;
     }
 };

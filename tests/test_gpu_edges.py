@@ -367,3 +367,45 @@ def test_many_fixed_effect_columns(fam_name, p, p_zi):
         d["y"] = np.column_stack([np.clip(v, lo, hi), np.where(v > hi, 2.0, np.where(v < lo, 1.0, 0.0))])
         th["phis"] = np.array([np.log(0.7)])
     _check(d, th, fam_name)
+
+
+@pytest.mark.parametrize("fam_name,nagq", [("binomial", 11), ("poisson", 16), ("negative.binomial", 7), ("binomial", 3)])
+def test_pair_tile_random_intercepts(fam_name, nagq, monkeypatch):
+    """q = 1: two adjacent clusters of at most 8 observations share a warp (lanes 0..15 / 16..31 are their nodes).
+    Mixed sizes so that pairs, unpaired small clusters and larger clusters all occur; against the oracle, and
+    against the one-cluster-per-warp path (GLMMA_NO_PAIR) for the contributions and the EM passes."""
+    rng = np.random.default_rng(80 + nagq)
+    sizes = np.concatenate([rng.integers(1, 9, 60), rng.integers(9, 30, 8), rng.integers(1, 9, 31)])
+    rng.shuffle(sizes)
+    betas, D = np.array([0.2, 0.4, -0.3]), np.array([[0.6]])
+    d, N = _mk(rng, sizes, 1, fam_name)
+    d["offset"] = rng.normal(0, 0.2, N)
+    d["weights"] = rng.uniform(0.5, 1.5, len(sizes))
+    eta = d["X"] @ betas + d["offset"]
+    th = dict(betas=betas, D=D, nAGQ=nagq)
+    if fam_name == "negative.binomial":
+        d["y"] = rng.negative_binomial(2.0, 2.0 / (2.0 + np.exp(eta))).astype(float)
+        th["phis"] = np.array([np.log(2.0)])
+    elif fam_name == "poisson":
+        d["y"] = rng.poisson(np.exp(eta)).astype(float)
+    else:
+        d["y"] = (rng.random(N) < 1 / (1 + np.exp(-eta))).astype(float)
+    _check(d, th, fam_name)
+    out = {}
+    for tag in ("pair", "single"):
+        if tag == "single":
+            monkeypatch.setenv("GLMMA_NO_PAIR", "1")
+        eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam_name, nAGQ=nagq, offset=d["offset"], weights=d["weights"])
+        eng.find_modes(betas, np.linalg.inv(D), th.get("phis"), None, warm=False)
+        c = eng.eval_contrib(betas, D, th.get("phis"), None)
+        es = eng.em_estep(betas, D, th.get("phis"), None)
+        ms = eng.em_score(betas + 0.03, th.get("phis"), None)
+        out[tag] = (eng.eval_raw(betas, D, th.get("phis"), None), c, es, ms)
+        eng.close()
+    monkeypatch.delenv("GLMMA_NO_PAIR")
+    (r1, c1, e1, m1), (r2, c2, e2, m2) = out["pair"], out["single"]
+    assert np.max(np.abs(r1 - r2)) < 1e-13 * np.max(np.abs(r2))
+    for k in ("ll_i", "zbar", "S_i"):
+        assert np.max(np.abs(c1[k] - c2[k])) <= 1e-12 * max(1.0, np.max(np.abs(c2[k]))), k
+    assert abs(e1["loglik"] - e2["loglik"]) < 1e-13 * abs(e2["loglik"])
+    assert np.max(np.abs(m1["g_beta"] - m2["g_beta"])) < 1e-11 * max(1.0, np.max(np.abs(m2["g_beta"])))
