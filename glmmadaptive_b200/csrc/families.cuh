@@ -449,8 +449,10 @@ struct FamHurdlePoisson : FamBase {
         if (pos) {
             double mu, lmu;
             link_log<CAREFUL>(eta, emu, mu, lmu);
-            if (!CAREFUL) {
+            if (!CAREFUL || mu < 1e300) {
                 // zero-truncated poisson: log f = y eta - mu - log(1 - e^-mu); score = y - mu / (1 - e^-mu)
+                // (also the generic kernel's form: mu >= eps by the link clamp, so 1 - e^-mu >= 2e-16 is in the
+                // table-based logarithm's range)
                 const double om = fast_one_minus_expneg(mu, cx);
                 double Lo, ro;
                 fast_log_rcp<false>(om, cx, Lo, ro);
@@ -488,7 +490,7 @@ struct FamHurdleNegBin : FamBase {
             const double yp = y + phi;
             const double lt = fp.a[1] - L;            // log(phi / (phi + mu)) = -log(1 + mu/phi)
             double lom, ratio;                        // log(1 - t^phi) and t^phi / (1 - t^phi), t = phi / (phi + mu)
-            if (!CAREFUL) {
+            if (!CAREFUL || (-phi * lt >= 1e-290 && -phi * lt < 1e300)) {
                 const double om = fast_one_minus_expneg(-phi * lt, cx);
                 double ro;
                 fast_log_rcp<false>(om, cx, lom, ro);

@@ -84,7 +84,7 @@ typedef struct glmma_data {
     int64_t n_obs;          /* N  = nrow(X)                                              */
     int64_t n_clusters;     /* n  = length(unique(id))                                   */
     int32_t p;              /* ncol(X)                                                   */
-    int32_t q_y;            /* ncol(Z)                                                   */
+    int32_t q_y;            /* ncol(Z);  q = q_y + q_zi <= 4 is compiled in (GLMMA_ERR_ARG beyond) */
     int32_t p_zi;           /* ncol(X_zi), 0 if zi_fixed absent                          */
     int32_t q_zi;           /* ncol(Z_zi), 0 if zi_random absent                         */
     int32_t n_phis;         /* length(phis)                                              */
