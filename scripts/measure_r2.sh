@@ -15,9 +15,8 @@ python scripts/family_sweep.py 200000 > gpurun_out/r2_family_sweep.txt 2>&1
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fit > gpurun_out/plain3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_dev.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-fit > gpurun_out/ncu3.log 2>&1
 python bench.py --steps 3 --warmup 3 --clusters 200000 --no-cpu-baseline --no-fit > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:eval_fast -s 3 -c 1 -f -o gpurun_out/prof_dev python bench.py --steps 3 --warmup 3 --clusters 200000 --no-cpu-baseline --no-fit > gpurun_out/ncu2.log 2>&1
 tail -2 gpurun_out/r2_family_sweep.txt
-for w in C4 C5a; do
-python bench.py --workload $w --steps 3 --warmup 3 --clusters 100000 --no-cpu-baseline --no-fit > gpurun_out/plain_$w.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:eval_fast -s 3 -c 1 -f -o gpurun_out/prof_$w python bench.py --workload $w --steps 3 --warmup 3 --clusters 100000 --no-cpu-baseline --no-fit > gpurun_out/ncu_$w.log 2>&1
-done
+# (the ncu --set full captures of the config-4 / config-5a kernels are taken one per call: scripts/iter_gq.sh -- three
+# reports in one call exceed what gpurun copies back)
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 # two-pass tile against the generic kernel on the same data
 {
