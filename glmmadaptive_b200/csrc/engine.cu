@@ -1485,12 +1485,14 @@ int glmma_observed_information(glmma_handle* h, const double* betas, const doubl
     ia.ksm = h->K <= 1024 ? h->K : 0;        // 4 warps x K doubles of the kernel's (opt-in) dynamic shared memory
     const int grid = (int)std::min<int64_t>((h->d.n + 3) / 4, 148 * 8);
     double* d_part = nullptr;
-    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * (size_t)grid * GLMMA_INFO_NPAIR);
+    const int pm = P <= 12 ? 12 : GLMMA_INFO_PMAX;           // capacity of the instantiation that runs
+    const int npair = pm * (pm + 1) / 2;
+    cudaError_t e = cudaMalloc(&d_part, sizeof(double) * (size_t)grid * npair);
     if (e != cudaSuccess) return cuda_fail(h, e, "cudaMalloc (observed information)");
     ia.partials = d_part;
-    h->ops->info(ia, grid, h->stream);
+    h->ops->info(ia, grid, pm, h->stream);
     h->launches++;
-    std::vector<double> part((size_t)grid * GLMMA_INFO_NPAIR);
+    std::vector<double> part((size_t)grid * npair);
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), d_part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1498,9 +1500,9 @@ int glmma_observed_information(glmma_handle* h, const double* betas, const doubl
     if (e != cudaSuccess) return cuda_fail(h, e, "info_kernel");
     for (int r = 0; r < P; ++r)
         for (int c = r; c < P; ++c) {
-            const int t = info_pair(r, c);
+            const int t = info_pair_pm(r, c, pm);
             double s = 0.0;
-            for (int b = 0; b < grid; ++b) s += part[(size_t)b * GLMMA_INFO_NPAIR + t];    // fixed order
+            for (int b = 0; b < grid; ++b) s += part[(size_t)b * npair + t];    // fixed order
             H[r + c * P] = -s;             // Hessian of the NEGATIVE log-likelihood
             H[c + r * P] = -s;
         }

@@ -20,7 +20,7 @@ struct FamOps {
     void (*eval_fast)(const EvalArgs&, int score, int nj, int grid, int threads, size_t smem, cudaStream_t);
     void (*sphi)(const EvalArgs&, int grid, int threads, size_t smem, cudaStream_t);
     void (*modes)(const ModeArgs&, int G, cudaStream_t);
-    void (*info)(const InfoArgs&, int grid, cudaStream_t);      // observed information, one pass
+    void (*info)(const InfoArgs&, int grid, int pm, cudaStream_t);      // observed information, one pass (pm: 12 or GLMMA_INFO_PMAX)
     void (*logpost)(const ModeArgs&, const double* b, double* out, cudaStream_t);
     void (*rinv)(const DevData&, cudaStream_t);
     void (*pack)(const DevData&, cudaStream_t);       // packed per-cluster records of the register variant

@@ -2765,8 +2765,9 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS) sphi_obs_kernel(EvalAr
 // derivatives.  A warp owns a cluster, lanes own nodes; two passes over the nodes (log-sum-exp, then the
 // derivatives).  Run once per fit: clarity over speed (accumulators in local memory).
 // ------------------------------------------------------------------------------
+// capacity of the kernel in parameters: two instantiations, PM = 12 (accumulators of 78 pairs per thread in local
+// memory) and PM = 24 (300 pairs: q = 4 with a full D alone has 10 D parameters) -- the small one is twice as fast
 #define GLMMA_INFO_PMAX 24
-#define GLMMA_INFO_NPAIR (GLMMA_INFO_PMAX * (GLMMA_INFO_PMAX + 1) / 2)
 #define GLMMA_INFO_NDMAX (GLMMA_QMAX * (GLMMA_QMAX + 1) / 2)
 #define GLMMA_INFO_NDPAIR (GLMMA_INFO_NDMAX * (GLMMA_INFO_NDMAX + 1) / 2)
 #define GLMMA_INFO_JT 16
@@ -2788,12 +2789,14 @@ struct InfoArgs {
                                                           // memory (pass 2 then reads them instead of recomputing), else 0
 };
 
-__host__ __device__ __forceinline__ int info_pair(int r, int c) {      // r <= c, packed row-major over the upper triangle of P x P
-    return r * (2 * GLMMA_INFO_PMAX - r + 1) / 2 + (c - r);
+__host__ __device__ __forceinline__ int info_pair_pm(int r, int c, int pm) {      // r <= c, packed row-major over the upper triangle of pm x pm
+    return r * (2 * pm - r + 1) / 2 + (c - r);
 }
 
-template <class F, int QY, int QZ>
+template <class F, int QY, int QZ, int PM>
 __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
+    constexpr int NPAIR_ = PM * (PM + 1) / 2;
+    auto info_pair = [](int r, int c) { return info_pair_pm(r, c, PM); };
     using L = EvalLayout<F, QY, QZ>;
     constexpr int Q = L::Q;
     constexpr int NP = L::NP;
@@ -2808,9 +2811,9 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
     const int P = p + nD + nphi + pz;
     const int oD = p, oPhi = p + nD, oG = p + nD + nphi;
     const int xw = p + pz;
-    double* rec = smem + L::head_doubles() + wib * (size_t)(JT * L::W + JT * GLMMA_INFO_PMAX + ((A.ksm + 1) & ~1));
+    double* rec = smem + L::head_doubles() + wib * (size_t)(JT * L::W + JT * PM + ((A.ksm + 1) & ~1));
     double* xt = rec + JT * L::W;                         // design rows of the staged tile: X | X_zi
-    double* aks = xt + JT * GLMMA_INFO_PMAX;              // the cluster's K node terms a_k (pass 1 -> pass 2)
+    double* aks = xt + JT * PM;              // the cluster's K node terms a_k (pass 1 -> pass 2)
     const int nagq = A.grid->nagq, K = A.grid->K;
     const unsigned rcp_nagq = nagq_rcp(nagq);
     load_fmtab(fmtab, A.fmtab);
@@ -2824,8 +2827,8 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
     const int nrounds = (K + 31) >> 5;
     const double ie = 0.5 / A.eps_eta, ip = 0.5 / A.eps_phi;
 
-    double tot[GLMMA_INFO_NPAIR];                         // this lane's share of the block total
-    for (int t = 0; t < GLMMA_INFO_NPAIR; ++t) tot[t] = 0.0;
+    double tot[NPAIR_];                         // this lane's share of the block total
+    for (int t = 0; t < NPAIR_; ++t) tot[t] = 0.0;
 
     auto point_at = [&](const double* rj, double eta, double ez, const FamPar& fam, double& ld, double& se, double& sz, double& sp) {
         const double emu = F::NEED_EMU ? fast_exp(eta, cx) : 0.0;
@@ -2837,7 +2840,7 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
         stage_tile<F, QY, QZ>(d, r0, cnt, lane, rec);
         for (int t = lane; t < cnt * xw; t += 32) {
             const int j = t / xw, l = t - j * xw;
-            xt[j * GLMMA_INFO_PMAX + l] = l < p ? d.X[r0 + j + (int64_t)l * d.N] : d.X_zi[r0 + j + (int64_t)(l - p) * d.N];
+            xt[j * PM + l] = l < p ? d.X[r0 + j + (int64_t)l * d.N] : d.X_zi[r0 + j + (int64_t)(l - p) * d.N];
         }
         __syncwarp();
     };
@@ -2886,9 +2889,9 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
         const bool ok = fabs(lse) < INFINITY;
 
         // pass 2: derivatives
-        double Aacc[GLMMA_INFO_NPAIR], gbar[GLMMA_INFO_PMAX];
-        for (int t = 0; t < GLMMA_INFO_NPAIR; ++t) Aacc[t] = 0.0;
-        for (int t = 0; t < GLMMA_INFO_PMAX; ++t) gbar[t] = 0.0;
+        double Aacc[NPAIR_], gbar[PM];
+        for (int t = 0; t < NPAIR_; ++t) Aacc[t] = 0.0;
+        for (int t = 0; t < PM; ++t) gbar[t] = 0.0;
         for (int r = 0; r < nrounds && ok; ++r) {
             const int k = (r << 5) + lane;
             const bool valid = k < K;
@@ -2913,14 +2916,14 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
                 }
             }
             const double pik = valid ? exp(a - lse) : 0.0;
-            double g[GLMMA_INFO_PMAX];
-            for (int t = 0; t < GLMMA_INFO_PMAX; ++t) g[t] = 0.0;
+            double g[PM];
+            for (int t = 0; t < PM; ++t) g[t] = 0.0;
             for (int j0 = 0; j0 < ni; j0 += JT) {
                 const int cnt = min(JT, ni - j0);
                 stage(r0 + j0, cnt);
                 for (int j = 0; j < cnt; ++j) {
                     const double* rj = rec + j * L::W;
-                    const double* xj = xt + j * GLMMA_INFO_PMAX;
+                    const double* xj = xt + j * PM;
                     double eta = rj[2], ez = F::HAS_ZI ? rj[L::OFF_XG] : 0.0;
 #pragma unroll
                     for (int dd = 0; dd < QY; ++dd) eta = fma(rj[L::OFF_Z + dd], b[dd], eta);
@@ -3026,13 +3029,13 @@ __global__ void __launch_bounds__(128) info_kernel(InfoArgs A) {
     for (int r_ = 0; r_ < P; ++r_)
         for (int c_ = r_; c_ < P; ++c_) {
             const int t = info_pair(r_, c_);
-            if (((r_ * P + c_) & 31) == lane) red[wib * GLMMA_INFO_NPAIR + t] = tot[t];
+            if (((r_ * P + c_) & 31) == lane) red[wib * NPAIR_ + t] = tot[t];
         }
     __syncthreads();
-    for (int t = threadIdx.x; t < GLMMA_INFO_NPAIR; t += blockDim.x) {
+    for (int t = threadIdx.x; t < NPAIR_; t += blockDim.x) {
         double v = 0.0;
-        for (int ww = 0; ww < wpb; ++ww) v += red[ww * GLMMA_INFO_NPAIR + t];
-        A.partials[(int64_t)blockIdx.x * GLMMA_INFO_NPAIR + t] = v;
+        for (int ww = 0; ww < wpb; ++ww) v += red[ww * NPAIR_ + t];
+        A.partials[(int64_t)blockIdx.x * NPAIR_ + t] = v;
     }
 }
 

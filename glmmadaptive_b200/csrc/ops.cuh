@@ -136,11 +136,16 @@ struct OpsImpl {
         else if (G == 8) modes_kernel<F, QY, QZ, 8><<<blocks, 128, 0, s>>>(a);
         else modes_kernel<F, QY, QZ, 32><<<blocks, 128, 0, s>>>(a);
     }
-    static void info(const InfoArgs& a, int grid, cudaStream_t s) {
+    static void info(const InfoArgs& a, int grid, int pm, cudaStream_t s) {
         using LL = EvalLayout<F, QY, QZ>;
-        const size_t smem = sizeof(double) * (LL::head_doubles() + 4 * (size_t)(GLMMA_INFO_JT * LL::W + GLMMA_INFO_JT * GLMMA_INFO_PMAX + ((a.ksm + 1) & ~1)));
-        cudaFuncSetAttribute(info_kernel<F, QY, QZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
-        info_kernel<F, QY, QZ><<<grid, 128, smem, s>>>(a);
+        const size_t smem = sizeof(double) * (LL::head_doubles() + 4 * (size_t)(GLMMA_INFO_JT * LL::W + GLMMA_INFO_JT * pm + ((a.ksm + 1) & ~1)));
+        if (pm == 12) {
+            cudaFuncSetAttribute(info_kernel<F, QY, QZ, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
+            info_kernel<F, QY, QZ, 12><<<grid, 128, smem, s>>>(a);
+        } else {
+            cudaFuncSetAttribute(info_kernel<F, QY, QZ, GLMMA_INFO_PMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, glmma_optin_smem());
+            info_kernel<F, QY, QZ, GLMMA_INFO_PMAX><<<grid, 128, smem, s>>>(a);
+        }
     }
     static void logpost(const ModeArgs& a, const double* b, double* out, cudaStream_t s) {
         const unsigned blocks = (unsigned)((a.d.n * 8 + 127) / 128);

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import glmmadaptive_b200 as gb
 from glmmadaptive_b200 import synth
-d, th = synth.make("C3", n=1_000_000)
+d, th = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3", n=1_000_000)
 fam = d.pop("family")
 eng = gb.Engine(d["y"], d["X"], d["Z"], d["id"], fam, nAGQ=th["nAGQ"])
 inits = gb.starting_values_device(eng, False)
