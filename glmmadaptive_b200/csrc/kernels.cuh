@@ -1078,7 +1078,7 @@ struct FastLayout {
     static constexpr int CG = 32 / NJ;                      // columns copied side by side by one prefetch trip
     static_assert(NJ <= 32, "a lane stages one observation");
     __host__ __device__ static int pre(int xw) { return XOFF + ((NJ * xw + 1) & ~1); }      // one prefetch buffer
-    static constexpr int FIXED0 = (NACCS * NJR * 32 + NJ + NTOT * 32 + 4 + 1) & ~1;   // scratch, wv, per-lane totals, warp totals
+    static constexpr int FIXED0 = (NACCS * NJR * 32 + NJ + NTOT * 32 + 4 + 4 + 1) & ~1;   // scratch, wv, per-lane totals, warp totals, two list records
     // "ZP" mode (zero part hoisted, kernel header): per-lane marginal node weights of the zero-part
     // dimension (nz x 32) and the per-node sum of log(1 + exp(eta_zi)) over the cluster (nz), after tabL
     static constexpr bool ZP = F::HAS_ZI && QZ <= 1 && F::FAST_KIND == 0;
@@ -1250,13 +1250,17 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
     const int p0 = (int)blockIdx.x * wpb + wib;
     const int n_pos = (int)A.n_order;
     const int4* __restrict__ order = A.order;
-    // cluster id, first row and size of the current and the next cluster are kept in registers
-    int4 cur = make_int4(0, 0, 0, 0), nxt = make_int4(0, 0, 0, 0);
+    // The current list record {cluster, first row, n_i, flags} is kept in registers; the record after it travels
+    // through shared memory with the same cp.async group as the current cluster's data (lane 0, 16 bytes), two
+    // clusters ahead -- a plain load into registers made its first consumer wait for the load in flight (ncu, C3:
+    // 3-6 % of the stall samples, as a write-after-write hazard or a spill store depending on the build)
+    int4 cur = make_int4(0, 0, 0, 0);
+    int4* nslot = reinterpret_cast<int4*>(tots + 4);
     if (p0 < n_pos) {
         cur = order[p0];
+        if (lane == 0 && p0 + nwarps < n_pos) cp_async16(reinterpret_cast<double*>(nslot), reinterpret_cast<const double*>(order + p0 + nwarps));
         prefetch(cur.x, cur.y, cur.z, pre0);
     }
-    if (p0 + nwarps < n_pos) nxt = order[p0 + nwarps];
     int pbuf = 0;
     for (int pos = p0; pos < n_pos; pos += nwarps) {
         double* rec = pre0 + pbuf * PRE;
@@ -1275,12 +1279,15 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         const int rflags = FL::TP ? cur.w : 0;
         // pair tile: clusters i (rows 0 .. nA - 1 of the staged tile) and i + 1 (the rest)
         const int nA = PAIR ? cur.w : nic;
-        cur = nxt;
         // (pos + 2 nwarps may pass 2^31: compare the remaining distance instead)
         cp_async_wait_all();
         __syncwarp();
-        if (n_pos - pos > nwarps) prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * PRE);
-        if (n_pos - pos > 2 * nwarps) nxt = order[pos + 2 * nwarps];
+        if (n_pos - pos > nwarps) {
+            cur = nslot[pbuf];
+            if (lane == 0 && n_pos - pos > 2 * nwarps)
+                cp_async16(reinterpret_cast<double*>(nslot + (pbuf ^ 1)), reinterpret_cast<const double*>(order + pos + 2 * nwarps));
+            prefetch(cur.x, cur.y, cur.z, pre0 + (pbuf ^ 1) * PRE);
+        }
         pbuf ^= 1;
         if (FL::TP && rflags == 0) continue;
         if (nic > NJ) {
