@@ -850,8 +850,8 @@ int glmma_create(const glmma_data* data, int device, glmma_handle** out) {
                         h->yoff_w = acc;
                     }
                 }
-                TRY(dev_alloc(h, &h->d_counter, 1));
-                cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned), h->stream);
+                TRY(dev_alloc(h, &h->d_counter, 2));       // [0] blocks done, [1] clusters deferred in this evaluation
+                cudaMemsetAsync(h->d_counter, 0, 2 * sizeof(unsigned), h->stream);
             }
             cudaStreamSynchronize(h->stream);      // lists / flags are block-local; errors surface at the final check
         }
@@ -1102,6 +1102,8 @@ static int enqueue_eval(glmma_handle* h, const double* betas, const double* D, c
         }
         ea.fused = 1; ea.xw = h->xw; ea.zbar_out = dd_override ? 1 : 0; ea.ytab = h->ops->y_table ? h->d_ytab : nullptr;
         ea.fin_counter = h->d_counter; ea.fin_partials = h->d_partials; ea.fin_want_score = s; ea.fin_result = d_out;
+        // (per-observation contributions walk every cluster in eval_kernel's work arrays: no short cut there)
+        ea.defer_count = dd_override ? nullptr : h->d_counter + 1; ea.defer_static = h->n_defer_list > 0 ? 1 : 0;
         // node-independent terms of the register variant's clusters, once per evaluation
         h->ops->consts(h->d, fp, h->d_ytab, h->d_roww, h->d_cpart, h->n_cpart, h->stream);
         h->launches++;

@@ -50,6 +50,11 @@ struct EvalArgs {
     const double* ytab;      // 2 x GLMMA_YTAB table of obs_const(y) (count families) or null
     CoefPar coef;            // fixed effects (fused mode)
     unsigned* fin_counter;   // eval_kernel: blocks-done counter; null = separate finalize launch
+    // clusters the register variant left to eval_kernel in THIS evaluation (counted where d.defer is raised); with
+    // none -- the usual case -- eval_kernel's blocks skip their table set-up and the scan of the flags and go
+    // straight to the finalisation.  defer_static: clusters no tile takes exist (always scan).  null: always scan
+    unsigned* defer_count;
+    int defer_static;
     const double* fin_partials;   // first block partial of this evaluation (all launches)
     int fin_blocks;          // block partials written by this evaluation's launches in total
     int fin_want_score;
@@ -485,10 +490,14 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
     double* scr_zi = scr_eta + jt * L::SCRW;
     double* ev = scr_eta + ((L::NSCR * jt * L::SCRW + 1) & ~1);
 
-    load_fmtab(fmtab, A.fmtab);
-    if (threadIdx.x < GLMMA_NAGQ_MAX) {
-        gx[threadIdx.x] = A.grid->x[threadIdx.x];
-        glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+    // (grid-uniform: the counter is final before this launch starts and is reset only by the finalising block)
+    const bool any_work = !(A.only_deferred && A.defer_count != nullptr && !A.defer_static && __ldcg(A.defer_count) == 0u);
+    if (any_work) {
+        load_fmtab(fmtab, A.fmtab);
+        if (threadIdx.x < GLMMA_NAGQ_MAX) {
+            gx[threadIdx.x] = A.grid->x[threadIdx.x];
+            glw[threadIdx.x] = A.grid->lw[threadIdx.x];
+        }
     }
     __syncthreads();
     const MathCtx cx = make_mathctx(fmtab + 2 * (threadIdx.x & 7), fmtab + GLMMA_FM_LOG_DOUBLES + (threadIdx.x & 15), A.fmc);
@@ -505,7 +514,8 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
     // only_deferred: every warp owns blocks of 32 consecutive clusters, reads their flags with
     // one coalesced load and walks the set bits (the register variant did the others)
     const int64_t span = A.only_deferred ? 32 : 1;
-    for (int64_t ib = ((int64_t)blockIdx.x * wpb + wib) * span; ib < d.n; ib += nwarps * span) {
+    const int64_t n_walk = any_work ? d.n : 0;
+    for (int64_t ib = ((int64_t)blockIdx.x * wpb + wib) * span; ib < n_walk; ib += nwarps * span) {
       unsigned todo = 1u;
       if (A.only_deferred) {
           const int64_t ci = ib + lane;
@@ -910,7 +920,10 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
             finalize_block(A.fin_partials, A.fin_blocks, nullptr, 0, true, d.p, d.n_phis, d.p_zi, Q, A.fin_want_score,
                            A.fin_result, smem + (size_t)wpb * GLMMA_PSTRIDE + 2, A.fin_cpart, A.fin_ncpart, A.fin_ll_const,
                            A.em_mode != 2, &A.xchg, &A.hout);
-            if (threadIdx.x == 0) *A.fin_counter = 0u;
+            if (threadIdx.x == 0) {
+                *A.fin_counter = 0u;
+                if (A.defer_count != nullptr) *A.defer_count = 0u;
+            }
         }
     }
 }
@@ -1291,7 +1304,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
         pbuf ^= 1;
         if (FL::TP && rflags == 0) continue;
         if (nic > NJ) {
-            if (lane == 0) d.defer[i] = 1;
+            if (lane == 0) { d.defer[i] = 1; if (A.defer_count) atomicAdd(A.defer_count, 1u); }
             continue;
         }
         // modes and sqrt(2) R^-1 (the factor of b_k = mode + sqrt(2) R^-1 z_k is folded in once)
@@ -1441,13 +1454,13 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
             __syncwarp();
             if (lane == 0) {
                 tp_st[3] = tp_dead ? 1.0 : 0.0;
-                if (rflags & 4) d.defer[i] = tp_dead ? 1 : 0;
+                if (rflags & 4) { d.defer[i] = tp_dead ? 1 : 0; if (tp_dead && A.defer_count) atomicAdd(A.defer_count, 1u); }
             }
             __syncwarp();
             if (tp_dead && !(rflags & 8)) continue;       // its pass B records write the work arrays of their rows
         } else if (PAIR) {
             // (a failed range test in either cluster leaves both to eval_kernel)
-            if (lane == 0) { d.defer[i] = bad ? 1 : 0; d.defer[i + 1] = bad ? 1 : 0; }
+            if (lane == 0) { d.defer[i] = bad ? 1 : 0; d.defer[i + 1] = bad ? 1 : 0; if (bad && A.defer_count) atomicAdd(A.defer_count, 2u); }
             if (bad) {
                 double2 cc = make_double2(0.0, 0.0);
                 double wrow = 0.0;
@@ -1470,7 +1483,7 @@ __global__ void __launch_bounds__(GLMMA_FAST_MAX_THREADS, 1) eval_fast_kernel(Ev
                 __syncwarp();
                 continue;
             }
-        } else if (lane == 0) d.defer[i] = bad ? 1 : 0;
+        } else if (lane == 0) { d.defer[i] = bad ? 1 : 0; if (bad && A.defer_count) atomicAdd(A.defer_count, 1u); }
         if (!PAIR && (FL::TP ? tp_dead : bad)) {
             // eval_kernel takes this cluster from the work arrays the prep kernel would have written
             double s_ll, s_phi;
