@@ -492,6 +492,14 @@ __global__ void __launch_bounds__(GLMMA_EVAL_MAX_THREADS, 1) eval_kernel(EvalArg
 
     // (grid-uniform: the counter is final before this launch starts and is reset only by the finalising block)
     const bool any_work = !(A.only_deferred && A.defer_count != nullptr && !A.defer_static && __ldcg(A.defer_count) == 0u);
+    if (!any_work && A.fin_counter != nullptr) {
+        // nothing left to this kernel: block 0 alone turns the register variant's block partials (complete: this
+        // launch follows them on the stream) into the result vector, the other blocks leave at once
+        if (blockIdx.x != 0) return;
+        finalize_block(A.fin_partials, A.fin_blocks - (int)gridDim.x, nullptr, 0, true, d.p, d.n_phis, d.p_zi, Q, A.fin_want_score,
+                       A.fin_result, smem, A.fin_cpart, A.fin_ncpart, A.fin_ll_const, A.em_mode != 2, &A.xchg, &A.hout);
+        return;
+    }
     if (any_work) {
         load_fmtab(fmtab, A.fmtab);
         if (threadIdx.x < GLMMA_NAGQ_MAX) {
