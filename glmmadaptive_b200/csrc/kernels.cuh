@@ -1042,8 +1042,16 @@ __global__ void __launch_bounds__(256) prep_cluster_kernel(PrepArgs A, CoefPar C
 // sums (non-finite, or left to eval_kernel) takes its share back here, on a rare path.
 //
 // Shared memory per block: [fastmath | gx, glw | column table | node table (z.., lw per node) | node
-// idx | per-warp areas: 2 prefetch buffers (records, scalars, design columns), tabF, tabL, acc (also
-// scratch), wv, totals].
+// idx | per-warp areas: 2 prefetch buffers (records, scalars, design columns), acc (also scratch), wv,
+// per-lane totals, warp totals, two list records, tabF, tabL, mode-specific tail (ZP / two-pass state)].
+//
+// Forms of the round loop, chosen at compile time:
+//   FAST_KIND 1 / 2   carrier families, chunks of four observations                     (one pass, NJ <= 16)
+//   FAST_KIND 0       one functor call per observation; zero-inflated / hurdle families with the zero part
+//                     hoisted to the node and the observations sorted by class ("ZP")   (one pass, NJ <= 16)
+//   FAST_KIND 3       censored.normal: Gaussian part as a quadratic form per node ("GQ") (one pass, NJ <= 16)
+//   NJ == 32 (TP)     two passes over tiles of 32 rows, any cluster size, carrier families
+//   PAIR              two random-intercept clusters per warp, carrier families
 // ------------------------------------------------------------------------------
 #define GLMMA_NAGQ_FAST 16
 #ifndef GLMMA_NODE_PERM
